@@ -1,0 +1,152 @@
+/*
+ * sahs_b200.h -- C ABI of libsahs_b200.so, the B200-native (sm_100a) per-ray render/train hot path of
+ * SAHS-Deformable-Nerf.
+ *
+ * The reference has no FFI layer: its boundary is the Python surface of nerf-pytorch/nerf
+ * (SURVEY.md section 8b).  Each entry point below names the reference function (file:line, relative to
+ * /root/reference/nerf-pytorch) whose arithmetic it replaces.  The Python host package `sahs_b200`
+ * binds these with ctypes and re-exposes the reference's own signatures.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer unless the name ends in _host;
+ *   - returns 0 on success, a negative SAHS_E* code otherwise; no exception crosses the ABI;
+ *     sahs_last_error() returns a thread-local message for the last failure;
+ *   - allocates nothing: outputs and workspaces are caller-provided (sizes via the *_bytes queries);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and re-entrant per stream;
+ *   - fp32 tensors are dense row-major unless a stride argument says otherwise.
+ */
+#ifndef SAHS_B200_H
+#define SAHS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAHS_OK 0
+#define SAHS_EINVAL (-1)      /* bad argument / unsupported configuration */
+#define SAHS_ECUDA (-2)       /* a CUDA runtime call or kernel launch failed */
+#define SAHS_EUNSUPPORTED (-3)
+
+#define SAHS_RAW_CH 16        /* rgb3 | seg12 | sigma1, ref: nerf/modules.py:295 */
+#define SAHS_MAP_CH 15        /* rgb3 | seg12, ref: nerf/train_utils.py:205-206 */
+#define SAHS_DRIVING_DIM 76
+#define SAHS_POSE_CODE_DIM 36
+#define SAHS_GRID_CH 32
+#define SAHS_GRID_RES 32
+
+int sahs_abi_version(void);
+const char* sahs_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches evidence) */
+uint64_t sahs_launch_count(void);
+
+/* ---- architecture description: the dimensions NeRFaceModel.__init__ derives from the YAML
+ *      (ref: nerf/models.py:189-299, nerf/modules.py:168-252, :323-369, :401-442) ------------------- */
+typedef struct sahs_model_spec {
+  int32_t xyz_L, xyz_inc;            /* models.coarse.num_encoding_fn_xyz / include_input_xyz        */
+  int32_t dir_L, dir_inc;            /* num_encoding_fn_dir / include_input_dir                       */
+  int32_t use_ambient, amb_dim, amb_L, amb_inc;   /* models.hyper.*                                   */
+  int32_t use_warp, warp_layers, warp_hidden, warp_skip;
+  int32_t hyper_layers, hyper_hidden, hyper_skip;
+  int32_t trunk_layers, trunk_hidden, trunk_skip; /* trunk_skip is the NeRFMLP default 3              */
+  int32_t trunk_driving, trunk_pose; /* include_driving (76 cols) / use_pose (36 cols) in the trunk   */
+  int32_t use_grid;                  /* use_spatial_embeddings                                        */
+} sahs_model_spec;
+
+/* Canonical order of the fp32 parameter pointers handed to sahs_pack_params / sahs_fold_frame
+ * (weights are nn.Linear [out,in] row-major, ref state_dict names in SURVEY.md Appendix A):
+ *   [0]                 spatial_embeddings [1,32,32,32,32]            (NULL if !use_grid)
+ *   then for i in 0..warp_layers-1:  warp_field_mlp.layers_xyz.i.{weight,bias}; fc_final.{weight,bias}
+ *   then for i in 0..hyper_layers-1: hyper_sheep_mlp.layers_ambient.i.{weight,bias}; fc_ambient.{weight,bias}
+ *   then, for the requested level:   layers_xyz.i.{weight,bias} (trunk_layers), fc_feat, fc_alpha,
+ *                                    layers_dir.0-3, fc_rgb, layers_seg.0-3, fc_seg   ({weight,bias} each)
+ * sahs_param_count(spec) returns the length of that list. */
+int sahs_param_count(const sahs_model_spec* spec);
+
+/* ---- (1) ray generation, stratified depths, positional encoding --------------------------------- */
+/* get_ray_bundle, ref: nerf/nerf_helpers.py:178-233.  c2w: device [3,4] row-major (ld = 4).
+ * ro, rd: [H*W,3] (pixel (row j, col i) at j*W+i).  Bit-exact with the reference's fp32 op order. */
+int sahs_get_ray_bundle(int height, int width, float fx, float fy, float cx, float cy, const float* c2w,
+                        float* ro, float* rd, void* stream);
+/* coarse depths, ref: nerf/train_utils.py:93-113.  t_vals: device [S] = linspace(0,1,S) (host-made so it is
+ * bit-identical to torch.linspace); t_rand: device [R,S] uniforms or NULL for no perturbation. */
+int sahs_coarse_z(int num_rays, int num_samples, float near_, float far_, int lindisp, const float* t_vals,
+                  const float* t_rand, float* z_out, void* stream);
+/* positional_encoding (log sampling), ref: nerf/nerf_helpers.py:305-349.  x [n,d] -> out [n, d*(inc+2L)]. */
+int sahs_positional_encoding(const float* x, int64_t n, int d, int num_freqs, int include_input, float* out,
+                             void* stream);
+
+/* ---- (2) fused deformation + hyper-sheet + grid gather + radiance MLP (tcgen05/TMEM, TMA-fed) ---- */
+/* Bytes of the packed bf16 weight image of one level (warp+hyper+trunk+heads, UMMA 128B-swizzled stage
+ * images in consumption order) and of the per-frame constant block (fp32 biases with the frame-constant
+ * driving/pose columns folded in + the small fp32 head weights). */
+int sahs_field_sizes(const sahs_model_spec* spec, size_t* packed_bytes, size_t* frame_const_bytes,
+                     size_t* grid_bytes);
+/* fp32 state_dict -> packed bf16 image for `level` (0 coarse, 1 fine); also re-lays the embedding grid
+ * channel-last (grid_out may be NULL when !use_grid).  Replaces nothing in the reference (new layout step);
+ * must be re-run after every optimizer step. */
+int sahs_pack_params(const sahs_model_spec* spec, int level, const float* const* params_host_array,
+                     void* packed_out, float* grid_out, void* stream);
+/* Per-frame constant folding: driving [76] and pose_code [36] are identical for every point of a frame
+ * (ref: nerf/models.py:518-521), so W[:, const cols] @ (driving|pose) becomes a bias. */
+int sahs_fold_frame(const sahs_model_spec* spec, int level, const float* const* params_host_array,
+                    const float* driving, const float* pose_code, float* frame_const_out, void* stream);
+/* raw[R,S,16] = model(level, ro + rd*z, rd, driving, pose), ref: nerf/train_utils.py:9-50 (run_network),
+ * nerf/models.py:514-528 / :367-380 (forward), :301-365, nerf/modules.py:254-295, :371-390, :444-462.
+ * debug: optional device buffer [128*256] fp32 + debug_pass id (see SAHS_DBG_*), else NULL/-1. */
+int sahs_field_fwd(const sahs_model_spec* spec, int level, const void* packed, const float* frame_const,
+                   const float* grid_cl, const float* ro, const float* rd, const float* z, int num_rays,
+                   int num_samples, float* raw_out, float* debug, int debug_pass, void* stream);
+
+/* ---- (3) alpha compositing ---------------------------------------------------------------------- */
+/* volume_render_radiance_field, ref: nerf/volume_rendering_utils.py:7-78 (+ cumprod_exclusive,
+ * nerf/nerf_helpers.py:99-120) fused with the background overwrite raw[:, -1, :-1] = background_prior
+ * (ref: nerf/train_utils.py:135-136; applied on the fly when apply_bg_overwrite != 0, raw is not modified).
+ * raw [R,S,16]; z [R,S]; rd [R,3]; noise [R,S] (already scaled) or NULL; bg [R,bg_ch] or NULL (bg_ch 15 => seg
+ * softmax branch).  Outputs rgb_map [R,15], disp/acc/depth [R], weights [R,S]. */
+int sahs_composite_fwd(const float* raw, const float* z, const float* rd, const float* noise, const float* bg,
+                       int bg_ch, int apply_bg_overwrite, int num_rays, int num_samples, int white_background,
+                       float* rgb_map, float* disp, float* acc, float* weights, float* depth, void* stream);
+/* backward of the above w.r.t. raw: inputs d_rgb_map [R,15], d_disp/d_acc/d_depth [R] (NULL = zero),
+ * d_weights [R,S] (NULL = zero); output d_raw [R,S,16]. */
+int sahs_composite_bwd(const float* raw, const float* z, const float* rd, const float* noise, const float* bg,
+                       int bg_ch, int apply_bg_overwrite, int num_rays, int num_samples, int white_background,
+                       const float* d_rgb_map, const float* d_disp, const float* d_acc, const float* d_weights,
+                       const float* d_depth, float* d_raw, void* stream);
+
+/* ---- (4) hierarchical importance resampling + merge ---------------------------------------------- */
+/* sample_pdf_2 on bins = mid(z), weights[...,1:-1] (ref: nerf/nerf_helpers.py:454-497, call site
+ * nerf/train_utils.py:157-164) followed by sort(cat(z, z_samples)) (ref: nerf/train_utils.py:166).
+ * z [R,S], weights [R,S] (full compositing weights), u: device [n_fine] shared (det) when u_per_ray == 0 or
+ * [R,n_fine] when u_per_ray != 0.  Outputs z_samples [R,n_fine], z_merged [R,S+n_fine], inds [R,n_fine] int64
+ * (inds may be NULL).  Reproduces ATen's CPU summation orders so indices are bit-exact vs the reference on CPU. */
+int sahs_sample_pdf_merge(const float* z, const float* weights, const float* u, int u_per_ray, int num_rays,
+                          int num_samples, int num_fine, float* z_samples, float* z_merged, int64_t* inds,
+                          void* stream);
+
+/* sample_pdf_2(bins [R,nb], weights [R,nb-1], num_fine) alone, the reference's public helper signature
+ * (ref: nerf/nerf_helpers.py:454-497); same arithmetic as above without the merge. */
+int sahs_sample_pdf(const float* bins, const float* weights, const float* u, int u_per_ray, int num_rays,
+                    int num_bins, int num_fine, float* samples, int64_t* inds, void* stream);
+
+/* Diagnostic word written by the field kernel when a bounded mbarrier wait times out (0 = healthy):
+ * out4_host[0] code, [1] tag, [2] block, [3] thread.  Synchronous (device -> host copy). */
+int sahs_field_status(int* out4_host);
+
+/* Host-only plan introspection for the CPU test-suite (no device work); layouts documented in field_host.cu. */
+int sahs_debug_plan(const sahs_model_spec* spec, int param_count, int32_t* stages, int max_stages, int32_t* folds,
+                    int max_folds, int32_t* copies, int max_copies, int32_t* dims_out);
+
+/* debug_pass ids for sahs_field_fwd (value after bias+activation of that pass, fp32, tile 0, [128,256]) */
+#define SAHS_DBG_NONE (-1)
+#define SAHS_DBG_WARP(i) (i)            /* merged warp|hyper layer i: cols 0..wh-1 warp, wh.. hyper     */
+#define SAHS_DBG_MAPPED 16              /* cols 0-2 mapped xyz, 3.. ambient, 8..39 grid feature         */
+#define SAHS_DBG_TRUNK(i) (32 + (i))    /* trunk layer i; i == trunk_layers is fc_feat                  */
+#define SAHS_DBG_HEAD(i) (64 + (i))     /* cols 0-127 dir hidden i, 128-255 seg hidden i                */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAHS_B200_H */

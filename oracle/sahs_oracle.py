@@ -152,7 +152,7 @@ def audio_net(sd: Dict[str, torch.Tensor], audio: torch.Tensor, prefix="audNet_h
     return x.reshape(-1)
 
 
-def _skip_mlp(sd, prefix, n_layers, skip, x_in, act):
+def _skip_mlp(sd, prefix, n_layers, skip, x_in, act, taps=None, tap_name=None):
     """Shared body of WarpFieldMLP / HyperSheetMLP / NeRFMLP trunk: at layer `skip` the input is
     cat(x, initial) (ref: nerf/modules.py:254-262, :371-388, :444-460)."""
     x = x_in
@@ -160,6 +160,8 @@ def _skip_mlp(sd, prefix, n_layers, skip, x_in, act):
         if i == skip:
             x = torch.cat((x, x_in), dim=-1)
         x = act(F.linear(x, sd[f"{prefix}.{i}.weight"], sd[f"{prefix}.{i}.bias"]))
+        if taps is not None:
+            taps[f"{tap_name}{i}"] = x
     return x
 
 
@@ -199,14 +201,14 @@ def field_forward(sd: Dict[str, torch.Tensor], spec: ModelSpec, level: str, xyz:
     mapped = xyz
     if spec.use_warp:
         h = _skip_mlp(sd, "warp_field_mlp.layers_xyz", spec.warp_layers, spec.warp_skip,
-                      torch.cat((e0, drv, pcode), -1), F.relu)
+                      torch.cat((e0, drv, pcode), -1), F.relu, inter, "warp")
         dx = torch.tanh(F.linear(h, sd["warp_field_mlp.fc_final.weight"], sd["warp_field_mlp.fc_final.bias"]))
         mapped = xyz + dx
         inter["dx"] = dx
     amb = None
     if spec.use_ambient:
         h = _skip_mlp(sd, "hyper_sheep_mlp.layers_ambient", spec.hyper_layers, spec.hyper_skip,
-                      torch.cat((e0, drv, pcode), -1), F.relu)
+                      torch.cat((e0, drv, pcode), -1), F.relu, inter, "hyper")
         amb = F.linear(h, sd["hyper_sheep_mlp.fc_ambient.weight"], sd["hyper_sheep_mlp.fc_ambient.bias"])
         inter["amb"] = amb
     emb = None
@@ -227,7 +229,7 @@ def field_forward(sd: Dict[str, torch.Tensor], spec: ModelSpec, level: str, xyz:
     if spec.trunk_pose:
         initial = torch.cat((initial, pcode), -1)
     lrelu = lambda t: F.leaky_relu(t, 0.01)
-    h = _skip_mlp(sd, p + "layers_xyz", spec.trunk_layers, spec.trunk_skip, initial, lrelu)
+    h = _skip_mlp(sd, p + "layers_xyz", spec.trunk_layers, spec.trunk_skip, initial, lrelu, inter, "trunk")
     feat = F.linear(h, sd[p + "fc_feat.weight"], sd[p + "fc_feat.bias"])
     sigma = F.linear(feat, sd[p + "fc_alpha.weight"], sd[p + "fc_alpha.bias"])
     hd = feat
@@ -237,10 +239,12 @@ def field_forward(sd: Dict[str, torch.Tensor], spec: ModelSpec, level: str, xyz:
             hd = torch.cat((hd, emb), -1)
     for i in range(4):
         hd = lrelu(F.linear(hd, sd[p + f"layers_dir.{i}.weight"], sd[p + f"layers_dir.{i}.bias"]))
+        inter[f"dir{i}"] = hd
     rgb = F.linear(hd, sd[p + "fc_rgb.weight"], sd[p + "fc_rgb.bias"])
     hs = feat
     for i in range(4):
         hs = lrelu(F.linear(hs, sd[p + f"layers_seg.{i}.weight"], sd[p + f"layers_seg.{i}.bias"]))
+        inter[f"seg{i}"] = hs
     seg = F.linear(hs, sd[p + "fc_seg.weight"], sd[p + "fc_seg.bias"])
     raw = torch.cat((rgb, seg, sigma), -1)
     if return_intermediates:

@@ -1,0 +1,139 @@
+// Network plan of the fused field kernel: how the reference's three MLPs (WarpFieldMLP, HyperSheetMLP,
+// NeRFMLP; ref: nerf/modules.py:168-295, :323-390, :401-462) are cut into tensor-core "stages".
+//
+// Data layout
+//   * activation buffer X (shared memory): 4 K-chunks of [128 points x 64 features] bf16, each chunk a UMMA
+//     K-major SWIZZLE_128B operand tile (16 KB).  Chunk c holds features 64c..64c+63.
+//   * a stage = one B operand block [n rows (outputs) x 64 inputs] bf16 in the same swizzled layout
+//     (n*128 bytes), streamed by the TMA unit from the packed weight image in consumption order.
+//   * accumulators: TMEM columns 0..255 (fp32), row i of the tile <-> TMEM lane i.
+//   * a pass = the stages issued between two worker phases (epilogue / encoding writes).
+#pragma once
+#include <stdint.h>
+#include "../../include/sahs_b200.h"
+
+constexpr int kTileRows = 128;
+constexpr int kChunkCols = 64;
+constexpr int kChunkBytes = kTileRows * kChunkCols * 2;  // 16 KB
+constexpr int kMaxStages = 160;
+constexpr int kStageSlotBytes = 16384;
+
+enum : uint8_t { ST_WAIT_A = 1, ST_COMMIT = 2, ST_FRESH = 4 };
+
+struct StageRec {   // 4 bytes, lives in kernel parameter space
+  uint8_t n8;       // N / 8
+  uint8_t kflags;   // ksteps (low 3 bits) | flags << 3
+  uint8_t a_chunk;  // which X chunk is the A operand
+  uint8_t d_col8;   // accumulator column offset / 8
+};
+
+struct FieldPlan {
+  int32_t num_stages;
+  int32_t total_bytes;  // packed image bytes of one level
+  StageRec st[kMaxStages];
+};
+
+struct PackSrc {      // part of a stage image copied from one fp32 [out,in] weight matrix
+  const float* w;     // device pointer (NULL: unused)
+  int32_t ld;         // in_features
+  int32_t src_row0, src_col0;
+  int32_t dst_row0, nrows, ncols;
+};
+struct PackStage {
+  PackSrc src[2];
+  uint32_t dst_off;   // byte offset in the packed image
+  int32_t n;          // rows of the image (zero padded)
+};
+
+// fp32 per-frame constant block: offsets in floats
+struct FoldSection {
+  const float* bias;  // [n]
+  const float* w;     // [n, ld] weight whose constant columns are folded (NULL: plain copy of bias)
+  int32_t ld, col0, ncols, c_off;  // fold W[:, col0:col0+ncols] @ cvec[c_off:c_off+ncols]
+  int32_t n, dst;
+};
+struct CopySection {  // small fp32 head weights copied verbatim
+  const float* src;
+  int32_t count, dst;
+};
+
+// Dimensions derived from the spec, shared by host plan builder and device worker code.
+struct NetDims {
+  int e0_dim, e0_k, e0_chunks;      // PE(xyz): 63->64 | 93->96
+  int amb_pe;                       // ambient PE width
+  int e1_dim, e1_k, e1_chunks;      // PE(mapped xyz) | PE(ambient)
+  int wh, hh, whh;                  // warp hidden, hyper hidden, merged width
+  int w_layers, w_skip;             // merged deformation net depth / skip layer (warp & hyper agree)
+  int e0_resident;                  // E0 stays in X next to the hidden activations during the W phase
+  int e0_chunk_base;                // first X chunk of E0 for layer 0 / skip pass
+  int th, t_layers, t_skip;
+  int hd;                           // head hidden (th/2)
+  int xtra_dim, xtra_k;             // dir PE (+ grid) appended to feat for layers_dir.0
+  int ct_off, ct_len;               // trunk constant vector = cvec[ct_off : ct_off+ct_len]
+  int use_w;                        // deformation phase present
+  // frame-constant block offsets (floats)
+  int off_wbias, off_wfinal, off_tbias, off_featb, off_alpha, off_hbias, off_outb, fc_total;
+};
+
+inline int sahs_round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// returns 0 on success
+inline int sahs_make_dims(const sahs_model_spec& s, NetDims& d) {
+  d = NetDims{};
+  d.e0_dim = (s.xyz_inc ? 3 : 0) + 6 * s.xyz_L;
+  d.e0_k = sahs_round_up(d.e0_dim, 16);
+  d.e0_chunks = (d.e0_k + 63) / 64;
+  d.amb_pe = s.use_ambient ? ((s.amb_inc ? s.amb_dim : 0) + 2 * s.amb_dim * s.amb_L) : 0;
+  d.e1_dim = d.e0_dim + d.amb_pe;
+  d.e1_k = sahs_round_up(d.e1_dim, 16);
+  d.e1_chunks = (d.e1_k + 63) / 64;
+  d.use_w = (s.use_warp && s.use_ambient) ? 1 : 0;
+  if (s.use_warp != s.use_ambient) return -1;  // shipped configs enable both or neither
+  d.wh = s.warp_hidden;
+  d.hh = s.hyper_hidden;
+  d.whh = d.wh + d.hh;
+  d.w_layers = s.warp_layers;
+  d.w_skip = s.warp_skip;
+  if (d.use_w) {
+    if (s.hyper_layers != s.warp_layers || s.hyper_skip != s.warp_skip) return -2;
+    if (d.wh % 64 || d.hh % 64 || d.wh > 128 || d.hh > 128 || d.whh > 256) return -3;
+    if (d.w_skip <= 0 || d.w_skip >= d.w_layers) return -4;
+  }
+  d.e0_resident = (d.whh / 64 + d.e0_chunks <= 4) ? 1 : 0;
+  d.e0_chunk_base = d.e0_resident ? d.whh / 64 : 0;
+  d.th = s.trunk_hidden;
+  d.t_layers = s.trunk_layers;
+  d.t_skip = s.trunk_skip;
+  if (d.th != 256) return -5;
+  if (d.t_skip <= 0 || d.t_skip >= d.t_layers) return -6;
+  if (d.e0_chunks > 2 || d.e1_chunks > 2) return -7;
+  d.hd = d.th / 2;
+  d.xtra_dim = (s.dir_inc ? 3 : 0) + 6 * s.dir_L + (s.use_grid ? SAHS_GRID_CH : 0);
+  d.xtra_k = sahs_round_up(d.xtra_dim, 16);
+  if (d.xtra_k > 64) return -8;
+  d.ct_off = s.trunk_driving ? 0 : SAHS_DRIVING_DIM;
+  d.ct_len = (s.trunk_driving ? SAHS_DRIVING_DIM : 0) + (s.trunk_pose ? SAHS_POSE_CODE_DIM : 0);
+  if (s.amb_dim > 4 || s.amb_dim < 0) return -9;
+  int o = 0;
+  d.off_wbias = o;  o += d.use_w ? d.w_layers * d.whh : 0;
+  d.off_wfinal = o; o += d.use_w ? sahs_round_up(3 * d.wh + 3 + s.amb_dim * d.hh + s.amb_dim, 4) : 0;
+  d.off_tbias = o;  o += d.t_layers * d.th;
+  d.off_featb = o;  o += d.th;
+  d.off_alpha = o;  o += d.th + 4;
+  d.off_hbias = o;  o += 4 * 2 * d.hd;
+  d.off_outb = o;   o += 16;
+  d.fc_total = o;
+  return 0;
+}
+
+// host-only: plan + pack/fold descriptors (field_host.cu)
+struct HostPlan {
+  NetDims dims;
+  FieldPlan plan;
+  PackStage pack[kMaxStages];
+  FoldSection fold[64];
+  int num_fold;
+  CopySection copy[8];
+  int num_copy;
+};
+int sahs_build_host_plan(const sahs_model_spec& spec, const float* const* params, HostPlan& hp);

@@ -1,0 +1,187 @@
+// (4) hierarchical importance resampling + merge: one warp per ray.
+// ref: nerf/nerf_helpers.py:454-497 (sample_pdf_2), call site nerf/train_utils.py:157-166.
+//
+// Bit-exactness contract: fed the reference's weights, the indices returned by
+// searchsorted must equal the reference's on CPU.  That requires reproducing ATen's CPU reduction orders:
+//   * sum(w): vectorized_inner_sum -- 8 fp32 lanes, 4 interleaved accumulators over whole 8-wide vectors,
+//     remaining vectors into accumulator 0, accumulators folded 1..3 into 0, scalar tail summed first into a
+//     scalar, then the 8 lanes added to it in lane order.  No FMA.
+//   * pdf = w / sum: IEEE division.
+//   * cumsum: double accumulator, rounded to fp32 per element.  For this domain (pdf in [~1e-5/(1+eps), 1],
+//     <= 254 terms) every partial double sum is exact (<= 24+17+8 significant bits), so a parallel scan in
+//     double gives the same bits as ATen's sequential loop.
+//   * z_mid, t, sample: separate fp32 mul/add (no contraction).
+#include "sahs_common.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kMaxS = 256;      // coarse samples per ray
+constexpr int kMaxMerged = 512; // S + n_fine
+
+struct WarpScratch {
+  float w[kMaxS];        // w[j] = weights[j+1] + 1e-5, j < n = S-2
+  float cdf[kMaxS];      // n+1 entries
+  float bins[kMaxS];     // S-1 mid points
+  float merged[kMaxMerged];
+};
+
+__device__ __forceinline__ double shfl_up_double(double v, int o) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_up_sync(0xffffffffu, lo, o);
+  hi = __shfl_up_sync(0xffffffffu, hi, o);
+  return __hiloint2double(hi, lo);
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+sample_pdf_merge_kernel(const float* __restrict__ z, const float* __restrict__ bins_in,
+                        const float* __restrict__ weights, const float* __restrict__ u, int u_per_ray, int R, int S,
+                        int NF, float* __restrict__ z_samples, float* __restrict__ z_merged,
+                        int64_t* __restrict__ inds_out) {
+  __shared__ WarpScratch scratch[kWarps];
+  WarpScratch& sm = scratch[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const int n = S - 2;        // number of pdf entries
+  const int nb = S - 1;       // number of bins == number of cdf entries
+  const int warps_total = gridDim.x * kWarps;
+  for (int r = blockIdx.x * kWarps + (threadIdx.x >> 5); r < R; r += warps_total) {
+    if (bins_in) {
+      // public sample_pdf_2(bins, weights, ...) form: bins [R,S-1], weights [R,S-2], no merge
+      for (int j = lane; j < n; j += 32) sm.w[j] = __fadd_rn(weights[(size_t)r * n + j], 1e-5f);
+      for (int j = lane; j < nb; j += 32) sm.bins[j] = bins_in[(size_t)r * nb + j];
+    } else {
+      const float* zr = z + (size_t)r * S;
+      const float* wr = weights + (size_t)r * S;
+      for (int j = lane; j < n; j += 32) sm.w[j] = __fadd_rn(wr[j + 1], 1e-5f);
+      for (int j = lane; j < nb; j += 32) sm.bins[j] = __fmul_rn(0.5f, __fadd_rn(zr[j + 1], zr[j]));
+      for (int j = lane; j < S; j += 32) sm.merged[j] = zr[j];
+    }
+    __syncwarp();
+    // ---- total in ATen's vectorized_inner_sum order -------------------------------------------
+    const int nv = n / 8, size_ilp = nv / 4;
+    float p0 = 0.f;
+    if (lane < 8) {
+      float p1 = 0.f, p2 = 0.f, p3 = 0.f;
+      for (int i = 0; i < size_ilp; ++i) {
+        p0 = __fadd_rn(p0, sm.w[(4 * i + 0) * 8 + lane]);
+        p1 = __fadd_rn(p1, sm.w[(4 * i + 1) * 8 + lane]);
+        p2 = __fadd_rn(p2, sm.w[(4 * i + 2) * 8 + lane]);
+        p3 = __fadd_rn(p3, sm.w[(4 * i + 3) * 8 + lane]);
+      }
+      for (int i = size_ilp * 4; i < nv; ++i) p0 = __fadd_rn(p0, sm.w[i * 8 + lane]);
+      p0 = __fadd_rn(p0, p1);
+      p0 = __fadd_rn(p0, p2);
+      p0 = __fadd_rn(p0, p3);
+    }
+    float total = 0.f;
+    for (int k = nv * 8; k < n; ++k) total = __fadd_rn(total, sm.w[k]);
+#pragma unroll
+    for (int l = 0; l < 8; ++l) total = __fadd_rn(total, __shfl_sync(0xffffffffu, p0, l));
+    // ---- pdf and cdf ---------------------------------------------------------------------------
+    // lane owns the contiguous slice [lane*per, lane*per+per) of the pdf
+    const int per = (n + 31) / 32;
+    double local = 0.0;
+    for (int q = 0; q < per; ++q) {
+      int j = lane * per + q;
+      if (j < n) local += (double)__fdiv_rn(sm.w[j], total);
+    }
+    double incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      double up = shfl_up_double(incl, o);
+      if (lane >= o) incl += up;
+    }
+    double run = incl - local;  // exclusive prefix of this lane's slice
+    if (lane == 0) sm.cdf[0] = 0.f;
+    for (int q = 0; q < per; ++q) {
+      int j = lane * per + q;
+      if (j < n) {
+        run += (double)__fdiv_rn(sm.w[j], total);
+        sm.cdf[j + 1] = (float)run;
+      }
+    }
+    __syncwarp();
+    // ---- invert the cdf --------------------------------------------------------------------------
+    for (int i = lane; i < NF; i += 32) {
+      const float uu = u_per_ray ? u[(size_t)r * NF + i] : u[i];
+      // searchsorted(right=True): first index with cdf[idx] > u  == number of entries <= u
+      int lo = 0, hi = nb;
+      while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (sm.cdf[mid] <= uu) lo = mid + 1; else hi = mid;
+      }
+      const int ind = lo;
+      const int below = max(ind - 1, 0), above = min(ind, nb - 1);
+      const float cb = sm.cdf[below], ca = sm.cdf[above];
+      const float bb = sm.bins[below], ba = sm.bins[above];
+      float denom = __fsub_rn(ca, cb);
+      if (denom < 1e-5f) denom = 1.0f;
+      const float t = __fdiv_rn(__fsub_rn(uu, cb), denom);
+      const float smp = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
+      z_samples[(size_t)r * NF + i] = smp;
+      if (!bins_in) sm.merged[S + i] = smp;
+      if (inds_out) inds_out[(size_t)r * NF + i] = ind;
+    }
+    __syncwarp();
+    if (bins_in) continue;
+    // ---- sort(cat(z, z_samples)): bitonic network over the next power of two ---------------------
+    const int tot = S + NF;
+    int P = 1;
+    while (P < tot) P <<= 1;
+    for (int j = tot + lane; j < P; j += 32) sm.merged[j] = __int_as_float(0x7f800000);  // +inf padding
+    __syncwarp();
+    for (int k = 2; k <= P; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = lane; i < P; i += 32) {
+          int ixj = i ^ j;
+          if (ixj > i) {
+            float a = sm.merged[i], b = sm.merged[ixj];
+            bool up = (i & k) == 0;
+            if ((a > b) == up) {
+              sm.merged[i] = b;
+              sm.merged[ixj] = a;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    for (int j = lane; j < tot; j += 32) z_merged[(size_t)r * tot + j] = sm.merged[j];
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+extern "C" int sahs_sample_pdf_merge(const float* z, const float* weights, const float* u, int u_per_ray,
+                                     int num_rays, int num_samples, int num_fine, float* z_samples, float* z_merged,
+                                     int64_t* inds, void* stream) {
+  SAHS_CHECK_ARG(z && weights && u && z_samples && z_merged, "null pointer");
+  SAHS_CHECK_ARG(num_samples >= 3 && num_samples <= kMaxS, "num_samples must be in [3,256]");
+  SAHS_CHECK_ARG(num_fine >= 1 && num_samples + num_fine <= kMaxMerged, "num_samples + num_fine must be <= 512");
+  if (num_rays == 0) return SAHS_OK;
+  int blocks = (num_rays + kWarps - 1) / kWarps;
+  int cap = sahs_num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  sample_pdf_merge_kernel<<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(z, nullptr, weights, u, u_per_ray, num_rays,
+                                                                          num_samples, num_fine, z_samples, z_merged,
+                                                                          inds);
+  SAHS_LAUNCH_CHECK();
+  return SAHS_OK;
+}
+
+extern "C" int sahs_sample_pdf(const float* bins, const float* weights, const float* u, int u_per_ray, int num_rays,
+                               int num_bins, int num_fine, float* samples, int64_t* inds, void* stream) {
+  SAHS_CHECK_ARG(bins && weights && u && samples, "null pointer");
+  SAHS_CHECK_ARG(num_bins >= 2 && num_bins + 1 <= kMaxS, "num_bins must be in [2,255]");
+  SAHS_CHECK_ARG(num_fine >= 1 && num_fine <= kMaxMerged, "num_fine must be <= 512");
+  if (num_rays == 0) return SAHS_OK;
+  int blocks = (num_rays + kWarps - 1) / kWarps;
+  int cap = sahs_num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  sample_pdf_merge_kernel<<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(nullptr, bins, weights, u, u_per_ray,
+                                                                          num_rays, num_bins + 1, num_fine, samples,
+                                                                          nullptr, inds);
+  SAHS_LAUNCH_CHECK();
+  return SAHS_OK;
+}

@@ -1,0 +1,107 @@
+"""ctypes binding of libsahs_b200.so (include/sahs_b200.h).
+
+There is deliberately no fallback: if the CUDA library is missing or a call fails, a RuntimeError is raised.
+PyTorch is used only for device memory, streams and torch.distributed; every tensor crosses the ABI as a raw
+device pointer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_PKG), "lib", "libsahs_b200.so")
+
+_lib: Optional[C.CDLL] = None
+
+
+class ModelSpecC(C.Structure):
+    """struct sahs_model_spec"""
+    _fields_ = [(n, C.c_int32) for n in (
+        "xyz_L", "xyz_inc", "dir_L", "dir_inc", "use_ambient", "amb_dim", "amb_L", "amb_inc",
+        "use_warp", "warp_layers", "warp_hidden", "warp_skip", "hyper_layers", "hyper_hidden", "hyper_skip",
+        "trunk_layers", "trunk_hidden", "trunk_skip", "trunk_driving", "trunk_pose", "use_grid")]
+
+
+EXPORTS = (
+    "sahs_abi_version", "sahs_last_error", "sahs_launch_count", "sahs_param_count", "sahs_get_ray_bundle",
+    "sahs_coarse_z", "sahs_positional_encoding", "sahs_field_sizes", "sahs_pack_params", "sahs_fold_frame",
+    "sahs_field_fwd", "sahs_composite_fwd", "sahs_composite_bwd", "sahs_sample_pdf_merge", "sahs_sample_pdf",
+    "sahs_field_status", "sahs_debug_plan",
+)
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"libsahs_b200.so not found at {LIB_PATH}; build it with `make -C sahs-deformable-nerf_b200` "
+            "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU/PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
+    spec_p = C.POINTER(ModelSpecC)
+    sigs = {
+        "sahs_abi_version": (C.c_int, []),
+        "sahs_last_error": (C.c_char_p, []),
+        "sahs_launch_count": (C.c_uint64, []),
+        "sahs_param_count": (C.c_int, [spec_p]),
+        "sahs_get_ray_bundle": (C.c_int, [i32, i32, f32, f32, f32, f32, vp, vp, vp, vp]),
+        "sahs_coarse_z": (C.c_int, [i32, i32, f32, f32, i32, vp, vp, vp, vp]),
+        "sahs_positional_encoding": (C.c_int, [vp, i64, i32, i32, i32, vp, vp]),
+        "sahs_field_sizes": (C.c_int, [spec_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+        "sahs_pack_params": (C.c_int, [spec_p, i32, C.POINTER(vp), vp, vp, vp]),
+        "sahs_fold_frame": (C.c_int, [spec_p, i32, C.POINTER(vp), vp, vp, vp, vp]),
+        "sahs_field_fwd": (C.c_int, [spec_p, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, i32, vp]),
+        "sahs_composite_fwd": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+        "sahs_composite_bwd": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+        "sahs_sample_pdf_merge": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
+        "sahs_sample_pdf": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]),
+        "sahs_debug_plan": (C.c_int, [spec_p, i32, C.POINTER(C.c_int32), i32, C.POINTER(C.c_int32), i32,
+                                      C.POINTER(C.c_int32), i32, C.POINTER(C.c_int32)]),
+        "sahs_field_status": (C.c_int, [C.POINTER(C.c_int)]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().sahs_last_error()
+        raise RuntimeError(f"libsahs_b200 {what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Raw device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("sahs_b200 ops need CUDA tensors (there is no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError("internal error: non-contiguous tensor handed to the C ABI")
+    return t.data_ptr()
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def f32c(t: torch.Tensor) -> torch.Tensor:
+    """fp32 + contiguous view/copy (inputs may be non-contiguous views)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def param_ptr_array(tensors: Sequence[Optional[torch.Tensor]]):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = ptr(t) if t is not None else None
+    return arr

@@ -1,0 +1,140 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/sahs_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import lib as L
+
+MAP_CH = 15
+RAW_CH = 16
+
+
+def _linspace_dev(steps: int, device) -> torch.Tensor:
+    # made on the host so the values are bit-identical to the reference's CPU torch.linspace
+    return torch.linspace(0.0, 1.0, steps, dtype=torch.float32).to(device)
+
+
+def get_ray_bundle(height: int, width: int, intrinsics, c2w: torch.Tensor):
+    """ref: nerf/nerf_helpers.py:178-233.  Returns (ro, rd) of shape (H, W, 3)."""
+    lib = L.load()
+    fx, fy, cx, cy = [float(v) for v in intrinsics]
+    pose = L.f32c(c2w[:3, :4])
+    ro = torch.empty(height, width, 3, dtype=torch.float32, device=pose.device)
+    rd = torch.empty_like(ro)
+    L.check(lib.sahs_get_ray_bundle(height, width, fx, fy, cx, cy, L.ptr(pose), L.ptr(ro), L.ptr(rd),
+                                    L.stream_ptr(pose.device)), "get_ray_bundle")
+    return ro, rd
+
+
+def coarse_z(num_rays: int, num_samples: int, near: float, far: float, lindisp: bool, device,
+             t_rand: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ref: nerf/train_utils.py:93-113."""
+    lib = L.load()
+    t_vals = _linspace_dev(num_samples, device)
+    z = torch.empty(num_rays, num_samples, dtype=torch.float32, device=device)
+    tr = L.f32c(t_rand) if t_rand is not None else None
+    L.check(lib.sahs_coarse_z(num_rays, num_samples, float(near), float(far), int(bool(lindisp)), L.ptr(t_vals),
+                              L.ptr(tr), L.ptr(z), L.stream_ptr(device)), "coarse_z")
+    return z
+
+
+def positional_encoding(x: torch.Tensor, num_freqs: int, include_input: bool = True) -> torch.Tensor:
+    """ref: nerf/nerf_helpers.py:305-349 (log sampling)."""
+    lib = L.load()
+    xc = L.f32c(x)
+    d = xc.shape[-1]
+    n = xc.numel() // d
+    width = d * ((1 if include_input else 0) + 2 * num_freqs)
+    if width == d and include_input:
+        return x
+    out = torch.empty(*xc.shape[:-1], width, dtype=torch.float32, device=xc.device)
+    L.check(lib.sahs_positional_encoding(L.ptr(xc), n, d, num_freqs, int(include_input), L.ptr(out),
+                                         L.stream_ptr(xc.device)), "positional_encoding")
+    return out
+
+
+def composite_fwd(raw, z, rd, noise=None, bg=None, apply_bg_overwrite=False, white_background=False):
+    """ref: nerf/volume_rendering_utils.py:7-78.  Returns (rgb_map, disp, acc, weights, depth)."""
+    lib = L.load()
+    raw, z, rd = L.f32c(raw), L.f32c(z), L.f32c(rd)
+    R, S = z.shape
+    if raw.shape != (R, S, RAW_CH):
+        raise RuntimeError(f"radiance_field must be [R,S,16], got {tuple(raw.shape)}")
+    noise = L.f32c(noise) if noise is not None else None
+    bg = L.f32c(bg) if bg is not None else None
+    if bg is not None and bg.shape[-1] != MAP_CH:
+        raise RuntimeError("background_prior must have 15 channels (rgb 3 + semantic 12)")
+    dev = raw.device
+    rgb = torch.empty(R, MAP_CH, dtype=torch.float32, device=dev)
+    disp = torch.empty(R, dtype=torch.float32, device=dev)
+    acc = torch.empty_like(disp)
+    depth = torch.empty_like(disp)
+    w = torch.empty(R, S, dtype=torch.float32, device=dev)
+    L.check(lib.sahs_composite_fwd(L.ptr(raw), L.ptr(z), L.ptr(rd), L.ptr(noise), L.ptr(bg), MAP_CH,
+                                   int(apply_bg_overwrite), R, S, int(white_background), L.ptr(rgb), L.ptr(disp),
+                                   L.ptr(acc), L.ptr(w), L.ptr(depth), L.stream_ptr(dev)), "composite_fwd")
+    return rgb, disp, acc, w, depth
+
+
+def composite_bwd(raw, z, rd, noise, bg, apply_bg_overwrite, white_background, d_rgb, d_disp, d_acc, d_w, d_depth):
+    lib = L.load()
+    raw, z, rd = L.f32c(raw), L.f32c(z), L.f32c(rd)
+    R, S = z.shape
+    c = lambda t: L.f32c(t) if t is not None else None
+    noise, bg, d_rgb, d_disp, d_acc, d_w, d_depth = map(c, (noise, bg, d_rgb, d_disp, d_acc, d_w, d_depth))
+    d_raw = torch.empty_like(raw)
+    L.check(lib.sahs_composite_bwd(L.ptr(raw), L.ptr(z), L.ptr(rd), L.ptr(noise), L.ptr(bg), MAP_CH,
+                                   int(apply_bg_overwrite), R, S, int(white_background), L.ptr(d_rgb), L.ptr(d_disp),
+                                   L.ptr(d_acc), L.ptr(d_w), L.ptr(d_depth), L.ptr(d_raw), L.stream_ptr(raw.device)),
+            "composite_bwd")
+    return d_raw
+
+
+def sample_pdf_merge(z, weights, num_fine: int, u: Optional[torch.Tensor] = None, return_inds: bool = False):
+    """sample_pdf_2(mid(z), weights[...,1:-1], num_fine) + sort(cat(z, samples)).
+    ref: nerf/nerf_helpers.py:454-497, nerf/train_utils.py:157-166.  u=None -> deterministic linspace."""
+    lib = L.load()
+    z, weights = L.f32c(z), L.f32c(weights)
+    R, S = z.shape
+    dev = z.device
+    if u is None:
+        uu, per_ray = _linspace_dev(num_fine, dev), 0
+    else:
+        uu, per_ray = L.f32c(u), 1
+        if uu.shape != (R, num_fine):
+            raise RuntimeError("u must be [R, num_fine]")
+    zs = torch.empty(R, num_fine, dtype=torch.float32, device=dev)
+    zm = torch.empty(R, S + num_fine, dtype=torch.float32, device=dev)
+    inds = torch.empty(R, num_fine, dtype=torch.int64, device=dev) if return_inds else None
+    L.check(lib.sahs_sample_pdf_merge(L.ptr(z), L.ptr(weights), L.ptr(uu), per_ray, R, S, num_fine, L.ptr(zs),
+                                      L.ptr(zm), L.ptr(inds), L.stream_ptr(dev)), "sample_pdf_merge")
+    return (zs, zm, inds) if return_inds else (zs, zm)
+
+
+def sample_pdf_bins(bins, weights, num_fine: int, u: Optional[torch.Tensor] = None, return_inds: bool = False):
+    """sample_pdf_2(bins, weights, num_fine, det=(u is None)), ref: nerf/nerf_helpers.py:454-497."""
+    lib = L.load()
+    bins, weights = L.f32c(bins), L.f32c(weights)
+    R, nb = bins.shape
+    if weights.shape != (R, nb - 1):
+        raise RuntimeError("weights must be [R, bins-1]")
+    dev = bins.device
+    if u is None:
+        uu, per_ray = _linspace_dev(num_fine, dev), 0
+    else:
+        uu, per_ray = L.f32c(u), 1
+    out = torch.empty(R, num_fine, dtype=torch.float32, device=dev)
+    inds = torch.empty(R, num_fine, dtype=torch.int64, device=dev) if return_inds else None
+    L.check(lib.sahs_sample_pdf(L.ptr(bins), L.ptr(weights), L.ptr(uu), per_ray, R, nb, num_fine, L.ptr(out),
+                                L.ptr(inds), L.stream_ptr(dev)), "sample_pdf")
+    return (out, inds) if return_inds else out
+
+
+def field_status():
+    lib = L.load()
+    out = (C.c_int * 4)()
+    L.check(lib.sahs_field_status(out), "field_status")
+    return list(out)

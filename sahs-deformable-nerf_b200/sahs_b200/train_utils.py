@@ -1,0 +1,106 @@
+"""The per-ray pipeline with the reference's call signatures.
+
+ref: nerf/train_utils.py:9-50 (run_network), :72-206 (predict_and_render_radiance), :209-321
+(run_one_iter_of_nerf).  One call = a fixed sequence of CUDA kernels per ray chunk:
+  coarse_z -> fold_frame -> field(coarse) -> composite -> sample_pdf+merge -> field(fine) -> composite
+with no Python loop over point chunks (`chunksize` only bounds the ray chunk, as a memory hint).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+from .volume_rendering_utils import composite
+
+# rays per internal chunk: raw_fine is [rays, 128, 16] fp32 = 8 KB/ray -> 4 GB at 512k rays
+MAX_RAYS_PER_CHUNK = 1 << 19
+
+
+def run_network(level, network_fn, pts, ray_batch, chunksize, use_viewdirs, driving=None, pose=None, pose_c=None,
+                latent_code=None, spatial_embeddings=None):
+    """ref: nerf/train_utils.py:9-50.  Evaluates the field at explicit points (all chunks in one launch)."""
+    dirs = ray_batch[..., None, 3:6].expand(pts.shape)
+    x = torch.cat((pts.reshape(-1, 3), dirs.reshape(-1, 3)), dim=-1)
+    raw = network_fn(level, x, driving, pose, pose_c, latent_code=latent_code)
+    return raw.reshape(*pts.shape[:-1], raw.shape[-1])
+
+
+def _render_chunk(model, nerf_opts, ro, rd, near, far, driving_vec, pose_code, bg, draws):
+    R = ro.shape[0]
+    dev = ro.device
+    nc, nf = int(nerf_opts.num_coarse), int(nerf_opts.num_fine)
+    perturb = bool(nerf_opts.perturb)
+    noise_std = float(nerf_opts.radiance_field_noise_std)
+    white = bool(nerf_opts.white_background)
+    draws = draws or {}
+    t_rand = None
+    if perturb:
+        t_rand = draws.get("t_rand")
+        if t_rand is None:
+            t_rand = torch.rand(R, nc, dtype=torch.float32, device=dev)
+
+    def noise_for(key, S):
+        if noise_std <= 0.0:
+            return None
+        n = draws.get(key)
+        return n if n is not None else torch.randn(R, S, dtype=torch.float32, device=dev) * noise_std
+
+    z_c = ops.coarse_z(R, nc, near, far, bool(nerf_opts.lindisp), dev, t_rand)
+    raw_c = model.field("coarse", ro, rd, z_c, driving_vec, pose_code)
+    rgb_c, disp_c, acc_c, w_c, depth_c = composite(raw_c, z_c, rd, noise_for("noise_c", nc), bg, bg is not None, white)
+    if nf <= 0:
+        raise RuntimeError("num_fine == 0 is a dead branch in the reference (depth_fine undefined, "
+                           "ref: nerf/train_utils.py:205-206); not supported")
+    u = None
+    if perturb:                                   # det = (perturb == 0.0), ref: nerf/train_utils.py:162
+        u = draws.get("u")
+        if u is None:
+            u = torch.rand(R, nf, dtype=torch.float32, device=dev)
+    z_s, z_f = ops.sample_pdf_merge(z_c, w_c.detach(), nf, u)      # z_samples.detach(), ref: :164
+    raw_f = model.field("fine", ro, rd, z_f, driving_vec, pose_code)
+    rgb_f, disp_f, acc_f, w_f, depth_f = composite(raw_f, z_f, rd, noise_for("noise_f", nc + nf), bg, bg is not None,
+                                                   white)
+    return rgb_c, disp_c, acc_c, rgb_f, disp_f, acc_f, w_f[:, -1], depth_f
+
+
+def predict_and_render_radiance(ray_batch, model, options, mode="train", driving=None, pose=None, pose_c=None,
+                                background_prior=None, latent_code=None, spatial_embeddings=None, ray_dirs_fake=None,
+                                _draws=None):
+    """ref: nerf/train_utils.py:72-206.  ray_batch[r] = (ro 3 | rd 3 | near | far | mask...)."""
+    ro, rd = ray_batch[..., :3], ray_batch[..., 3:6]
+    near, far = float(ray_batch[0, 6]), float(ray_batch[0, 7])
+    dvec = model.driving_vector(driving)
+    pcode = model.pose_code(pose)
+    return _render_chunk(model, getattr(options.nerf, mode), ro, rd, near, far, dvec, pcode, background_prior, _draws)
+
+
+def run_one_iter_of_nerf(height, width, focal_length, model, ray_origins, ray_directions, options, mode="train",
+                         driving=None, pose=None, pose_c=None, background_prior=None, latent_code=None,
+                         ray_directions_ablation=None, spatial_embeddings=None, inHead=None, _draws=None):
+    """ref: nerf/train_utils.py:209-321.  Returns the 8-tuple (rgb_coarse, disp_coarse, acc_coarse, rgb_fine,
+    disp_fine, acc_fine, weights_fine[:, -1], depth_fine); "validation" mode restores image shapes."""
+    if options.dataset.no_ndc is False:
+        raise RuntimeError("NDC rays are a dead branch in the reference (every config sets no_ndc: True and "
+                           "rd_ablations would be undefined, ref: nerf/train_utils.py:243-254); not supported")
+    ro = ray_origins.reshape(-1, 3)
+    rd = ray_directions.reshape(-1, 3)
+    near, far = float(options.dataset.near), float(options.dataset.far)
+    nerf_opts = getattr(options.nerf, mode)
+    dvec = model.driving_vector(driving)            # once per call (the reference re-runs AudioNet per chunk)
+    pcode = model.pose_code(pose)
+    R = ro.shape[0]
+    chunk = min(MAX_RAYS_PER_CHUNK, max(int(nerf_opts.chunksize), 1) * 4)
+    outs = []
+    for i in range(0, R, chunk):
+        bg = background_prior[i:i + chunk] if background_prior is not None else None
+        dr = None
+        if _draws:
+            dr = {k: (v[i:i + chunk] if v is not None else None) for k, v in _draws.items()}
+        outs.append(_render_chunk(model, nerf_opts, ro[i:i + chunk], rd[i:i + chunk], near, far, dvec, pcode, bg, dr))
+    images = [torch.cat(parts, dim=0) if len(parts) > 1 else parts[0] for parts in zip(*outs)]
+    if mode == "validation":
+        shp = tuple(ray_directions.shape[:-1])
+        images = [im.view(*shp, im.shape[-1]) if im.dim() == 2 else im.view(shp) for im in images]
+    return tuple(images)
