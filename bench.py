@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Benchmark of the per-ray render hot path (BASELINE.json: rays/s, ms per 512x512 frame).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config audio/person_2_auto]
+
+A step = one Stage-I render of a 512x512 frame (262,144 rays, 64 coarse + 128 fine samples per ray) of the
+named config with random-init ("dense" fixture) weights and synthetic per-frame inputs.
+  value   rays/s with rays and per-frame inputs already resident in HBM (CUDA events, max over ranks)
+  e2e     the same through the public API with HOST inputs: per frame H2D of pose/audio/mask from pinned memory,
+          get_ray_bundle, run_one_iter_of_nerf, D2H of the fine rgb+semantic map, depth and acc
+N > 1 (torchrun, NCCL plumbing only): weak scaling, every rank renders its own frames (frame f -> rank f mod N);
+there is no data-path collective.  --impl reference times the CPU oracle port (the reference's algorithm in
+torch-CPU ops) on the host cores; rank 0 only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+for p in (REPO, os.path.join(REPO, "tests"), os.path.join(REPO, "sahs-deformable-nerf_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+H = W = 512
+
+
+def algorithmic_macs_per_point(spec) -> int:
+    """Dense-layer MACs per sample point with the frame-constant input columns folded into biases
+    (866,432 for the audio configs)."""
+    e0 = spec.xyz_dim
+    e1 = e0 + spec.amb_pe_dim
+    macs = 0
+    if spec.use_warp:
+        wh = spec.warp_hidden
+        macs += e0 * wh + (spec.warp_layers - 2) * wh * wh + (wh + e0) * wh + wh * 3
+    if spec.use_ambient:
+        hh = spec.hyper_hidden
+        macs += e0 * hh + (spec.hyper_layers - 2) * hh * hh + (hh + e0) * hh + hh * spec.amb_dim
+    th = spec.trunk_hidden
+    macs += e1 * th + (spec.trunk_layers - 2) * th * th + (th + e1) * th       # trunk
+    macs += th * th + th                                                        # fc_feat, fc_alpha
+    hd = th // 2
+    macs += (th + spec.dir_dim + 32) * hd + 3 * hd * hd + hd * 3                # direction head
+    macs += th * hd + 3 * hd * hd + hd * 12                                     # semantic head
+    return macs
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_rays_per_s(cfg_name, n_rays, repeats=1):
+    """The oracle port (reference algorithm, torch-CPU ops, all host threads) on a bounded ray sample."""
+    import sahs_fixtures as FX
+    from oracle import sahs_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = FX.load_cfg(cfg_name)
+    spec = O.spec_from_cfg(cfg)
+    sd = FX.make_state_dict(spec, seed=42, dense=True)
+    fr = FX.make_frame_inputs(spec, H, W, seed=0)
+    opts = O.opts_from_cfg(cfg, "validation")
+    opts.perturb, opts.noise_std = False, 0.0
+    ro, rd = O.get_ray_bundle(H, W, fr["intrinsics"], fr["pose"])
+    sel = torch.linspace(0, H * W - 1, n_rays).long()
+    ro, rd, bg = ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel], fr["background"].view(-1, 15)[sel]
+    best = None
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            O.run_one_iter(sd, spec, opts, ro, rd, fr["driving"], fr["pose"], bg)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return n_rays / best, best, torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    n_rays = args.cpu_rays
+    times = []
+    for i in range(args.warmup + args.steps):
+        rps, dt, cores = cpu_port_rays_per_s(args.config, n_rays)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = n_rays / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "render_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"Stage-I 512x512 render, {args.config}, 64 coarse + 128 fine samples/ray",
+                   "sample": f"{n_rays} rays of the frame per step (CPU)", "weights": "random-init dense fixture"},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_rays} evenly spaced rays of one 512x512 frame per step, oracle port "
+                                   "(reference algorithm in torch-CPU ops), all host threads"},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="audio/person_2_auto")
+    ap.add_argument("--cpu-rays", type=int, default=2048, help="rays per CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    import sahs_b200
+    import sahs_fixtures as FX
+    from oracle import sahs_oracle as O          # fixture generator + CPU baseline only; never on the timed path
+    from sahs_b200 import lib as L
+    from sahs_b200.models import ModelSpec
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.load()
+    warmup = max(args.warmup, 3)
+
+    cfg = FX.load_cfg(args.config)
+    cfg.nerf.validation.perturb = False            # deterministic sampling, as for the parity runs
+    ospec = O.spec_from_cfg(cfg)
+    mspec = ModelSpec.from_cfg(cfg)
+    sd = FX.make_state_dict(ospec, seed=42, dense=True)
+    model = getattr(sahs_b200.models, cfg.models.mask.type)(cfg)
+    model.load_state_dict(sd)
+    model = model.to(dev)
+    nsteps_total = warmup + args.steps
+    frames = [FX.make_frame_inputs(ospec, H, W, seed=100 + rank + world * i) for i in range(2)]
+    bg_dev = frames[0]["background"].view(-1, 15).to(dev)
+    R = H * W
+    flops_per_point = 2.0 * algorithmic_macs_per_point(mspec)
+
+    # ------------------------------ device-resident arm -----------------------------------------
+    dev_frames = []
+    for fr in frames:
+        pose = fr["pose"].to(dev)
+        ro, rd = sahs_b200.get_ray_bundle(H, W, fr["intrinsics"], pose)
+        dev_frames.append(dict(pose=pose, driving=fr["driving"].to(dev), ro=ro, rd=rd, mask=fr["mask"].to(dev)))
+
+    field_events = []
+    orig_field = model.field
+
+    def timed_field(level, ro, rd, z, *a, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig_field(level, ro, rd, z, *a, **k)
+        e1.record()
+        field_events.append((level, z.numel(), e0, e1))
+        return out
+
+    def step_resident(i):
+        f = dev_frames[i % len(dev_frames)]
+        with torch.no_grad():
+            return sahs_b200.run_one_iter_of_nerf(H, W, 1200.0, model, f["ro"], f["rd"], cfg, mode="validation",
+                                                  driving=f["driving"], pose=f["pose"], background_prior=bg_dev,
+                                                  inHead=f["mask"])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(warmup):
+        step_resident(i)
+    barrier()
+    model.field = timed_field
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.sahs_launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(args.steps):
+        step_resident(warmup + i)
+    t1.record()
+    barrier()
+    launches = lib.sahs_launch_count() - launches0
+    clocks = sampler.stop()
+    model.field = orig_field
+    ms_total = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_step = float(ms_total) / args.steps
+    value = world * R / (ms_step / 1e3)
+
+    fine = [(n, a.elapsed_time(b)) for lvl, n, a, b in field_events if lvl == "fine"]
+    fine_ms = sum(t for _, t in fine) / len(fine)
+    all_field_ms = sum(a.elapsed_time(b) for _, _, a, b in field_events) / args.steps
+    achieved = fine[0][0] * flops_per_point / (fine_ms / 1e3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    roofline = {"bound": "tensor", "kernel": "field_fwd_kernel (fine level, 262144 rays x 128 samples per launch)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks
+                                else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"),
+                "frac_of_burst_peak": achieved / float(peaks.get("bf16_tflops", 1590.0)),
+                "algorithmic_flop_per_point": flops_per_point, "points_per_launch": fine[0][0],
+                "avg_launch_ms": fine_ms, "field_share_of_step": all_field_ms / ms_step, "traffic": None}
+
+    # ------------------------------ end-to-end arm (host buffers) -------------------------------
+    host = [dict(pose=fr["pose"].pin_memory(), driving=fr["driving"].pin_memory(), mask=fr["mask"].pin_memory())
+            for fr in frames]
+    out_rgb = torch.empty(H, W, 15, dtype=torch.float32).pin_memory()
+    out_depth = torch.empty(H, W, dtype=torch.float32).pin_memory()
+    out_acc = torch.empty(H, W, dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in host[0].values())
+    d2h = sum(t.numel() * t.element_size() for t in (out_rgb, out_depth, out_acc))
+
+    def step_e2e(i):
+        hfr, fr = host[i % len(host)], frames[i % len(frames)]
+        pose = hfr["pose"].to(dev, non_blocking=True)
+        driving = hfr["driving"].to(dev, non_blocking=True)
+        mask = hfr["mask"].to(dev, non_blocking=True)
+        with torch.no_grad():
+            ro, rd = sahs_b200.get_ray_bundle(H, W, fr["intrinsics"], pose)
+            out = sahs_b200.run_one_iter_of_nerf(H, W, 1200.0, model, ro, rd, cfg, mode="validation", driving=driving,
+                                                 pose=pose, background_prior=bg_dev, inHead=mask)
+        out_rgb.copy_(out[3], non_blocking=True)
+        out_depth.copy_(out[7], non_blocking=True)
+        out_acc.copy_(out[5], non_blocking=True)
+        torch.cuda.current_stream().synchronize()     # the frame is on the host before the next one starts
+
+    for i in range(2):
+        step_e2e(i)
+    barrier()
+    w0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - w0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * R * args.steps / float(e2e_s)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rps, dt, cores = cpu_port_rays_per_s(args.config, args.cpu_rays)
+        cpu_baseline = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
+                        "sample": f"{args.cpu_rays} evenly spaced rays of one 512x512 frame ({dt:.1f} s), oracle port "
+                                  "(reference algorithm in torch-CPU ops), all host threads"}
+    if rank == 0:
+        line = {
+            "metric": "render_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"Stage-I 512x512 render (BASELINE config 2), {args.config}, 64 coarse + 128 fine "
+                                   "samples/ray, deterministic sampling", "rays_per_step_per_gpu": R,
+                       "weights": "random-init dense fixture (seed 42)", "parallelism": f"frames over {world} GPU(s)",
+                       "l2": "working set per step (raw 3.2 GB) exceeds the 126 MB L2; no flush needed"},
+            "ms_per_frame": ms_step,
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_frame": 1e3 * float(e2e_s) / args.steps},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -67,8 +67,9 @@ int sahs_param_count(const sahs_model_spec* spec);
 
 /* ---- (1) ray generation, stratified depths, positional encoding --------------------------------- */
 /* get_ray_bundle, ref: nerf/nerf_helpers.py:178-233.  c2w: device [3,4] row-major (ld = 4).
- * ro, rd: [H*W,3] (pixel (row j, col i) at j*W+i).  Bit-exact with the reference's fp32 op order. */
-int sahs_get_ray_bundle(int height, int width, float fx, float fy, float cx, float cy, const float* c2w,
+ * ro, rd: [H*W,3] (pixel (row j, col i) at j*W+i).  Bit-exact with the reference's fp32 op order; cx, cy are
+ * doubles because the reference forms width*cx in double before rounding to fp32. */
+int sahs_get_ray_bundle(int height, int width, float fx, float fy, double cx, double cy, const float* c2w,
                         float* ro, float* rd, void* stream);
 /* coarse depths, ref: nerf/train_utils.py:93-113.  t_vals: device [S] = linspace(0,1,S) (host-made so it is
  * bit-identical to torch.linspace); t_rand: device [R,S] uniforms or NULL for no perturbation. */

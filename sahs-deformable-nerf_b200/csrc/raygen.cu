@@ -22,12 +22,12 @@ __global__ void ray_bundle_kernel(int H, int W, float fx, float fy, float wcx, f
   }
 }
 
-extern "C" int sahs_get_ray_bundle(int height, int width, float fx, float fy, float cx, float cy,
+extern "C" int sahs_get_ray_bundle(int height, int width, float fx, float fy, double cx, double cy,
                                    const float* c2w, float* ro, float* rd, void* stream) {
   SAHS_CHECK_ARG(height > 0 && width > 0 && c2w && ro && rd, "bad arguments");
   // width * cx is evaluated in double by the reference (python int * numpy float64) and then rounded to fp32
-  float wcx = (float)((double)width * (double)cx);
-  float hcy = (float)((double)height * (double)cy);
+  float wcx = (float)((double)width * cx);
+  float hcy = (float)((double)height * cy);
   int n = height * width;
   ray_bundle_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(height, width, fx, fy, wcx, hcy, c2w, ro, rd);
   SAHS_LAUNCH_CHECK();

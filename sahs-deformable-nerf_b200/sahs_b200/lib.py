@@ -50,7 +50,7 @@ def load() -> C.CDLL:
         "sahs_last_error": (C.c_char_p, []),
         "sahs_launch_count": (C.c_uint64, []),
         "sahs_param_count": (C.c_int, [spec_p]),
-        "sahs_get_ray_bundle": (C.c_int, [i32, i32, f32, f32, f32, f32, vp, vp, vp, vp]),
+        "sahs_get_ray_bundle": (C.c_int, [i32, i32, f32, f32, C.c_double, C.c_double, vp, vp, vp, vp]),
         "sahs_coarse_z": (C.c_int, [i32, i32, f32, f32, i32, vp, vp, vp, vp]),
         "sahs_positional_encoding": (C.c_int, [vp, i64, i32, i32, i32, vp, vp]),
         "sahs_field_sizes": (C.c_int, [spec_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),

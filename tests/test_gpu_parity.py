@@ -1,0 +1,315 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (ctypes) behind the reference's Python
+signatures, against the golden vectors frozen from the live reference and against the CPU oracle on the same
+seeded inputs.  Bars (BASELINE.json north_star): bit-exact for index/integer work (sample_pdf indices, merged
+depths, ray bundle, coarse depths); rendered rgb/depth max-abs <= 1e-2 and PSNR >= 50 dB (bf16 tensor-core MLP)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import sahs_fixtures as FX
+from oracle import sahs_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(FX.REPO, "tests", "golden")
+load = lambda n: np.load(os.path.join(GOLD, n + ".npz"))
+DEV = "cuda:0"
+G = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+C = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+
+
+def maxabs(a, b):
+    return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
+
+
+def psnr(a, b):
+    mse = float(((a.detach().double().cpu() - b.detach().double().cpu()) ** 2).mean())
+    return 99.0 if mse == 0 else -10.0 * math.log10(mse)
+
+
+@pytest.fixture(scope="module")
+def sahs():
+    import sahs_b200
+    from sahs_b200 import lib
+    lib.load()                       # fails loudly if the CUDA library is missing: there is no fallback
+    return sahs_b200
+
+
+def _model(sahs, cfg_name):
+    cfg = FX.load_cfg(cfg_name)
+    spec = O.spec_from_cfg(cfg)
+    sd = FX.make_state_dict(spec, seed=42, dense=True)
+    model = getattr(sahs.models, cfg.models.mask.type)(cfg)
+    model.load_state_dict(sd, strict=True)
+    return cfg, spec, sd, model.to(DEV)
+
+
+# ------------------------------------------------------------------------------------------------------
+# (1) ray generation, depths, positional encoding
+# ------------------------------------------------------------------------------------------------------
+def test_ray_bundle_bit_exact(sahs):
+    g = load("helpers")
+    ro, rd = sahs.get_ray_bundle(12, 20, g["intr"], G(g["pose"]))
+    assert torch.equal(rd.cpu(), C(g["rd"])) and torch.equal(ro.cpu(), C(g["ro"]))
+    # scalar focal form + a frame-sized bundle against the oracle
+    pose = FX.make_pose(4, 0.78, 10.0)
+    ro, rd = sahs.get_ray_bundle(512, 512, [1200.0, 1200.0, 0.5, 0.5], pose.to(DEV))
+    ro_o, rd_o = O.get_ray_bundle(512, 512, [1200.0, 1200.0, 0.5, 0.5], pose)
+    assert torch.equal(rd.cpu(), rd_o) and torch.equal(ro.cpu(), ro_o.contiguous())
+
+
+def test_positional_encoding(sahs):
+    g = load("helpers")
+    for L, inc in ((10, 1), (15, 1), (4, 1), (3, 0)):
+        out = sahs.positional_encoding(G(g["x"]), L, bool(inc))
+        assert maxabs(out, C(g[f"pe_L{L}_inc{inc}"])) <= 2e-6        # sincosf (<= 2 ulp) vs glibc
+    assert sahs.positional_encoding(G(g["x"]), 0, True).shape == (257, 3)
+    empty = sahs.positional_encoding(torch.zeros(0, 3, device=DEV), 4, True)
+    assert empty.shape == (0, 27)
+
+
+@pytest.mark.parametrize("lindisp", [False, True])
+def test_coarse_depths_bit_exact(sahs, lindisp):
+    from sahs_b200 import ops
+    opts = O.RenderOpts(num_coarse=64, near=0.483771014213562, far=1.083771014213562, lindisp=lindisp)
+    z = ops.coarse_z(37, 64, opts.near, opts.far, lindisp, DEV)
+    assert torch.equal(z.cpu(), O.coarse_z(opts, 37))
+    tr = torch.rand(37, 64, generator=torch.Generator().manual_seed(3))
+    opts.perturb = True
+    z = ops.coarse_z(37, 64, opts.near, opts.far, lindisp, DEV, tr.to(DEV))
+    assert torch.equal(z.cpu(), O.coarse_z(opts, 37, tr))
+
+
+# ------------------------------------------------------------------------------------------------------
+# (4) sample_pdf + merge: bit-exact indices when fed the reference's weights
+# ------------------------------------------------------------------------------------------------------
+def test_sample_pdf_bit_exact_vs_reference_golden(sahs):
+    from sahs_b200 import ops
+    g = load("sample_pdf_2048")
+    R = g["weights"].shape[0]
+    z = C(g["z"]).expand(R, 64).contiguous()
+    bins = 0.5 * (z[:, 1:] + z[:, :-1])
+    s, inds = ops.sample_pdf_bins(bins.to(DEV), G(g["weights"]), 64, None, return_inds=True)
+    assert torch.equal(inds.cpu(), C(g["ref_inds"].astype(np.int64)))
+    assert torch.equal(s.cpu(), C(g["ref_samples"]))
+    # public reference signature
+    assert torch.equal(sahs.sample_pdf_2(bins.to(DEV), G(g["weights"]), 64, det=True).cpu(), C(g["ref_samples"]))
+    # pipeline form: depths + full compositing weights -> samples + merged (sorted) depths
+    wfull = torch.zeros(R, 64)
+    wfull[:, 1:-1] = C(g["weights"])
+    zs, zm, inds2 = ops.sample_pdf_merge(z.to(DEV), wfull.to(DEV), 64, None, return_inds=True)
+    assert torch.equal(inds2.cpu(), C(g["ref_inds"].astype(np.int64)))
+    assert torch.equal(zs.cpu(), C(g["ref_samples"])) and torch.equal(zm.cpu(), C(g["ref_z_merged"]))
+    # stochastic u (unsorted samples exercise the bitonic merge)
+    ss = ops.sample_pdf_bins(bins.to(DEV), G(g["weights"]), 64, G(g["u_s"]))
+    assert torch.equal(ss.cpu(), C(g["ref_samples_s"]))
+    zs, zm = ops.sample_pdf_merge(z.to(DEV), wfull.to(DEV), 64, G(g["u_s"]))
+    want, _ = torch.sort(torch.cat((z, C(g["ref_samples_s"])), -1), -1)
+    assert torch.equal(zm.cpu(), want)
+
+
+def test_sample_pdf_properties_full_frame(sahs):
+    """Size-independent properties at the BASELINE ray count (262,144 rays): merged depths are sorted, are a
+    permutation of (z, samples), samples stay inside [bin_0, bin_last]; oracle equality on a strided subset."""
+    from sahs_b200 import ops
+    R = 262144
+    gen = torch.Generator().manual_seed(5)
+    opts = O.RenderOpts(num_coarse=64, near=0.4838, far=1.0838)
+    z = ops.coarse_z(R, 64, opts.near, opts.far, False, DEV)
+    w = (torch.rand(R, 64, generator=gen) ** 8).to(DEV)
+    zs, zm, inds = ops.sample_pdf_merge(z, w, 64, None, return_inds=True)
+    assert bool((zm[:, 1:] >= zm[:, :-1]).all())
+    both, _ = torch.sort(torch.cat((z, zs), -1), -1)
+    assert torch.equal(both, zm)
+    mids = 0.5 * (z[:, 1:] + z[:, :-1])
+    assert bool((zs >= mids[:, :1]).all()) and bool((zs <= mids[:, -1:]).all())
+    assert int(inds.min()) >= 1 and int(inds.max()) <= 63
+    sub = slice(0, R, 4099)
+    s_o, i_o = O.sample_pdf(mids[sub].cpu(), w[sub, 1:-1].cpu(), 64, det=True, return_inds=True)
+    assert torch.equal(inds[sub].cpu(), i_o) and torch.equal(zs[sub].cpu(), s_o)
+
+
+# ------------------------------------------------------------------------------------------------------
+# (3) compositing
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["composite_bg", "composite_nobg_white"])
+def test_composite_forward_golden(sahs, name):
+    from sahs_b200 import ops
+    g = load(name)
+    with_bg, white = bool(int(g["with_bg"])), bool(int(g["white"]))
+    bg = G(g["bg"]) if with_bg else None
+    out = ops.composite_fwd(G(g["raw"]), G(g["z"]), G(g["rd"]), None, bg, with_bg, white)
+    for n, o in zip(["rgb", "disp", "acc", "weights", "depth"], out):
+        ref = C(g["ref_" + n])
+        if n == "disp":
+            rel = float(((o.cpu() - ref).abs() / ref.abs()).max())
+            assert rel <= 1e-4, rel
+        else:
+            assert maxabs(o, ref) <= 2e-5, (n, maxabs(o, ref))        # fp32, different exp/scan order only
+    # reference signature: the caller has already overwritten the last sample with the background
+    raw_in = G(g["raw"]).clone()
+    if with_bg:
+        raw_in[:, -1, :-1] = bg
+    rgb, disp, acc, w, depth = sahs.volume_render_radiance_field(raw_in, G(g["z"]), G(g["rd"]), 0.0, white, bg)
+    assert maxabs(rgb, C(g["ref_rgb"])) <= 2e-5 and maxabs(w, C(g["ref_weights"])) <= 2e-5
+
+
+@pytest.mark.parametrize("name", ["composite_bg", "composite_nobg_white"])
+def test_composite_backward_vs_oracle_autograd(sahs, name):
+    from sahs_b200 import ops
+    g = load(name)
+    with_bg, white = bool(int(g["with_bg"])), bool(int(g["white"]))
+    raw = C(g["raw"]).clone().requires_grad_(True)
+    z, rd = C(g["z"]), C(g["rd"])
+    bg = C(g["bg"]) if with_bg else None
+    rin = raw
+    if with_bg:      # out-of-place version of raw[:, -1, :-1] = bg
+        rin = torch.cat((raw[:, :-1], torch.cat((bg, raw[:, -1, -1:]), -1)[:, None]), 1)
+    outs = O.composite(rin, z, rd, None, white, bg)
+    gen = torch.Generator().manual_seed(1)
+    gs = [torch.randn(t.shape, generator=gen) for t in outs]
+    sum((a * b).sum() for a, b in zip(outs, gs)).backward()
+    d_raw = ops.composite_bwd(G(g["raw"]), z.to(DEV), rd.to(DEV), None, bg.to(DEV) if with_bg else None, with_bg, white,
+                              *[t.to(DEV) for t in gs])
+    ref = raw.grad
+    assert maxabs(d_raw, ref) <= 2e-4 * float(ref.abs().max())
+    # autograd.Function wiring
+    raw_g = G(g["raw"]).clone().requires_grad_(True)
+    from sahs_b200.volume_rendering_utils import composite
+    o2 = composite(raw_g, z.to(DEV), rd.to(DEV), None, bg.to(DEV) if with_bg else None, with_bg, white)
+    sum((a * b.to(DEV)).sum() for a, b in zip(o2, gs)).backward()
+    assert maxabs(raw_g.grad, ref) <= 2e-4 * float(ref.abs().max())
+
+
+def test_composite_linearity_full_frame(sahs):
+    """262,144 rays x 128 samples: acc == 1 with a background prior (last alpha is 1), rgb_map is linear in the
+    background colour, weights are non-negative and sum to acc."""
+    from sahs_b200 import ops
+    R, S = 262144, 128
+    gen = torch.Generator(device=DEV).manual_seed(7)
+    raw = torch.randn(R, S, 16, device=DEV, generator=gen)
+    raw[..., -1] = torch.randn(R, S, device=DEV, generator=gen) * 20
+    z = torch.sort(torch.rand(R, S, device=DEV, generator=gen) * 0.6 + 0.48, -1)[0]
+    rd = torch.randn(R, 3, device=DEV, generator=gen)
+    bg0 = torch.zeros(R, 15, device=DEV)
+    bg1 = torch.rand(R, 15, device=DEV, generator=gen)
+    rgb0, _, acc, w, _ = ops.composite_fwd(raw, z, rd, None, bg0, True, False)
+    rgb1, _, _, w1, _ = ops.composite_fwd(raw, z, rd, None, bg1, True, False)
+    assert float((acc - 1).abs().max()) <= 2e-5
+    assert float((w.sum(-1) - acc).abs().max()) <= 2e-5 and float(w.min()) >= 0
+    assert torch.equal(w, w1)
+    assert float((rgb1 - rgb0 - w[:, -1:] * bg1).abs().max()) <= 2e-5
+
+
+# ------------------------------------------------------------------------------------------------------
+# (2) fused field kernel
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["field_audio", "field_expr2"])
+def test_field_forward_vs_reference_golden(sahs, name):
+    g = load(name)
+    cfg, spec, sd, model = _model(sahs, str(g["cfg_name"]))
+    assert abs(FX.state_checksum(sd) - float(g["state_checksum"])) <= 1e-9 * float(g["state_checksum"])
+    n = g["xyz"].shape[0]
+    x = torch.cat((G(g["xyz"]), G(g["dirs"]), torch.zeros(n, 12, device=DEV)), -1)
+    fr = FX.make_frame_inputs(spec, 8, 8, seed=int(g["seed"]), pose_z=0.78)
+    with torch.no_grad():
+        for level in ("coarse", "fine"):
+            raw = model(level, x, fr["driving"].to(DEV), G(g["pose"]), None)       # reference call signature
+            ref = C(g["ref_raw_" + level])
+            assert raw.shape == (n, 16) and not bool(torch.isnan(raw).any())
+            # bf16 operands, fp32 accumulate: relative to the logit scale of each head
+            for sl in (slice(0, 3), slice(3, 15), slice(15, 16)):
+                scale = max(1.0, float(ref[:, sl].abs().max()))
+                assert maxabs(raw[:, sl], ref[:, sl]) <= 3e-2 * scale, (level, sl, maxabs(raw[:, sl], ref[:, sl]), scale)
+    from sahs_b200 import ops
+    assert ops.field_status()[0] == 0
+
+
+def test_field_forward_no_deformation_config(sahs):
+    cfg, spec, sd, model = _model(sahs, "expression/person_1")
+    gen = torch.Generator().manual_seed(9)
+    n = 300                                                     # ragged: not a multiple of the 128-row tile
+    xyz = (torch.rand(n, 3, generator=gen) * 2 - 1) * 0.35
+    dirs = torch.randn(n, 3, generator=gen) * 0.3 + torch.tensor([0, 0, -1.0])
+    fr = FX.make_frame_inputs(spec, 8, 8, seed=1)
+    ref = O.field_forward(sd, spec, "fine", xyz, dirs, fr["driving"], fr["pose"])
+    x = torch.cat((xyz, dirs), -1).to(DEV)
+    with torch.no_grad():
+        raw = model("fine", x, fr["driving"].to(DEV), fr["pose"].to(DEV), None)
+    for sl in (slice(0, 3), slice(3, 15), slice(15, 16)):
+        scale = max(1.0, float(ref[:, sl].abs().max()))
+        assert maxabs(raw[:, sl], ref[:, sl]) <= 3e-2 * scale
+
+
+def test_field_empty_and_ragged(sahs):
+    cfg, spec, sd, model = _model(sahs, "audio/person_2_auto")
+    fr = FX.make_frame_inputs(spec, 8, 8, seed=1)
+    with torch.no_grad():
+        out = model("coarse", torch.zeros(0, 18, device=DEV), fr["driving"].to(DEV), fr["pose"].to(DEV), None)
+        assert out.shape == (0, 16)
+        one = model("coarse", torch.tensor([[0.1, 0.0, -0.1, 0, 0, -1.0]], device=DEV), fr["driving"].to(DEV),
+                    fr["pose"].to(DEV), None)
+        many = model("coarse", torch.tensor([[0.1, 0.0, -0.1, 0, 0, -1.0]], device=DEV).expand(129, 6).contiguous(),
+                     fr["driving"].to(DEV), fr["pose"].to(DEV), None)
+    assert torch.equal(one[0], many[0]) and torch.equal(many[0], many[128])   # tile position does not matter
+
+
+# ------------------------------------------------------------------------------------------------------
+# end to end: run_one_iter_of_nerf
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["e2e_audio_val", "e2e_expr2_val", "e2e_audio_train_stoch"])
+def test_run_one_iter_vs_reference_golden(sahs, name):
+    g = load(name)
+    cfg, spec, sd, model = _model(sahs, str(g["cfg_name"]))
+    H, W, mode = int(g["H"]), int(g["W"]), str(g["mode"])
+    fr = FX.make_frame_inputs(spec, H, W, seed=int(g["seed"]), pose_z=float(g["pose_z"]))
+    node = getattr(cfg.nerf, mode)
+    draws = None
+    if int(g["stochastic"]):
+        node.perturb, node.radiance_field_noise_std = True, 0.1
+        draws = {k: G(g["draw_" + k]) for k in ("t_rand", "noise_c", "u", "noise_f")}
+    else:
+        node.perturb, node.radiance_field_noise_std = False, 0.0
+    pose = fr["pose"].to(DEV)
+    with torch.no_grad():
+        ro, rd = sahs.get_ray_bundle(H, W, fr["intrinsics"], pose)
+        out = sahs.run_one_iter_of_nerf(H, W, fr["intrinsics"][0], model, ro, rd, cfg, mode=mode,
+                                        driving=fr["driving"].to(DEV), pose=pose, pose_c=None,
+                                        background_prior=fr["background"].view(-1, 15).to(DEV),
+                                        inHead=fr["mask"].to(DEV), _draws=draws)
+    assert len(out) == 8
+    if mode == "validation":
+        assert out[0].shape == (H, W, 15) and out[3].shape == (H, W, 15) and out[7].shape == (H, W)
+    names = ["rgb_c", "disp_c", "acc_c", "rgb_f", "disp_f", "acc_f", "w_last_f", "depth_f"]
+    flat = {n: (o.reshape(-1, 15) if o.shape[-1] == 15 and o.dim() > 1 else o.reshape(-1)) for n, o in zip(names, out)}
+    # north-star tolerance: max-abs 1e-2 on rgb (and the semantic channels) and depth, PSNR >= 50 dB
+    for n in ("rgb_c", "rgb_f"):
+        assert maxabs(flat[n], C(g["ref_" + n])) <= 1e-2, (n, maxabs(flat[n], C(g["ref_" + n])))
+        assert psnr(flat[n][:, :3], C(g["ref_" + n])[:, :3]) >= 50.0
+    assert maxabs(flat["depth_f"], C(g["ref_depth_f"])) <= 1e-2
+    assert maxabs(flat["acc_f"], C(g["ref_acc_f"])) <= 1e-4 and maxabs(flat["w_last_f"], C(g["ref_w_last_f"])) <= 1e-2
+    rel = float(((flat["disp_f"].cpu() - C(g["ref_disp_f"])).abs() / C(g["ref_disp_f"]).abs()).max())
+    assert rel <= 2e-2
+
+
+def test_render_is_chunking_invariant(sahs):
+    """Rays are independent: rendering a ray set in one call or in two halves gives identical bits."""
+    cfg, spec, sd, model = _model(sahs, "audio/person_2_auto")
+    cfg.nerf.validation.perturb = False
+    H, W = 8, 24
+    fr = FX.make_frame_inputs(spec, H, W, seed=3)
+    pose = fr["pose"].to(DEV)
+    bg = fr["background"].view(-1, 15).to(DEV)
+    with torch.no_grad():
+        ro, rd = sahs.get_ray_bundle(H, W, fr["intrinsics"], pose)
+        ro, rd = ro.reshape(-1, 3), rd.reshape(-1, 3)
+        kw = dict(mode="train", driving=fr["driving"].to(DEV), pose=pose)
+        cfg.nerf.train.perturb, cfg.nerf.train.radiance_field_noise_std = False, 0.0
+        full = sahs.run_one_iter_of_nerf(H, W, 1.0, model, ro, rd, cfg, background_prior=bg, **kw)
+        a = sahs.run_one_iter_of_nerf(H, W, 1.0, model, ro[:100], rd[:100], cfg, background_prior=bg[:100], **kw)
+        b = sahs.run_one_iter_of_nerf(H, W, 1.0, model, ro[100:], rd[100:], cfg, background_prior=bg[100:], **kw)
+    for f, x, y in zip(full, a, b):
+        assert torch.equal(f, torch.cat((x, y), 0))

@@ -1,0 +1,124 @@
+"""CPU tests (-m "not gpu"): the oracle restatement against the golden vectors frozen from the live reference
+(oracle/make_golden.py), plus host-side config logic.  No CUDA compute."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import sahs_fixtures as FX
+from oracle import ref_harness as RH
+from oracle import sahs_oracle as O
+
+GOLD = os.path.join(FX.REPO, "tests", "golden")
+load = lambda n: np.load(os.path.join(GOLD, n + ".npz"))
+T = torch.from_numpy
+
+
+def test_helpers_golden():
+    g = load("helpers")
+    ro, rd = O.get_ray_bundle(12, 20, list(g["intr"]), T(g["pose"]))
+    assert torch.equal(rd, T(g["rd"])) and torch.equal(ro.contiguous(), T(g["ro"]))
+    for L, inc in ((10, 1), (15, 1), (4, 1), (3, 0)):
+        assert torch.equal(O.positional_encoding(T(g["x"]), L, bool(inc)), T(g[f"pe_L{L}_inc{inc}"]))
+    assert torch.equal(O.pose_code(T(g["pose"])), T(g["pose_code"]))
+
+
+def test_sample_pdf_golden_bit_exact():
+    g = load("sample_pdf_2048")
+    R = g["weights"].shape[0]
+    z = T(g["z"]).expand(R, 64).contiguous()
+    bins = 0.5 * (z[:, 1:] + z[:, :-1])
+    s, inds = O.sample_pdf(bins, T(g["weights"]), 64, det=True, return_inds=True)
+    assert torch.equal(inds, T(g["ref_inds"].astype(np.int64)))
+    assert torch.equal(s, T(g["ref_samples"]))
+    assert torch.equal(O.sample_pdf(bins, T(g["weights"]), 64, det=False, u=T(g["u_s"])), T(g["ref_samples_s"]))
+    zm, _ = torch.sort(torch.cat((z, s), -1), -1)
+    assert torch.equal(zm, T(g["ref_z_merged"]))
+
+
+@pytest.mark.parametrize("name", ["composite_bg", "composite_nobg_white"])
+def test_composite_golden(name):
+    g = load(name)
+    bg = T(g["bg"]) if int(g["with_bg"]) else None
+    raw = T(g["raw"]).clone()
+    if bg is not None:
+        raw[:, -1, :-1] = bg
+    out = O.composite(raw, T(g["z"]), T(g["rd"]), None, bool(int(g["white"])), bg)
+    for n, o in zip(["rgb", "disp", "acc", "weights", "depth"], out):
+        assert torch.equal(o, T(g["ref_" + n])), n
+
+
+@pytest.mark.parametrize("name", ["field_audio", "field_expr2"])
+def test_field_golden(name):
+    g = load(name)
+    cfg = FX.load_cfg(str(g["cfg_name"]))
+    spec = O.spec_from_cfg(cfg)
+    sd = FX.make_state_dict(spec, seed=42, dense=True)
+    assert abs(FX.state_checksum(sd) - float(g["state_checksum"])) <= 1e-9 * float(g["state_checksum"])
+    with torch.no_grad():
+        for level in ("coarse", "fine"):
+            raw = O.field_forward(sd, spec, level, T(g["xyz"]), T(g["dirs"]), T(g["driving_vec"]), T(g["pose"]))
+            ref = T(g["ref_raw_" + level])
+            assert float((raw - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("name", ["e2e_audio_val", "e2e_expr2_val", "e2e_audio_train_stoch"])
+def test_e2e_golden(name):
+    g = load(name)
+    cfg = FX.load_cfg(str(g["cfg_name"]))
+    spec = O.spec_from_cfg(cfg)
+    sd = FX.make_state_dict(spec, seed=42, dense=True)
+    H, W, mode = int(g["H"]), int(g["W"]), str(g["mode"])
+    fr = FX.make_frame_inputs(spec, H, W, seed=int(g["seed"]), pose_z=float(g["pose_z"]))
+    assert np.array_equal(fr["pose"].numpy(), g["pose"])
+    opts = O.opts_from_cfg(cfg, mode)
+    draws = {}
+    if int(g["stochastic"]):
+        opts.perturb, opts.noise_std = True, 0.1
+        draws = {k: T(g["draw_" + k]) for k in ("t_rand", "noise_c", "u", "noise_f")}
+    else:
+        opts.perturb, opts.noise_std = False, 0.0
+    ro, rd = O.get_ray_bundle(H, W, fr["intrinsics"], fr["pose"])
+    with torch.no_grad():
+        out = O.run_one_iter(sd, spec, opts, ro, rd, fr["driving"], fr["pose"], fr["background"].view(-1, 15), **draws)
+    names = ["rgb_c", "disp_c", "acc_c", "rgb_f", "disp_f", "acc_f", "w_last_f", "depth_f"]
+    for n, o in zip(names, out):
+        ref = T(g["ref_" + n])
+        tol = 2e-5 * max(1.0, float(ref.abs().max()))
+        assert float((o - ref).abs().max()) <= tol, n
+
+
+def test_builtin_configs_match_reference_yaml():
+    if not RH.reference_available():
+        pytest.skip("reference tree not present on this machine")
+    for name in ("audio/person_1_auto", "audio/person_2_auto", "audio/Obama_auto", "expression/person_1",
+                 "expression/person_2", "expression/person_3"):
+        rcfg = RH.load_reference_cfg(f"config/{name}.yml")
+        cfg = FX.load_cfg(name)
+        assert O.spec_from_cfg(rcfg) == O.spec_from_cfg(cfg), name
+        for mode in ("train", "validation"):
+            assert O.opts_from_cfg(rcfg, mode) == O.opts_from_cfg(cfg, mode), (name, mode)
+        assert rcfg.nerf.train.num_random_rays == cfg.nerf.train.num_random_rays
+        assert rcfg.dataset.no_ndc == cfg.dataset.no_ndc and rcfg.nerf.use_viewdirs == cfg.nerf.use_viewdirs
+
+
+def test_cfgnode_behaviour():
+    from sahs_b200 import CfgNode
+    c = CfgNode({"a": {"b": 1, "c": {"d": [1, 2]}}, "e": "x"})
+    assert c.a.b == 1 and c.a.c.d == [1, 2] and c.e == "x"
+    assert hasattr(c, "a") and not hasattr(c, "fine")
+    assert "b: 1" in c.dump()
+    c.a.b = 3
+    assert c.clone().a.b == 3
+
+
+def test_model_state_dict_layout_matches_reference_names():
+    """Checkpoint compatibility: our modules expose exactly the reference's parameter names and shapes."""
+    import sahs_b200
+    for name in ("audio/person_2_auto", "expression/person_2", "expression/person_1"):
+        cfg = FX.load_cfg(name)
+        model = getattr(sahs_b200.models, cfg.models.mask.type)(cfg)
+        want = FX.linear_shapes(O.spec_from_cfg(cfg))
+        got = {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        assert got == want, set(got.items()) ^ set(want.items())
