@@ -304,6 +304,7 @@ extern "C" int sahs_composite_fwd(const float* raw, const float* z, const float*
                                   const float* bg, int bg_ch, int apply_bg_overwrite, int num_rays, int num_samples,
                                   int white_background, float* rgb_map, float* disp, float* acc, float* weights,
                                   float* depth, void* stream) {
+  if (num_rays == 0) return SAHS_OK;
   SAHS_CHECK_ARG(raw && z && rd && rgb_map && disp && acc && weights && depth, "null pointer");
   SAHS_CHECK_ARG(num_samples >= 1 && num_samples <= 32 * kMaxChunks, "num_samples must be in [1,256]");
   SAHS_CHECK_ARG(bg == nullptr || bg_ch == SAHS_MAP_CH, "background_prior must have 15 channels");
@@ -321,6 +322,7 @@ extern "C" int sahs_composite_bwd(const float* raw, const float* z, const float*
                                   int white_background, const float* d_rgb_map, const float* d_disp,
                                   const float* d_acc, const float* d_weights, const float* d_depth, float* d_raw,
                                   void* stream) {
+  if (num_rays == 0) return SAHS_OK;
   SAHS_CHECK_ARG(raw && z && rd && d_raw, "null pointer");
   SAHS_CHECK_ARG(num_samples >= 1 && num_samples <= 32 * kMaxChunks, "num_samples must be in [1,256]");
   SAHS_CHECK_ARG(bg == nullptr || bg_ch == SAHS_MAP_CH, "background_prior must have 15 channels");

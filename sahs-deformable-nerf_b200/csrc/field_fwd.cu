@@ -4,41 +4,40 @@
 // ref: nerf/train_utils.py:9-50 (run_network), nerf/models.py:301-380, :514-528, nerf/modules.py:254-295,
 //      :371-390, :444-462, nerf/nerf_helpers.py:305-349.
 //
-// Execution model (sm_100a): 192 threads per CTA, 2 CTAs per SM (TMEM 2 x 256 columns, smem 2 x 113 KB).
-//   warps 0-3  workers : thread t owns tile row t == TMEM lane t; encodings, epilogues (TMEM -> bias/act ->
-//                        bf16 -> swizzled smem), small heads in fp32, final store
-//   warp  4    TMA     : streams the packed weight image stage by stage with cp.async.bulk (UBLKCP)
-//   warp  5    MMA     : single-thread tcgen05.mma issue (UTCHMMA), accumulators in TMEM
+// Execution model (sm_100a): 320 threads per CTA, 2 CTAs per SM (TMEM 2 x 256 columns, smem 2 x 113 KB).
+//   warps 0-7  workers : thread t owns tile row (t & 127) == TMEM lane; the two warp groups (t >> 7) split the
+//                        columns of every epilogue (TMEM -> +bias -> activation -> 16-bit -> swizzled smem),
+//                        the encodings, the small fp32 heads and the final store
+//   warp  8    TMA     : streams the packed weight image stage by stage with cp.async.bulk (UBLKCP)
+//   warp  9    MMA     : single-thread tcgen05.mma issue (UTCHMMA), accumulators in TMEM
 // Within a CTA the tile is processed pass by pass (bulk synchronous through two mbarriers); the co-resident CTA
 // on the same SM fills the tensor pipe while this one runs its epilogue.
+//
+// Precision: the deformation phase (warp | hyper-sheet) uses fp16 operands (11-bit significand) because the
+// positional encoding applied to its output amplifies coordinate error by up to 2^(L-1); the radiance trunk and
+// heads use bf16 operands.  All accumulation is fp32 in TMEM; dx, ambient and sigma heads are evaluated in fp32.
+#include <cuda_fp16.h>
 #include "sahs_common.cuh"
 #include "field_plan.cuh"
 
 namespace {
 
-constexpr int kWorkerThreads = 128;
-constexpr int kThreads = 192;
+constexpr int kWorkerThreads = 256;
+constexpr int kThreads = 320;
+constexpr int kTmaWarp = 8, kMmaWarp = 9;
 constexpr int kSlots = 3;
 constexpr int kTmemCols = 256;
 constexpr int kSmemX = 4 * kChunkBytes;                       // 64 KB
 constexpr int kSmemSlots = kSlots * kStageSlotBytes;          // 48 KB
 constexpr int kSmemBar = kSmemX + kSmemSlots;                 // barriers after the tiles
-constexpr int kSmemTotal = kSmemBar + 128;
+constexpr int kSmemXchg = kSmemBar + 128;                     // 128 floats exchanged between the two groups
+constexpr int kSmemTotal = kSmemXchg + 512;
 
 __device__ int g_field_status[4];
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
 
-template <int ACT>
-__device__ __forceinline__ float act_fn(float v) {
-  if (ACT == ACT_RELU) return fmaxf(v, 0.f);
-  if (ACT == ACT_LEAKY) return fmaxf(v, 0.01f * v);
-  return v;
-}
-
 struct Sync {
-  uint64_t* full;
-  uint64_t* empty;
   uint64_t* a_ready;
   uint64_t* acc_ready;
   uint32_t acc_par;
@@ -55,100 +54,171 @@ __device__ __forceinline__ void wait_acc(Sync& sy, int tag) {
   sy.acc_par ^= 1;
   tc_fence_after();
 }
-
-// store N (multiple of 8) fp32 values of this row as bf16 into X chunks starting at chunk0
-template <int N>
-__device__ __forceinline__ void store_row(uint8_t* X, int chunk0, int row, const float (&e)[N]) {
-  static_assert(N % 8 == 0, "row width must be a multiple of 8");
-  uint8_t* rowp = X + (row >> 3) * 1024 + (row & 7) * 128;
-#pragma unroll
-  for (int u = 0; u < N / 8; ++u) {
-    uint4 q;
-    q.x = pack_bf16x2(e[8 * u + 0], e[8 * u + 1]);
-    q.y = pack_bf16x2(e[8 * u + 2], e[8 * u + 3]);
-    q.z = pack_bf16x2(e[8 * u + 4], e[8 * u + 5]);
-    q.w = pack_bf16x2(e[8 * u + 6], e[8 * u + 7]);
-    uint8_t* p = rowp + (chunk0 + (u >> 3)) * kChunkBytes + ((((u & 7) ^ row) & 7) << 4);
-    *reinterpret_cast<uint4*>(p) = q;
-  }
+__device__ __forceinline__ void group_sync() {  // the 256 worker threads only
+  asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
-// positional encoding of D values into e[base ...] in the reference's order (nerf_helpers.py:341-349).
-// Accurate sincosf every 5th octave (2^k * x is exact), double-angle recurrence in between (error < 2e-6).
-template <int L, bool INC, int D, int N>
-__device__ __forceinline__ void pe_fill(float (&e)[N], int base, const float (&x)[D]) {
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  if (F16) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {  // FADD2
+  unsigned long long a, b, d;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(a0), "=f"(a1) : "l"(d));
+}
+
+// activation on a packed 16-bit pair (HMNMX2 / HFMA2): relu and leaky-relu(0.01)
+template <int ACT, bool F16>
+__device__ __forceinline__ uint32_t act2(uint32_t p) {
+  if (ACT == ACT_NONE) return p;
+  if (F16) {
+    __half2 v = *reinterpret_cast<__half2*>(&p);
+    __half2 r = (ACT == ACT_RELU) ? __hmax2(v, __float2half2_rn(0.f)) : __hmax2(v, __hmul2(v, __float2half2_rn(0.01f)));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&p);
+  __nv_bfloat162 r = (ACT == ACT_RELU) ? __hmax2(v, __float2bfloat162_rn(0.f))
+                                       : __hmax2(v, __hmul2(v, __float2bfloat162_rn(0.01f)));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+// Streams consecutive feature columns of one tile row into X (16-bit, 128B-swizzled K-chunks), eight columns
+// (one 16-byte unit) at a time.  Both worker groups generate every column; a group only stores the units it owns
+// (first or second half), which keeps the generators free of cross-group exchanges.  All indices are compile-time
+// after unrolling.
+template <bool F16, int NUNITS, bool SPLIT = true>
+struct RowStream {
+  uint8_t* rowp;   // X + row offset inside a chunk
+  int chunk0, row, grp;
+  float buf[8];
+  __device__ __forceinline__ RowStream(uint8_t* X, int chunk0_, int row_, int grp_)
+      : rowp(X + (row_ >> 3) * 1024 + (row_ & 7) * 128), chunk0(chunk0_), row(row_), grp(grp_) {}
+  __device__ __forceinline__ void put(int col, float v) {
+    buf[col & 7] = v;
+    if ((col & 7) == 7) {
+      const int u = col >> 3;
+      const int owner = (u < (NUNITS + 1) / 2) ? 0 : 1;
+      if (!SPLIT || owner == grp) {
+        uint4 q;
+        q.x = pack2<F16>(buf[0], buf[1]);
+        q.y = pack2<F16>(buf[2], buf[3]);
+        q.z = pack2<F16>(buf[4], buf[5]);
+        q.w = pack2<F16>(buf[6], buf[7]);
+        *reinterpret_cast<uint4*>(rowp + (chunk0 + (u >> 3)) * kChunkBytes + ((((u & 7) ^ row) & 7) << 4)) = q;
+      }
+    }
+  }
+};
+
+// positional encoding of D values streamed in the reference's column order (nerf_helpers.py:341-349):
+// [x_0..x_{D-1}] (if INC), then per octave k: sin(2^k x_d) for all d, cos(2^k x_d) for all d.
+// Accurate sincosf every 5th octave (2^k * x is exact in fp32), double-angle recurrence in between (err < 2e-6).
+template <int L, bool INC, int D, class Stream>
+__device__ __forceinline__ int pe_stream(Stream& st, int col, const float (&x)[D]) {
   if (INC) {
 #pragma unroll
-    for (int d = 0; d < D; ++d) e[base + d] = x[d];
+    for (int d = 0; d < D; ++d) st.put(col++, x[d]);
   }
-  constexpr int o = INC ? D : 0;
+  float s[D], c[D];
 #pragma unroll
-  for (int d = 0; d < D; ++d) {
-    float s = 0.f, c = 1.f;
+  for (int k = 0; k < L; ++k) {
 #pragma unroll
-    for (int k = 0; k < L; ++k) {
+    for (int d = 0; d < D; ++d) {
       if (k % 5 == 0) {
-        sincosf(x[d] * (float)(1 << k), &s, &c);
+        sincosf(x[d] * (float)(1 << k), &s[d], &c[d]);
       } else {
-        float s2 = 2.f * s * c;
-        float c2 = 1.f - 2.f * s * s;
-        s = s2; c = c2;
+        const float s2 = 2.f * s[d] * c[d];
+        c[d] = 1.f - 2.f * s[d] * s[d];
+        s[d] = s2;
       }
-      e[base + o + (2 * k) * D + d] = s;
-      e[base + o + (2 * k + 1) * D + d] = c;
     }
+#pragma unroll
+    for (int d = 0; d < D; ++d) st.put(col++, s[d]);
+#pragma unroll
+    for (int d = 0; d < D; ++d) st.put(col++, c[d]);
   }
+  return col;
 }
 
-// epilogue of one pass: TMEM accumulator -> +bias -> activation -> bf16 -> X (in place, swizzled)
-// optional extras: fp32 dot with a weight row (sigma head), debug dump
-template <int ACT, bool DOT>
-__device__ __forceinline__ float epilogue_store(uint32_t tmem_row, int ncols, const float* __restrict__ bias,
-                                                uint8_t* X, int row, const float* __restrict__ dot_w,
-                                                float* __restrict__ dbg_row) {
+// one 32-column block of an epilogue: +bias (FADD2), optional fp32 dot, pack, activation, swizzled store
+template <int ACT, bool F16, bool DOT, bool DBG>
+__device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const float4 (&b)[8], int c0, uint8_t* rowp, int row,
+                                          const float* __restrict__ dot_w, float& dot, float* dbg_row) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float f0 = __uint_as_float(v[4 * j + 0]), f1 = __uint_as_float(v[4 * j + 1]);
+    float f2 = __uint_as_float(v[4 * j + 2]), f3 = __uint_as_float(v[4 * j + 3]);
+    add2(f0, f1, b[j].x, b[j].y);
+    add2(f2, f3, b[j].z, b[j].w);
+    if (DOT) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(dot_w + c0 + 4 * j));
+      dot += f0 * w.x + f1 * w.y + f2 * w.z + f3 * w.w;
+    }
+    pk[2 * j] = act2<ACT, F16>(pack2<F16>(f0, f1));
+    pk[2 * j + 1] = act2<ACT, F16>(pack2<F16>(f2, f3));
+    if (DBG && dbg_row) {
+      const float lk = ACT == ACT_LEAKY ? 0.01f : 0.f;
+      const bool a = ACT != ACT_NONE;
+      dbg_row[c0 + 4 * j + 0] = a ? fmaxf(f0, lk * f0) : f0;
+      dbg_row[c0 + 4 * j + 1] = a ? fmaxf(f1, lk * f1) : f1;
+      dbg_row[c0 + 4 * j + 2] = a ? fmaxf(f2, lk * f2) : f2;
+      dbg_row[c0 + 4 * j + 3] = a ? fmaxf(f3, lk * f3) : f3;
+    }
+  }
+  uint8_t* chunk = rowp + (c0 >> 6) * kChunkBytes;
+  const int u0 = (c0 & 63) >> 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(chunk + ((((u0 + q) ^ row) & 7) << 4)) =
+        make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+}
+
+// Epilogue of one pass for this group's NBLK 32-column blocks starting at column cbeg.  TMEM loads are double
+// buffered against the math of the previous block; bias loads are issued before the TMEM wait.
+template <int ACT, bool F16, bool DOT, bool DBG, int NBLK>
+__device__ __forceinline__ float epilogue(uint32_t tmem_row, int cbeg, const float* __restrict__ bias, uint8_t* X,
+                                          int row, const float* __restrict__ dot_w, float* dbg_row) {
   float dot = 0.f;
   uint8_t* rowp = X + (row >> 3) * 1024 + (row & 7) * 128;
-  for (int c0 = 0; c0 < ncols; c0 += 32) {
-    uint32_t v[32];
-    tmem_ld32(tmem_row + c0, v);
+  uint32_t va[32], vb[32];
+  float4 b[8];
+  tmem_ld32(tmem_row + cbeg, va);
+#pragma unroll
+  for (int blk = 0; blk < NBLK; ++blk) {
+    const int c0 = cbeg + 32 * blk;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
     tmem_ld_wait();
-    uint32_t pk[16];
-#pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c0 + j));
-      float f0 = act_fn<ACT>(__uint_as_float(v[j + 0]) + b.x);
-      float f1 = act_fn<ACT>(__uint_as_float(v[j + 1]) + b.y);
-      float f2 = act_fn<ACT>(__uint_as_float(v[j + 2]) + b.z);
-      float f3 = act_fn<ACT>(__uint_as_float(v[j + 3]) + b.w);
-      if (DOT) {
-        const float4 w = __ldg(reinterpret_cast<const float4*>(dot_w + c0 + j));
-        dot += f0 * w.x + f1 * w.y + f2 * w.z + f3 * w.w;
-      }
-      if (dbg_row) {
-        dbg_row[c0 + j + 0] = f0; dbg_row[c0 + j + 1] = f1; dbg_row[c0 + j + 2] = f2; dbg_row[c0 + j + 3] = f3;
-      }
-      pk[j / 2] = pack_bf16x2(f0, f1);
-      pk[j / 2 + 1] = pack_bf16x2(f2, f3);
-    }
-    uint8_t* chunk = rowp + (c0 >> 6) * kChunkBytes;
-    const int u0 = (c0 & 63) >> 3;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint4 val = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-      *reinterpret_cast<uint4*>(chunk + ((((u0 + q) ^ row) & 7) << 4)) = val;
+    if (blk & 1) {
+      if (blk + 1 < NBLK) tmem_ld32(tmem_row + c0 + 32, va);
+      epi_block<ACT, F16, DOT, DBG>(vb, b, c0, rowp, row, dot_w, dot, dbg_row);
+    } else {
+      if (blk + 1 < NBLK) tmem_ld32(tmem_row + c0 + 32, vb);
+      epi_block<ACT, F16, DOT, DBG>(va, b, c0, rowp, row, dot_w, dot, dbg_row);
     }
   }
   return dot;
 }
 
-// trilinear gather from the channel-last embedding grid, ref: nerf/models.py:346-365 (align_corners=True,
-// zero padding, raw warped coordinates; x -> last grid dim, z -> first)
-__device__ __forceinline__ void grid_gather(const float* __restrict__ g, float x, float y, float z, float (&out)[32]) {
+// trilinear gather of 16 of the 32 channels from the channel-last embedding grid, ref: nerf/models.py:346-365
+// (align_corners=True, zero padding, raw warped coordinates; x -> last grid dim, z -> first)
+__device__ __forceinline__ void grid_gather16(const float* __restrict__ g, int ch0, float x, float y, float z,
+                                              float (&out)[16]) {
   const float sc = 0.5f * (SAHS_GRID_RES - 1);
   const float ix = (x + 1.f) * sc, iy = (y + 1.f) * sc, iz = (z + 1.f) * sc;
   const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
 #pragma unroll
-  for (int c = 0; c < 32; ++c) out[c] = 0.f;
+  for (int c = 0; c < 16; ++c) out[c] = 0.f;
 #pragma unroll
   for (int corner = 0; corner < 8; ++corner) {
     const float xi = fx + (corner & 1), yi = fy + ((corner >> 1) & 1), zi = fz + (corner >> 2);
@@ -157,9 +227,9 @@ __device__ __forceinline__ void grid_gather(const float* __restrict__ g, float x
                     zi <= SAHS_GRID_RES - 1;
     if (ok) {
       const float4* p = reinterpret_cast<const float4*>(
-          g + ((((size_t)(int)zi * SAHS_GRID_RES + (int)yi) * SAHS_GRID_RES + (int)xi) * SAHS_GRID_CH));
+          g + ((((size_t)(int)zi * SAHS_GRID_RES + (int)yi) * SAHS_GRID_RES + (int)xi) * SAHS_GRID_CH) + ch0);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < 4; ++q) {
         const float4 v = __ldg(p + q);
         out[4 * q + 0] += w * v.x; out[4 * q + 1] += w * v.y; out[4 * q + 2] += w * v.z; out[4 * q + 3] += w * v.w;
       }
@@ -167,7 +237,7 @@ __device__ __forceinline__ void grid_gather(const float* __restrict__ g, float x
   }
 }
 
-template <int XYZ_L_, int AMB_DIM_, int AMB_L_, bool AMB_INC_, int DIR_L_, bool USE_W_, bool USE_GRID_>
+template <int XYZ_L_, int AMB_DIM_, int AMB_L_, bool AMB_INC_, int DIR_L_, bool USE_W_>
 struct FieldCfg {
   static constexpr int XYZ_L = XYZ_L_;
   static constexpr int AMB_DIM = AMB_DIM_;
@@ -175,17 +245,15 @@ struct FieldCfg {
   static constexpr bool AMB_INC = AMB_INC_;
   static constexpr int DIR_L = DIR_L_;
   static constexpr bool USE_W = USE_W_;
-  static constexpr bool USE_GRID = USE_GRID_;
   static constexpr int E0_DIM = 3 + 6 * XYZ_L;                                      // include_input is always on
   static constexpr int E0_PAD = (E0_DIM + 15) / 16 * 16;
   static constexpr int AMB_PE = USE_W ? ((AMB_INC ? AMB_DIM : 0) + 2 * AMB_DIM * AMB_L) : 0;
   static constexpr int E1_DIM = E0_DIM + AMB_PE;
   static constexpr int E1_PAD = (E1_DIM + 15) / 16 * 16;
   static constexpr int DIR_DIM = 3 + 6 * DIR_L;
-  static constexpr int XTRA_DIM = DIR_DIM + (USE_GRID ? 32 : 0);
 };
 
-template <class C>
+template <class C, bool DBG>
 __global__ void __launch_bounds__(kThreads, 2)
 field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__ NetDims dm,
                  const uint8_t* __restrict__ packed, const float* __restrict__ fc, const float* __restrict__ grid,
@@ -201,6 +269,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
   uint64_t* a_ready = bars + 2 * kSlots;
   uint64_t* acc_ready = bars + 2 * kSlots + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kSlots + 2);
+  float* xchg = reinterpret_cast<float*>(smem + kSmemXchg);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long ntiles = (P + kTileRows - 1) / kTileRows;
@@ -215,13 +284,13 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
     mbar_init(acc_ready, 1);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc(tmem_ptr, kTmemCols);
+  if (warp == kMmaWarp) tmem_alloc(tmem_ptr, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 4) {
+  if (warp == kTmaWarp) {
     // ================================ TMA producer ==============================================
     uint32_t slot = 0, phase = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -238,7 +307,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         if (++slot == kSlots) { slot = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ================================ MMA issuer ================================================
     uint32_t slot = 0, phase = 0, a_par = 0;
     const uint32_t x_addr = smem_u32(X), s_addr = smem_u32(slots);
@@ -253,12 +322,12 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         mbar_wait(&full[slot], phase, status, 400 + st);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t idesc = umma_idesc_bf16_m128((uint32_t)r.n8 * 8u);
+          const uint32_t idesc = umma_idesc_m128((uint32_t)r.n8 * 8u, (flags & ST_F16) != 0);
           const uint64_t a0 = umma_smem_desc_sw128(x_addr + r.a_chunk * kChunkBytes);
           const uint64_t b0 = umma_smem_desc_sw128(s_addr + slot * kStageSlotBytes);
           const uint32_t d = tmem_base + (uint32_t)r.d_col8 * 8u;
           for (uint32_t k = 0; k < ksteps; ++k) {
-            // advancing K by 16 bf16 = 32 bytes = 2 descriptor address units inside the 128B swizzle atom
+            // advancing K by 16 elements = 32 bytes = 2 descriptor address units inside the 128B swizzle atom
             tc_mma_bf16(d, a0 + 2 * k, b0 + 2 * k, idesc, (k > 0 || !(flags & ST_FRESH)) ? 1u : 0u);
           }
           tc_commit(&empty[slot]);
@@ -270,9 +339,10 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
     }
   } else {
     // ================================ workers ===================================================
-    Sync sy{full, empty, a_ready, acc_ready, 0u, status};
-    const int row = threadIdx.x;
-    const uint32_t tmem_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+    Sync sy{a_ready, acc_ready, 0u, status};
+    const int row = threadIdx.x & (kTileRows - 1);
+    const int grp = threadIdx.x >> 7;
+    const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const long long p = tile * kTileRows + row;
       const bool valid = p < P;
@@ -283,94 +353,100 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       float pt[3];
 #pragma unroll
       for (int k = 0; k < 3; ++k) pt[k] = __fadd_rn(ro[ray * 3 + k], __fmul_rn(dir[k], zz));
-      float* dbg_row = (dbg && tile == 0) ? dbg + row * 256 : nullptr;
+      float* dbg_row = (DBG && dbg && tile == 0) ? dbg + row * 256 : nullptr;
       float mapped[3] = {pt[0], pt[1], pt[2]};
       float amb[C::AMB_DIM > 0 ? C::AMB_DIM : 1] = {};
 
       if (C::USE_W) {
-        // -------- deformation phase: warp | hyper-sheet --------
-        {
-          float e[C::E0_PAD];
+        // -------- deformation phase: warp | hyper-sheet (fp16 operands) --------
+        auto write_e0 = [&](int chunk0) {
+          RowStream<true, C::E0_PAD / 8> st(X, chunk0, row, grp);
+          int col = pe_stream<C::XYZ_L, true, 3>(st, 0, pt);
 #pragma unroll
-          for (int i = C::E0_DIM; i < C::E0_PAD; ++i) e[i] = 0.f;
-          pe_fill<C::XYZ_L, true, 3>(e, 0, pt);
-          store_row<C::E0_PAD>(X, dm.e0_chunk_base, row, e);
-        }
+          for (int i = C::E0_DIM; i < C::E0_PAD; ++i) st.put(col++, 0.f);
+        };
+        write_e0(dm.e0_chunk_base);
         signal_a(sy);
-        for (int i = 0; i < dm.w_layers; ++i) {
+        for (int i = 0; i < dm.w_layers - 1; ++i) {
           wait_acc(sy, 1000 + i);
           if (i == dm.w_skip && !dm.e0_resident) {
-            float e[C::E0_PAD];
-#pragma unroll
-            for (int k = C::E0_DIM; k < C::E0_PAD; ++k) e[k] = 0.f;
-            pe_fill<C::XYZ_L, true, 3>(e, 0, pt);
-            store_row<C::E0_PAD>(X, 0, row, e);
+            write_e0(0);
             signal_a(sy);
             wait_acc(sy, 1100 + i);
           }
+          // whh = 192: three 32-column blocks per group
+          epilogue<ACT_RELU, true, false, DBG, 3>(tmem_row, grp * 96, fc + dm.off_wbias + i * dm.whh, X, row, nullptr,
+                                                  (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) ? dbg_row : nullptr);
+          signal_a(sy);
+        }
+        {
+          // last hidden layer stays in fp32: dx = tanh(fc_final h_w), ambient = fc_ambient h_h.  Group g reduces its
+          // 96 columns; the 5 partial sums per row are exchanged through the (idle) X buffer.
+          const int i = dm.w_layers - 1;
+          wait_acc(sy, 1000 + i);
+          if (i == dm.w_skip && !dm.e0_resident) { write_e0(0); signal_a(sy); wait_acc(sy, 1100 + i); }
           const float* bias = fc + dm.off_wbias + i * dm.whh;
-          if (i < dm.w_layers - 1) {
-            epilogue_store<ACT_RELU, false>(tmem_row, dm.whh, bias, X, row, nullptr,
-                                            (dbg_row && dbg_pass == SAHS_DBG_WARP(i)) ? dbg_row : nullptr);
-            signal_a(sy);
-          } else {
-            // last hidden layer stays in fp32: dx = tanh(fc_final h_w), ambient = fc_ambient h_h
-            const float* wf = fc + dm.off_wfinal;
-            const float* bf = wf + 3 * dm.wh;
-            const float* wa = bf + 3;
-            const float* ba = wa + C::AMB_DIM * dm.hh;
-            float acc_dx[3] = {0.f, 0.f, 0.f};
-            float acc_am[C::AMB_DIM > 0 ? C::AMB_DIM : 1] = {};
-            for (int c0 = 0; c0 < dm.whh; c0 += 32) {
-              uint32_t v[32];
-              tmem_ld32(tmem_row + c0, v);
-              tmem_ld_wait();
+          const float* wf = fc + dm.off_wfinal;
+          const float* bf = wf + 3 * dm.wh;
+          const float* wa = bf + 3;
+          const float* ba = wa + C::AMB_DIM * dm.hh;
+          float part[3 + (C::AMB_DIM > 0 ? C::AMB_DIM : 1)] = {};
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float h = fmaxf(__uint_as_float(v[j]) + __ldg(bias + c0 + j), 0.f);
-                if (dbg_row && dbg_pass == SAHS_DBG_WARP(i)) dbg_row[c0 + j] = h;
-                const int c = c0 + j;
-                if (c0 < dm.wh) {
+          for (int blk = 0; blk < 3; ++blk) {
+            const int c0 = grp * 96 + 32 * blk;
+            uint32_t v[32];
+            tmem_ld32(tmem_row + c0, v);
+            tmem_ld_wait();
 #pragma unroll
-                  for (int k = 0; k < 3; ++k) acc_dx[k] += h * __ldg(wf + k * dm.wh + c);
-                } else {
+            for (int j = 0; j < 32; ++j) {
+              const float h = fmaxf(__uint_as_float(v[j]) + __ldg(bias + c0 + j), 0.f);
+              if (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) dbg_row[c0 + j] = h;
+              if (c0 < dm.wh) {
 #pragma unroll
-                  for (int k = 0; k < C::AMB_DIM; ++k) acc_am[k] += h * __ldg(wa + k * dm.hh + (c - dm.wh));
-                }
+                for (int k = 0; k < 3; ++k) part[k] += h * __ldg(wf + k * dm.wh + c0 + j);
+              } else {
+#pragma unroll
+                for (int k = 0; k < C::AMB_DIM; ++k) part[3 + k] += h * __ldg(wa + k * dm.hh + (c0 + j - dm.wh));
               }
             }
+          }
+          float* scratch = reinterpret_cast<float*>(X);   // [2][128][8]
 #pragma unroll
-            for (int k = 0; k < 3; ++k) mapped[k] = pt[k] + tanhf(acc_dx[k] + __ldg(bf + k));
+          for (int k = 0; k < 3 + C::AMB_DIM; ++k) scratch[(grp * 128 + row) * 8 + k] = part[k];
+          group_sync();
 #pragma unroll
-            for (int k = 0; k < C::AMB_DIM; ++k) amb[k] = acc_am[k] + __ldg(ba + k);
+          for (int k = 0; k < 3; ++k)
+            mapped[k] = pt[k] + tanhf(scratch[row * 8 + k] + scratch[(128 + row) * 8 + k] + __ldg(bf + k));
+#pragma unroll
+          for (int k = 0; k < C::AMB_DIM; ++k)
+            amb[k] = scratch[row * 8 + 3 + k] + scratch[(128 + row) * 8 + 3 + k] + __ldg(ba + k);
+          group_sync();   // scratch is dead before E1 overwrites it
+        }
+      }
+      // -------- spatial embedding gather: each group keeps its 16 channels packed until layers_dir.0 --------
+      uint32_t emb_pk[8];
+      {
+        float emb[16];
+        grid_gather16(grid, grp * 16, mapped[0], mapped[1], mapped[2], emb);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) emb_pk[q] = pack2<false>(emb[2 * q], emb[2 * q + 1]);
+        if (DBG && dbg_row && dbg_pass == SAHS_DBG_MAPPED) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) dbg_row[8 + grp * 16 + q] = emb[q];
+          if (grp == 0) {
+            dbg_row[0] = mapped[0]; dbg_row[1] = mapped[1]; dbg_row[2] = mapped[2];
+#pragma unroll
+            for (int k = 0; k < C::AMB_DIM; ++k) dbg_row[3 + k] = amb[k];
           }
         }
       }
-      // -------- spatial embedding gather (kept packed until layers_dir.0) --------
-      uint32_t emb_pk[16];
-      if (C::USE_GRID) {
-        float emb[32];
-        grid_gather(grid, mapped[0], mapped[1], mapped[2], emb);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) emb_pk[q] = pack_bf16x2(emb[2 * q], emb[2 * q + 1]);
-        if (dbg_row && dbg_pass == SAHS_DBG_MAPPED) {
-#pragma unroll
-          for (int q = 0; q < 32; ++q) dbg_row[8 + q] = emb[q];
-        }
-      }
-      if (dbg_row && dbg_pass == SAHS_DBG_MAPPED) {
-        dbg_row[0] = mapped[0]; dbg_row[1] = mapped[1]; dbg_row[2] = mapped[2];
-#pragma unroll
-        for (int k = 0; k < C::AMB_DIM; ++k) dbg_row[3 + k] = amb[k];
-      }
-      // -------- trunk --------
+      // -------- trunk (bf16 operands) --------
       auto write_e1 = [&]() {
-        float e[C::E1_PAD];
+        RowStream<false, C::E1_PAD / 8> st(X, 0, row, grp);
+        int col = pe_stream<C::XYZ_L, true, 3>(st, 0, mapped);
+        if (C::AMB_PE > 0) col = pe_stream<C::AMB_L, C::AMB_INC, (C::AMB_DIM > 0 ? C::AMB_DIM : 1)>(st, col, amb);
 #pragma unroll
-        for (int i = C::E1_DIM; i < C::E1_PAD; ++i) e[i] = 0.f;
-        pe_fill<C::XYZ_L, true, 3>(e, 0, mapped);
-        if (C::AMB_PE > 0) pe_fill<C::AMB_L, C::AMB_INC, (C::AMB_DIM > 0 ? C::AMB_DIM : 1)>(e, C::E0_DIM, amb);
-        store_row<C::E1_PAD>(X, 0, row, e);
+        for (int i = C::E1_DIM; i < C::E1_PAD; ++i) st.put(col++, 0.f);
       };
       write_e1();
       signal_a(sy);
@@ -381,54 +457,54 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
           signal_a(sy);
           wait_acc(sy, 2100 + i);
         }
-        epilogue_store<ACT_LEAKY, false>(tmem_row, dm.th, fc + dm.off_tbias + i * dm.th, X, row, nullptr,
-                                         (dbg_row && dbg_pass == SAHS_DBG_TRUNK(i)) ? dbg_row : nullptr);
+        epilogue<ACT_LEAKY, false, false, DBG, 4>(tmem_row, grp * 128, fc + dm.off_tbias + i * dm.th, X, row, nullptr,
+                                                  (DBG && dbg_row && dbg_pass == SAHS_DBG_TRUNK(i)) ? dbg_row : nullptr);
         signal_a(sy);
       }
-      // fc_feat (no activation) + sigma = fc_alpha(feat) in fp32
+      // fc_feat (no activation) + sigma = fc_alpha(feat) in fp32 (partial dot per group)
       wait_acc(sy, 2200);
-      float sigma = epilogue_store<ACT_NONE, true>(tmem_row, dm.th, fc + dm.off_featb, X, row, fc + dm.off_alpha,
-                                                   (dbg_row && dbg_pass == SAHS_DBG_TRUNK(dm.t_layers)) ? dbg_row : nullptr);
-      sigma += __ldg(fc + dm.off_alpha + dm.th);
+      float sigma = epilogue<ACT_NONE, false, true, DBG, 4>(
+          tmem_row, grp * 128, fc + dm.off_featb, X, row, fc + dm.off_alpha,
+          (DBG && dbg_row && dbg_pass == SAHS_DBG_TRUNK(dm.t_layers)) ? dbg_row : nullptr);
+      if (grp == 1) xchg[row] = sigma;
       signal_a(sy);
       // -------- heads: layers_dir.0 = [feat | PE(dir) | emb], layers_seg.0 = feat --------
       wait_acc(sy, 3000);
       {
-        float e[64];
+        // extra K-chunk: cols [0,27) PE(dir), [27,59) embedding, zero padding up to 64
+        RowStream<false, 8, false> st(X, 0, row, 0);
+        if (grp == 0) {
+          int col = pe_stream<C::DIR_L, true, 3>(st, 0, dir);
 #pragma unroll
-        for (int i = 0; i < 64; ++i) e[i] = 0.f;
-        pe_fill<C::DIR_L, true, 3>(e, 0, dir);
-        store_row<64>(X, 0, row, e);
-        if (C::USE_GRID) {
-          // overwrite the embedding columns DIR_DIM .. DIR_DIM+31 (bf16 pairs are not 4-byte aligned when
-          // DIR_DIM is odd, so go through the scalar path)
-          uint8_t* rowp = X + (row >> 3) * 1024 + (row & 7) * 128;
+          for (int i = C::DIR_DIM; i < 64; ++i) st.put(col++, 0.f);
+        }
+        group_sync();     // group 0's zero fill precedes the scalar embedding stores of both groups
+        uint8_t* rowp = X + (row >> 3) * 1024 + (row & 7) * 128;
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            const int col = C::DIR_DIM + q;
-            const uint32_t pair = emb_pk[q >> 1];
-            const uint16_t hv = (q & 1) ? (uint16_t)(pair >> 16) : (uint16_t)(pair & 0xffffu);
-            *reinterpret_cast<uint16_t*>(rowp + ((((col >> 3) ^ row) & 7) << 4) + (col & 7) * 2) = hv;
-          }
+        for (int q = 0; q < 16; ++q) {
+          const int col = C::DIR_DIM + grp * 16 + q;
+          const uint32_t pair = emb_pk[q >> 1];
+          const uint16_t hv = (q & 1) ? (uint16_t)(pair >> 16) : (uint16_t)(pair & 0xffffu);
+          *reinterpret_cast<uint16_t*>(rowp + ((((col >> 3) ^ row) & 7) << 4) + (col & 7) * 2) = hv;
         }
       }
       signal_a(sy);
       for (int i = 0; i < 4; ++i) {
         wait_acc(sy, 3100 + i);
-        epilogue_store<ACT_LEAKY, false>(tmem_row, 2 * dm.hd, fc + dm.off_hbias + i * 2 * dm.hd, X, row, nullptr,
-                                         (dbg_row && dbg_pass == SAHS_DBG_HEAD(i)) ? dbg_row : nullptr);
+        epilogue<ACT_LEAKY, false, false, DBG, 4>(tmem_row, grp * 128, fc + dm.off_hbias + i * 2 * dm.hd, X, row, nullptr,
+                                                  (DBG && dbg_row && dbg_pass == SAHS_DBG_HEAD(i)) ? dbg_row : nullptr);
         signal_a(sy);
       }
       // -------- output layer: cols 0-2 rgb, 3-14 seg (+ sigma) --------
       wait_acc(sy, 3200);
-      {
+      if (grp == 0) {
         uint32_t v[16];
         tmem_ld16(tmem_row, v);
         tmem_ld_wait();
         float o[16];
 #pragma unroll
         for (int k = 0; k < 15; ++k) o[k] = __uint_as_float(v[k]) + __ldg(fc + dm.off_outb + k);
-        o[15] = sigma;
+        o[15] = sigma + xchg[row] + __ldg(fc + dm.off_alpha + dm.th);
         if (valid) {
           float4* dst = reinterpret_cast<float4*>(raw_out + p * SAHS_RAW_CH);
 #pragma unroll
@@ -436,10 +512,11 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         }
       }
       tc_fence_before();
+      group_sync();   // xchg[] consumed before the next tile's fc_feat epilogue rewrites it
     }
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -449,12 +526,8 @@ template <class C>
 int launch_field(const HostPlan& hp, const void* packed, const float* fc, const float* grid, const float* ro,
                  const float* rd, const float* z, int R, int S, float* raw, float* dbg, int dbg_pass,
                  cudaStream_t st) {
-  auto kfn = field_fwd_kernel<C>;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    SAHS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-    attr_set = true;
-  }
+  auto kfn = (dbg != nullptr) ? field_fwd_kernel<C, true> : field_fwd_kernel<C, false>;
+  SAHS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
   int* status = nullptr;
   SAHS_CUDA(cudaGetSymbolAddress((void**)&status, g_field_status));
   const long long P = (long long)R * S;
@@ -477,22 +550,24 @@ extern "C" int sahs_field_status(int* out4_host) {
 extern "C" int sahs_field_fwd(const sahs_model_spec* spec, int level, const void* packed, const float* frame_const,
                               const float* grid_cl, const float* ro, const float* rd, const float* z, int num_rays,
                               int num_samples, float* raw_out, float* debug, int debug_pass, void* stream) {
-  SAHS_CHECK_ARG(spec && packed && frame_const && ro && rd && z && raw_out, "null pointer");
+  SAHS_CHECK_ARG(spec, "null spec");
   SAHS_CHECK_ARG(level == 0 || level == 1, "level must be 0 (coarse) or 1 (fine)");
   SAHS_CHECK_ARG(num_rays >= 0 && num_samples > 0, "bad extents");
-  SAHS_CHECK_ARG(!spec->use_grid || grid_cl, "grid pointer required when use_spatial_embeddings");
   if (num_rays == 0) return SAHS_OK;
+  SAHS_CHECK_ARG(packed && frame_const && ro && rd && z && raw_out, "null pointer");
+  SAHS_CHECK_ARG(spec->use_grid && grid_cl, "use_spatial_embeddings and its grid are required (all shipped configs)");
   static thread_local HostPlan hp;
   int rc = sahs_build_host_plan(*spec, nullptr, hp);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const sahs_model_spec& s = *spec;
   SAHS_CHECK_ARG(s.xyz_inc && s.dir_inc && s.dir_L == 4, "include_input_xyz/dir and num_encoding_fn_dir=4 expected");
+  SAHS_CHECK_ARG(!hp.dims.use_w || hp.dims.whh == 192, "warp 128 + hyper 64 hidden units expected");
 #define SAHS_TRY(XL, AD, AL, AI, UW)                                                                             \
   if (s.xyz_L == XL && (UW ? (s.amb_dim == AD && s.amb_L == AL && (s.amb_inc != 0) == AI) : true) &&             \
-      ((s.use_warp != 0) == UW) && s.use_grid)                                                                   \
-    return launch_field<FieldCfg<XL, AD, AL, AI, 4, UW, true>>(hp, packed, frame_const, grid_cl, ro, rd, z,      \
-                                                               num_rays, num_samples, raw_out, debug, debug_pass, st);
+      ((s.use_warp != 0) == UW))                                                                                 \
+    return launch_field<FieldCfg<XL, AD, AL, AI, 4, UW>>(hp, packed, frame_const, grid_cl, ro, rd, z, num_rays,  \
+                                                         num_samples, raw_out, debug, debug_pass, st);
   SAHS_TRY(10, 2, 4, true, true)     // config/audio/*.yml
   SAHS_TRY(15, 1, 15, false, true)   // config/expression/person_{2,3}.yml
   SAHS_TRY(10, 0, 0, false, false)   // config/expression/person_1.yml (no deformation, no hyper space)

@@ -2,6 +2,7 @@
 // images), per-frame constant folding.  See field_plan.cuh for the layout.
 #include <string.h>
 #include <vector>
+#include <cuda_fp16.h>
 #include "sahs_common.cuh"
 #include "field_plan.cuh"
 
@@ -46,13 +47,14 @@ struct Builder {
   int ns = 0;
   uint32_t off = 0;
   bool pass_open = false;
+  bool f16 = false;   // operand format of the stages being emitted
 
   // one stage: rows [row0,row0+n) x cols [col0, col0+kvalid) of weight `pidx` (ld = in_features)
   void stage(int pidx, int ld, int row0, int n, int col0, int kvalid, int a_chunk, int d_col, bool fresh) {
     StageRec& r = hp.plan.st[ns];
     int ksteps = (kvalid + 15) / 16;
     r.n8 = (uint8_t)(n / 8);
-    uint8_t flags = (fresh ? ST_FRESH : 0) | (pass_open ? 0 : ST_WAIT_A);
+    uint8_t flags = (fresh ? ST_FRESH : 0) | (pass_open ? 0 : ST_WAIT_A) | (f16 ? ST_F16 : 0);
     r.kflags = (uint8_t)(ksteps | (flags << 3));
     r.a_chunk = (uint8_t)a_chunk;
     r.d_col8 = (uint8_t)(d_col / 8);
@@ -60,6 +62,7 @@ struct Builder {
     memset(&ps, 0, sizeof(ps));
     ps.dst_off = off;
     ps.n = n;
+    ps.f16 = f16 ? 1 : 0;
     ps.src[0].w = P ? P[pidx] : nullptr;
     ps.src[0].ld = ld;
     ps.src[0].src_row0 = row0; ps.src[0].src_col0 = col0;
@@ -104,6 +107,7 @@ int sahs_build_host_plan(const sahs_model_spec& s, const float* const* params, H
   const int CW = SAHS_DRIVING_DIM + SAHS_POSE_CODE_DIM;  // 112 frame-constant inputs of warp/hyper
   // ---------------- deformation phase: warp | hyper merged -------------------------------------------
   if (d.use_w) {
+    b.f16 = true;   // fp16 operands: the encoding of the warped point amplifies coordinate error by 2^(L-1)
     const int in0 = d.e0_dim + CW;
     for (int i = 0; i < d.w_layers; ++i) {
       const bool first = i == 0, skip = i == d.w_skip;
@@ -138,6 +142,7 @@ int sahs_build_host_plan(const sahs_model_spec& s, const float* const* params, H
     hp.copy[hp.num_copy++] = CopySection{P(pi.warp_fb), 3, o}; o += 3;
     hp.copy[hp.num_copy++] = CopySection{P(pi.hyp_fw), s.amb_dim * d.hh, o}; o += s.amb_dim * d.hh;
     hp.copy[hp.num_copy++] = CopySection{P(pi.hyp_fb), s.amb_dim, o};
+    b.f16 = false;
   }
   // ---------------- trunk ---------------------------------------------------------------------------
   {
@@ -226,7 +231,10 @@ __global__ void pack_stage_kernel(const __grid_constant__ PackBatch batch, uint8
       if (s.w && row >= s.dst_row0 && row < s.dst_row0 + s.nrows && col < s.ncols)
         v = s.w[(size_t)(s.src_row0 + row - s.dst_row0) * s.ld + s.src_col0 + col];
     }
-    *reinterpret_cast<__nv_bfloat16*>(out + ps.dst_off + sw128_offset(row, col)) = __float2bfloat16_rn(v);
+    if (ps.f16)
+      *reinterpret_cast<__half*>(out + ps.dst_off + sw128_offset(row, col)) = __float2half_rn(v);
+    else
+      *reinterpret_cast<__nv_bfloat16*>(out + ps.dst_off + sw128_offset(row, col)) = __float2bfloat16_rn(v);
   }
 }
 

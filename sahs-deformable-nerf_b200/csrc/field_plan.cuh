@@ -18,7 +18,7 @@ constexpr int kChunkBytes = kTileRows * kChunkCols * 2;  // 16 KB
 constexpr int kMaxStages = 160;
 constexpr int kStageSlotBytes = 16384;
 
-enum : uint8_t { ST_WAIT_A = 1, ST_COMMIT = 2, ST_FRESH = 4 };
+enum : uint8_t { ST_WAIT_A = 1, ST_COMMIT = 2, ST_FRESH = 4, ST_F16 = 8 };  // F16: fp16 operands (else bf16)
 
 struct StageRec {   // 4 bytes, lives in kernel parameter space
   uint8_t n8;       // N / 8
@@ -43,6 +43,7 @@ struct PackStage {
   PackSrc src[2];
   uint32_t dst_off;   // byte offset in the packed image
   int32_t n;          // rows of the image (zero padded)
+  int32_t f16;        // store fp16 instead of bf16
 };
 
 // fp32 per-frame constant block: offsets in floats

@@ -59,9 +59,10 @@ __global__ void coarse_z_kernel(int R, int S, float near_, float far_, int lindi
 
 extern "C" int sahs_coarse_z(int num_rays, int num_samples, float near_, float far_, int lindisp,
                              const float* t_vals, const float* t_rand, float* z_out, void* stream) {
-  SAHS_CHECK_ARG(num_rays >= 0 && num_samples > 0 && t_vals && z_out, "bad arguments");
+  SAHS_CHECK_ARG(num_rays >= 0 && num_samples > 0, "bad arguments");
   int64_t n = (int64_t)num_rays * num_samples;
   if (n == 0) return SAHS_OK;
+  SAHS_CHECK_ARG(t_vals && z_out, "null pointer");
   coarse_z_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(num_rays, num_samples, near_, far_,
                                                                                lindisp, t_vals, t_rand, z_out);
   SAHS_LAUNCH_CHECK();
@@ -92,8 +93,9 @@ __global__ void posenc_kernel(const float* __restrict__ x, int64_t n, int d, int
 
 extern "C" int sahs_positional_encoding(const float* x, int64_t n, int d, int num_freqs, int include_input,
                                         float* out, void* stream) {
-  SAHS_CHECK_ARG(n >= 0 && d > 0 && num_freqs >= 0 && x && out, "bad arguments");
+  SAHS_CHECK_ARG(n >= 0 && d > 0 && num_freqs >= 0, "bad arguments");
   if (n == 0) return SAHS_OK;
+  SAHS_CHECK_ARG(x && out, "null pointer");
   int64_t tot = n * d;
   posenc_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, n, d, num_freqs,
                                                                               include_input ? 1 : 0, out);

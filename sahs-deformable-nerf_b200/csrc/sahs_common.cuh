@@ -175,9 +175,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                               // layout type SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M=128
-__device__ __forceinline__ uint32_t umma_idesc_bf16_m128(uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+// kind::f16 instruction descriptor: D fp32, A/B both bf16 (format 1) or both fp16 (format 0), K-major, M=128
+__device__ __forceinline__ uint32_t umma_idesc_m128(uint32_t n, bool f16) {
+  const uint32_t fmt = f16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 // byte offset of element (row, col) inside one [rows x 64] bf16 K-chunk with 128B swizzle
 __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t col) {

@@ -156,6 +156,7 @@ sample_pdf_merge_kernel(const float* __restrict__ z, const float* __restrict__ b
 extern "C" int sahs_sample_pdf_merge(const float* z, const float* weights, const float* u, int u_per_ray,
                                      int num_rays, int num_samples, int num_fine, float* z_samples, float* z_merged,
                                      int64_t* inds, void* stream) {
+  if (num_rays == 0) return SAHS_OK;
   SAHS_CHECK_ARG(z && weights && u && z_samples && z_merged, "null pointer");
   SAHS_CHECK_ARG(num_samples >= 3 && num_samples <= kMaxS, "num_samples must be in [3,256]");
   SAHS_CHECK_ARG(num_fine >= 1 && num_samples + num_fine <= kMaxMerged, "num_samples + num_fine must be <= 512");
@@ -172,6 +173,7 @@ extern "C" int sahs_sample_pdf_merge(const float* z, const float* weights, const
 
 extern "C" int sahs_sample_pdf(const float* bins, const float* weights, const float* u, int u_per_ray, int num_rays,
                                int num_bins, int num_fine, float* samples, int64_t* inds, void* stream) {
+  if (num_rays == 0) return SAHS_OK;
   SAHS_CHECK_ARG(bins && weights && u && samples, "null pointer");
   SAHS_CHECK_ARG(num_bins >= 2 && num_bins + 1 <= kMaxS, "num_bins must be in [2,255]");
   SAHS_CHECK_ARG(num_fine >= 1 && num_fine <= kMaxMerged, "num_fine must be <= 512");
