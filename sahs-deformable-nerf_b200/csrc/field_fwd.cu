@@ -149,19 +149,50 @@ __device__ __forceinline__ int pe_stream(Stream& st, int col, const float (&x)[D
   return col;
 }
 
-// one 32-column block of an epilogue: +bias (FADD2), optional fp32 dot, pack, activation, swizzled store
-template <int ACT, bool F16, bool DOT, bool DBG>
-__device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const float4 (&b)[8], int c0, uint8_t* rowp, int row,
-                                          const float* __restrict__ dot_w, float& dot, float* dbg_row) {
-  uint32_t pk[16];
+// bias / small-weight loads keep their lines in the (28 KB) L1 ahead of the streaming traffic
+__device__ __forceinline__ float4 ldg_keep(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldg_keep1(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_stream(const float* p) {   // read-once data: do not allocate in L1
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void load_bias(float4 (&b)[4], const float* __restrict__ bias) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float f0 = __uint_as_float(v[4 * j + 0]), f1 = __uint_as_float(v[4 * j + 1]);
-    float f2 = __uint_as_float(v[4 * j + 2]), f3 = __uint_as_float(v[4 * j + 3]);
-    add2(f0, f1, b[j].x, b[j].y);
-    add2(f2, f3, b[j].z, b[j].w);
+  for (int j = 0; j < 4; ++j) b[j] = ldg_keep(bias + 4 * j);
+}
+
+// one 16-column block of an epilogue: +bias (FADD2), optional fp32 dot, pack, activation, swizzled store.
+// The bias registers are dead after the adds, so the next block's bias is fetched before the pack/store part.
+template <int ACT, bool F16, bool DOT, bool DBG>
+__device__ __forceinline__ void epi_block(uint32_t (&v)[16], float4 (&b)[4], const float* __restrict__ next_bias, int c0,
+                                          uint8_t* rowp, int row, const float* __restrict__ dot_w, float& dot,
+                                          float* dbg_row) {
+  float f[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[4 * j + 0] = __uint_as_float(v[4 * j + 0]); f[4 * j + 1] = __uint_as_float(v[4 * j + 1]);
+    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]); f[4 * j + 3] = __uint_as_float(v[4 * j + 3]);
+    add2(f[4 * j + 0], f[4 * j + 1], b[j].x, b[j].y);
+    add2(f[4 * j + 2], f[4 * j + 3], b[j].z, b[j].w);
+  }
+  if (next_bias) load_bias(b, next_bias);
+  uint32_t pk[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float f0 = f[4 * j], f1 = f[4 * j + 1], f2 = f[4 * j + 2], f3 = f[4 * j + 3];
     if (DOT) {
-      const float4 w = __ldg(reinterpret_cast<const float4*>(dot_w + c0 + 4 * j));
+      const float4 w = ldg_keep(dot_w + c0 + 4 * j);
       dot += f0 * w.x + f1 * w.y + f2 * w.z + f3 * w.w;
     }
     pk[2 * j] = act2<ACT, F16>(pack2<F16>(f0, f1));
@@ -178,33 +209,32 @@ __device__ __forceinline__ void epi_block(const uint32_t (&v)[32], const float4 
   uint8_t* chunk = rowp + (c0 >> 6) * kChunkBytes;
   const int u0 = (c0 & 63) >> 3;
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
+  for (int q = 0; q < 2; ++q)
     *reinterpret_cast<uint4*>(chunk + ((((u0 + q) ^ row) & 7) << 4)) =
         make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
 }
 
-// Epilogue of one pass for this group's NBLK 32-column blocks starting at column cbeg.  TMEM loads are double
-// buffered against the math of the previous block; bias loads are issued before the TMEM wait.
+// Epilogue of one pass for this group's NBLK 16-column blocks starting at column cbeg.  TMEM loads are double
+// buffered against the math of the previous block; `b` arrives pre-loaded with the first block's bias (fetched by
+// the caller before it waited for the accumulator).
 template <int ACT, bool F16, bool DOT, bool DBG, int NBLK>
-__device__ __forceinline__ float epilogue(uint32_t tmem_row, int cbeg, const float* __restrict__ bias, uint8_t* X,
-                                          int row, const float* __restrict__ dot_w, float* dbg_row) {
+__device__ __forceinline__ float epilogue(uint32_t tmem_row, int cbeg, const float* __restrict__ bias, float4 (&b)[4],
+                                          uint8_t* X, int row, const float* __restrict__ dot_w, float* dbg_row) {
   float dot = 0.f;
   uint8_t* rowp = X + (row >> 3) * 1024 + (row & 7) * 128;
-  uint32_t va[32], vb[32];
-  float4 b[8];
-  tmem_ld32(tmem_row + cbeg, va);
+  uint32_t va[16], vb[16];
+  tmem_ld16(tmem_row + cbeg, va);
 #pragma unroll
   for (int blk = 0; blk < NBLK; ++blk) {
-    const int c0 = cbeg + 32 * blk;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) b[j] = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+    const int c0 = cbeg + 16 * blk;
+    const float* nb = (blk + 1 < NBLK) ? bias + c0 + 16 : nullptr;
     tmem_ld_wait();
     if (blk & 1) {
-      if (blk + 1 < NBLK) tmem_ld32(tmem_row + c0 + 32, va);
-      epi_block<ACT, F16, DOT, DBG>(vb, b, c0, rowp, row, dot_w, dot, dbg_row);
+      if (blk + 1 < NBLK) tmem_ld16(tmem_row + c0 + 16, va);
+      epi_block<ACT, F16, DOT, DBG>(vb, b, nb, c0, rowp, row, dot_w, dot, dbg_row);
     } else {
-      if (blk + 1 < NBLK) tmem_ld32(tmem_row + c0 + 32, vb);
-      epi_block<ACT, F16, DOT, DBG>(va, b, c0, rowp, row, dot_w, dot, dbg_row);
+      if (blk + 1 < NBLK) tmem_ld16(tmem_row + c0 + 16, vb);
+      epi_block<ACT, F16, DOT, DBG>(va, b, nb, c0, rowp, row, dot_w, dot, dbg_row);
     }
   }
   return dot;
@@ -230,7 +260,7 @@ __device__ __forceinline__ void grid_gather16(const float* __restrict__ g, int c
           g + ((((size_t)(int)zi * SAHS_GRID_RES + (int)yi) * SAHS_GRID_RES + (int)xi) * SAHS_GRID_CH) + ch0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 v = __ldg(p + q);
+        const float4 v = ldg_stream(reinterpret_cast<const float*>(p + q));
         out[4 * q + 0] += w * v.x; out[4 * q + 1] += w * v.y; out[4 * q + 2] += w * v.z; out[4 * q + 3] += w * v.w;
       }
     }
@@ -368,14 +398,19 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         write_e0(dm.e0_chunk_base);
         signal_a(sy);
         for (int i = 0; i < dm.w_layers - 1; ++i) {
+          const float* bias = fc + dm.off_wbias + i * dm.whh;
+          const bool two_pass = (i == dm.w_skip && !dm.e0_resident);
+          float4 b[4];
+          if (!two_pass) load_bias(b, bias + grp * 96);
           wait_acc(sy, 1000 + i);
-          if (i == dm.w_skip && !dm.e0_resident) {
+          if (two_pass) {
             write_e0(0);
             signal_a(sy);
+            load_bias(b, bias + grp * 96);
             wait_acc(sy, 1100 + i);
           }
           // whh = 192: three 32-column blocks per group
-          epilogue<ACT_RELU, true, false, DBG, 3>(tmem_row, grp * 96, fc + dm.off_wbias + i * dm.whh, X, row, nullptr,
+          epilogue<ACT_RELU, true, false, DBG, 6>(tmem_row, grp * 96, bias, b, X, row, nullptr,
                                                   (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) ? dbg_row : nullptr);
           signal_a(sy);
         }
@@ -387,8 +422,8 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
           if (i == dm.w_skip && !dm.e0_resident) { write_e0(0); signal_a(sy); wait_acc(sy, 1100 + i); }
           const float* bias = fc + dm.off_wbias + i * dm.whh;
           const float* wf = fc + dm.off_wfinal;
-          const float* bf = wf + 3 * dm.wh;
-          const float* wa = bf + 3;
+          const float* bf = wf + 3 * dm.wh;          // [wf 3*wh | bf 4 | wa amb*hh | ba 4], all 16-byte aligned
+          const float* wa = bf + 4;
           const float* ba = wa + C::AMB_DIM * dm.hh;
           float part[3 + (C::AMB_DIM > 0 ? C::AMB_DIM : 1)] = {};
 #pragma unroll
@@ -398,15 +433,26 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
             tmem_ld32(tmem_row + c0, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float h = fmaxf(__uint_as_float(v[j]) + __ldg(bias + c0 + j), 0.f);
-              if (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) dbg_row[c0 + j] = h;
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = ldg_keep(bias + c0 + 4 * j);
+              float h[4] = {fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.f), fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.f),
+                            fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.f)};
+              if (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dbg_row[c0 + 4 * j + q] = h[q];
+              }
               if (c0 < dm.wh) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) part[k] += h * __ldg(wf + k * dm.wh + c0 + j);
+                for (int k = 0; k < 3; ++k) {
+                  const float4 w = ldg_keep(wf + k * dm.wh + c0 + 4 * j);
+                  part[k] += h[0] * w.x + h[1] * w.y + h[2] * w.z + h[3] * w.w;
+                }
               } else {
 #pragma unroll
-                for (int k = 0; k < C::AMB_DIM; ++k) part[3 + k] += h * __ldg(wa + k * dm.hh + (c0 + j - dm.wh));
+                for (int k = 0; k < C::AMB_DIM; ++k) {
+                  const float4 w = ldg_keep(wa + k * dm.hh + (c0 + 4 * j - dm.wh));
+                  part[3 + k] += h[0] * w.x + h[1] * w.y + h[2] * w.z + h[3] * w.w;
+                }
               }
             }
           }
@@ -416,10 +462,10 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
           group_sync();
 #pragma unroll
           for (int k = 0; k < 3; ++k)
-            mapped[k] = pt[k] + tanhf(scratch[row * 8 + k] + scratch[(128 + row) * 8 + k] + __ldg(bf + k));
+            mapped[k] = pt[k] + tanhf(scratch[row * 8 + k] + scratch[(128 + row) * 8 + k] + ldg_keep1(bf + k));
 #pragma unroll
           for (int k = 0; k < C::AMB_DIM; ++k)
-            amb[k] = scratch[row * 8 + 3 + k] + scratch[(128 + row) * 8 + 3 + k] + __ldg(ba + k);
+            amb[k] = scratch[row * 8 + 3 + k] + scratch[(128 + row) * 8 + 3 + k] + ldg_keep1(ba + k);
           group_sync();   // scratch is dead before E1 overwrites it
         }
       }
@@ -451,20 +497,26 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       write_e1();
       signal_a(sy);
       for (int i = 0; i < dm.t_layers; ++i) {
+        const float* bias = fc + dm.off_tbias + i * dm.th;
+        float4 b[4];
+        if (i != dm.t_skip) load_bias(b, bias + grp * 128);
         wait_acc(sy, 2000 + i);
         if (i == dm.t_skip) {
           write_e1();
           signal_a(sy);
+          load_bias(b, bias + grp * 128);
           wait_acc(sy, 2100 + i);
         }
-        epilogue<ACT_LEAKY, false, false, DBG, 4>(tmem_row, grp * 128, fc + dm.off_tbias + i * dm.th, X, row, nullptr,
+        epilogue<ACT_LEAKY, false, false, DBG, 8>(tmem_row, grp * 128, bias, b, X, row, nullptr,
                                                   (DBG && dbg_row && dbg_pass == SAHS_DBG_TRUNK(i)) ? dbg_row : nullptr);
         signal_a(sy);
       }
       // fc_feat (no activation) + sigma = fc_alpha(feat) in fp32 (partial dot per group)
+      float4 bfe[4];
+      load_bias(bfe, fc + dm.off_featb + grp * 128);
       wait_acc(sy, 2200);
-      float sigma = epilogue<ACT_NONE, false, true, DBG, 4>(
-          tmem_row, grp * 128, fc + dm.off_featb, X, row, fc + dm.off_alpha,
+      float sigma = epilogue<ACT_NONE, false, true, DBG, 8>(
+          tmem_row, grp * 128, fc + dm.off_featb, bfe, X, row, fc + dm.off_alpha,
           (DBG && dbg_row && dbg_pass == SAHS_DBG_TRUNK(dm.t_layers)) ? dbg_row : nullptr);
       if (grp == 1) xchg[row] = sigma;
       signal_a(sy);
@@ -490,8 +542,11 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       }
       signal_a(sy);
       for (int i = 0; i < 4; ++i) {
+        const float* bias = fc + dm.off_hbias + i * 2 * dm.hd;
+        float4 b[4];
+        load_bias(b, bias + grp * 128);
         wait_acc(sy, 3100 + i);
-        epilogue<ACT_LEAKY, false, false, DBG, 4>(tmem_row, grp * 128, fc + dm.off_hbias + i * 2 * dm.hd, X, row, nullptr,
+        epilogue<ACT_LEAKY, false, false, DBG, 8>(tmem_row, grp * 128, bias, b, X, row, nullptr,
                                                   (DBG && dbg_row && dbg_pass == SAHS_DBG_HEAD(i)) ? dbg_row : nullptr);
         signal_a(sy);
       }

@@ -139,7 +139,7 @@ int sahs_build_host_plan(const sahs_model_spec& s, const float* const* params, H
     }
     int o = d.off_wfinal;
     hp.copy[hp.num_copy++] = CopySection{P(pi.warp_fw), 3 * d.wh, o}; o += 3 * d.wh;
-    hp.copy[hp.num_copy++] = CopySection{P(pi.warp_fb), 3, o}; o += 3;
+    hp.copy[hp.num_copy++] = CopySection{P(pi.warp_fb), 3, o}; o += 4;
     hp.copy[hp.num_copy++] = CopySection{P(pi.hyp_fw), s.amb_dim * d.hh, o}; o += s.amb_dim * d.hh;
     hp.copy[hp.num_copy++] = CopySection{P(pi.hyp_fb), s.amb_dim, o};
     b.f16 = false;

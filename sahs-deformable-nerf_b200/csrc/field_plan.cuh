@@ -117,7 +117,7 @@ inline int sahs_make_dims(const sahs_model_spec& s, NetDims& d) {
   if (s.amb_dim > 4 || s.amb_dim < 0) return -9;
   int o = 0;
   d.off_wbias = o;  o += d.use_w ? d.w_layers * d.whh : 0;
-  d.off_wfinal = o; o += d.use_w ? sahs_round_up(3 * d.wh + 3 + s.amb_dim * d.hh + s.amb_dim, 4) : 0;
+  d.off_wfinal = o; o += d.use_w ? (3 * d.wh + 4 + s.amb_dim * d.hh + 4) : 0;   // [wf | bf(4) | wa | ba(4)]
   d.off_tbias = o;  o += d.t_layers * d.th;
   d.off_featb = o;  o += d.th;
   d.off_alpha = o;  o += d.th + 4;

@@ -123,7 +123,7 @@ def _emulate(spec_model, ospec, sd, level, xyz, dirs, driving_vec, pose):
         o = dm["off_wfinal"]
         wh, hh = s.warp_hidden, s.hyper_hidden
         wf = fc[o:o + 3 * wh].reshape(3, wh); bf = fc[o + 3 * wh:o + 3 * wh + 3]
-        o2 = o + 3 * wh + 3
+        o2 = o + 3 * wh + 4
         wa = fc[o2:o2 + s.amb_dim * hh].reshape(s.amb_dim, hh); ba = fc[o2 + s.amb_dim * hh:o2 + s.amb_dim * hh + s.amb_dim]
         mapped = pts + np.tanh(h[:, :wh] @ wf.T + bf)
         amb = h[:, wh:] @ wa.T + ba
