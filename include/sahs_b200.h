@@ -136,7 +136,8 @@ int sahs_sample_pdf(const float* bins, const float* weights, const float* u, int
  * out4_host[0] code, [1] tag, [2] block, [3] thread.  Synchronous (device -> host copy). */
 int sahs_field_status(int* out4_host);
 
-/* Host-only plan introspection for the CPU test-suite (no device work); layouts documented in field_host.cu. */
+/* Host-only plan introspection for the CPU test-suite (no device work); layouts documented in field_host.cu
+ * (14 ints per stage, 8 per fold section, 3 per copy section, 21 dims). */
 int sahs_debug_plan(const sahs_model_spec* spec, int param_count, int32_t* stages, int max_stages, int32_t* folds,
                     int max_folds, int32_t* copies, int max_copies, int32_t* dims_out);
 

@@ -240,6 +240,106 @@ __device__ __forceinline__ float epilogue(uint32_t tmem_row, int cbeg, const flo
   return dot;
 }
 
+// ---- split-precision (fp16 hi + lo) variants used by the deformation phase when the encoding has > 10 octaves ----
+// Streams a row as two fp16 planes: hi = fp16(v) into chunk0.., lo = fp16(v - hi) into chunk0 + lo_off..
+template <int NUNITS>
+struct RowStreamSplit {
+  uint8_t* rowp;
+  int chunk0, lo_off, row, grp;
+  float buf[8];
+  __device__ __forceinline__ RowStreamSplit(uint8_t* X, int chunk0_, int lo_off_, int row_, int grp_)
+      : rowp(X + (row_ >> 3) * 1024 + (row_ & 7) * 128), chunk0(chunk0_), lo_off(lo_off_), row(row_), grp(grp_) {}
+  __device__ __forceinline__ void put(int col, float v) {
+    buf[col & 7] = v;
+    if ((col & 7) == 7) {
+      const int u = col >> 3;
+      const int owner = (u < (NUNITS + 1) / 2) ? 0 : 1;
+      if (owner == grp) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          __half2 h = __floats2half2_rn(buf[2 * q], buf[2 * q + 1]);
+          const float2 hf = __half22float2(h);
+          hi[q] = *reinterpret_cast<uint32_t*>(&h);
+          lo[q] = pack2<true>(buf[2 * q] - hf.x, buf[2 * q + 1] - hf.y);
+        }
+        uint8_t* p = rowp + (chunk0 + (u >> 3)) * kChunkBytes + ((((u & 7) ^ row) & 7) << 4);
+        *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(p + lo_off * kChunkBytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+  }
+};
+
+// relu epilogue writing hi/lo fp16 planes: columns [cbeg, cbeg + 16*NBLK) of the accumulator
+template <bool DBG, int NBLK>
+__device__ __forceinline__ void epilogue_split(uint32_t tmem_row, int cbeg, const float* __restrict__ bias, uint8_t* X,
+                                               int row, int lo_off, float* dbg_row, int dbg_col0) {
+  uint8_t* rowp = X + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+  for (int blk = 0; blk < NBLK; ++blk) {
+    const int c0 = cbeg + 16 * blk;
+    float4 b[4];
+    load_bias(b, bias + c0);
+    uint32_t v[16];
+    tmem_ld16(tmem_row + c0, v);
+    tmem_ld_wait();
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float f0 = fmaxf(__uint_as_float(v[4 * j + 0]) + b[j].x, 0.f), f1 = fmaxf(__uint_as_float(v[4 * j + 1]) + b[j].y, 0.f);
+      const float f2 = fmaxf(__uint_as_float(v[4 * j + 2]) + b[j].z, 0.f), f3 = fmaxf(__uint_as_float(v[4 * j + 3]) + b[j].w, 0.f);
+      if (DBG && dbg_row) {
+        dbg_row[dbg_col0 + c0 + 4 * j + 0] = f0; dbg_row[dbg_col0 + c0 + 4 * j + 1] = f1;
+        dbg_row[dbg_col0 + c0 + 4 * j + 2] = f2; dbg_row[dbg_col0 + c0 + 4 * j + 3] = f3;
+      }
+      __half2 h0 = __floats2half2_rn(f0, f1), h1 = __floats2half2_rn(f2, f3);
+      const float2 g0 = __half22float2(h0), g1 = __half22float2(h1);
+      hi[2 * j] = *reinterpret_cast<uint32_t*>(&h0);
+      hi[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
+      lo[2 * j] = pack2<true>(f0 - g0.x, f1 - g0.y);
+      lo[2 * j + 1] = pack2<true>(f2 - g1.x, f3 - g1.y);
+    }
+    uint8_t* chunk = rowp + (c0 >> 6) * kChunkBytes;
+    const int u0 = (c0 & 63) >> 3;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      uint8_t* p = chunk + ((((u0 + q) ^ row) & 7) << 4);
+      *reinterpret_cast<uint4*>(p) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+      *reinterpret_cast<uint4*>(p + lo_off * kChunkBytes) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+    }
+  }
+}
+
+// fp32 reduction of the last hidden layer against NOUT small-head weight rows: columns [cbeg, cbeg+16*NBLK)
+template <bool DBG, int NBLK, int NOUT>
+__device__ __forceinline__ void final_partial(uint32_t tmem_row, int cbeg, const float* __restrict__ bias,
+                                              const float* __restrict__ w, int ld, float (&part)[NOUT], float* dbg_row,
+                                              int dbg_col0) {
+#pragma unroll
+  for (int blk = 0; blk < NBLK; ++blk) {
+    const int c0 = cbeg + 16 * blk;
+    uint32_t v[16];
+    tmem_ld16(tmem_row + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 bb = ldg_keep(bias + c0 + 4 * j);
+      const float h0 = fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.f), h1 = fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.f);
+      const float h2 = fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.f), h3 = fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.f);
+      if (DBG && dbg_row) {
+        dbg_row[dbg_col0 + c0 + 4 * j + 0] = h0; dbg_row[dbg_col0 + c0 + 4 * j + 1] = h1;
+        dbg_row[dbg_col0 + c0 + 4 * j + 2] = h2; dbg_row[dbg_col0 + c0 + 4 * j + 3] = h3;
+      }
+#pragma unroll
+      for (int k = 0; k < NOUT; ++k) {
+        const float4 ww = ldg_keep(w + k * ld + c0 + 4 * j);
+        part[k] += h0 * ww.x + h1 * ww.y + h2 * ww.z + h3 * ww.w;
+      }
+    }
+  }
+}
+
 // trilinear gather of 16 of the 32 channels from the channel-last embedding grid, ref: nerf/models.py:346-365
 // (align_corners=True, zero padding, raw warped coordinates; x -> last grid dim, z -> first)
 __device__ __forceinline__ void grid_gather16(const float* __restrict__ g, int ch0, float x, float y, float z,
@@ -360,6 +460,10 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
             // advancing K by 16 elements = 32 bytes = 2 descriptor address units inside the 128B swizzle atom
             tc_mma_bf16(d, a0 + 2 * k, b0 + 2 * k, idesc, (k > 0 || !(flags & ST_FRESH)) ? 1u : 0u);
           }
+          if (r.a_chunk2 != 0xFF) {   // split precision: the residual (lo) activations times the same weights
+            const uint64_t a1 = umma_smem_desc_sw128(x_addr + r.a_chunk2 * kChunkBytes);
+            for (uint32_t k = 0; k < ksteps; ++k) tc_mma_bf16(d, a1 + 2 * k, b0 + 2 * k, idesc, 1u);
+          }
           tc_commit(&empty[slot]);
           if (flags & ST_COMMIT) tc_commit(acc_ready);
         }
@@ -387,8 +491,62 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       float mapped[3] = {pt[0], pt[1], pt[2]};
       float amb[C::AMB_DIM > 0 ? C::AMB_DIM : 1] = {};
 
-      if (C::USE_W) {
-        // -------- deformation phase: warp | hyper-sheet (fp16 operands) --------
+      if (C::USE_W && dm.w_split) {
+        // -------- deformation phase in split precision: warp net, then hyper-sheet net --------
+        auto write_e0s = [&]() {
+          RowStreamSplit<C::E0_PAD / 8> st(X, 0, 2, row, grp);
+          int col = pe_stream<C::XYZ_L, true, 3>(st, 0, pt);
+#pragma unroll
+          for (int i = C::E0_DIM; i < C::E0_PAD; ++i) st.put(col++, 0.f);
+        };
+        const float* wf = fc + dm.off_wfinal;
+        const float* bf = wf + 3 * dm.wh;
+        const float* wa = bf + 4;
+        const float* ba = wa + C::AMB_DIM * dm.hh;
+        float* scratch = reinterpret_cast<float*>(X);   // [2][128][8]
+#pragma unroll 1
+        for (int net = 0; net < 2; ++net) {
+          const int boff = net == 0 ? 0 : dm.wh;
+          write_e0s();
+          signal_a(sy);
+          for (int i = 0; i < dm.w_layers; ++i) {
+            wait_acc(sy, 1000 + 16 * net + i);
+            if (i == dm.w_skip) {
+              write_e0s();
+              signal_a(sy);
+              wait_acc(sy, 1100 + 16 * net + i);
+            }
+            const float* bias = fc + dm.off_wbias + i * dm.whh + boff;
+            float* dr = (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) ? dbg_row : nullptr;
+            if (i < dm.w_layers - 1) {
+              if (net == 0) epilogue_split<DBG, 4>(tmem_row, grp * 64, bias, X, row, 2, dr, 0);
+              else epilogue_split<DBG, 2>(tmem_row, grp * 32, bias, X, row, 1, dr, dm.wh);
+              signal_a(sy);
+            } else if (net == 0) {
+              float part[3] = {0.f, 0.f, 0.f};
+              final_partial<DBG, 4, 3>(tmem_row, grp * 64, bias, wf, dm.wh, part, dr, 0);
+#pragma unroll
+              for (int k = 0; k < 3; ++k) scratch[(grp * 128 + row) * 8 + k] = part[k];
+              group_sync();
+#pragma unroll
+              for (int k = 0; k < 3; ++k)
+                mapped[k] = pt[k] + tanhf(scratch[row * 8 + k] + scratch[(128 + row) * 8 + k] + ldg_keep1(bf + k));
+              group_sync();
+            } else {
+              float part[C::AMB_DIM > 0 ? C::AMB_DIM : 1] = {};
+              final_partial<DBG, 2, (C::AMB_DIM > 0 ? C::AMB_DIM : 1)>(tmem_row, grp * 32, bias, wa, dm.hh, part, dr, dm.wh);
+#pragma unroll
+              for (int k = 0; k < C::AMB_DIM; ++k) scratch[(grp * 128 + row) * 8 + k] = part[k];
+              group_sync();
+#pragma unroll
+              for (int k = 0; k < C::AMB_DIM; ++k)
+                amb[k] = scratch[row * 8 + k] + scratch[(128 + row) * 8 + k] + ldg_keep1(ba + k);
+              group_sync();
+            }
+          }
+        }
+      } else if (C::USE_W) {
+        // -------- deformation phase: warp | hyper-sheet merged (fp16 operands) --------
         auto write_e0 = [&](int chunk0) {
           RowStream<true, C::E0_PAD / 8> st(X, chunk0, row, grp);
           int col = pe_stream<C::XYZ_L, true, 3>(st, 0, pt);

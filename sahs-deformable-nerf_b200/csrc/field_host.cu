@@ -48,6 +48,8 @@ struct Builder {
   uint32_t off = 0;
   bool pass_open = false;
   bool f16 = false;   // operand format of the stages being emitted
+  bool lo = false;    // emit the residual image fp16(w - fp16(w))
+  int a_chunk2 = 0xFF;
 
   // one stage: rows [row0,row0+n) x cols [col0, col0+kvalid) of weight `pidx` (ld = in_features)
   void stage(int pidx, int ld, int row0, int n, int col0, int kvalid, int a_chunk, int d_col, bool fresh) {
@@ -58,11 +60,14 @@ struct Builder {
     r.kflags = (uint8_t)(ksteps | (flags << 3));
     r.a_chunk = (uint8_t)a_chunk;
     r.d_col8 = (uint8_t)(d_col / 8);
+    r.a_chunk2 = (uint8_t)a_chunk2;
+    r.pad[0] = r.pad[1] = r.pad[2] = 0;
     PackStage& ps = hp.pack[ns];
     memset(&ps, 0, sizeof(ps));
     ps.dst_off = off;
     ps.n = n;
     ps.f16 = f16 ? 1 : 0;
+    ps.lo = lo ? 1 : 0;
     ps.src[0].w = P ? P[pidx] : nullptr;
     ps.src[0].ld = ld;
     ps.src[0].src_row0 = row0; ps.src[0].src_col0 = col0;
@@ -106,7 +111,48 @@ int sahs_build_host_plan(const sahs_model_spec& s, const float* const* params, H
   };
   const int CW = SAHS_DRIVING_DIM + SAHS_POSE_CODE_DIM;  // 112 frame-constant inputs of warp/hyper
   // ---------------- deformation phase: warp | hyper merged -------------------------------------------
-  if (d.use_w) {
+  if (d.use_w && d.w_split) {
+    // split precision: activations and weights as fp16 hi + lo, products hi*hi + lo*hi + hi*lo (fp32 accumulate).
+    // X chunks: hidden hi at [0, n/64), lo at [n/64, 2n/64); encoding hi at [0,2), lo at [2,4).
+    b.f16 = true;
+    const int in0 = d.e0_dim + CW;
+    for (int net = 0; net < 2; ++net) {
+      const int n = net == 0 ? d.wh : d.hh;
+      const int* wi = net == 0 ? pi.warp_w : pi.hyp_w;
+      const int* bi = net == 0 ? pi.warp_b : pi.hyp_b;
+      const int boff = net == 0 ? 0 : d.wh;
+      auto part = [&](int pidx, int ld, int col0, int kvalid, int hi0, int lo0, bool& fresh) {
+        for (int kc = 0; kc * 64 < kvalid; ++kc) {
+          int kv = kvalid - 64 * kc; if (kv > 64) kv = 64;
+          b.lo = false; b.a_chunk2 = lo0 + kc;
+          b.stage(pidx, ld, 0, n, col0 + 64 * kc, kv, hi0 + kc, 0, fresh); fresh = false;
+          b.lo = true; b.a_chunk2 = 0xFF;
+          b.stage(pidx, ld, 0, n, col0 + 64 * kc, kv, hi0 + kc, 0, false);
+        }
+        b.lo = false; b.a_chunk2 = 0xFF;
+      };
+      for (int i = 0; i < d.w_layers; ++i) {
+        const bool first = i == 0, skip = i == d.w_skip;
+        const int ld = first ? in0 : (skip ? n + in0 : n);
+        bool fresh = true;
+        if (!first) part(wi[i], ld, 0, n, 0, n / 64, fresh);
+        if (first || skip) {
+          if (skip) b.end_pass();
+          part(wi[i], ld, first ? 0 : n, d.e0_dim, 0, 2, fresh);
+          fold(bi[i], wi[i], ld, (first ? 0 : n) + d.e0_dim, CW, 0, n, d.off_wbias + i * d.whh + boff);
+        } else {
+          fold(bi[i], -1, 0, 0, 0, 0, n, d.off_wbias + i * d.whh + boff);
+        }
+        b.end_pass();
+      }
+    }
+    int o = d.off_wfinal;
+    hp.copy[hp.num_copy++] = CopySection{P(pi.warp_fw), 3 * d.wh, o}; o += 3 * d.wh;
+    hp.copy[hp.num_copy++] = CopySection{P(pi.warp_fb), 3, o}; o += 4;
+    hp.copy[hp.num_copy++] = CopySection{P(pi.hyp_fw), s.amb_dim * d.hh, o}; o += s.amb_dim * d.hh;
+    hp.copy[hp.num_copy++] = CopySection{P(pi.hyp_fb), s.amb_dim, o};
+    b.f16 = false;
+  } else if (d.use_w) {
     b.f16 = true;   // fp16 operands: the encoding of the warped point amplifies coordinate error by 2^(L-1)
     const int in0 = d.e0_dim + CW;
     for (int i = 0; i < d.w_layers; ++i) {
@@ -231,8 +277,11 @@ __global__ void pack_stage_kernel(const __grid_constant__ PackBatch batch, uint8
       if (s.w && row >= s.dst_row0 && row < s.dst_row0 + s.nrows && col < s.ncols)
         v = s.w[(size_t)(s.src_row0 + row - s.dst_row0) * s.ld + s.src_col0 + col];
     }
-    if (ps.f16)
-      *reinterpret_cast<__half*>(out + ps.dst_off + sw128_offset(row, col)) = __float2half_rn(v);
+    if (ps.f16) {
+      __half h = __float2half_rn(v);
+      if (ps.lo) h = __float2half_rn(v - __half2float(h));
+      *reinterpret_cast<__half*>(out + ps.dst_off + sw128_offset(row, col)) = h;
+    }
     else
       *reinterpret_cast<__nv_bfloat16*>(out + ps.dst_off + sw128_offset(row, col)) = __float2bfloat16_rn(v);
   }
@@ -335,7 +384,8 @@ extern "C" int sahs_fold_frame(const sahs_model_spec* spec, int level, const flo
 
 // Host-only introspection of the plan (no device work): used by the CPU test-suite to check the stage table and
 // the pack/fold descriptors against the reference layer shapes.  `params` entries are treated as opaque ids.
-// Per stage 12 ints: n, ksteps, flags, a_chunk, d_col, dst_off, param_id, src_row0, src_col0, dst_row0, nrows, ncols.
+// Per stage 14 ints: n, ksteps, flags, a_chunk, d_col, dst_off, param_id, src_row0, src_col0, dst_row0, nrows, ncols,
+// a_chunk2 (255 = none), lo.
 // Per fold section 8 ints: bias_id, w_id (0 = none), ld, col0, ncols, c_off, n, dst.  Per copy 3 ints: id, count, dst.
 extern "C" int sahs_debug_plan(const sahs_model_spec* spec, int param_count, int32_t* stages, int max_stages,
                                int32_t* folds, int max_folds, int32_t* copies, int max_copies, int32_t* dims_out) {
@@ -351,10 +401,10 @@ extern "C" int sahs_debug_plan(const sahs_model_spec* spec, int param_count, int
   for (int i = 0; i < hp.plan.num_stages; ++i) {
     const StageRec& r = hp.plan.st[i];
     const PackStage& ps = hp.pack[i];
-    int32_t* o = stages + 12 * i;
+    int32_t* o = stages + 14 * i;
     o[0] = r.n8 * 8; o[1] = r.kflags & 7; o[2] = r.kflags >> 3; o[3] = r.a_chunk; o[4] = r.d_col8 * 8;
     o[5] = (int32_t)ps.dst_off; o[6] = id_of(ps.src[0].w); o[7] = ps.src[0].src_row0; o[8] = ps.src[0].src_col0;
-    o[9] = ps.src[0].dst_row0; o[10] = ps.src[0].nrows; o[11] = ps.src[0].ncols;
+    o[9] = ps.src[0].dst_row0; o[10] = ps.src[0].nrows; o[11] = ps.src[0].ncols; o[12] = r.a_chunk2; o[13] = ps.lo;
   }
   for (int i = 0; i < hp.num_fold; ++i) {
     const FoldSection& f = hp.fold[i];
@@ -369,7 +419,7 @@ extern "C" int sahs_debug_plan(const sahs_model_spec* spec, int param_count, int
   const NetDims& d = hp.dims;
   int32_t dd[] = {hp.plan.num_stages, hp.num_fold, hp.num_copy, hp.plan.total_bytes, d.fc_total, d.e0_dim, d.e0_k,
                   d.e1_dim, d.e1_k, d.e0_resident, d.e0_chunk_base, d.whh, d.off_wbias, d.off_wfinal, d.off_tbias,
-                  d.off_featb, d.off_alpha, d.off_hbias, d.off_outb, d.xtra_dim};
+                  d.off_featb, d.off_alpha, d.off_hbias, d.off_outb, d.xtra_dim, d.w_split};
   memcpy(dims_out, dd, sizeof(dd));
   return SAHS_OK;
 }

@@ -20,11 +20,13 @@ constexpr int kStageSlotBytes = 16384;
 
 enum : uint8_t { ST_WAIT_A = 1, ST_COMMIT = 2, ST_FRESH = 4, ST_F16 = 8 };  // F16: fp16 operands (else bf16)
 
-struct StageRec {   // 4 bytes, lives in kernel parameter space
+struct StageRec {   // 8 bytes, lives in kernel parameter space
   uint8_t n8;       // N / 8
   uint8_t kflags;   // ksteps (low 3 bits) | flags << 3
   uint8_t a_chunk;  // which X chunk is the A operand
   uint8_t d_col8;   // accumulator column offset / 8
+  uint8_t a_chunk2; // second A chunk multiplied by the same stage (split precision: the lo part), 0xFF = none
+  uint8_t pad[3];
 };
 
 struct FieldPlan {
@@ -44,6 +46,7 @@ struct PackStage {
   uint32_t dst_off;   // byte offset in the packed image
   int32_t n;          // rows of the image (zero padded)
   int32_t f16;        // store fp16 instead of bf16
+  int32_t lo;         // store the residual fp16(w - fp16(w)) (split-precision deformation phase)
 };
 
 // fp32 per-frame constant block: offsets in floats
@@ -72,6 +75,8 @@ struct NetDims {
   int xtra_dim, xtra_k;             // dir PE (+ grid) appended to feat for layers_dir.0
   int ct_off, ct_len;               // trunk constant vector = cvec[ct_off : ct_off+ct_len]
   int use_w;                        // deformation phase present
+  int w_split;                      // deformation phase in split precision (fp16 hi + lo), warp and hyper nets run
+                                    // one after the other: needed when the encoding has more than 10 octaves
   // frame-constant block offsets (floats)
   int off_wbias, off_wfinal, off_tbias, off_featb, off_alpha, off_hbias, off_outb, fc_total;
 };
@@ -100,7 +105,9 @@ inline int sahs_make_dims(const sahs_model_spec& s, NetDims& d) {
     if (d.wh % 64 || d.hh % 64 || d.wh > 128 || d.hh > 128 || d.whh > 256) return -3;
     if (d.w_skip <= 0 || d.w_skip >= d.w_layers) return -4;
   }
-  d.e0_resident = (d.whh / 64 + d.e0_chunks <= 4) ? 1 : 0;
+  d.w_split = (d.use_w && s.xyz_L > 10) ? 1 : 0;
+  if (d.w_split && (d.wh != 128 || d.hh != 64)) return -10;
+  d.e0_resident = (!d.w_split && d.whh / 64 + d.e0_chunks <= 4) ? 1 : 0;
   d.e0_chunk_base = d.e0_resident ? d.whh / 64 : 0;
   d.th = s.trunk_hidden;
   d.t_layers = s.trunk_layers;

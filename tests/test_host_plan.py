@@ -11,7 +11,7 @@ import torch
 import sahs_fixtures as FX
 from oracle import sahs_oracle as O
 
-ST_WAIT_A, ST_COMMIT, ST_FRESH = 1, 2, 4
+ST_WAIT_A, ST_COMMIT, ST_FRESH, ST_F16 = 1, 2, 4, 8
 
 
 def _ordered_param_names(spec, level):
@@ -42,17 +42,17 @@ def _plan(spec_model):
     lib = L.load()
     cs = spec_model.to_c()
     n = lib.sahs_param_count(C.byref(cs))
-    stages = (C.c_int32 * (12 * 160))()
+    stages = (C.c_int32 * (14 * 160))()
     folds = (C.c_int32 * (8 * 64))()
     copies = (C.c_int32 * (3 * 8))()
-    dims = (C.c_int32 * 20)()
+    dims = (C.c_int32 * 32)()
     L.check(lib.sahs_debug_plan(C.byref(cs), n, stages, 160, folds, 64, copies, 8, dims), "debug_plan")
     dims = list(dims)
     ns, nf, nc = dims[0], dims[1], dims[2]
     keys = ["num_stages", "num_fold", "num_copy", "total_bytes", "fc_total", "e0_dim", "e0_k", "e1_dim", "e1_k",
             "e0_resident", "e0_chunk_base", "whh", "off_wbias", "off_wfinal", "off_tbias", "off_featb", "off_alpha",
-            "off_hbias", "off_outb", "xtra_dim"]
-    return (np.array(stages[:12 * ns]).reshape(ns, 12), np.array(folds[:8 * nf]).reshape(nf, 8),
+            "off_hbias", "off_outb", "xtra_dim", "w_split"]
+    return (np.array(stages[:14 * ns]).reshape(ns, 14), np.array(folds[:8 * nf]).reshape(nf, 8),
             np.array(copies[:3 * nc]).reshape(nc, 3), dict(zip(keys, dims)), n)
 
 
@@ -90,12 +90,17 @@ def _emulate(spec_model, ospec, sd, level, xyz, dirs, driving_vec, pose):
 
     def run_pass():
         written = set()
-        for n, ks, flags, a_chunk, d_col, dst_off, pid, r0, c0, dr0, nr, ncol in next(it):
+        for n, ks, flags, a_chunk, d_col, dst_off, pid, r0, c0, dr0, nr, ncol, a_chunk2, lo in next(it):
             W = get(pid)
             img = np.zeros((n, 64), np.float32)
             img[dr0:dr0 + nr, :ncol] = W[r0:r0 + nr, c0:c0 + ncol]
+            if dm["w_split"] and (flags & ST_F16):       # emulate the fp16 hi / lo weight planes exactly
+                hi = img.astype(np.float16).astype(np.float32)
+                img = (img - hi).astype(np.float16).astype(np.float32) if lo else hi
             k = 16 * ks
             contrib = X[:, a_chunk * 64:a_chunk * 64 + k] @ img[:, :k].T
+            if a_chunk2 != 255:
+                contrib = contrib + X[:, a_chunk2 * 64:a_chunk2 * 64 + k] @ img[:, :k].T
             if flags & ST_FRESH:
                 D[:, d_col:d_col + n] = contrib
             else:
@@ -106,7 +111,38 @@ def _emulate(spec_model, ospec, sd, level, xyz, dirs, driving_vec, pose):
     s = ospec
     pts = xyz.numpy()
     mapped, amb = pts.copy(), None
-    if s.use_warp:
+    f16 = lambda a: a.astype(np.float16).astype(np.float32)
+    if s.use_warp and dm["w_split"]:
+        e0 = pe(pts, s.xyz_L, True)
+        o = dm["off_wfinal"]
+        wh, hh = s.warp_hidden, s.hyper_hidden
+        wf = fc[o:o + 3 * wh].reshape(3, wh); bf = fc[o + 3 * wh:o + 3 * wh + 3]
+        o2 = o + 3 * wh + 4
+        wa = fc[o2:o2 + s.amb_dim * hh].reshape(s.amb_dim, hh); ba = fc[o2 + s.amb_dim * hh:o2 + s.amb_dim * hh + s.amb_dim]
+
+        def write_split(vals, hi0, lo0, width):
+            X[:, hi0 * 64:hi0 * 64 + width] = 0
+            X[:, lo0 * 64:lo0 * 64 + width] = 0
+            hi = f16(vals)
+            X[:, hi0 * 64:hi0 * 64 + vals.shape[1]] = hi
+            X[:, lo0 * 64:lo0 * 64 + vals.shape[1]] = f16(vals - hi)
+
+        for net, n, boff in ((0, wh, 0), (1, hh, wh)):
+            write_split(e0, 0, 2, 128)
+            for i in range(s.warp_layers):
+                if i == s.warp_skip:
+                    run_pass()
+                    write_split(e0, 0, 2, 128)
+                run_pass()
+                b0 = dm["off_wbias"] + i * dm["whh"] + boff
+                h = np.maximum(D[:, :n] + fc[b0:b0 + n], 0)
+                if i < s.warp_layers - 1:
+                    write_split(h, 0, n // 64, n)
+            if net == 0:
+                mapped = pts + np.tanh(h @ wf.T + bf)
+            else:
+                amb = h @ wa.T + ba
+    elif s.use_warp:
         e0 = pe(pts, s.xyz_L, True)
         cb = dm["e0_chunk_base"]
         X[:, cb * 64:cb * 64 + e0.shape[1]] = e0
@@ -183,6 +219,8 @@ def test_plan_interpreter_matches_oracle(cfg_name):
         scale = max(1.0, np.abs(ref).max())
         assert err < 2e-4 * scale, (cfg_name, level, err)
         # stage images are laid out back to back in consumption order
+        if dm["w_split"]:
+            assert np.abs(got - ref).max() < 5e-4 * scale      # split precision: ~1e-6 on the warped point (x 2^14 x 400 on sigma)
         offs = stages[:, 5]
         assert offs[0] == 0 and np.all(np.diff(offs) == stages[:-1, 0] * 128)
         assert dm["total_bytes"] == offs[-1] + stages[-1, 0] * 128
