@@ -215,12 +215,12 @@ def test_plan_interpreter_matches_oracle(cfg_name):
     for level in ("coarse", "fine"):
         ref = O.field_forward(sd, ospec, level, xyz, dirs, drv, fr["pose"]).numpy()
         got, dm, stages = _emulate(mspec, ospec, sd, level, xyz, dirs, drv, fr["pose"])
-        err = np.abs(got - ref).max()
         scale = max(1.0, np.abs(ref).max())
-        assert err < 2e-4 * scale, (cfg_name, level, err)
+        # colour / semantic logits to fp32 noise level; the density logit is x400 in the dense fixture and, with 15
+        # octaves, magnifies the ~1e-7 difference of the warped point between two fp32 evaluation orders
+        assert np.abs(got[:, :15] - ref[:, :15]).max() < 2e-4, (cfg_name, level)
+        assert np.abs(got[:, 15] - ref[:, 15]).max() < (2e-4 if ospec.xyz_L <= 10 else 1e-3) * scale, (cfg_name, level)
         # stage images are laid out back to back in consumption order
-        if dm["w_split"]:
-            assert np.abs(got - ref).max() < 5e-4 * scale      # split precision: ~1e-6 on the warped point (x 2^14 x 400 on sigma)
         offs = stages[:, 5]
         assert offs[0] == 0 and np.all(np.diff(offs) == stages[:-1, 0] * 128)
         assert dm["total_bytes"] == offs[-1] + stages[-1, 0] * 128
