@@ -13,9 +13,10 @@
 // Within a CTA the tile is processed pass by pass (bulk synchronous through two mbarriers); the co-resident CTA
 // on the same SM fills the tensor pipe while this one runs its epilogue.
 //
-// Precision: the deformation phase (warp | hyper-sheet) uses fp16 operands (11-bit significand) because the
-// positional encoding applied to its output amplifies coordinate error by up to 2^(L-1); the radiance trunk and
-// heads use bf16 operands.  All accumulation is fp32 in TMEM; dx, ambient and sigma heads are evaluated in fp32.
+// Precision: all MMA operands are fp16 (11-bit significand, saturating conversion; same tensor rate as bf16 and 8x
+// finer), accumulation is fp32 in TMEM; dx, ambient and sigma heads are evaluated in fp32.  With more than 10
+// encoding octaves the deformation phase runs in split precision (fp16 hi + lo operands, ~fp32 accuracy) because
+// the encoding of the warped point amplifies its error by 2^(L-1).
 #include <cuda_fp16.h>
 #include "sahs_common.cuh"
 #include "field_plan.cuh"
@@ -27,6 +28,7 @@ constexpr int kThreads = 320;
 constexpr int kTmaWarp = 8, kMmaWarp = 9;
 constexpr int kSlots = 3;
 constexpr int kTmemCols = 256;
+constexpr bool kTrunkF16 = true;   // operand format of trunk and heads (fp16: 8x finer than bf16 at the same MMA rate)
 constexpr int kSmemX = 4 * kChunkBytes;                       // 64 KB
 constexpr int kSmemSlots = kSlots * kStageSlotBytes;          // 48 KB
 constexpr int kSmemBar = kSmemX + kSmemSlots;                 // barriers after the tiles
@@ -58,11 +60,13 @@ __device__ __forceinline__ void group_sync() {  // the 256 worker threads only
   asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
+// fp32 pair -> packed 16-bit pair.  fp16 conversions saturate to +-65504 instead of producing inf.
 template <bool F16>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   if (F16) {
-    __half2 v = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&v);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
   }
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -633,7 +637,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         float emb[16];
         grid_gather16(grid, grp * 16, mapped[0], mapped[1], mapped[2], emb);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) emb_pk[q] = pack2<false>(emb[2 * q], emb[2 * q + 1]);
+        for (int q = 0; q < 8; ++q) emb_pk[q] = pack2<kTrunkF16>(emb[2 * q], emb[2 * q + 1]);
         if (DBG && dbg_row && dbg_pass == SAHS_DBG_MAPPED) {
 #pragma unroll
           for (int q = 0; q < 16; ++q) dbg_row[8 + grp * 16 + q] = emb[q];
@@ -646,7 +650,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       }
       // -------- trunk (bf16 operands) --------
       auto write_e1 = [&]() {
-        RowStream<false, C::E1_PAD / 8> st(X, 0, row, grp);
+        RowStream<kTrunkF16, C::E1_PAD / 8> st(X, 0, row, grp);
         int col = pe_stream<C::XYZ_L, true, 3>(st, 0, mapped);
         if (C::AMB_PE > 0) col = pe_stream<C::AMB_L, C::AMB_INC, (C::AMB_DIM > 0 ? C::AMB_DIM : 1)>(st, col, amb);
 #pragma unroll
@@ -665,7 +669,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
           load_bias(b, bias + grp * 128);
           wait_acc(sy, 2100 + i);
         }
-        epilogue<ACT_LEAKY, false, false, DBG, 8>(tmem_row, grp * 128, bias, b, X, row, nullptr,
+        epilogue<ACT_LEAKY, kTrunkF16, false, DBG, 8>(tmem_row, grp * 128, bias, b, X, row, nullptr,
                                                   (DBG && dbg_row && dbg_pass == SAHS_DBG_TRUNK(i)) ? dbg_row : nullptr);
         signal_a(sy);
       }
@@ -673,7 +677,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       float4 bfe[4];
       load_bias(bfe, fc + dm.off_featb + grp * 128);
       wait_acc(sy, 2200);
-      float sigma = epilogue<ACT_NONE, false, true, DBG, 8>(
+      float sigma = epilogue<ACT_NONE, kTrunkF16, true, DBG, 8>(
           tmem_row, grp * 128, fc + dm.off_featb, bfe, X, row, fc + dm.off_alpha,
           (DBG && dbg_row && dbg_pass == SAHS_DBG_TRUNK(dm.t_layers)) ? dbg_row : nullptr);
       if (grp == 1) xchg[row] = sigma;
@@ -682,7 +686,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       wait_acc(sy, 3000);
       {
         // extra K-chunk: cols [0,27) PE(dir), [27,59) embedding, zero padding up to 64
-        RowStream<false, 8, false> st(X, 0, row, 0);
+        RowStream<kTrunkF16, 8, false> st(X, 0, row, 0);
         if (grp == 0) {
           int col = pe_stream<C::DIR_L, true, 3>(st, 0, dir);
 #pragma unroll
@@ -704,7 +708,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         float4 b[4];
         load_bias(b, bias + grp * 128);
         wait_acc(sy, 3100 + i);
-        epilogue<ACT_LEAKY, false, false, DBG, 8>(tmem_row, grp * 128, bias, b, X, row, nullptr,
+        epilogue<ACT_LEAKY, kTrunkF16, false, DBG, 8>(tmem_row, grp * 128, bias, b, X, row, nullptr,
                                                   (DBG && dbg_row && dbg_pass == SAHS_DBG_HEAD(i)) ? dbg_row : nullptr);
         signal_a(sy);
       }

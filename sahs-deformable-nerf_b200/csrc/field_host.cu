@@ -101,6 +101,7 @@ int sahs_build_host_plan(const sahs_model_spec& s, const float* const* params, H
   ParamIndex pi;
   if (!index_params(s, pi)) return SAHS_EINVAL;
   Builder b{hp, params};
+  b.f16 = true;   // all operands fp16 (see field_fwd.cu "Precision")
   hp.num_fold = 0;
   hp.num_copy = 0;
   auto P = [&](int i) -> const float* { return params ? params[i] : nullptr; };
@@ -151,7 +152,6 @@ int sahs_build_host_plan(const sahs_model_spec& s, const float* const* params, H
     hp.copy[hp.num_copy++] = CopySection{P(pi.warp_fb), 3, o}; o += 4;
     hp.copy[hp.num_copy++] = CopySection{P(pi.hyp_fw), s.amb_dim * d.hh, o}; o += s.amb_dim * d.hh;
     hp.copy[hp.num_copy++] = CopySection{P(pi.hyp_fb), s.amb_dim, o};
-    b.f16 = false;
   } else if (d.use_w) {
     b.f16 = true;   // fp16 operands: the encoding of the warped point amplifies coordinate error by 2^(L-1)
     const int in0 = d.e0_dim + CW;
@@ -188,7 +188,6 @@ int sahs_build_host_plan(const sahs_model_spec& s, const float* const* params, H
     hp.copy[hp.num_copy++] = CopySection{P(pi.warp_fb), 3, o}; o += 4;
     hp.copy[hp.num_copy++] = CopySection{P(pi.hyp_fw), s.amb_dim * d.hh, o}; o += s.amb_dim * d.hh;
     hp.copy[hp.num_copy++] = CopySection{P(pi.hyp_fb), s.amb_dim, o};
-    b.f16 = false;
   }
   // ---------------- trunk ---------------------------------------------------------------------------
   {
