@@ -122,3 +122,36 @@ def test_model_state_dict_layout_matches_reference_names():
         want = FX.linear_shapes(O.spec_from_cfg(cfg))
         got = {k: tuple(v.shape) for k, v in model.state_dict().items()}
         assert got == want, set(got.items()) ^ set(want.items())
+
+
+def test_fine_pass_conditioning():
+    """Evidence for the tolerance note in tests/test_gpu_parity.py: with 15 encoding octaves (expression/person_2) the
+    reference algorithm's fine render moves by >1e-3 when the fine depths are jittered by about one fp32 ulp, while the
+    10-octave audio config moves by <1e-5.  (Dense random-weight fixture; fp32 oracle, no GPU involved.)"""
+    out = {}
+    for cfg_name, gname in (("expression/person_2", "e2e_expr2_val"), ("audio/person_2_auto", "e2e_audio_val")):
+        g = load(gname)
+        cfg = FX.load_cfg(cfg_name)
+        spec = O.spec_from_cfg(cfg)
+        sd = FX.make_state_dict(spec, seed=42, dense=True)
+        H, W = int(g["H"]), int(g["W"])
+        fr = FX.make_frame_inputs(spec, H, W, seed=int(g["seed"]), pose_z=float(g["pose_z"]))
+        ro, rd = O.get_ray_bundle(H, W, fr["intrinsics"], fr["pose"])
+        ro, rd = ro.reshape(-1, 3)[:48], rd.reshape(-1, 3)[:48]
+        bg = fr["background"].view(-1, 15)[:48]
+        drv = O.driving_vector(sd, spec, fr["driving"])
+        z_f = T(g["z_f"])[:48]
+
+        def fine(zf):
+            R, S = zf.shape
+            pts = (ro[:, None, :] + rd[:, None, :] * zf[:, :, None]).reshape(-1, 3)
+            dirs = rd[:, None, :].expand(R, S, 3).reshape(-1, 3)
+            raw = O.field_forward(sd, spec, "fine", pts, dirs, drv, fr["pose"]).reshape(R, S, 16)
+            raw[:, -1, :-1] = bg
+            return O.composite(raw, zf, rd, None, False, bg)[0]
+
+        with torch.no_grad():
+            gen = torch.Generator().manual_seed(0)
+            zp, _ = torch.sort(z_f * (1 + (torch.rand(z_f.shape, generator=gen) * 2 - 1) * 2e-7), -1)
+            out[cfg_name] = float((fine(z_f) - fine(zp)).abs().max())
+    assert out["expression/person_2"] > 1e-3 and out["audio/person_2_auto"] < 1e-5, out
