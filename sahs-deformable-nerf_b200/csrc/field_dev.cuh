@@ -1,0 +1,434 @@
+// Device-side building blocks shared by the fused field kernels (forward: field_fwd.cu, backward: field_bwd.cu).
+#pragma once
+#include <cuda_fp16.h>
+#include "sahs_common.cuh"
+#include "field_plan.cuh"
+
+namespace {
+
+
+constexpr int kWorkerThreads = 256;
+constexpr int kThreads = 320;
+constexpr int kTmaWarp = 8, kMmaWarp = 9;
+constexpr int kSlots = 3;
+constexpr int kTmemCols = 256;
+constexpr bool kTrunkF16 = true;   // operand format of trunk and heads (fp16: 8x finer than bf16 at the same MMA rate)
+constexpr int kSmemX = 4 * kChunkBytes;                       // 64 KB
+constexpr int kSmemSlots = kSlots * kStageSlotBytes;          // 48 KB
+constexpr int kSmemBar = kSmemX + kSmemSlots;                 // barriers after the tiles
+constexpr int kSmemXchg = kSmemBar + 128;                     // 128 floats exchanged between the two groups
+constexpr int kSmemTotal = kSmemXchg + 512;
+
+__device__ int g_field_status[4];
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
+
+struct Sync {
+  uint64_t* a_ready;
+  uint64_t* acc_ready;
+  uint32_t acc_par;
+  int* status;
+};
+
+__device__ __forceinline__ void signal_a(Sync& sy) {
+  fence_proxy_async_smem();
+  tc_fence_before();
+  mbar_arrive(sy.a_ready);
+}
+__device__ __forceinline__ void wait_acc(Sync& sy, int tag) {
+  mbar_wait(sy.acc_ready, sy.acc_par, sy.status, tag);
+  sy.acc_par ^= 1;
+  tc_fence_after();
+}
+__device__ __forceinline__ void group_sync() {  // the 256 worker threads only
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+
+// fp32 pair -> packed 16-bit pair.  fp16 conversions saturate to +-65504 instead of producing inf.
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  if (F16) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+  }
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {  // FADD2
+  unsigned long long a, b, d;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(a0), "=f"(a1) : "l"(d));
+}
+
+// activation on a packed 16-bit pair (HMNMX2 / HFMA2): relu and leaky-relu(0.01)
+template <int ACT, bool F16>
+__device__ __forceinline__ uint32_t act2(uint32_t p) {
+  if (ACT == ACT_NONE) return p;
+  if (F16) {
+    __half2 v = *reinterpret_cast<__half2*>(&p);
+    __half2 r = (ACT == ACT_RELU) ? __hmax2(v, __float2half2_rn(0.f)) : __hmax2(v, __hmul2(v, __float2half2_rn(0.01f)));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&p);
+  __nv_bfloat162 r = (ACT == ACT_RELU) ? __hmax2(v, __float2bfloat162_rn(0.f))
+                                       : __hmax2(v, __hmul2(v, __float2bfloat162_rn(0.01f)));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+// Streams consecutive feature columns of one tile row into X (16-bit, 128B-swizzled K-chunks), eight columns
+// (one 16-byte unit) at a time.  Both worker groups generate every column; a group only stores the units it owns
+// (first or second half), which keeps the generators free of cross-group exchanges.  All indices are compile-time
+// after unrolling.
+template <bool F16, int NUNITS, bool SPLIT = true>
+struct RowStream {
+  uint8_t* rowp;   // X + row offset inside a chunk
+  int chunk0, row, grp;
+  float buf[8];
+  __device__ __forceinline__ RowStream(uint8_t* X, int chunk0_, int row_, int grp_)
+      : rowp(X + (row_ >> 3) * 1024 + (row_ & 7) * 128), chunk0(chunk0_), row(row_), grp(grp_) {}
+  __device__ __forceinline__ void put(int col, float v) {
+    buf[col & 7] = v;
+    if ((col & 7) == 7) {
+      const int u = col >> 3;
+      const int owner = (u < (NUNITS + 1) / 2) ? 0 : 1;
+      if (!SPLIT || owner == grp) {
+        uint4 q;
+        q.x = pack2<F16>(buf[0], buf[1]);
+        q.y = pack2<F16>(buf[2], buf[3]);
+        q.z = pack2<F16>(buf[4], buf[5]);
+        q.w = pack2<F16>(buf[6], buf[7]);
+        *reinterpret_cast<uint4*>(rowp + (chunk0 + (u >> 3)) * kChunkBytes + ((((u & 7) ^ row) & 7) << 4)) = q;
+      }
+    }
+  }
+};
+
+// positional encoding of D values streamed in the reference's column order (nerf_helpers.py:341-349):
+// [x_0..x_{D-1}] (if INC), then per octave k: sin(2^k x_d) for all d, cos(2^k x_d) for all d.
+// Accurate sincosf every 5th octave (2^k * x is exact in fp32), double-angle recurrence in between (err < 2e-6).
+template <int L, bool INC, int D, class Stream>
+__device__ __forceinline__ int pe_stream(Stream& st, int col, const float (&x)[D]) {
+  if (INC) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) st.put(col++, x[d]);
+  }
+  float s[D], c[D];
+#pragma unroll
+  for (int k = 0; k < L; ++k) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      if (k % 5 == 0) {
+        sincosf(x[d] * (float)(1 << k), &s[d], &c[d]);
+      } else {
+        const float s2 = 2.f * s[d] * c[d];
+        c[d] = 1.f - 2.f * s[d] * s[d];
+        s[d] = s2;
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) st.put(col++, s[d]);
+#pragma unroll
+    for (int d = 0; d < D; ++d) st.put(col++, c[d]);
+  }
+  return col;
+}
+
+// bias / small-weight loads keep their lines in the (28 KB) L1 ahead of the streaming traffic
+__device__ __forceinline__ float4 ldg_keep(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ldg_keep1(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_stream(const float* p) {   // read-once data: do not allocate in L1
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void load_bias(float4 (&b)[4], const float* __restrict__ bias) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) b[j] = ldg_keep(bias + 4 * j);
+}
+
+// one 16-column block of an epilogue: +bias (FADD2), optional fp32 dot, pack, activation, swizzled store.
+// The bias registers are dead after the adds, so the next block's bias is fetched before the pack/store part.
+template <int ACT, bool F16, bool DOT, bool DBG>
+__device__ __forceinline__ void epi_block(uint32_t (&v)[16], float4 (&b)[4], const float* __restrict__ next_bias, int c0,
+                                          uint8_t* rowp, int row, const float* __restrict__ dot_w, float& dot,
+                                          float* dbg_row) {
+  float f[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[4 * j + 0] = __uint_as_float(v[4 * j + 0]); f[4 * j + 1] = __uint_as_float(v[4 * j + 1]);
+    f[4 * j + 2] = __uint_as_float(v[4 * j + 2]); f[4 * j + 3] = __uint_as_float(v[4 * j + 3]);
+    add2(f[4 * j + 0], f[4 * j + 1], b[j].x, b[j].y);
+    add2(f[4 * j + 2], f[4 * j + 3], b[j].z, b[j].w);
+  }
+  if (next_bias) load_bias(b, next_bias);
+  uint32_t pk[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float f0 = f[4 * j], f1 = f[4 * j + 1], f2 = f[4 * j + 2], f3 = f[4 * j + 3];
+    if (DOT) {
+      const float4 w = ldg_keep(dot_w + c0 + 4 * j);
+      dot += f0 * w.x + f1 * w.y + f2 * w.z + f3 * w.w;
+    }
+    pk[2 * j] = act2<ACT, F16>(pack2<F16>(f0, f1));
+    pk[2 * j + 1] = act2<ACT, F16>(pack2<F16>(f2, f3));
+    if (DBG && dbg_row) {
+      const float lk = ACT == ACT_LEAKY ? 0.01f : 0.f;
+      const bool a = ACT != ACT_NONE;
+      dbg_row[c0 + 4 * j + 0] = a ? fmaxf(f0, lk * f0) : f0;
+      dbg_row[c0 + 4 * j + 1] = a ? fmaxf(f1, lk * f1) : f1;
+      dbg_row[c0 + 4 * j + 2] = a ? fmaxf(f2, lk * f2) : f2;
+      dbg_row[c0 + 4 * j + 3] = a ? fmaxf(f3, lk * f3) : f3;
+    }
+  }
+  uint8_t* chunk = rowp + (c0 >> 6) * kChunkBytes;
+  const int u0 = (c0 & 63) >> 3;
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+    *reinterpret_cast<uint4*>(chunk + ((((u0 + q) ^ row) & 7) << 4)) =
+        make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+}
+
+// Epilogue of one pass for this group's NBLK 16-column blocks starting at column cbeg.  TMEM loads are double
+// buffered against the math of the previous block; `b` arrives pre-loaded with the first block's bias (fetched by
+// the caller before it waited for the accumulator).
+template <int ACT, bool F16, bool DOT, bool DBG, int NBLK>
+__device__ __forceinline__ float epilogue(uint32_t tmem_row, int cbeg, const float* __restrict__ bias, float4 (&b)[4],
+                                          uint8_t* X, int row, const float* __restrict__ dot_w, float* dbg_row) {
+  float dot = 0.f;
+  uint8_t* rowp = X + (row >> 3) * 1024 + (row & 7) * 128;
+  uint32_t va[16], vb[16];
+  tmem_ld16(tmem_row + cbeg, va);
+#pragma unroll
+  for (int blk = 0; blk < NBLK; ++blk) {
+    const int c0 = cbeg + 16 * blk;
+    const float* nb = (blk + 1 < NBLK) ? bias + c0 + 16 : nullptr;
+    tmem_ld_wait();
+    if (blk & 1) {
+      if (blk + 1 < NBLK) tmem_ld16(tmem_row + c0 + 16, va);
+      epi_block<ACT, F16, DOT, DBG>(vb, b, nb, c0, rowp, row, dot_w, dot, dbg_row);
+    } else {
+      if (blk + 1 < NBLK) tmem_ld16(tmem_row + c0 + 16, vb);
+      epi_block<ACT, F16, DOT, DBG>(va, b, nb, c0, rowp, row, dot_w, dot, dbg_row);
+    }
+  }
+  return dot;
+}
+
+// ---- split-precision (fp16 hi + lo) variants used by the deformation phase when the encoding has > 10 octaves ----
+// Streams a row as two fp16 planes: hi = fp16(v) into chunk0.., lo = fp16(v - hi) into chunk0 + lo_off..
+template <int NUNITS>
+struct RowStreamSplit {
+  uint8_t* rowp;
+  int chunk0, lo_off, row, grp;
+  float buf[8];
+  __device__ __forceinline__ RowStreamSplit(uint8_t* X, int chunk0_, int lo_off_, int row_, int grp_)
+      : rowp(X + (row_ >> 3) * 1024 + (row_ & 7) * 128), chunk0(chunk0_), lo_off(lo_off_), row(row_), grp(grp_) {}
+  __device__ __forceinline__ void put(int col, float v) {
+    buf[col & 7] = v;
+    if ((col & 7) == 7) {
+      const int u = col >> 3;
+      const int owner = (u < (NUNITS + 1) / 2) ? 0 : 1;
+      if (owner == grp) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          __half2 h = __floats2half2_rn(buf[2 * q], buf[2 * q + 1]);
+          const float2 hf = __half22float2(h);
+          hi[q] = *reinterpret_cast<uint32_t*>(&h);
+          lo[q] = pack2<true>(buf[2 * q] - hf.x, buf[2 * q + 1] - hf.y);
+        }
+        uint8_t* p = rowp + (chunk0 + (u >> 3)) * kChunkBytes + ((((u & 7) ^ row) & 7) << 4);
+        *reinterpret_cast<uint4*>(p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(p + lo_off * kChunkBytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+  }
+};
+
+// relu epilogue writing hi/lo fp16 planes: columns [cbeg, cbeg + 16*NBLK) of the accumulator
+template <bool DBG, int NBLK>
+__device__ __forceinline__ void epilogue_split(uint32_t tmem_row, int cbeg, const float* __restrict__ bias, uint8_t* X,
+                                               int row, int lo_off, float* dbg_row, int dbg_col0) {
+  uint8_t* rowp = X + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+  for (int blk = 0; blk < NBLK; ++blk) {
+    const int c0 = cbeg + 16 * blk;
+    float4 b[4];
+    load_bias(b, bias + c0);
+    uint32_t v[16];
+    tmem_ld16(tmem_row + c0, v);
+    tmem_ld_wait();
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float f0 = fmaxf(__uint_as_float(v[4 * j + 0]) + b[j].x, 0.f), f1 = fmaxf(__uint_as_float(v[4 * j + 1]) + b[j].y, 0.f);
+      const float f2 = fmaxf(__uint_as_float(v[4 * j + 2]) + b[j].z, 0.f), f3 = fmaxf(__uint_as_float(v[4 * j + 3]) + b[j].w, 0.f);
+      if (DBG && dbg_row) {
+        dbg_row[dbg_col0 + c0 + 4 * j + 0] = f0; dbg_row[dbg_col0 + c0 + 4 * j + 1] = f1;
+        dbg_row[dbg_col0 + c0 + 4 * j + 2] = f2; dbg_row[dbg_col0 + c0 + 4 * j + 3] = f3;
+      }
+      __half2 h0 = __floats2half2_rn(f0, f1), h1 = __floats2half2_rn(f2, f3);
+      const float2 g0 = __half22float2(h0), g1 = __half22float2(h1);
+      hi[2 * j] = *reinterpret_cast<uint32_t*>(&h0);
+      hi[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
+      lo[2 * j] = pack2<true>(f0 - g0.x, f1 - g0.y);
+      lo[2 * j + 1] = pack2<true>(f2 - g1.x, f3 - g1.y);
+    }
+    uint8_t* chunk = rowp + (c0 >> 6) * kChunkBytes;
+    const int u0 = (c0 & 63) >> 3;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      uint8_t* p = chunk + ((((u0 + q) ^ row) & 7) << 4);
+      *reinterpret_cast<uint4*>(p) = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+      *reinterpret_cast<uint4*>(p + lo_off * kChunkBytes) = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+    }
+  }
+}
+
+// fp32 reduction of the last hidden layer against NOUT small-head weight rows: columns [cbeg, cbeg+16*NBLK)
+template <bool DBG, int NBLK, int NOUT>
+__device__ __forceinline__ void final_partial(uint32_t tmem_row, int cbeg, const float* __restrict__ bias,
+                                              const float* __restrict__ w, int ld, float (&part)[NOUT], float* dbg_row,
+                                              int dbg_col0) {
+#pragma unroll
+  for (int blk = 0; blk < NBLK; ++blk) {
+    const int c0 = cbeg + 16 * blk;
+    uint32_t v[16];
+    tmem_ld16(tmem_row + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 bb = ldg_keep(bias + c0 + 4 * j);
+      const float h0 = fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.f), h1 = fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.f);
+      const float h2 = fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.f), h3 = fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.f);
+      if (DBG && dbg_row) {
+        dbg_row[dbg_col0 + c0 + 4 * j + 0] = h0; dbg_row[dbg_col0 + c0 + 4 * j + 1] = h1;
+        dbg_row[dbg_col0 + c0 + 4 * j + 2] = h2; dbg_row[dbg_col0 + c0 + 4 * j + 3] = h3;
+      }
+#pragma unroll
+      for (int k = 0; k < NOUT; ++k) {
+        const float4 ww = ldg_keep(w + k * ld + c0 + 4 * j);
+        part[k] += h0 * ww.x + h1 * ww.y + h2 * ww.z + h3 * ww.w;
+      }
+    }
+  }
+}
+
+// trilinear gather of 16 of the 32 channels from the channel-last embedding grid, ref: nerf/models.py:346-365
+// (align_corners=True, zero padding, raw warped coordinates; x -> last grid dim, z -> first)
+__device__ __forceinline__ void grid_gather16(const float* __restrict__ g, int ch0, float x, float y, float z,
+                                              float (&out)[16]) {
+  const float sc = 0.5f * (SAHS_GRID_RES - 1);
+  const float ix = (x + 1.f) * sc, iy = (y + 1.f) * sc, iz = (z + 1.f) * sc;
+  const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+#pragma unroll
+  for (int c = 0; c < 16; ++c) out[c] = 0.f;
+#pragma unroll
+  for (int corner = 0; corner < 8; ++corner) {
+    const float xi = fx + (corner & 1), yi = fy + ((corner >> 1) & 1), zi = fz + (corner >> 2);
+    const float w = (1.f - fabsf(ix - xi)) * (1.f - fabsf(iy - yi)) * (1.f - fabsf(iz - zi));
+    const bool ok = xi >= 0.f && xi <= SAHS_GRID_RES - 1 && yi >= 0.f && yi <= SAHS_GRID_RES - 1 && zi >= 0.f &&
+                    zi <= SAHS_GRID_RES - 1;
+    if (ok) {
+      const float4* p = reinterpret_cast<const float4*>(
+          g + ((((size_t)(int)zi * SAHS_GRID_RES + (int)yi) * SAHS_GRID_RES + (int)xi) * SAHS_GRID_CH) + ch0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = ldg_stream(reinterpret_cast<const float*>(p + q));
+        out[4 * q + 0] += w * v.x; out[4 * q + 1] += w * v.y; out[4 * q + 2] += w * v.z; out[4 * q + 3] += w * v.w;
+      }
+    }
+  }
+}
+
+
+template <int XYZ_L_, int AMB_DIM_, int AMB_L_, bool AMB_INC_, int DIR_L_, bool USE_W_>
+struct FieldCfg {
+  static constexpr int XYZ_L = XYZ_L_;
+  static constexpr int AMB_DIM = AMB_DIM_;
+  static constexpr int AMB_L = AMB_L_;
+  static constexpr bool AMB_INC = AMB_INC_;
+  static constexpr int DIR_L = DIR_L_;
+  static constexpr bool USE_W = USE_W_;
+  static constexpr int E0_DIM = 3 + 6 * XYZ_L;                                      // include_input is always on
+  static constexpr int E0_PAD = (E0_DIM + 15) / 16 * 16;
+  static constexpr int AMB_PE = USE_W ? ((AMB_INC ? AMB_DIM : 0) + 2 * AMB_DIM * AMB_L) : 0;
+  static constexpr int E1_DIM = E0_DIM + AMB_PE;
+  static constexpr int E1_PAD = (E1_DIM + 15) / 16 * 16;
+  static constexpr int DIR_DIM = 3 + 6 * DIR_L;
+};
+
+// ---- warp-role loops shared by the forward and backward kernels ------------------------------------------------
+// TMA producer: streams the packed stage images of `plan` once per tile through the slot ring.
+__device__ __forceinline__ void tma_warp_loop(const FieldPlan& plan, const uint8_t* __restrict__ packed, uint8_t* slots,
+                                              uint64_t* full, uint64_t* empty, long long ntiles, int* status, int lane) {
+  uint32_t slot = 0, phase = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    uint32_t off = 0;
+    for (int st = 0; st < plan.num_stages; ++st) {
+      const uint32_t bytes = (uint32_t)plan.st[st].n8 * 1024u;
+      mbar_wait(&empty[slot], phase ^ 1, status, 100);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full[slot], bytes);
+        tma_bulk_g2s(slots + slot * kStageSlotBytes, packed + off, bytes, &full[slot]);
+      }
+      __syncwarp();
+      off += bytes;
+      if (++slot == kSlots) { slot = 0; phase ^= 1; }
+    }
+  }
+}
+
+// MMA issuer: one thread issues tcgen05.mma for every stage; passes are delimited by the a_ready / acc_ready barriers.
+__device__ __forceinline__ void mma_warp_loop(const FieldPlan& plan, uint8_t* X, uint8_t* slots, uint64_t* full,
+                                              uint64_t* empty, uint64_t* a_ready, uint64_t* acc_ready, uint32_t tmem_base,
+                                              long long ntiles, int* status, int lane) {
+  uint32_t slot = 0, phase = 0, a_par = 0;
+  const uint32_t x_addr = smem_u32(X), s_addr = smem_u32(slots);
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int st = 0; st < plan.num_stages; ++st) {
+      const StageRec r = plan.st[st];
+      const uint32_t flags = r.kflags >> 3, ksteps = r.kflags & 7;
+      if (flags & ST_WAIT_A) {
+        mbar_wait(a_ready, a_par, status, 200 + st);
+        a_par ^= 1;
+      }
+      mbar_wait(&full[slot], phase, status, 400 + st);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t idesc = umma_idesc_m128((uint32_t)r.n8 * 8u, (flags & ST_F16) != 0);
+        const uint64_t a0 = umma_smem_desc_sw128(x_addr + r.a_chunk * kChunkBytes);
+        const uint64_t b0 = umma_smem_desc_sw128(s_addr + slot * kStageSlotBytes);
+        const uint32_t d = tmem_base + (uint32_t)r.d_col8 * 8u;
+        for (uint32_t k = 0; k < ksteps; ++k) {
+          // advancing K by 16 elements = 32 bytes = 2 descriptor address units inside the 128B swizzle atom
+          tc_mma_bf16(d, a0 + 2 * k, b0 + 2 * k, idesc, (k > 0 || !(flags & ST_FRESH)) ? 1u : 0u);
+        }
+        if (r.a_chunk2 != 0xFF) {   // split precision: the residual (lo) activations times the same weights
+          const uint64_t a1 = umma_smem_desc_sw128(x_addr + r.a_chunk2 * kChunkBytes);
+          for (uint32_t k = 0; k < ksteps; ++k) tc_mma_bf16(d, a1 + 2 * k, b0 + 2 * k, idesc, 1u);
+        }
+        tc_commit(&empty[slot]);
+        if (flags & ST_COMMIT) tc_commit(acc_ready);
+      }
+      __syncwarp();
+      if (++slot == kSlots) { slot = 0; phase ^= 1; }
+    }
+  }
+}
+
+}  // namespace
