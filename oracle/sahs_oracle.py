@@ -323,7 +323,7 @@ def linspace_f32(steps: int) -> np.ndarray:
 def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, num_samples: int, det: bool = True,
                u: Optional[torch.Tensor] = None, return_inds: bool = False):
     """Inverse-CDF importance sampling, ref: nerf/nerf_helpers.py:454-497 (sample_pdf_2)."""
-    w = (weights.numpy().astype(np.float32) + np.float32(1e-5)).astype(np.float32)
+    w = (weights.detach().numpy().astype(np.float32) + np.float32(1e-5)).astype(np.float32)
     total = _aten_inner_sum_f32(np.ascontiguousarray(w))
     pdf = (w / total[:, None]).astype(np.float32)
     cdf = np.concatenate((np.zeros((w.shape[0], 1), np.float32), _aten_cumsum_f32(pdf)), -1)
@@ -337,7 +337,7 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, num_samples: int, det:
     inds = (cdf[:, None, :] <= uu[:, :, None]).sum(-1).astype(np.int64)
     below = np.maximum(inds - 1, 0)
     above = np.minimum(inds, nb - 1)
-    b = bins.numpy().astype(np.float32)
+    b = bins.detach().numpy().astype(np.float32)
     cdf_b, cdf_a = np.take_along_axis(cdf, below, 1), np.take_along_axis(cdf, above, 1)
     bin_b, bin_a = np.take_along_axis(b, below, 1), np.take_along_axis(b, above, 1)
     denom = (cdf_a - cdf_b).astype(np.float32)

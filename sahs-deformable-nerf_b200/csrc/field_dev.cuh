@@ -87,6 +87,7 @@ template <bool F16, int NUNITS, bool SPLIT = true>
 struct RowStream {
   uint8_t* rowp;   // X + row offset inside a chunk
   int chunk0, row, grp;
+  __nv_bfloat16* tape = nullptr;   // training: this row's slice of the activation tape (bf16, row-major)
   float buf[8];
   __device__ __forceinline__ RowStream(uint8_t* X, int chunk0_, int row_, int grp_)
       : rowp(X + (row_ >> 3) * 1024 + (row_ & 7) * 128), chunk0(chunk0_), row(row_), grp(grp_) {}
@@ -102,6 +103,10 @@ struct RowStream {
         q.z = pack2<F16>(buf[4], buf[5]);
         q.w = pack2<F16>(buf[6], buf[7]);
         *reinterpret_cast<uint4*>(rowp + (chunk0 + (u >> 3)) * kChunkBytes + ((((u & 7) ^ row) & 7) << 4)) = q;
+        if (tape)
+          *reinterpret_cast<uint4*>(tape + 8 * u) =
+              make_uint4(pack2<false>(buf[0], buf[1]), pack2<false>(buf[2], buf[3]), pack2<false>(buf[4], buf[5]),
+                         pack2<false>(buf[6], buf[7]));
       }
     }
   }
@@ -162,10 +167,10 @@ __device__ __forceinline__ void load_bias(float4 (&b)[4], const float* __restric
 
 // one 16-column block of an epilogue: +bias (FADD2), optional fp32 dot, pack, activation, swizzled store.
 // The bias registers are dead after the adds, so the next block's bias is fetched before the pack/store part.
-template <int ACT, bool F16, bool DOT, bool DBG>
+template <int ACT, bool F16, bool DOT, bool DBG, bool TRAIN = false>
 __device__ __forceinline__ void epi_block(uint32_t (&v)[16], float4 (&b)[4], const float* __restrict__ next_bias, int c0,
                                           uint8_t* rowp, int row, const float* __restrict__ dot_w, float& dot,
-                                          float* dbg_row) {
+                                          float* dbg_row, __nv_bfloat16* tape_row = nullptr, uint32_t* mbits = nullptr) {
   float f[16];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -175,6 +180,24 @@ __device__ __forceinline__ void epi_block(uint32_t (&v)[16], float4 (&b)[4], con
     add2(f[4 * j + 2], f[4 * j + 3], b[j].z, b[j].w);
   }
   if (next_bias) load_bias(b, next_bias);
+  if (TRAIN) {
+    // training: sign bits for the activation derivative and the activated values (bf16, row-major) for the wgrad
+    uint32_t bits = 0;
+    uint32_t tp[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a0 = f[2 * j], a1 = f[2 * j + 1];
+      bits |= (a0 > 0.f ? 1u : 0u) << (2 * j);
+      bits |= (a1 > 0.f ? 1u : 0u) << (2 * j + 1);
+      const float lk = ACT == ACT_LEAKY ? 0.01f : 0.f;
+      tp[j] = (ACT == ACT_NONE) ? pack2<false>(a0, a1) : pack2<false>(fmaxf(a0, lk * a0), fmaxf(a1, lk * a1));
+    }
+    if (mbits) *mbits = bits;
+    if (tape_row) {
+      *reinterpret_cast<uint4*>(tape_row + c0) = make_uint4(tp[0], tp[1], tp[2], tp[3]);
+      *reinterpret_cast<uint4*>(tape_row + c0 + 8) = make_uint4(tp[4], tp[5], tp[6], tp[7]);
+    }
+  }
   uint32_t pk[8];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -205,10 +228,12 @@ __device__ __forceinline__ void epi_block(uint32_t (&v)[16], float4 (&b)[4], con
 // Epilogue of one pass for this group's NBLK 16-column blocks starting at column cbeg.  TMEM loads are double
 // buffered against the math of the previous block; `b` arrives pre-loaded with the first block's bias (fetched by
 // the caller before it waited for the accumulator).
-template <int ACT, bool F16, bool DOT, bool DBG, int NBLK>
+template <int ACT, bool F16, bool DOT, bool DBG, int NBLK, bool TRAIN = false>
 __device__ __forceinline__ float epilogue(uint32_t tmem_row, int cbeg, const float* __restrict__ bias, float4 (&b)[4],
-                                          uint8_t* X, int row, const float* __restrict__ dot_w, float* dbg_row) {
+                                          uint8_t* X, int row, const float* __restrict__ dot_w, float* dbg_row,
+                                          __nv_bfloat16* tape_row = nullptr, uint4* mask_out = nullptr) {
   float dot = 0.f;
+  uint32_t mw[4] = {0u, 0u, 0u, 0u};
   uint8_t* rowp = X + (row >> 3) * 1024 + (row & 7) * 128;
   uint32_t va[16], vb[16];
   tmem_ld16(tmem_row + cbeg, va);
@@ -217,14 +242,17 @@ __device__ __forceinline__ float epilogue(uint32_t tmem_row, int cbeg, const flo
     const int c0 = cbeg + 16 * blk;
     const float* nb = (blk + 1 < NBLK) ? bias + c0 + 16 : nullptr;
     tmem_ld_wait();
+    uint32_t bits = 0;
     if (blk & 1) {
       if (blk + 1 < NBLK) tmem_ld16(tmem_row + c0 + 16, va);
-      epi_block<ACT, F16, DOT, DBG>(vb, b, nb, c0, rowp, row, dot_w, dot, dbg_row);
+      epi_block<ACT, F16, DOT, DBG, TRAIN>(vb, b, nb, c0, rowp, row, dot_w, dot, dbg_row, tape_row, &bits);
     } else {
       if (blk + 1 < NBLK) tmem_ld16(tmem_row + c0 + 16, vb);
-      epi_block<ACT, F16, DOT, DBG>(va, b, nb, c0, rowp, row, dot_w, dot, dbg_row);
+      epi_block<ACT, F16, DOT, DBG, TRAIN>(va, b, nb, c0, rowp, row, dot_w, dot, dbg_row, tape_row, &bits);
     }
+    if (TRAIN) mw[blk >> 1] |= bits << ((blk & 1) * 16);
   }
+  if (TRAIN && mask_out) *mask_out = make_uint4(mw[0], mw[1], mw[2], mw[3]);
   return dot;
 }
 

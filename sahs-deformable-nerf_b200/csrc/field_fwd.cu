@@ -17,18 +17,28 @@
 // finer), accumulation is fp32 in TMEM; dx, ambient and sigma heads are evaluated in fp32.  With more than 10
 // encoding octaves the deformation phase runs in split precision (fp16 hi + lo operands, ~fp32 accuracy) because
 // the encoding of the warped point amplifies its error by 2^(L-1).
+#include <string.h>
 #include "field_dev.cuh"
 
 
 namespace {
 
-template <class C, bool DBG>
+// TRAIN: additionally records what the backward pass needs -- every layer's activated output (bf16, row-major
+// "activation tape" [P, dm.tx_total]), the sign bits of the pre-activations ([layer][P][2] x 128 bit) and the warped
+// point / ambient coordinates ([P,8] fp32).
+struct TrainOut {
+  __nv_bfloat16* tape_x;
+  uint4* masks;
+  float* saves;
+};
+
+template <class C, bool DBG, bool TRAIN>
 __global__ void __launch_bounds__(kThreads, 2)
 field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__ NetDims dm,
                  const uint8_t* __restrict__ packed, const float* __restrict__ fc, const float* __restrict__ grid,
                  const float* __restrict__ ro, const float* __restrict__ rd, const float* __restrict__ zv,
                  int S, long long P, float* __restrict__ raw_out, float* __restrict__ dbg, int dbg_pass,
-                 int* __restrict__ status) {
+                 int* __restrict__ status, TrainOut tr) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* X = smem;
   uint8_t* slots = smem + kSmemX;
@@ -80,6 +90,11 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
 #pragma unroll
       for (int k = 0; k < 3; ++k) pt[k] = __fadd_rn(ro[ray * 3 + k], __fmul_rn(dir[k], zz));
       float* dbg_row = (DBG && dbg && tile == 0) ? dbg + row * 256 : nullptr;
+      // training tape slices of this row (null for padding rows of the last tile)
+      __nv_bfloat16* tape = (TRAIN && valid) ? tr.tape_x + p * dm.tx_total : nullptr;
+      auto mask_slot = [&](int layer) -> uint4* {
+        return (TRAIN && valid) ? tr.masks + ((size_t)layer * P + p) * 2 + grp : nullptr;
+      };
       float mapped[3] = {pt[0], pt[1], pt[2]};
       float amb[C::AMB_DIM > 0 ? C::AMB_DIM : 1] = {};
 
@@ -141,6 +156,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         // -------- deformation phase: warp | hyper-sheet merged (fp16 operands) --------
         auto write_e0 = [&](int chunk0) {
           RowStream<true, C::E0_PAD / 8> st(X, chunk0, row, grp);
+          if (TRAIN && tape) st.tape = tape + dm.tx_e0;
           int col = pe_stream<C::XYZ_L, true, 3>(st, 0, pt);
 #pragma unroll
           for (int i = C::E0_DIM; i < C::E0_PAD; ++i) st.put(col++, 0.f);
@@ -160,8 +176,9 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
             wait_acc(sy, 1100 + i);
           }
           // whh = 192: three 32-column blocks per group
-          epilogue<ACT_RELU, true, false, DBG, 6>(tmem_row, grp * 96, bias, b, X, row, nullptr,
-                                                  (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) ? dbg_row : nullptr);
+          epilogue<ACT_RELU, true, false, DBG, 6, TRAIN>(tmem_row, grp * 96, bias, b, X, row, nullptr,
+                                                         (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) ? dbg_row : nullptr,
+                                                         tape ? tape + dm.tx_wh + i * dm.whh : nullptr, mask_slot(i));
           signal_a(sy);
         }
         {
@@ -176,6 +193,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
           const float* wa = bf + 4;
           const float* ba = wa + C::AMB_DIM * dm.hh;
           float part[3 + (C::AMB_DIM > 0 ? C::AMB_DIM : 1)] = {};
+          uint32_t hmask[3] = {0u, 0u, 0u};
 #pragma unroll
           for (int blk = 0; blk < 3; ++blk) {
             const int c0 = grp * 96 + 32 * blk;
@@ -187,6 +205,13 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
               const float4 bb = ldg_keep(bias + c0 + 4 * j);
               float h[4] = {fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.f), fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.f),
                             fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.f)};
+              if (TRAIN) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) hmask[blk] |= (h[q] > 0.f ? 1u : 0u) << (4 * j + q);
+                if (tape)
+                  *reinterpret_cast<uint2*>(tape + dm.tx_wh + i * dm.whh + c0 + 4 * j) =
+                      make_uint2(pack2<false>(h[0], h[1]), pack2<false>(h[2], h[3]));
+              }
               if (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) dbg_row[c0 + 4 * j + q] = h[q];
@@ -206,6 +231,10 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
               }
             }
           }
+          if (TRAIN) {
+            uint4* ms = mask_slot(i);
+            if (ms) *ms = make_uint4(hmask[0], hmask[1], hmask[2], 0u);
+          }
           float* scratch = reinterpret_cast<float*>(X);   // [2][128][8]
 #pragma unroll
           for (int k = 0; k < 3 + C::AMB_DIM; ++k) scratch[(grp * 128 + row) * 8 + k] = part[k];
@@ -218,6 +247,12 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
             amb[k] = scratch[row * 8 + 3 + k] + scratch[(128 + row) * 8 + 3 + k] + ldg_keep1(ba + k);
           group_sync();   // scratch is dead before E1 overwrites it
         }
+      }
+      if (TRAIN && valid && grp == 0) {
+        float* sv = tr.saves + p * 8;
+        sv[0] = mapped[0]; sv[1] = mapped[1]; sv[2] = mapped[2];
+#pragma unroll
+        for (int k = 0; k < C::AMB_DIM; ++k) sv[3 + k] = amb[k];
       }
       // -------- spatial embedding gather: each group keeps its 16 channels packed until layers_dir.0 --------
       uint32_t emb_pk[8];
@@ -239,6 +274,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       // -------- trunk (bf16 operands) --------
       auto write_e1 = [&]() {
         RowStream<kTrunkF16, C::E1_PAD / 8> st(X, 0, row, grp);
+        if (TRAIN && tape) st.tape = tape + dm.tx_e1;
         int col = pe_stream<C::XYZ_L, true, 3>(st, 0, mapped);
         if (C::AMB_PE > 0) col = pe_stream<C::AMB_L, C::AMB_INC, (C::AMB_DIM > 0 ? C::AMB_DIM : 1)>(st, col, amb);
 #pragma unroll
@@ -257,17 +293,20 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
           load_bias(b, bias + grp * 128);
           wait_acc(sy, 2100 + i);
         }
-        epilogue<ACT_LEAKY, kTrunkF16, false, DBG, 8>(tmem_row, grp * 128, bias, b, X, row, nullptr,
-                                                  (DBG && dbg_row && dbg_pass == SAHS_DBG_TRUNK(i)) ? dbg_row : nullptr);
+        epilogue<ACT_LEAKY, kTrunkF16, false, DBG, 8, TRAIN>(
+            tmem_row, grp * 128, bias, b, X, row, nullptr,
+            (DBG && dbg_row && dbg_pass == SAHS_DBG_TRUNK(i)) ? dbg_row : nullptr,
+            tape ? tape + dm.tx_th + i * dm.th : nullptr, mask_slot((C::USE_W ? dm.w_layers : 0) + i));
         signal_a(sy);
       }
       // fc_feat (no activation) + sigma = fc_alpha(feat) in fp32 (partial dot per group)
       float4 bfe[4];
       load_bias(bfe, fc + dm.off_featb + grp * 128);
       wait_acc(sy, 2200);
-      float sigma = epilogue<ACT_NONE, kTrunkF16, true, DBG, 8>(
+      float sigma = epilogue<ACT_NONE, kTrunkF16, true, DBG, 8, TRAIN>(
           tmem_row, grp * 128, fc + dm.off_featb, bfe, X, row, fc + dm.off_alpha,
-          (DBG && dbg_row && dbg_pass == SAHS_DBG_TRUNK(dm.t_layers)) ? dbg_row : nullptr);
+          (DBG && dbg_row && dbg_pass == SAHS_DBG_TRUNK(dm.t_layers)) ? dbg_row : nullptr,
+          tape ? tape + dm.tx_feat : nullptr, nullptr);
       if (grp == 1) xchg[row] = sigma;
       signal_a(sy);
       // -------- heads: layers_dir.0 = [feat | PE(dir) | emb], layers_seg.0 = feat --------
@@ -275,6 +314,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       {
         // extra K-chunk: cols [0,27) PE(dir), [27,59) embedding, zero padding up to 64
         RowStream<kTrunkF16, 8, false> st(X, 0, row, 0);
+        if (TRAIN && tape) st.tape = tape + dm.tx_xtra;
         if (grp == 0) {
           int col = pe_stream<C::DIR_L, true, 3>(st, 0, dir);
 #pragma unroll
@@ -288,6 +328,10 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
           const uint32_t pair = emb_pk[q >> 1];
           const uint16_t hv = (q & 1) ? (uint16_t)(pair >> 16) : (uint16_t)(pair & 0xffffu);
           *reinterpret_cast<uint16_t*>(rowp + ((((col >> 3) ^ row) & 7) << 4) + (col & 7) * 2) = hv;
+          if (TRAIN && tape) {   // bf16 copy of the embedding value for the wgrad of layers_dir.0
+            const __half hh = __ushort_as_half(hv);
+            tape[dm.tx_xtra + col] = __float2bfloat16_rn(__half2float(hh));
+          }
         }
       }
       signal_a(sy);
@@ -296,8 +340,10 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         float4 b[4];
         load_bias(b, bias + grp * 128);
         wait_acc(sy, 3100 + i);
-        epilogue<ACT_LEAKY, kTrunkF16, false, DBG, 8>(tmem_row, grp * 128, bias, b, X, row, nullptr,
-                                                  (DBG && dbg_row && dbg_pass == SAHS_DBG_HEAD(i)) ? dbg_row : nullptr);
+        epilogue<ACT_LEAKY, kTrunkF16, false, DBG, 8, TRAIN>(
+            tmem_row, grp * 128, bias, b, X, row, nullptr,
+            (DBG && dbg_row && dbg_pass == SAHS_DBG_HEAD(i)) ? dbg_row : nullptr,
+            tape ? tape + dm.tx_hh + i * 2 * dm.hd : nullptr, mask_slot((C::USE_W ? dm.w_layers : 0) + dm.t_layers + i));
         signal_a(sy);
       }
       // -------- output layer: cols 0-2 rgb, 3-14 seg (+ sigma) --------
@@ -330,8 +376,9 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
 template <class C>
 int launch_field(const HostPlan& hp, const void* packed, const float* fc, const float* grid, const float* ro,
                  const float* rd, const float* z, int R, int S, float* raw, float* dbg, int dbg_pass,
-                 cudaStream_t st) {
-  auto kfn = (dbg != nullptr) ? field_fwd_kernel<C, true> : field_fwd_kernel<C, false>;
+                 cudaStream_t st, TrainOut tr = TrainOut{nullptr, nullptr, nullptr}) {
+  auto kfn = tr.tape_x ? field_fwd_kernel<C, false, true>
+                       : ((dbg != nullptr) ? field_fwd_kernel<C, true, false> : field_fwd_kernel<C, false, false>);
   SAHS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
   int* status = nullptr;
   SAHS_CUDA(cudaGetSymbolAddress((void**)&status, g_field_status));
@@ -340,21 +387,28 @@ int launch_field(const HostPlan& hp, const void* packed, const float* fc, const 
   long long grid_dim = 2LL * sahs_num_sms();
   if (grid_dim > ntiles) grid_dim = ntiles;
   kfn<<<(unsigned)grid_dim, kThreads, kSmemTotal, st>>>(hp.plan, hp.dims, (const uint8_t*)packed, fc, grid, ro, rd, z, S,
-                                                       P, raw, dbg, dbg_pass, status);
+                                                       P, raw, dbg, dbg_pass, status, tr);
   SAHS_LAUNCH_CHECK();
   return SAHS_OK;
 }
 
 }  // namespace
 
+int sahs_bwd_status_internal(int* out4_host);
+
 extern "C" int sahs_field_status(int* out4_host) {
   SAHS_CUDA(cudaMemcpyFromSymbol(out4_host, g_field_status, sizeof(int) * 4));
+  if (out4_host[0] == 0) {   // forward healthy: report the backward kernel's word
+    int b[4] = {0, 0, 0, 0};
+    if (sahs_bwd_status_internal(b) == 0 && b[0] != 0) memcpy(out4_host, b, sizeof(b));
+  }
   return SAHS_OK;
 }
 
-extern "C" int sahs_field_fwd(const sahs_model_spec* spec, int level, const void* packed, const float* frame_const,
-                              const float* grid_cl, const float* ro, const float* rd, const float* z, int num_rays,
-                              int num_samples, float* raw_out, float* debug, int debug_pass, void* stream) {
+static int field_fwd_impl(const sahs_model_spec* spec, int level, const void* packed, const float* frame_const,
+                          const float* grid_cl, const float* ro, const float* rd, const float* z, int num_rays,
+                          int num_samples, float* raw_out, float* debug, int debug_pass, void* stream, bool train,
+                          TrainOut tr) {
   SAHS_CHECK_ARG(spec, "null spec");
   SAHS_CHECK_ARG(level == 0 || level == 1, "level must be 0 (coarse) or 1 (fine)");
   SAHS_CHECK_ARG(num_rays >= 0 && num_samples > 0, "bad extents");
@@ -362,7 +416,7 @@ extern "C" int sahs_field_fwd(const sahs_model_spec* spec, int level, const void
   SAHS_CHECK_ARG(packed && frame_const && ro && rd && z && raw_out, "null pointer");
   SAHS_CHECK_ARG(spec->use_grid && grid_cl, "use_spatial_embeddings and its grid are required (all shipped configs)");
   static thread_local HostPlan hp;
-  int rc = sahs_build_host_plan(*spec, nullptr, hp);
+  int rc = sahs_build_host_plan(*spec, nullptr, hp, train);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const sahs_model_spec& s = *spec;
@@ -372,11 +426,27 @@ extern "C" int sahs_field_fwd(const sahs_model_spec* spec, int level, const void
   if (s.xyz_L == XL && (UW ? (s.amb_dim == AD && s.amb_L == AL && (s.amb_inc != 0) == AI) : true) &&             \
       ((s.use_warp != 0) == UW))                                                                                 \
     return launch_field<FieldCfg<XL, AD, AL, AI, 4, UW>>(hp, packed, frame_const, grid_cl, ro, rd, z, num_rays,  \
-                                                         num_samples, raw_out, debug, debug_pass, st);
+                                                         num_samples, raw_out, debug, debug_pass, st, tr);
   SAHS_TRY(10, 2, 4, true, true)     // config/audio/*.yml
   SAHS_TRY(15, 1, 15, false, true)   // config/expression/person_{2,3}.yml
   SAHS_TRY(10, 0, 0, false, false)   // config/expression/person_1.yml (no deformation, no hyper space)
 #undef SAHS_TRY
   sahs_set_error("sahs_field_fwd: no kernel instantiated for this model spec");
   return SAHS_EUNSUPPORTED;
+}
+
+extern "C" int sahs_field_fwd(const sahs_model_spec* spec, int level, const void* packed, const float* frame_const,
+                              const float* grid_cl, const float* ro, const float* rd, const float* z, int num_rays,
+                              int num_samples, float* raw_out, float* debug, int debug_pass, void* stream) {
+  return field_fwd_impl(spec, level, packed, frame_const, grid_cl, ro, rd, z, num_rays, num_samples, raw_out, debug,
+                        debug_pass, stream, false, TrainOut{nullptr, nullptr, nullptr});
+}
+
+extern "C" int sahs_field_fwd_train(const sahs_model_spec* spec, int level, const void* packed_train,
+                                    const float* frame_const, const float* grid_cl, const float* ro, const float* rd,
+                                    const float* z, int num_rays, int num_samples, float* raw_out, void* tape_x,
+                                    void* masks, float* saves, void* stream) {
+  SAHS_CHECK_ARG(num_rays == 0 || (tape_x && masks && saves), "training buffers required");
+  return field_fwd_impl(spec, level, packed_train, frame_const, grid_cl, ro, rd, z, num_rays, num_samples, raw_out,
+                        nullptr, -1, stream, true, TrainOut{(__nv_bfloat16*)tape_x, (uint4*)masks, saves});
 }

@@ -76,6 +76,17 @@ struct Builder {
     pass_open = true;
     ++ns;
   }
+  // dgrad stage: image rows = input features [in_col0, in_col0 + n_valid) (zero padded to n), image columns
+  // [dst_col0, dst_col0 + k_valid) = output features [out_row0, out_row0 + k_valid); the A operand is the 64-wide chunk
+  // of output-feature gradients `a_chunk`.
+  void tstage(int pidx, int ld, int out_row0, int k_valid, int dst_col0, int in_col0, int n, int n_valid, int a_chunk,
+              int d_col, bool fresh) {
+    stage(pidx, ld, 0, n, 0, dst_col0 + k_valid, a_chunk, d_col, fresh);
+    PackSrc& src = hp.pack[ns - 1].src[0];
+    src.transpose = 1;
+    src.src_row0 = out_row0; src.src_col0 = in_col0;
+    src.dst_row0 = 0; src.nrows = n_valid; src.ncols = k_valid; src.dst_col0 = dst_col0;
+  }
   void end_pass() {
     StageRec& r = hp.plan.st[ns - 1];
     r.kflags |= (uint8_t)(ST_COMMIT << 3);
@@ -91,9 +102,9 @@ extern "C" int sahs_param_count(const sahs_model_spec* spec) {
   return pi.count;
 }
 
-int sahs_build_host_plan(const sahs_model_spec& s, const float* const* params, HostPlan& hp) {
+int sahs_build_host_plan(const sahs_model_spec& s, const float* const* params, HostPlan& hp, bool train) {
   NetDims& d = hp.dims;
-  int rc = sahs_make_dims(s, d);
+  int rc = sahs_make_dims(s, d, train);
   if (rc) {
     sahs_set_error("unsupported model spec (dims check %d)", rc);
     return SAHS_EUNSUPPORTED;
@@ -256,10 +267,75 @@ int sahs_build_host_plan(const sahs_model_spec& s, const float* const* params, H
   return SAHS_OK;
 }
 
+int sahs_build_bwd_plan(const sahs_model_spec& s, const float* const* params, HostPlan& hp) {
+  NetDims& d = hp.dims;
+  int rc = sahs_make_dims(s, d, true);
+  if (rc) {
+    sahs_set_error("unsupported model spec (dims check %d)", rc);
+    return SAHS_EUNSUPPORTED;
+  }
+  ParamIndex pi;
+  if (!index_params(s, pi)) return SAHS_EINVAL;
+  Builder b{hp, params};
+  b.f16 = false;   // gradients and the transposed weights are bf16 (range), accumulation fp32
+  hp.num_fold = 0;
+  hp.num_copy = 0;
+  const int CW = SAHS_DRIVING_DIM + SAHS_POSE_CODE_DIM;
+  const int hd = d.hd, th = d.th;
+  // output layer: dOUT (chunk 0, cols 0-2 rgb, 3-14 seg) -> d(dir hidden) | d(seg hidden)
+  b.tstage(pi.rgb_w, hd, 0, 3, 0, 0, hd, hd, 0, 0, true);
+  b.tstage(pi.segf_w, hd, 0, 12, 3, 0, hd, hd, 0, hd, true);
+  b.end_pass();
+  for (int i = 3; i >= 1; --i) {
+    for (int kc = 0; kc < hd / 64; ++kc) b.tstage(pi.dir_w[i], hd, 64 * kc, 64, 0, 0, hd, hd, kc, 0, kc == 0);
+    for (int kc = 0; kc < hd / 64; ++kc) b.tstage(pi.seg_w[i], hd, 64 * kc, 64, 0, 0, hd, hd, hd / 64 + kc, hd, kc == 0);
+    b.end_pass();
+  }
+  const int ld0 = th + d.xtra_dim;
+  for (int kc = 0; kc < hd / 64; ++kc) b.tstage(pi.dir_w[0], ld0, 64 * kc, 64, 0, th, 64, d.xtra_dim, kc, 0, kc == 0);
+  b.end_pass();   // d[PE(dir) | embedding]
+  for (int half = 0; half < th / 128; ++half) {
+    for (int kc = 0; kc < hd / 64; ++kc) b.tstage(pi.dir_w[0], ld0, 64 * kc, 64, 0, 128 * half, 128, 128, kc, 128 * half, kc == 0);
+    for (int kc = 0; kc < hd / 64; ++kc) b.tstage(pi.seg_w[0], th, 64 * kc, 64, 0, 128 * half, 128, 128, hd / 64 + kc, 128 * half, false);
+  }
+  b.end_pass();   // d feat
+  for (int half = 0; half < th / 128; ++half)
+    for (int kc = 0; kc < th / 64; ++kc) b.tstage(pi.feat_w, th, 64 * kc, 64, 0, 128 * half, 128, 128, kc, 128 * half, kc == 0);
+  b.end_pass();
+  const int tin = d.e1_dim + d.ct_len;
+  for (int i = d.t_layers - 1; i >= 0; --i) {
+    const bool first = i == 0, skip = i == d.t_skip;
+    const int ld = first ? tin : (skip ? th + tin : th);
+    if (first || skip) {
+      for (int kc = 0; kc < th / 64; ++kc)
+        b.tstage(pi.trunk_w[i], ld, 64 * kc, 64, 0, first ? 0 : th, d.e1_k, d.e1_dim, kc, 0, kc == 0);
+      b.end_pass();   // d encoding
+    }
+    if (!first) {
+      for (int half = 0; half < th / 128; ++half)
+        for (int kc = 0; kc < th / 64; ++kc) b.tstage(pi.trunk_w[i], ld, 64 * kc, 64, 0, 128 * half, 128, 128, kc, 128 * half, kc == 0);
+      b.end_pass();
+    }
+  }
+  if (d.use_w) {
+    const int in0 = d.e0_dim + CW;
+    for (int i = d.w_layers - 1; i >= 1; --i) {
+      const bool skip = i == d.w_skip;
+      const int ldw = skip ? d.wh + in0 : d.wh, ldh = skip ? d.hh + in0 : d.hh;
+      for (int kc = 0; kc < d.wh / 64; ++kc) b.tstage(pi.warp_w[i], ldw, 64 * kc, 64, 0, 0, d.wh, d.wh, kc, 0, kc == 0);
+      for (int kc = 0; kc < d.hh / 64; ++kc) b.tstage(pi.hyp_w[i], ldh, 64 * kc, 64, 0, 0, d.hh, d.hh, d.wh / 64 + kc, d.wh, kc == 0);
+      b.end_pass();
+    }
+  }
+  hp.plan.num_stages = b.ns;
+  hp.plan.total_bytes = (int32_t)b.off;
+  return SAHS_OK;
+}
+
 // --------------------------------------------------------------------------------------------------------
 // pack kernel: one block per stage, fp32 -> bf16, written at the 128B-swizzled offset
 // --------------------------------------------------------------------------------------------------------
-constexpr int kPackBatch = 48;
+constexpr int kPackBatch = 40;
 struct PackBatch {
   PackStage st[kPackBatch];
 };
@@ -273,8 +349,9 @@ __global__ void pack_stage_kernel(const __grid_constant__ PackBatch batch, uint8
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const PackSrc& s = ps.src[q];
-      if (s.w && row >= s.dst_row0 && row < s.dst_row0 + s.nrows && col < s.ncols)
-        v = s.w[(size_t)(s.src_row0 + row - s.dst_row0) * s.ld + s.src_col0 + col];
+      if (s.w && row >= s.dst_row0 && row < s.dst_row0 + s.nrows && col >= s.dst_col0 && col < s.dst_col0 + s.ncols)
+        v = s.transpose ? s.w[(size_t)(s.src_row0 + col - s.dst_col0) * s.ld + s.src_col0 + (row - s.dst_row0)]
+                        : s.w[(size_t)(s.src_row0 + row - s.dst_row0) * s.ld + s.src_col0 + col - s.dst_col0];
     }
     if (ps.f16) {
       __half h = __float2half_rn(v);
@@ -420,5 +497,62 @@ extern "C" int sahs_debug_plan(const sahs_model_spec* spec, int param_count, int
                   d.e1_dim, d.e1_k, d.e0_resident, d.e0_chunk_base, d.whh, d.off_wbias, d.off_wfinal, d.off_tbias,
                   d.off_featb, d.off_alpha, d.off_hbias, d.off_outb, d.xtra_dim, d.w_split};
   memcpy(dims_out, dd, sizeof(dd));
+  return SAHS_OK;
+}
+
+
+// ---- training support ----------------------------------------------------------------------------------------------
+extern "C" int sahs_train_layout(const sahs_model_spec* spec, int32_t* out, int max_out) {
+  SAHS_CHECK_ARG(spec && out && max_out >= 40, "need room for 40 ints");
+  NetDims d;
+  int rc = sahs_make_dims(*spec, d, true);
+  if (rc) { sahs_set_error("unsupported model spec (dims check %d)", rc); return SAHS_EUNSUPPORTED; }
+  static thread_local HostPlan hp;
+  rc = sahs_build_host_plan(*spec, nullptr, hp, true);
+  if (rc) return rc;
+  const int32_t train_packed_bytes = hp.plan.total_bytes;
+  rc = sahs_build_bwd_plan(*spec, nullptr, hp);
+  if (rc) return rc;
+  int32_t v[40] = {d.tx_e0, d.e0_k, d.tx_wh, d.whh, d.w_layers, d.tx_e1, d.e1_k, d.tx_th, d.th, d.t_layers, d.tx_feat,
+                   d.tx_xtra, d.tx_hh, d.tx_total, d.td_wh, d.td_final, d.td_th, d.td_feat, d.td_hh, d.td_out, d.td_total,
+                   d.n_mask_layers, d.e0_dim, d.e1_dim, d.xtra_dim, d.wh, d.hh, d.w_skip, d.t_skip, d.ct_off, d.ct_len,
+                   d.use_w, d.hd, hp.plan.total_bytes, hp.plan.num_stages, d.fc_total, train_packed_bytes, 0, 0, 0};
+  memcpy(out, v, sizeof(v));
+  return SAHS_OK;
+}
+
+extern "C" int sahs_pack_params_train(const sahs_model_spec* spec, int level, const float* const* params,
+                                      void* packed_out, void* stream) {
+  SAHS_CHECK_ARG(spec && params && packed_out, "null pointer");
+  SAHS_CHECK_ARG(level == 0 || level == 1, "level must be 0 (coarse) or 1 (fine)");
+  static thread_local HostPlan hp;
+  int rc = sahs_build_host_plan(*spec, params, hp, true);
+  if (rc) return rc;
+  for (int s0 = 0; s0 < hp.plan.num_stages; s0 += kPackBatch) {
+    PackBatch pb;
+    int cnt = hp.plan.num_stages - s0 < kPackBatch ? hp.plan.num_stages - s0 : kPackBatch;
+    memcpy(pb.st, hp.pack + s0, sizeof(PackStage) * cnt);
+    pack_stage_kernel<<<cnt, 256, 0, (cudaStream_t)stream>>>(pb, (uint8_t*)packed_out);
+    SAHS_LAUNCH_CHECK();
+  }
+  return SAHS_OK;
+}
+
+extern "C" int sahs_pack_params_bwd(const sahs_model_spec* spec, int level, const float* const* params,
+                                    void* packed_t_out, void* stream) {
+  SAHS_CHECK_ARG(spec && params && packed_t_out, "null pointer");
+  SAHS_CHECK_ARG(level == 0 || level == 1, "level must be 0 (coarse) or 1 (fine)");
+  static thread_local HostPlan hp;
+  int rc = sahs_build_bwd_plan(*spec, params, hp);
+  if (rc) return rc;
+  for (int i = 0; i < hp.plan.num_stages; ++i)
+    SAHS_CHECK_ARG(hp.pack[i].src[0].w != nullptr, "a required parameter pointer is NULL");
+  for (int s0 = 0; s0 < hp.plan.num_stages; s0 += kPackBatch) {
+    PackBatch pb;
+    int cnt = hp.plan.num_stages - s0 < kPackBatch ? hp.plan.num_stages - s0 : kPackBatch;
+    memcpy(pb.st, hp.pack + s0, sizeof(PackStage) * cnt);
+    pack_stage_kernel<<<cnt, 256, 0, (cudaStream_t)stream>>>(pb, (uint8_t*)packed_t_out);
+    SAHS_LAUNCH_CHECK();
+  }
   return SAHS_OK;
 }

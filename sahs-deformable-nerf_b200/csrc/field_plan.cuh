@@ -40,6 +40,8 @@ struct PackSrc {      // part of a stage image copied from one fp32 [out,in] wei
   int32_t ld;         // in_features
   int32_t src_row0, src_col0;
   int32_t dst_row0, nrows, ncols;
+  int32_t dst_col0;   // first image column the block lands in (0 except for the fused output layer of the dgrad plan)
+  int32_t transpose;  // image(row, col) = w[(src_row0 + col) * ld + src_col0 + (row - dst_row0)]  (dgrad images)
 };
 struct PackStage {
   PackSrc src[2];
@@ -79,12 +81,17 @@ struct NetDims {
                                     // one after the other: needed when the encoding has more than 10 octaves
   // frame-constant block offsets (floats)
   int off_wbias, off_wfinal, off_tbias, off_featb, off_alpha, off_hbias, off_outb, fc_total;
+  // training tapes (row-major bf16, one row per point): column offsets of the saved activations (tx_*) and of the
+  // activation gradients (td_*); sign masks are indexed by layer (W i -> i, T i -> w_layers + i, H i -> .. + t_layers + i)
+  int tx_e0, tx_wh, tx_e1, tx_th, tx_feat, tx_xtra, tx_hh, tx_total;
+  int td_wh, td_final, td_th, td_feat, td_hh, td_out, td_total;
+  int n_mask_layers;
 };
 
 inline int sahs_round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 // returns 0 on success
-inline int sahs_make_dims(const sahs_model_spec& s, NetDims& d) {
+inline int sahs_make_dims(const sahs_model_spec& s, NetDims& d, bool train = false) {
   d = NetDims{};
   d.e0_dim = (s.xyz_inc ? 3 : 0) + 6 * s.xyz_L;
   d.e0_k = sahs_round_up(d.e0_dim, 16);
@@ -105,7 +112,7 @@ inline int sahs_make_dims(const sahs_model_spec& s, NetDims& d) {
     if (d.wh % 64 || d.hh % 64 || d.wh > 128 || d.hh > 128 || d.whh > 256) return -3;
     if (d.w_skip <= 0 || d.w_skip >= d.w_layers) return -4;
   }
-  d.w_split = (d.use_w && s.xyz_L > 10) ? 1 : 0;
+  d.w_split = (d.use_w && s.xyz_L > 10 && !train) ? 1 : 0;   // training always uses the merged fp16 phase
   if (d.w_split && (d.wh != 128 || d.hh != 64)) return -10;
   d.e0_resident = (!d.w_split && d.whh / 64 + d.e0_chunks <= 4) ? 1 : 0;
   d.e0_chunk_base = d.e0_resident ? d.whh / 64 : 0;
@@ -131,6 +138,24 @@ inline int sahs_make_dims(const sahs_model_spec& s, NetDims& d) {
   d.off_hbias = o;  o += 4 * 2 * d.hd;
   d.off_outb = o;   o += 16;
   d.fc_total = o;
+  int t = 0;
+  d.tx_e0 = t;   t += d.use_w ? d.e0_k : 0;
+  d.tx_wh = t;   t += d.use_w ? d.w_layers * d.whh : 0;
+  d.tx_e1 = t;   t += d.e1_k;
+  d.tx_th = t;   t += d.t_layers * d.th;
+  d.tx_feat = t; t += d.th;
+  d.tx_xtra = t; t += 64;
+  d.tx_hh = t;   t += 4 * 2 * d.hd;
+  d.tx_total = t;
+  t = 0;
+  d.td_wh = t;    t += d.use_w ? d.w_layers * d.whh : 0;
+  d.td_final = t; t += d.use_w ? 16 : 0;
+  d.td_th = t;    t += d.t_layers * d.th;
+  d.td_feat = t;  t += d.th;
+  d.td_hh = t;    t += 4 * 2 * d.hd;
+  d.td_out = t;   t += 16;
+  d.td_total = t;
+  d.n_mask_layers = (d.use_w ? d.w_layers : 0) + d.t_layers + 4;
   return 0;
 }
 
@@ -144,4 +169,6 @@ struct HostPlan {
   CopySection copy[8];
   int num_copy;
 };
-int sahs_build_host_plan(const sahs_model_spec& spec, const float* const* params, HostPlan& hp);
+int sahs_build_host_plan(const sahs_model_spec& spec, const float* const* params, HostPlan& hp, bool train = false);
+// dgrad plan: stages hold transposed bf16 weight blocks in the order the backward kernel consumes them
+int sahs_build_bwd_plan(const sahs_model_spec& spec, const float* const* params, HostPlan& hp);

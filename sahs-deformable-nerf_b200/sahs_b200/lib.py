@@ -30,7 +30,8 @@ EXPORTS = (
     "sahs_abi_version", "sahs_last_error", "sahs_launch_count", "sahs_param_count", "sahs_get_ray_bundle",
     "sahs_coarse_z", "sahs_positional_encoding", "sahs_field_sizes", "sahs_pack_params", "sahs_fold_frame",
     "sahs_field_fwd", "sahs_composite_fwd", "sahs_composite_bwd", "sahs_sample_pdf_merge", "sahs_sample_pdf",
-    "sahs_field_status", "sahs_debug_plan",
+    "sahs_field_status", "sahs_debug_plan", "sahs_train_layout", "sahs_pack_params_train", "sahs_pack_params_bwd",
+    "sahs_field_fwd_train", "sahs_field_bwd",
 )
 
 
@@ -63,6 +64,11 @@ def load() -> C.CDLL:
         "sahs_sample_pdf": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp, vp, vp]),
         "sahs_debug_plan": (C.c_int, [spec_p, i32, C.POINTER(C.c_int32), i32, C.POINTER(C.c_int32), i32,
                                       C.POINTER(C.c_int32), i32, C.POINTER(C.c_int32)]),
+        "sahs_train_layout": (C.c_int, [spec_p, C.POINTER(C.c_int32), i32]),
+        "sahs_pack_params_train": (C.c_int, [spec_p, i32, C.POINTER(vp), vp, vp]),
+        "sahs_pack_params_bwd": (C.c_int, [spec_p, i32, C.POINTER(vp), vp, vp]),
+        "sahs_field_fwd_train": (C.c_int, [spec_p, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]),
+        "sahs_field_bwd": (C.c_int, [spec_p, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
         "sahs_field_status": (C.c_int, [C.POINTER(C.c_int)]),
     }
     for name, (res, args) in sigs.items():

@@ -257,6 +257,10 @@ class NeRFaceModel(torch.nn.Module):
     def field(self, level: str, ro, rd, z, driving_vec, pose_code, frame_const=None, debug=None, debug_pass=-1):
         """raw[R,S,16] for points ro + rd*z (the fused kernel).  ref: nerf/train_utils.py:9-50."""
         lib = L.load()
+        if debug is None and frame_const is None and torch.is_grad_enabled() and \
+                any(p.requires_grad for p in self.parameters()):
+            from .train import field_train          # training: tapes + hand-written backward
+            return field_train(self, level, ro, rd, z, driving_vec, pose_code)
         st = self.packed_level(level)
         fc = frame_const if frame_const is not None else self.frame_constants(level, driving_vec, pose_code)
         ro, rd, z = L.f32c(ro), L.f32c(rd), L.f32c(z)

@@ -1,0 +1,206 @@
+"""Training path of the fused field: forward with tapes + hand-written activation-gradient chain (CUDA), weight
+gradients as GEMMs over the tapes.
+
+What the reference gets from autograd through WarpFieldMLP / HyperSheetMLP / NeRFMLP / grid_sample / the positional
+encodings (ref: nerf/modules.py:254-295, :371-390, :444-462, nerf/models.py:301-365) is produced here by
+  * `sahs_field_fwd_train`  -- the fused forward, additionally writing every layer's activated output (bf16,
+                               row-major "activation tape"), the activation sign masks and the warped point;
+  * `sahs_field_bwd`        -- the fused activation-gradient chain (tcgen05, transposed bf16 weights), writing every
+                               layer's dY to the "gradient tape" and scattering into the embedding-grid gradient;
+  * dW_l = dY_l^T X_{l-1}   -- plain GEMMs over column slices of the two tapes (torch.mm -> cuBLAS, the one place a
+                               library GEMM is used; a hand-written tcgen05 wgrad kernel is planned);
+  * the frame-constant input columns (driving 76 | pose code 36) were folded into biases in the forward, so their
+    weight gradient is the rank-1 product db x cvec and d(driving) = W_const^T db.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+
+from . import lib as L
+
+_LAYOUT_KEYS = ["tx_e0", "e0_k", "tx_wh", "whh", "w_layers", "tx_e1", "e1_k", "tx_th", "th", "t_layers", "tx_feat",
+                "tx_xtra", "tx_hh", "tx_total", "td_wh", "td_final", "td_th", "td_feat", "td_hh", "td_out", "td_total",
+                "n_mask_layers", "e0_dim", "e1_dim", "xtra_dim", "wh", "hh", "w_skip", "t_skip", "ct_off", "ct_len",
+                "use_w", "hd", "packed_t_bytes", "bwd_stages", "fc_total", "packed_train_bytes"]
+
+
+def train_layout(cspec) -> Dict[str, int]:
+    lib = L.load()
+    out = (C.c_int32 * 40)()
+    L.check(lib.sahs_train_layout(C.byref(cspec), out, 40), "train_layout")
+    return dict(zip(_LAYOUT_KEYS, list(out)))
+
+
+def _mm_t(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """dy^T @ x with fp32 accumulation and fp32 output (bf16 operands)."""
+    try:
+        return torch.mm(dy.t(), x, out_dtype=torch.float32)
+    except (TypeError, RuntimeError):
+        return torch.mm(dy.t().float(), x.float())
+
+
+class TrainState:
+    """Per-level packed images for training, rebuilt when parameters change (same keying as packed_level)."""
+
+    def __init__(self, model, level: str):
+        lib = L.load()
+        lvl = 0 if level == "coarse" else 1
+        st = model.packed_level(level)                      # inference image also gives the pointer table + grid
+        self.cspec, self.arr, self.params, self.grid = st["cspec"], st["arr"], st["params"], st["grid"]
+        self.key = st["key"]
+        self.lay = train_layout(self.cspec)
+        dev = st["packed"].device
+        self.packed_train = torch.empty(self.lay["packed_train_bytes"], dtype=torch.uint8, device=dev)
+        self.packed_t = torch.empty(self.lay["packed_t_bytes"], dtype=torch.uint8, device=dev)
+        s = L.stream_ptr(dev)
+        L.check(lib.sahs_pack_params_train(C.byref(self.cspec), lvl, self.arr, L.ptr(self.packed_train), s), "pack_train")
+        L.check(lib.sahs_pack_params_bwd(C.byref(self.cspec), lvl, self.arr, L.ptr(self.packed_t), s), "pack_bwd")
+
+
+def train_state(model, level: str) -> TrainState:
+    cache = model.__dict__.setdefault("_train_states", {})
+    st = model.packed_level(level)
+    ts = cache.get(level)
+    if ts is None or ts.key != st["key"]:
+        ts = TrainState(model, level)
+        cache[level] = ts
+    return ts
+
+
+class FieldTrainFn(torch.autograd.Function):
+    """raw = field(level, ro + rd z, rd; driving_vec, params).  Gradients: params of that level (incl. the shared
+    deformation nets and the embedding grid) and driving_vec."""
+
+    @staticmethod
+    def forward(ctx, model, level, ro, rd, z, driving_vec, pose_code, *params):
+        lib = L.load()
+        ts = train_state(model, level)
+        lay = ts.lay
+        lvl = 0 if level == "coarse" else 1
+        ro, rd, z = L.f32c(ro.detach()), L.f32c(rd.detach()), L.f32c(z.detach())
+        R, S = z.shape
+        P = R * S
+        dev = z.device
+        fc = model.frame_constants(level, driving_vec.detach(), pose_code.detach())
+        raw = torch.empty(R, S, 16, dtype=torch.float32, device=dev)
+        tape_x = torch.empty(P, lay["tx_total"], dtype=torch.bfloat16, device=dev)
+        masks = torch.empty(lay["n_mask_layers"], P, 2, 4, dtype=torch.int32, device=dev)
+        saves = torch.empty(P, 8, dtype=torch.float32, device=dev)
+        L.check(lib.sahs_field_fwd_train(C.byref(ts.cspec), lvl, L.ptr(ts.packed_train), L.ptr(fc), L.ptr(ts.grid),
+                                         L.ptr(ro), L.ptr(rd), L.ptr(z), R, S, L.ptr(raw), L.ptr(tape_x), L.ptr(masks),
+                                         L.ptr(saves), L.stream_ptr(dev)), "field_fwd_train")
+        ctx.model, ctx.level, ctx.ts = model, level, ts
+        ctx.save_for_backward(ro, rd, z, fc, tape_x, masks, saves, driving_vec.detach(), pose_code.detach())
+        return raw
+
+    @staticmethod
+    def backward(ctx, d_raw):
+        lib = L.load()
+        model, level, ts = ctx.model, ctx.level, ctx.ts
+        lay = ts.lay
+        lvl = 0 if level == "coarse" else 1
+        ro, rd, z, fc, tape_x, masks, saves, drv, pcode = ctx.saved_tensors
+        R, S = z.shape
+        P = R * S
+        dev = z.device
+        d_raw = L.f32c(d_raw)
+        tape_d = torch.zeros(P, lay["td_total"], dtype=torch.bfloat16, device=dev)
+        grid_grad = torch.zeros(32, 32, 32, 32, dtype=torch.float32, device=dev)
+        L.check(lib.sahs_field_bwd(C.byref(ts.cspec), lvl, L.ptr(ts.packed_t), L.ptr(fc), L.ptr(ts.grid), L.ptr(ro),
+                                   L.ptr(rd), L.ptr(z), R, S, L.ptr(d_raw), L.ptr(masks), L.ptr(saves), L.ptr(tape_d),
+                                   L.ptr(grid_grad), L.stream_ptr(dev)), "field_bwd")
+        grads, d_cvec = _weight_grads(model, level, lay, tape_x, tape_d, torch.cat((drv.reshape(-1), pcode.reshape(-1))))
+        grads[0] = grid_grad.permute(3, 0, 1, 2).unsqueeze(0).contiguous() if model.spec.use_grid else None
+        d_driving = d_cvec[:76].reshape(drv.shape)
+        return (None, None, None, None, None, d_driving, None) + tuple(grads)
+
+
+def _weight_grads(model, level, lay, tx, td, cvec):
+    """dW / db for every parameter in the canonical order of model._level_params(level)."""
+    s = model.spec
+    X = lambda off, w: tx[:, off:off + w]
+    D = lambda off, w: td[:, off:off + w]
+    d_cvec = torch.zeros(112, dtype=torch.float32, device=tx.device)
+    grads: List[Optional[torch.Tensor]] = [None]                 # slot 0: embedding grid (filled by the caller)
+
+    def layer(W, dY, parts, const=None):
+        """parts: list of (col0 in W, input slice); const: (col0, c_off, c_len) of the folded columns."""
+        dW = torch.zeros_like(W, dtype=torch.float32)
+        for col0, xin in parts:
+            dW[:, col0:col0 + xin.shape[1]] = _mm_t(dY, xin)
+        db = dY.sum(dim=0, dtype=torch.float32)
+        if const is not None:
+            col0, c_off, c_len = const
+            if c_len > 0:
+                dW[:, col0:col0 + c_len] = torch.outer(db, cvec[c_off:c_off + c_len])
+                d_cvec[c_off:c_off + c_len] += W[:, col0:col0 + c_len].float().t() @ db
+        grads.extend([dW, db])
+
+    wh, hh, whh = lay["wh"], lay["hh"], lay["whh"]
+    e0d, e1d = lay["e0_dim"], lay["e1_dim"]
+    if s.use_warp:
+        for name, lo, n, mod in (("warp", 0, wh, model.warp_field_mlp.layers_xyz),
+                                 ("hyper", wh, hh, model.hyper_sheep_mlp.layers_ambient)):
+            for i, lin in enumerate(mod):
+                dY = D(lay["td_wh"] + i * whh + lo, n)
+                e0 = X(lay["tx_e0"], e0d)
+                if i == 0:
+                    layer(lin.weight, dY, [(0, e0)], (e0d, 0, 112))
+                else:
+                    xin = X(lay["tx_wh"] + (i - 1) * whh + lo, n)
+                    if i == lay["w_skip"]:
+                        layer(lin.weight, dY, [(0, xin), (n, e0)], (n + e0d, 0, 112))
+                    else:
+                        layer(lin.weight, dY, [(0, xin)])
+            h5 = X(lay["tx_wh"] + (lay["w_layers"] - 1) * whh + lo, n)
+            if name == "warp":
+                dF = D(lay["td_final"], 3)
+                grads.extend([_mm_t(dF, h5), dF.sum(0, dtype=torch.float32)])
+            else:
+                dA = D(lay["td_final"] + 3, s.amb_dim)
+                grads.extend([_mm_t(dA, h5), dA.sum(0, dtype=torch.float32)])
+    m = model.nerf_mlps[level]
+    th, hd = lay["th"], lay["hd"]
+    e1 = X(lay["tx_e1"], e1d)
+    for i, lin in enumerate(m.layers_xyz):
+        dY = D(lay["td_th"] + i * th, th)
+        if i == 0:
+            layer(lin.weight, dY, [(0, e1)], (e1d, lay["ct_off"], lay["ct_len"]))
+        else:
+            xin = X(lay["tx_th"] + (i - 1) * th, th)
+            if i == lay["t_skip"]:
+                layer(lin.weight, dY, [(0, xin), (th, e1)], (th + e1d, lay["ct_off"], lay["ct_len"]))
+            else:
+                layer(lin.weight, dY, [(0, xin)])
+    feat = X(lay["tx_feat"], th)
+    layer(m.fc_feat.weight, D(lay["td_feat"], th), [(0, X(lay["tx_th"] + (lay["t_layers"] - 1) * th, th))])
+    dsig = D(lay["td_out"] + 15, 1)
+    grads.extend([_mm_t(dsig, feat), dsig.sum(0, dtype=torch.float32)])
+    xtra = X(lay["tx_xtra"], lay["xtra_dim"])
+    for i, lin in enumerate(m.layers_dir):
+        dY = D(lay["td_hh"] + i * 2 * hd, hd)
+        if i == 0:
+            layer(lin.weight, dY, [(0, feat), (th, xtra)])
+        else:
+            layer(lin.weight, dY, [(0, X(lay["tx_hh"] + (i - 1) * 2 * hd, hd))])
+    h3 = lay["tx_hh"] + 3 * 2 * hd
+    d_rgb = D(lay["td_out"], 3)
+    grads.extend([_mm_t(d_rgb, X(h3, hd)), d_rgb.sum(0, dtype=torch.float32)])
+    for i, lin in enumerate(m.layers_seg):
+        dY = D(lay["td_hh"] + i * 2 * hd + hd, hd)
+        if i == 0:
+            layer(lin.weight, dY, [(0, feat)])
+        else:
+            layer(lin.weight, dY, [(0, X(lay["tx_hh"] + (i - 1) * 2 * hd + hd, hd))])
+    d_seg = D(lay["td_out"] + 3, 12)
+    grads.extend([_mm_t(d_seg, X(h3 + hd, hd)), d_seg.sum(0, dtype=torch.float32)])
+    return grads, d_cvec
+
+
+def field_train(model, level, ro, rd, z, driving_vec, pose_code):
+    params = model._level_params(level)
+    live = [p if p is not None else torch.empty(0, device=z.device) for p in params]
+    return FieldTrainFn.apply(model, level, ro, rd, z, driving_vec, pose_code, *live)
