@@ -105,10 +105,10 @@ int sahs_field_fwd(const sahs_model_spec* spec, int level, const void* packed, c
 /* Layout of the training tapes for this spec (40 ints: tx_e0, e0_k, tx_wh, whh, w_layers, tx_e1, e1_k, tx_th, th,
  * t_layers, tx_feat, tx_xtra, tx_hh, tx_total, td_wh, td_final, td_th, td_feat, td_hh, td_out, td_total,
  * n_mask_layers, e0_dim, e1_dim, xtra_dim, wh, hh, w_skip, t_skip, ct_off, ct_len, use_w, hd, packed_t_bytes,
- * bwd_stages, fc_total, packed_train_bytes, 0, 0, 0).  Tapes are row-major bf16, one row per sample point:
+ * bwd_stages, fc_total, packed_train_bytes, 0, 0, 0).  Tapes are row-major fp16, one row per sample point:
  * activation tape [P, tx_total], gradient tape [P, td_total]; masks are [n_mask_layers][P][2] x 16 bytes; saves [P,8]. */
 int sahs_train_layout(const sahs_model_spec* spec, int32_t* out, int max_out);
-/* Packed forward image used by training (always the merged fp16 deformation phase) and the transposed bf16 image
+/* Packed forward image used by training (always the merged fp16 deformation phase) and the transposed fp16 image
  * consumed by sahs_field_bwd. */
 int sahs_pack_params_train(const sahs_model_spec* spec, int level, const float* const* params_host_array,
                            void* packed_out, void* stream);
@@ -119,12 +119,13 @@ int sahs_field_fwd_train(const sahs_model_spec* spec, int level, const void* pac
                          const float* grid_cl, const float* ro, const float* rd, const float* z, int num_rays,
                          int num_samples, float* raw_out, void* tape_x, void* masks, float* saves, void* stream);
 /* d raw[R,S,16] -> activation gradients of every layer (gradient tape) + scatter into the embedding-grid gradient
- * (channel-last fp32, accumulated atomically; may be NULL).  What autograd does for the reference modules
+ * (channel-last fp32, accumulated atomically; may be NULL).  `scale` (device scalar) multiplies d_raw so that the fp16
+ * gradient chain stays in range; the gradient tape and grid_grad carry that factor (the caller divides it out).  What autograd does for the reference modules
  * (nerf/modules.py:254-295, :371-390, :444-462, nerf/models.py:301-365); weight gradients are dY^T X over the tapes. */
 int sahs_field_bwd(const sahs_model_spec* spec, int level, const void* packed_t, const float* frame_const,
                    const float* grid_cl, const float* ro, const float* rd, const float* z, int num_rays,
-                   int num_samples, const float* d_raw, const void* masks, const float* saves, void* tape_d,
-                   float* grid_grad, void* stream);
+                   int num_samples, const float* d_raw, const float* scale, const void* masks, const float* saves,
+                   void* tape_d, float* grid_grad, void* stream);
 
 /* ---- (3) alpha compositing ---------------------------------------------------------------------- */
 /* volume_render_radiance_field, ref: nerf/volume_rendering_utils.py:7-78 (+ cumprod_exclusive,

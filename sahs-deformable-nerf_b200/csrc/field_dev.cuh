@@ -87,7 +87,7 @@ template <bool F16, int NUNITS, bool SPLIT = true>
 struct RowStream {
   uint8_t* rowp;   // X + row offset inside a chunk
   int chunk0, row, grp;
-  __nv_bfloat16* tape = nullptr;   // training: this row's slice of the activation tape (bf16, row-major)
+  __half* tape = nullptr;          // training: this row's slice of the activation tape (fp16, row-major)
   float buf[8];
   __device__ __forceinline__ RowStream(uint8_t* X, int chunk0_, int row_, int grp_)
       : rowp(X + (row_ >> 3) * 1024 + (row_ & 7) * 128), chunk0(chunk0_), row(row_), grp(grp_) {}
@@ -105,8 +105,8 @@ struct RowStream {
         *reinterpret_cast<uint4*>(rowp + (chunk0 + (u >> 3)) * kChunkBytes + ((((u & 7) ^ row) & 7) << 4)) = q;
         if (tape)
           *reinterpret_cast<uint4*>(tape + 8 * u) =
-              make_uint4(pack2<false>(buf[0], buf[1]), pack2<false>(buf[2], buf[3]), pack2<false>(buf[4], buf[5]),
-                         pack2<false>(buf[6], buf[7]));
+              make_uint4(pack2<true>(buf[0], buf[1]), pack2<true>(buf[2], buf[3]), pack2<true>(buf[4], buf[5]),
+                         pack2<true>(buf[6], buf[7]));
       }
     }
   }
@@ -170,7 +170,7 @@ __device__ __forceinline__ void load_bias(float4 (&b)[4], const float* __restric
 template <int ACT, bool F16, bool DOT, bool DBG, bool TRAIN = false>
 __device__ __forceinline__ void epi_block(uint32_t (&v)[16], float4 (&b)[4], const float* __restrict__ next_bias, int c0,
                                           uint8_t* rowp, int row, const float* __restrict__ dot_w, float& dot,
-                                          float* dbg_row, __nv_bfloat16* tape_row = nullptr, uint32_t* mbits = nullptr) {
+                                          float* dbg_row, __half* tape_row = nullptr, uint32_t* mbits = nullptr) {
   float f[16];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -181,7 +181,7 @@ __device__ __forceinline__ void epi_block(uint32_t (&v)[16], float4 (&b)[4], con
   }
   if (next_bias) load_bias(b, next_bias);
   if (TRAIN) {
-    // training: sign bits for the activation derivative and the activated values (bf16, row-major) for the wgrad
+    // training: sign bits for the activation derivative and the activated values (fp16, row-major) for the wgrad
     uint32_t bits = 0;
     uint32_t tp[8];
 #pragma unroll
@@ -190,7 +190,7 @@ __device__ __forceinline__ void epi_block(uint32_t (&v)[16], float4 (&b)[4], con
       bits |= (a0 > 0.f ? 1u : 0u) << (2 * j);
       bits |= (a1 > 0.f ? 1u : 0u) << (2 * j + 1);
       const float lk = ACT == ACT_LEAKY ? 0.01f : 0.f;
-      tp[j] = (ACT == ACT_NONE) ? pack2<false>(a0, a1) : pack2<false>(fmaxf(a0, lk * a0), fmaxf(a1, lk * a1));
+      tp[j] = (ACT == ACT_NONE) ? pack2<true>(a0, a1) : pack2<true>(fmaxf(a0, lk * a0), fmaxf(a1, lk * a1));
     }
     if (mbits) *mbits = bits;
     if (tape_row) {
@@ -231,7 +231,7 @@ __device__ __forceinline__ void epi_block(uint32_t (&v)[16], float4 (&b)[4], con
 template <int ACT, bool F16, bool DOT, bool DBG, int NBLK, bool TRAIN = false>
 __device__ __forceinline__ float epilogue(uint32_t tmem_row, int cbeg, const float* __restrict__ bias, float4 (&b)[4],
                                           uint8_t* X, int row, const float* __restrict__ dot_w, float* dbg_row,
-                                          __nv_bfloat16* tape_row = nullptr, uint4* mask_out = nullptr) {
+                                          __half* tape_row = nullptr, uint4* mask_out = nullptr) {
   float dot = 0.f;
   uint32_t mw[4] = {0u, 0u, 0u, 0u};
   uint8_t* rowp = X + (row >> 3) * 1024 + (row & 7) * 128;

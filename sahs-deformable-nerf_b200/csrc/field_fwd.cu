@@ -23,11 +23,11 @@
 
 namespace {
 
-// TRAIN: additionally records what the backward pass needs -- every layer's activated output (bf16, row-major
+// TRAIN: additionally records what the backward pass needs -- every layer's activated output (fp16, row-major
 // "activation tape" [P, dm.tx_total]), the sign bits of the pre-activations ([layer][P][2] x 128 bit) and the warped
 // point / ambient coordinates ([P,8] fp32).
 struct TrainOut {
-  __nv_bfloat16* tape_x;
+  __half* tape_x;
   uint4* masks;
   float* saves;
 };
@@ -91,7 +91,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       for (int k = 0; k < 3; ++k) pt[k] = __fadd_rn(ro[ray * 3 + k], __fmul_rn(dir[k], zz));
       float* dbg_row = (DBG && dbg && tile == 0) ? dbg + row * 256 : nullptr;
       // training tape slices of this row (null for padding rows of the last tile)
-      __nv_bfloat16* tape = (TRAIN && valid) ? tr.tape_x + p * dm.tx_total : nullptr;
+      __half* tape = (TRAIN && valid) ? tr.tape_x + p * dm.tx_total : nullptr;
       auto mask_slot = [&](int layer) -> uint4* {
         return (TRAIN && valid) ? tr.masks + ((size_t)layer * P + p) * 2 + grp : nullptr;
       };
@@ -210,7 +210,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
                 for (int q = 0; q < 4; ++q) hmask[blk] |= (h[q] > 0.f ? 1u : 0u) << (4 * j + q);
                 if (tape)
                   *reinterpret_cast<uint2*>(tape + dm.tx_wh + i * dm.whh + c0 + 4 * j) =
-                      make_uint2(pack2<false>(h[0], h[1]), pack2<false>(h[2], h[3]));
+                      make_uint2(pack2<true>(h[0], h[1]), pack2<true>(h[2], h[3]));
               }
               if (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) {
 #pragma unroll
@@ -328,10 +328,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
           const uint32_t pair = emb_pk[q >> 1];
           const uint16_t hv = (q & 1) ? (uint16_t)(pair >> 16) : (uint16_t)(pair & 0xffffu);
           *reinterpret_cast<uint16_t*>(rowp + ((((col >> 3) ^ row) & 7) << 4) + (col & 7) * 2) = hv;
-          if (TRAIN && tape) {   // bf16 copy of the embedding value for the wgrad of layers_dir.0
-            const __half hh = __ushort_as_half(hv);
-            tape[dm.tx_xtra + col] = __float2bfloat16_rn(__half2float(hh));
-          }
+          if (TRAIN && tape) tape[dm.tx_xtra + col] = __ushort_as_half(hv);   // for the wgrad of layers_dir.0
         }
       }
       signal_a(sy);
@@ -448,5 +445,5 @@ extern "C" int sahs_field_fwd_train(const sahs_model_spec* spec, int level, cons
                                     void* masks, float* saves, void* stream) {
   SAHS_CHECK_ARG(num_rays == 0 || (tape_x && masks && saves), "training buffers required");
   return field_fwd_impl(spec, level, packed_train, frame_const, grid_cl, ro, rd, z, num_rays, num_samples, raw_out,
-                        nullptr, -1, stream, true, TrainOut{(__nv_bfloat16*)tape_x, (uint4*)masks, saves});
+                        nullptr, -1, stream, true, TrainOut{(__half*)tape_x, (uint4*)masks, saves});
 }

@@ -277,7 +277,7 @@ int sahs_build_bwd_plan(const sahs_model_spec& s, const float* const* params, Ho
   ParamIndex pi;
   if (!index_params(s, pi)) return SAHS_EINVAL;
   Builder b{hp, params};
-  b.f16 = false;   // gradients and the transposed weights are bf16 (range), accumulation fp32
+  b.f16 = true;    // fp16 operands; the caller scales d_raw into fp16's range (see field_bwd.cu)
   hp.num_fold = 0;
   hp.num_copy = 0;
   const int CW = SAHS_DRIVING_DIM + SAHS_POSE_CODE_DIM;

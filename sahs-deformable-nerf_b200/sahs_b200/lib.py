@@ -68,7 +68,7 @@ def load() -> C.CDLL:
         "sahs_pack_params_train": (C.c_int, [spec_p, i32, C.POINTER(vp), vp, vp]),
         "sahs_pack_params_bwd": (C.c_int, [spec_p, i32, C.POINTER(vp), vp, vp]),
         "sahs_field_fwd_train": (C.c_int, [spec_p, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]),
-        "sahs_field_bwd": (C.c_int, [spec_p, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
+        "sahs_field_bwd": (C.c_int, [spec_p, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
         "sahs_field_status": (C.c_int, [C.POINTER(C.c_int)]),
     }
     for name, (res, args) in sigs.items():

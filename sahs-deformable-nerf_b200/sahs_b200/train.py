@@ -3,9 +3,9 @@ gradients as GEMMs over the tapes.
 
 What the reference gets from autograd through WarpFieldMLP / HyperSheetMLP / NeRFMLP / grid_sample / the positional
 encodings (ref: nerf/modules.py:254-295, :371-390, :444-462, nerf/models.py:301-365) is produced here by
-  * `sahs_field_fwd_train`  -- the fused forward, additionally writing every layer's activated output (bf16,
+  * `sahs_field_fwd_train`  -- the fused forward, additionally writing every layer's activated output (fp16,
                                row-major "activation tape"), the activation sign masks and the warped point;
-  * `sahs_field_bwd`        -- the fused activation-gradient chain (tcgen05, transposed bf16 weights), writing every
+  * `sahs_field_bwd`        -- the fused activation-gradient chain (tcgen05, transposed fp16 weights, scaled), writing every
                                layer's dY to the "gradient tape" and scattering into the embedding-grid gradient;
   * dW_l = dY_l^T X_{l-1}   -- plain GEMMs over column slices of the two tapes (torch.mm -> cuBLAS, the one place a
                                library GEMM is used; a hand-written tcgen05 wgrad kernel is planned, DESIGN.md section 8);
@@ -35,7 +35,7 @@ def train_layout(cspec) -> Dict[str, int]:
 
 
 def _mm_t(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """dy^T @ x with fp32 accumulation and fp32 output (bf16 operands)."""
+    """dy^T @ x with fp32 accumulation and fp32 output (fp16 operands)."""
     try:
         return torch.mm(dy.t(), x, out_dtype=torch.float32)
     except (TypeError, RuntimeError):
@@ -86,7 +86,7 @@ class FieldTrainFn(torch.autograd.Function):
         dev = z.device
         fc = model.frame_constants(level, driving_vec.detach(), pose_code.detach())
         raw = torch.empty(R, S, 16, dtype=torch.float32, device=dev)
-        tape_x = torch.empty(P, lay["tx_total"], dtype=torch.bfloat16, device=dev)
+        tape_x = torch.empty(P, lay["tx_total"], dtype=torch.float16, device=dev)
         masks = torch.empty(lay["n_mask_layers"], P, 2, 4, dtype=torch.int32, device=dev)
         saves = torch.empty(P, 8, dtype=torch.float32, device=dev)
         L.check(lib.sahs_field_fwd_train(C.byref(ts.cspec), lvl, L.ptr(ts.packed_train), L.ptr(fc), L.ptr(ts.grid),
@@ -107,13 +107,18 @@ class FieldTrainFn(torch.autograd.Function):
         P = R * S
         dev = z.device
         d_raw = L.f32c(d_raw)
-        tape_d = torch.zeros(P, lay["td_total"], dtype=torch.bfloat16, device=dev)
+        tape_d = torch.zeros(P, lay["td_total"], dtype=torch.float16, device=dev)
         grid_grad = torch.zeros(32, 32, 32, 32, dtype=torch.float32, device=dev)
+        # fp16 range management without a host sync: scale d_raw so that its largest entry is 16
+        scale = (16.0 / d_raw.abs().amax().clamp_min(1e-30)).reshape(1).float()
         L.check(lib.sahs_field_bwd(C.byref(ts.cspec), lvl, L.ptr(ts.packed_t), L.ptr(fc), L.ptr(ts.grid), L.ptr(ro),
-                                   L.ptr(rd), L.ptr(z), R, S, L.ptr(d_raw), L.ptr(masks), L.ptr(saves), L.ptr(tape_d),
-                                   L.ptr(grid_grad), L.stream_ptr(dev)), "field_bwd")
+                                   L.ptr(rd), L.ptr(z), R, S, L.ptr(d_raw), L.ptr(scale), L.ptr(masks), L.ptr(saves),
+                                   L.ptr(tape_d), L.ptr(grid_grad), L.stream_ptr(dev)), "field_bwd")
         grads, d_cvec = _weight_grads(model, level, lay, tape_x, tape_d, torch.cat((drv.reshape(-1), pcode.reshape(-1))))
-        grads[0] = grid_grad.permute(3, 0, 1, 2).unsqueeze(0).contiguous() if model.spec.use_grid else None
+        inv = 1.0 / scale
+        grads = [g * inv if g is not None else None for g in grads]
+        d_cvec = d_cvec * inv
+        grads[0] = (grid_grad * inv).permute(3, 0, 1, 2).unsqueeze(0).contiguous() if model.spec.use_grid else None
         d_driving = d_cvec[:76].reshape(drv.shape)
         return (None, None, None, None, None, d_driving, None) + tuple(grads)
 
