@@ -24,6 +24,8 @@ gout = torch.randn(n, 16, generator=gen) * 1e-3
 sd_ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
 raw, inter = O.field_forward(sd_ref, spec, "fine", xyz, dirs, drv, fr["pose"], return_intermediates=True)
 inter["mapped"].retain_grad(); inter["amb"].retain_grad(); inter["emb"].retain_grad(); inter["dx"].retain_grad()
+for k, v in inter.items():
+    if v.requires_grad and not v.is_leaf: v.retain_grad()
 (raw * gout).sum().backward()
 dmap_ref = inter["mapped"].grad
 # ours
@@ -39,7 +41,25 @@ pcode = model.pose_code(fr["pose"].to(DEV))
 raw_g = model.field("fine", xyz.to(DEV), dirs.to(DEV), z0, drv.to(DEV).requires_grad_(True), pcode)
 (raw_g.reshape(n, 16) * gout.to(DEV)).sum().backward()
 torch.cuda.synchronize()
-lay, td = stash["lay"], stash["td"].float().cpu()
+scale = 16.0 / float(gout.abs().max())
+lay, td = stash["lay"], stash["td"].float().cpu() / scale
+def cmp(name, ours, ref):
+    a, b = ours.double().reshape(-1), ref.double().reshape(-1)
+    print(f"  {name:10s} cos {float((a*b).sum()/(a.norm()*b.norm()+1e-30)):.5f} ratio {float(a.norm()/(b.norm()+1e-30)):.4f}")
+lk = lambda h: torch.where(h > 0, torch.ones_like(h), torch.full_like(h, 0.01))
+rl = lambda h: (h > 0).float()
+print("per-layer d(pre-activation): ours (tape) vs oracle autograd")
+for i in range(3, -1, -1):
+    ref = torch.cat((inter[f"dir{i}"].grad * lk(inter[f"dir{i}"]), inter[f"seg{i}"].grad * lk(inter[f"seg{i}"])), 1).detach()
+    cmp(f"head{i}", td[:, lay["td_hh"] + i*256: lay["td_hh"] + (i+1)*256], ref)
+cmp("feat", td[:, lay["td_feat"]:lay["td_feat"]+256], inter["feat"].grad)
+for i in range(7, -1, -1):
+    h = inter[f"trunk{i}"]
+    cmp(f"trunk{i}", td[:, lay["td_th"] + i*256: lay["td_th"] + (i+1)*256], (h.grad * lk(h)).detach())
+for i in range(5, -1, -1):
+    hw, hh = inter[f"warp{i}"], inter[f"hyper{i}"]
+    ref = torch.cat(((hw.grad * rl(hw)), (hh.grad * rl(hh))), 1).detach()
+    cmp(f"warp|hyp{i}", td[:, lay["td_wh"] + i*192: lay["td_wh"] + (i+1)*192], ref)
 dpre = td[:, lay["td_final"]:lay["td_final"] + 3]
 damb = td[:, lay["td_final"] + 3:lay["td_final"] + 5]
 t = inter["dx"].detach()
