@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--config", default="audio/person_2_auto")
     ap.add_argument("--cpu-rays", type=int, default=2048, help="rays per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -298,6 +299,57 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * R * args.steps / float(e2e_s)
 
+    # ------------------------------ training step (BASELINE config 3) ----------------------------
+    train = None
+    if not args.no_train:
+        from sahs_b200 import parallel as PL
+        cfg_t = FX.load_cfg(args.config)                     # shipped stochastic settings: perturb, noise 0.1
+        nrays = int(cfg_t.nerf.train.num_random_rays)
+        tmodel = getattr(sahs_b200.models, cfg_t.models.mask.type)(cfg_t)
+        tmodel.load_state_dict(sd)
+        tmodel = tmodel.to(dev)
+        opt = torch.optim.Adam(tmodel.parameters(), lr=float(cfg_t.optimizer.lr))
+        f0 = dev_frames[0]
+        ro_all, rd_all = f0["ro"].reshape(-1, 3), f0["rd"].reshape(-1, 3)
+        maskf = f0["mask"].view(-1, 12).float()
+        gen = torch.Generator(device=dev).manual_seed(42 + rank)
+        target_all = torch.rand(R, 3, device=dev, generator=gen)
+        sample_prob = torch.ones(12, device=dev)
+
+        def train_step():
+            nonlocal sample_prob
+            probs = (maskf * sample_prob).sum(-1)            # semantic-weighted ray batch (train script :390-420)
+            sel = torch.multinomial(probs / probs.sum(), nrays, replacement=False, generator=gen)
+            out = sahs_b200.run_one_iter_of_nerf(H, W, 1200.0, tmodel, ro_all[sel], rd_all[sel], cfg_t, mode="train",
+                                                 driving=f0["driving"], pose=f0["pose"], background_prior=bg_dev[sel],
+                                                 inHead=f0["mask"].view(-1, 12)[sel])
+            loss, sample_prob = sahs_b200.stage1_loss(out[0], out[3], target_all[sel], maskf[sel])
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            PL.allreduce_gradients([p for p in tmodel.parameters()])
+            opt.step()
+            return loss
+
+        for _ in range(3):
+            train_step()
+        barrier()
+        l0 = lib.sahs_launch_count()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(args.steps):
+            last = train_step()
+        a1.record()
+        barrier()
+        tms = torch.tensor([a0.elapsed_time(a1)], device=dev)
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        tms_step = float(tms) / args.steps
+        train = {"metric": "train_rays_per_s", "value": world * nrays / (tms_step / 1e3), "unit": "rays/s",
+                 "ms_per_step": tms_step, "rays_per_step_per_gpu": nrays, "loss": float(last),
+                 "our_kernel_launches_per_step": int((lib.sahs_launch_count() - l0) / args.steps),
+                 "what": "fwd + bwd + grad all-reduce + Adam, semantic-weighted batch, perturb + noise 0.1; weight "
+                         "gradients are cuBLAS GEMMs over the tapes (library), everything else hand-written"}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rps, dt, cores = cpu_port_rays_per_s(args.config, args.cpu_rays)
@@ -308,7 +360,7 @@ def main():
         line = {
             "metric": "render_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "dtype": "f16", "data": "synthetic",
             "config": {"workload": f"Stage-I 512x512 render (BASELINE config 2), {args.config}, 64 coarse + 128 fine "
                                    "samples/ray, deterministic sampling", "rays_per_step_per_gpu": R,
                        "weights": "random-init dense fixture (seed 42)", "parallelism": f"frames over {world} GPU(s)",
@@ -317,6 +369,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_frame": 1e3 * float(e2e_s) / args.steps},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+            "train": train,
         }
         print(json.dumps(line))
     if world > 1:
