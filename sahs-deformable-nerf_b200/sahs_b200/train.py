@@ -107,7 +107,7 @@ class FieldTrainFn(torch.autograd.Function):
         P = R * S
         dev = z.device
         d_raw = L.f32c(d_raw)
-        tape_d = torch.zeros(P, lay["td_total"], dtype=torch.float16, device=dev)
+        tape_d = torch.empty(P, lay["td_total"], dtype=torch.float16, device=dev)   # every column is written by the kernel
         grid_grad = torch.zeros(32, 32, 32, 32, dtype=torch.float32, device=dev)
         # fp16 range management without a host sync: scale d_raw so that its largest entry is 16
         scale = (16.0 / d_raw.abs().amax().clamp_min(1e-30)).reshape(1).float()
@@ -130,13 +130,17 @@ def _weight_grads(model, level, lay, tx, td, cvec):
     D = lambda off, w: td[:, off:off + w]
     d_cvec = torch.zeros(112, dtype=torch.float32, device=tx.device)
     grads: List[Optional[torch.Tensor]] = [None]                 # slot 0: embedding grid (filled by the caller)
+    db_all = td.sum(dim=0, dtype=torch.float32)                  # every bias gradient in one pass over the tape
+    DB = lambda off, w: db_all[off:off + w]
 
-    def layer(W, dY, parts, const=None):
-        """parts: list of (col0 in W, input slice); const: (col0, c_off, c_len) of the folded columns."""
+    def layer(W, dyo, n, parts, const=None):
+        """dyo/n: column offset and width of dY in the gradient tape; parts: list of (col0 in W, input slice);
+        const: (col0, c_off, c_len) of the folded columns."""
+        dY = D(dyo, n)
         dW = torch.zeros_like(W, dtype=torch.float32)
         for col0, xin in parts:
             dW[:, col0:col0 + xin.shape[1]] = _mm_t(dY, xin)
-        db = dY.sum(dim=0, dtype=torch.float32)
+        db = DB(dyo, n)
         if const is not None:
             col0, c_off, c_len = const
             if c_len > 0:
@@ -150,58 +154,53 @@ def _weight_grads(model, level, lay, tx, td, cvec):
         for name, lo, n, mod in (("warp", 0, wh, model.warp_field_mlp.layers_xyz),
                                  ("hyper", wh, hh, model.hyper_sheep_mlp.layers_ambient)):
             for i, lin in enumerate(mod):
-                dY = D(lay["td_wh"] + i * whh + lo, n)
+                dyo = lay["td_wh"] + i * whh + lo
                 e0 = X(lay["tx_e0"], e0d)
                 if i == 0:
-                    layer(lin.weight, dY, [(0, e0)], (e0d, 0, 112))
+                    layer(lin.weight, dyo, n, [(0, e0)], (e0d, 0, 112))
                 else:
                     xin = X(lay["tx_wh"] + (i - 1) * whh + lo, n)
                     if i == lay["w_skip"]:
-                        layer(lin.weight, dY, [(0, xin), (n, e0)], (n + e0d, 0, 112))
+                        layer(lin.weight, dyo, n, [(0, xin), (n, e0)], (n + e0d, 0, 112))
                     else:
-                        layer(lin.weight, dY, [(0, xin)])
+                        layer(lin.weight, dyo, n, [(0, xin)])
             h5 = X(lay["tx_wh"] + (lay["w_layers"] - 1) * whh + lo, n)
             if name == "warp":
-                dF = D(lay["td_final"], 3)
-                grads.extend([_mm_t(dF, h5), dF.sum(0, dtype=torch.float32)])
+                grads.extend([_mm_t(D(lay["td_final"], 3), h5), DB(lay["td_final"], 3)])
             else:
-                dA = D(lay["td_final"] + 3, s.amb_dim)
-                grads.extend([_mm_t(dA, h5), dA.sum(0, dtype=torch.float32)])
+                grads.extend([_mm_t(D(lay["td_final"] + 3, s.amb_dim), h5), DB(lay["td_final"] + 3, s.amb_dim)])
     m = model.nerf_mlps[level]
     th, hd = lay["th"], lay["hd"]
     e1 = X(lay["tx_e1"], e1d)
     for i, lin in enumerate(m.layers_xyz):
-        dY = D(lay["td_th"] + i * th, th)
+        dyo = lay["td_th"] + i * th
         if i == 0:
-            layer(lin.weight, dY, [(0, e1)], (e1d, lay["ct_off"], lay["ct_len"]))
+            layer(lin.weight, dyo, th, [(0, e1)], (e1d, lay["ct_off"], lay["ct_len"]))
         else:
             xin = X(lay["tx_th"] + (i - 1) * th, th)
             if i == lay["t_skip"]:
-                layer(lin.weight, dY, [(0, xin), (th, e1)], (th + e1d, lay["ct_off"], lay["ct_len"]))
+                layer(lin.weight, dyo, th, [(0, xin), (th, e1)], (th + e1d, lay["ct_off"], lay["ct_len"]))
             else:
-                layer(lin.weight, dY, [(0, xin)])
+                layer(lin.weight, dyo, th, [(0, xin)])
     feat = X(lay["tx_feat"], th)
-    layer(m.fc_feat.weight, D(lay["td_feat"], th), [(0, X(lay["tx_th"] + (lay["t_layers"] - 1) * th, th))])
-    dsig = D(lay["td_out"] + 15, 1)
-    grads.extend([_mm_t(dsig, feat), dsig.sum(0, dtype=torch.float32)])
+    layer(m.fc_feat.weight, lay["td_feat"], th, [(0, X(lay["tx_th"] + (lay["t_layers"] - 1) * th, th))])
+    grads.extend([_mm_t(D(lay["td_out"] + 15, 1), feat), DB(lay["td_out"] + 15, 1)])
     xtra = X(lay["tx_xtra"], lay["xtra_dim"])
     for i, lin in enumerate(m.layers_dir):
-        dY = D(lay["td_hh"] + i * 2 * hd, hd)
+        dyo = lay["td_hh"] + i * 2 * hd
         if i == 0:
-            layer(lin.weight, dY, [(0, feat), (th, xtra)])
+            layer(lin.weight, dyo, hd, [(0, feat), (th, xtra)])
         else:
-            layer(lin.weight, dY, [(0, X(lay["tx_hh"] + (i - 1) * 2 * hd, hd))])
+            layer(lin.weight, dyo, hd, [(0, X(lay["tx_hh"] + (i - 1) * 2 * hd, hd))])
     h3 = lay["tx_hh"] + 3 * 2 * hd
-    d_rgb = D(lay["td_out"], 3)
-    grads.extend([_mm_t(d_rgb, X(h3, hd)), d_rgb.sum(0, dtype=torch.float32)])
+    grads.extend([_mm_t(D(lay["td_out"], 3), X(h3, hd)), DB(lay["td_out"], 3)])
     for i, lin in enumerate(m.layers_seg):
-        dY = D(lay["td_hh"] + i * 2 * hd + hd, hd)
+        dyo = lay["td_hh"] + i * 2 * hd + hd
         if i == 0:
-            layer(lin.weight, dY, [(0, feat)])
+            layer(lin.weight, dyo, hd, [(0, feat)])
         else:
-            layer(lin.weight, dY, [(0, X(lay["tx_hh"] + (i - 1) * 2 * hd + hd, hd))])
-    d_seg = D(lay["td_out"] + 3, 12)
-    grads.extend([_mm_t(d_seg, X(h3 + hd, hd)), d_seg.sum(0, dtype=torch.float32)])
+            layer(lin.weight, dyo, hd, [(0, X(lay["tx_hh"] + (i - 1) * 2 * hd + hd, hd))])
+    grads.extend([_mm_t(D(lay["td_out"] + 3, 12), X(h3 + hd, hd)), DB(lay["td_out"] + 3, 12)])
     return grads, d_cvec
 
 
