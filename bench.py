@@ -176,6 +176,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = L.load()
     warmup = max(args.warmup, 3)
@@ -345,7 +346,7 @@ def main():
             dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         tms_step = float(tms) / args.steps
         train = {"metric": "train_rays_per_s", "value": world * nrays / (tms_step / 1e3), "unit": "rays/s",
-                 "ms_per_step": tms_step, "rays_per_step_per_gpu": nrays, "loss": float(last),
+                 "ms_per_step": tms_step, "rays_per_step_per_gpu": nrays, "loss": float(last.detach()),
                  "our_kernel_launches_per_step": int((lib.sahs_launch_count() - l0) / args.steps),
                  "what": "fwd + bwd + grad all-reduce + Adam, semantic-weighted batch, perturb + noise 0.1; weight "
                          "gradients are cuBLAS GEMMs over the tapes (library), everything else hand-written"}
