@@ -127,6 +127,14 @@ int sahs_field_bwd(const sahs_model_spec* spec, int level, const void* packed_t,
                    int num_samples, const float* d_raw, const float* scale, const void* masks, const float* saves,
                    void* tape_d, float* grid_grad, void* stream);
 
+/* dW_l = dY_l^T X_{l-1} and db_l = sum_p dY_l for every layer, accumulated (atomically) into the caller's
+ * zero-initialised fp32 gradient buffers `grads_host_array` (device pointers in the canonical parameter order; entry 0,
+ * the embedding grid, is not touched).  Reads the two tapes with TMA tensor loads.  The frame-constant input columns
+ * of folded layers are left untouched (their gradient is the rank-1 product db x cvec).  `units_workspace`: >= 256 KB
+ * of device memory.  Results carry the `scale` factor of sahs_field_bwd. */
+int sahs_field_wgrad(const sahs_model_spec* spec, int level, float* const* grads_host_array, const void* tape_x,
+                     const void* tape_d, int num_points, void* units_workspace, size_t workspace_bytes, void* stream);
+
 /* ---- (3) alpha compositing ---------------------------------------------------------------------- */
 /* volume_render_radiance_field, ref: nerf/volume_rendering_utils.py:7-78 (+ cumprod_exclusive,
  * nerf/nerf_helpers.py:99-120) fused with the background overwrite raw[:, -1, :-1] = background_prior

@@ -392,12 +392,14 @@ int launch_field(const HostPlan& hp, const void* packed, const float* fc, const 
 }  // namespace
 
 int sahs_bwd_status_internal(int* out4_host);
+int sahs_wgrad_status_internal(int* out4_host);
 
 extern "C" int sahs_field_status(int* out4_host) {
   SAHS_CUDA(cudaMemcpyFromSymbol(out4_host, g_field_status, sizeof(int) * 4));
   if (out4_host[0] == 0) {   // forward healthy: report the backward kernel's word
     int b[4] = {0, 0, 0, 0};
     if (sahs_bwd_status_internal(b) == 0 && b[0] != 0) memcpy(out4_host, b, sizeof(b));
+    else if (sahs_wgrad_status_internal(b) == 0 && b[0] != 0) memcpy(out4_host, b, sizeof(b));
   }
   return SAHS_OK;
 }

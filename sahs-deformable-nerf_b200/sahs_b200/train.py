@@ -7,8 +7,9 @@ encodings (ref: nerf/modules.py:254-295, :371-390, :444-462, nerf/models.py:301-
                                row-major "activation tape"), the activation sign masks and the warped point;
   * `sahs_field_bwd`        -- the fused activation-gradient chain (tcgen05, transposed fp16 weights, scaled), writing every
                                layer's dY to the "gradient tape" and scattering into the embedding-grid gradient;
-  * dW_l = dY_l^T X_{l-1}   -- plain GEMMs over column slices of the two tapes (torch.mm -> cuBLAS, the one place a
-                               library GEMM is used; a hand-written tcgen05 wgrad kernel is planned, DESIGN.md section 8);
+  * `sahs_field_wgrad`      -- dW_l = dY_l^T X_{l-1} and db_l for every layer: tcgen05 GEMMs fed by TMA tensor loads of
+                               the two tapes, accumulators in TMEM across a tile range, red.global.add into fp32 grads
+                               (SAHS_WGRAD=library switches to torch.mm over tape slices, kept for cross-checking);
   * the frame-constant input columns (driving 76 | pose code 36) were folded into biases in the forward, so their
     weight gradient is the rank-1 product db x cvec and d(driving) = W_const^T db.
 """
@@ -32,6 +33,11 @@ def train_layout(cspec) -> Dict[str, int]:
     out = (C.c_int32 * 40)()
     L.check(lib.sahs_train_layout(C.byref(cspec), out, 40), "train_layout")
     return dict(zip(_LAYOUT_KEYS, list(out)))
+
+
+import os
+
+USE_LIBRARY_WGRAD = os.environ.get("SAHS_WGRAD", "kernel") == "library"
 
 
 def _mm_t(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
@@ -114,13 +120,62 @@ class FieldTrainFn(torch.autograd.Function):
         L.check(lib.sahs_field_bwd(C.byref(ts.cspec), lvl, L.ptr(ts.packed_t), L.ptr(fc), L.ptr(ts.grid), L.ptr(ro),
                                    L.ptr(rd), L.ptr(z), R, S, L.ptr(d_raw), L.ptr(scale), L.ptr(masks), L.ptr(saves),
                                    L.ptr(tape_d), L.ptr(grid_grad), L.stream_ptr(dev)), "field_bwd")
-        grads, d_cvec = _weight_grads(model, level, lay, tape_x, tape_d, torch.cat((drv.reshape(-1), pcode.reshape(-1))))
+        cvec = torch.cat((drv.reshape(-1), pcode.reshape(-1)))
+        if USE_LIBRARY_WGRAD:
+            grads, d_cvec = _weight_grads(model, level, lay, tape_x, tape_d, cvec)
+        else:
+            grads, d_cvec = _weight_grads_kernel(model, level, ts, lay, tape_x, tape_d, cvec, P)
         inv = 1.0 / scale
         grads = [g * inv if g is not None else None for g in grads]
         d_cvec = d_cvec * inv
         grads[0] = (grid_grad * inv).permute(3, 0, 1, 2).unsqueeze(0).contiguous() if model.spec.use_grid else None
         d_driving = d_cvec[:76].reshape(drv.shape)
         return (None, None, None, None, None, d_driving, None) + tuple(grads)
+
+
+def _weight_grads_kernel(model, level, ts, lay, tx, td, cvec, P):
+    """Hand-written wgrad: one kernel accumulates dW/db of every layer; the folded frame-constant columns are the
+    rank-1 products db x cvec (and d cvec = W_const^T db)."""
+    lib = L.load()
+    params = model._level_params(level)
+    dev = tx.device
+    grads: List[Optional[torch.Tensor]] = [None if p is None else torch.zeros_like(p, dtype=torch.float32) for p in params]
+    arr = (C.c_void_p * len(grads))()
+    for i, g in enumerate(grads):
+        arr[i] = g.data_ptr() if g is not None else None
+    ws = model.__dict__.setdefault("_wgrad_ws", None)
+    if ws is None or ws.device != dev:
+        ws = torch.empty(256 * 1024, dtype=torch.uint8, device=dev)
+        model.__dict__["_wgrad_ws"] = ws
+    L.check(lib.sahs_field_wgrad(C.byref(ts.cspec), 0 if level == "coarse" else 1, arr, L.ptr(tx), L.ptr(td), P,
+                                 L.ptr(ws), ws.numel(), L.stream_ptr(dev)), "field_wgrad")
+    d_cvec = torch.zeros(112, dtype=torch.float32, device=dev)
+    s = model.spec
+    e0d, e1d, wh, hh, th = lay["e0_dim"], lay["e1_dim"], lay["wh"], lay["hh"], lay["th"]
+
+    def fold(w_param, w_grad, b_grad, col0, c_off, c_len):
+        if c_len <= 0:
+            return
+        w_grad[:, col0:col0 + c_len] = torch.outer(b_grad, cvec[c_off:c_off + c_len])
+        d_cvec[c_off:c_off + c_len] += w_param[:, col0:col0 + c_len].detach().float().t() @ b_grad
+
+    k = 1
+    if s.use_warp:
+        for n in (wh, hh):
+            for i in range(lay["w_layers"]):
+                if i == 0:
+                    fold(params[k], grads[k], grads[k + 1], e0d, 0, 112)
+                elif i == lay["w_skip"]:
+                    fold(params[k], grads[k], grads[k + 1], n + e0d, 0, 112)
+                k += 2
+            k += 2                                   # fc_final / fc_ambient
+    for i in range(lay["t_layers"]):
+        if i == 0:
+            fold(params[k], grads[k], grads[k + 1], e1d, lay["ct_off"], lay["ct_len"])
+        elif i == lay["t_skip"]:
+            fold(params[k], grads[k], grads[k + 1], th + e1d, lay["ct_off"], lay["ct_len"])
+        k += 2
+    return grads, d_cvec
 
 
 def _weight_grads(model, level, lay, tx, td, cvec):
