@@ -348,8 +348,8 @@ def main():
         train = {"metric": "train_rays_per_s", "value": world * nrays / (tms_step / 1e3), "unit": "rays/s",
                  "ms_per_step": tms_step, "rays_per_step_per_gpu": nrays, "loss": float(last.detach()),
                  "our_kernel_launches_per_step": int((lib.sahs_launch_count() - l0) / args.steps),
-                 "what": "fwd + bwd + grad all-reduce + Adam, semantic-weighted batch, perturb + noise 0.1; weight "
-                         "gradients are cuBLAS GEMMs over the tapes (library), everything else hand-written"}
+                 "what": "fwd + bwd (hand-written compositing, dgrad-chain and wgrad kernels) + grad all-reduce + Adam, "
+                         "semantic-weighted batch of 2048 rays per GPU, perturb + noise 0.1"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
