@@ -166,6 +166,13 @@ int sahs_sample_pdf_merge(const float* z, const float* weights, const float* u, 
 int sahs_sample_pdf(const float* bins, const float* weights, const float* u, int u_per_ray, int num_rays,
                     int num_bins, int num_fine, float* samples, int64_t* inds, void* stream);
 
+/* ---- frame post-processing (the step after the path: what the eval script writes / Stage II consumes) ----------- */
+/* rgb_map[R,15] -> uint8 rgb [R,3] (clamp, *255, truncate; ref: eval_stage_rays.py:221-227), argmax semantic label [R]
+ * and its palette colour [R,3] in the reference's reversed channel order (ref: nerf/utils.py:112-140).  label_u8 and
+ * seg_color_u8 may be NULL. */
+int sahs_frame_postprocess(const float* map15, int64_t num_rays, uint8_t* rgb_u8, uint8_t* label_u8,
+                           uint8_t* seg_color_u8, void* stream);
+
 /* Diagnostic word written by the field kernel when a bounded mbarrier wait times out (0 = healthy):
  * out4_host[0] code, [1] tag, [2] block, [3] thread.  Synchronous (device -> host copy). */
 int sahs_field_status(int* out4_host);

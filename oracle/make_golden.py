@@ -225,11 +225,30 @@ def helpers_case(nerf, name):
                         rd=_np(rd), x=_np(x), pose_code=_np(code_ref), **out)
 
 
+def postprocess_case(nerf, name):
+    """label2color (ref: nerf/utils.py:112-140) and the ToPILImage conversion used by cast_to_image
+    (ref: eval_stage_rays.py:221-227)."""
+    import torchvision
+    from nerf import utils as ref_utils
+    g = torch.Generator().manual_seed(9)
+    m = torch.rand(37, 23, 15, generator=g) * 1.4 - 0.2
+    m[..., 3:] = torch.softmax(torch.randn(37, 23, 12, generator=g) * 3, -1)
+    col_ref = (ref_utils.label2color(m[..., 3:]) * 255).round().to(torch.uint8)
+    img_ref = torch.from_numpy(np.array(torchvision.transforms.ToPILImage()(m[..., :3].permute(2, 0, 1).clamp(0.0, 1.0))))
+    rgb, label, col = O.frame_postprocess(m)
+    assert torch.equal(col, col_ref) and torch.equal(rgb, img_ref)
+    assert torch.equal(label.long(), torch.argmax(m[..., 3:], -1))
+    print(f"[{name}] frame post-processing: exact")
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), map=_np(m), ref_rgb=_np(img_ref), ref_color=_np(col_ref),
+                        ref_label=_np(label))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     nerf = RH.import_reference()
     helpers_case(nerf, "helpers")
+    postprocess_case(nerf, "postprocess")
     sample_pdf_case(nerf, "sample_pdf_2048", 2048, 11)
     composite_case(nerf, "composite_bg", 256, 64, 21, True, False)
     composite_case(nerf, "composite_nobg_white", 100, 128, 22, False, True)

@@ -445,3 +445,17 @@ def run_one_iter(sd, spec: ModelSpec, opts: RenderOpts, ray_origins, ray_directi
         outs.append(render_rays(sd, spec, opts, ro[i:i + chunk_rays], rd[i:i + chunk_rays], drv, pose, bg,
                                 **{k: (v[i:i + chunk_rays] if v is not None else None) for k, v in draws.items()}))
     return tuple(torch.cat(parts, 0) for parts in zip(*outs))
+
+
+# ---- frame post-processing (what the eval script writes) ------------------------------------------------------
+_SEG_PALETTE = [[0, 0, 0], [204, 0, 0], [76, 153, 0], [204, 204, 0], [51, 51, 255], [0, 255, 255], [102, 51, 0],
+                [102, 204, 0], [255, 255, 0], [0, 0, 204], [255, 153, 51], [0, 204, 0]]
+
+
+def frame_postprocess(rgb_map: torch.Tensor):
+    """uint8 rgb (clamp, *255, truncate: torchvision ToPILImage on a float tensor, ref: eval_stage_rays.py:221-227),
+    argmax label and reversed-channel palette colour (ref: nerf/utils.py:112-140)."""
+    rgb = (rgb_map[..., :3].clamp(0.0, 1.0) * 255).to(torch.uint8)
+    label = torch.argmax(rgb_map[..., 3:], dim=-1)
+    pal = torch.tensor([c[::-1] for c in _SEG_PALETTE], dtype=torch.uint8)
+    return rgb, label.to(torch.uint8), pal[label]

@@ -133,6 +133,21 @@ def sample_pdf_bins(bins, weights, num_fine: int, u: Optional[torch.Tensor] = No
     return (out, inds) if return_inds else out
 
 
+def frame_postprocess(rgb_map: torch.Tensor):
+    """[..., 15] composited map -> (rgb uint8 [...,3], label uint8 [...], palette colour uint8 [...,3]).
+    ref: eval_stage_rays.py:221-227 (cast_to_image), nerf/utils.py:112-140 (label2color)."""
+    lib = L.load()
+    m = L.f32c(rgb_map)
+    shp = m.shape[:-1]
+    n = m.numel() // MAP_CH
+    rgb = torch.empty(*shp, 3, dtype=torch.uint8, device=m.device)
+    lab = torch.empty(*shp, dtype=torch.uint8, device=m.device)
+    col = torch.empty(*shp, 3, dtype=torch.uint8, device=m.device)
+    L.check(lib.sahs_frame_postprocess(L.ptr(m), n, L.ptr(rgb), L.ptr(lab), L.ptr(col), L.stream_ptr(m.device)),
+            "frame_postprocess")
+    return rgb, lab, col
+
+
 def field_status():
     lib = L.load()
     out = (C.c_int * 4)()

@@ -83,6 +83,17 @@ def test_coarse_depths_bit_exact(sahs, lindisp):
     assert torch.equal(z.cpu(), O.coarse_z(opts, 37, tr))
 
 
+def test_frame_postprocess_bit_exact(sahs):
+    g = load("postprocess")
+    rgb, label, col = sahs.frame_postprocess(G(g["map"]))
+    assert torch.equal(rgb.cpu(), C(g["ref_rgb"])) and torch.equal(label.cpu(), C(g["ref_label"]))
+    assert torch.equal(col.cpu(), C(g["ref_color"]))
+    big = torch.rand(512, 512, 15, device=DEV)
+    r2, l2, c2 = sahs.frame_postprocess(big)
+    ro, lo, co = O.frame_postprocess(big.cpu())
+    assert torch.equal(r2.cpu(), ro) and torch.equal(l2.cpu(), lo) and torch.equal(c2.cpu(), co)
+
+
 # ------------------------------------------------------------------------------------------------------
 # (4) sample_pdf + merge: bit-exact indices when fed the reference's weights
 # ------------------------------------------------------------------------------------------------------

@@ -37,6 +37,12 @@ def test_sample_pdf_golden_bit_exact():
     assert torch.equal(zm, T(g["ref_z_merged"]))
 
 
+def test_postprocess_golden():
+    g = load("postprocess")
+    rgb, label, col = O.frame_postprocess(T(g["map"]))
+    assert torch.equal(rgb, T(g["ref_rgb"])) and torch.equal(col, T(g["ref_color"])) and torch.equal(label, T(g["ref_label"]))
+
+
 @pytest.mark.parametrize("name", ["composite_bg", "composite_nobg_white"])
 def test_composite_golden(name):
     g = load(name)
