@@ -174,7 +174,8 @@ int sahs_frame_postprocess(const float* map15, int64_t num_rays, uint8_t* rgb_u8
                            uint8_t* seg_color_u8, void* stream);
 
 /* Diagnostic word written by the field kernel when a bounded mbarrier wait times out (0 = healthy):
- * out4_host[0] code, [1] tag, [2] block, [3] thread.  Synchronous (device -> host copy). */
+ * out4_host[0] code (+100 dgrad kernel, +200 wgrad kernel), [1] tag, [2] block, [3] thread.  The words live in mapped
+ * host memory, so this works (and issues no CUDA call) after a kernel trapped. */
 int sahs_field_status(int* out4_host);
 
 /* Host-only plan introspection for the CPU test-suite (no device work); layouts documented in field_host.cu
@@ -188,6 +189,7 @@ int sahs_debug_plan(const sahs_model_spec* spec, int param_count, int32_t* stage
 #define SAHS_DBG_MAPPED 16              /* cols 0-2 mapped xyz, 3.. ambient, 8..39 grid feature         */
 #define SAHS_DBG_TRUNK(i) (32 + (i))    /* trunk layer i; i == trunk_layers is fc_feat                  */
 #define SAHS_DBG_HEAD(i) (64 + (i))     /* cols 0-127 dir hidden i, 128-255 seg hidden i                */
+#define SAHS_DBG_PROF 99                /* debug buffer receives (tag, clock64) event pairs of one tile */
 
 #ifdef __cplusplus
 }

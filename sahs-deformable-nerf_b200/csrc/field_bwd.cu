@@ -167,7 +167,10 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
   uint64_t* acc_ready = bars + 2 * kSlots + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kSlots + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the role dispatch convergent and
+  // the MMA issue loop on the uniform datapath (with the plain threadIdx.x >> 5 every tcgen05 instruction below gets a
+  // divergence guard + R2UR moves with scoreboard waits, ~4x slower issue)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const long long ntiles = (P + kTileRows - 1) / kTileRows;
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) { status[0] = 2; __trap(); }
@@ -372,8 +375,8 @@ int launch_bwd(const HostPlan& hp, const void* packed_t, const float* fc, const 
                const float* rd, const float* z, int R, int S, BwdIO io, cudaStream_t st) {
   auto kfn = field_bwd_kernel<C>;
   SAHS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-  int* status = nullptr;
-  SAHS_CUDA(cudaGetSymbolAddress((void**)&status, g_field_status));
+  int* status = sahs_status_words(1);
+  SAHS_CHECK_ARG(status, "cannot allocate the diagnostic word");
   const long long P = (long long)R * S;
   const long long ntiles = (P + kTileRows - 1) / kTileRows;
   long long grid_dim = 2LL * sahs_num_sms();
@@ -386,9 +389,6 @@ int launch_bwd(const HostPlan& hp, const void* packed_t, const float* fc, const 
 
 }  // namespace
 
-int sahs_bwd_status_internal(int* out4_host) {
-  return cudaMemcpyFromSymbol(out4_host, g_field_status, sizeof(int) * 4) == cudaSuccess ? 0 : -1;
-}
 
 extern "C" int sahs_field_bwd(const sahs_model_spec* spec, int level, const void* packed_t, const float* frame_const,
                               const float* grid_cl, const float* ro, const float* rd, const float* z, int num_rays,

@@ -16,29 +16,53 @@ constexpr bool kTrunkF16 = true;   // operand format of trunk and heads (fp16: 8
 constexpr int kSmemX = 4 * kChunkBytes;                       // 64 KB
 constexpr int kSmemSlots = kSlots * kStageSlotBytes;          // 48 KB
 constexpr int kSmemBar = kSmemX + kSmemSlots;                 // barriers after the tiles
-constexpr int kSmemXchg = kSmemBar + 128;                     // 128 floats exchanged between the two groups
+constexpr int kSmemXchg = kSmemBar + 256;                     // 128 floats exchanged between the two groups
 constexpr int kSmemTotal = kSmemXchg + 512;
-
-__device__ int g_field_status[4];
+// CTA-pair variant (cluster of 2, tcgen05 cta_group::2): every CTA holds half of each weight stage (N/2 rows), so the
+// same 48 KB ring is twice as deep and the L2 -> SM weight traffic per point is halved.
+constexpr int kPairSlots = 6;
+constexpr int kPairSlotBytes = kStageSlotBytes / 2;
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
 
-struct Sync {
+template <bool PAIR>
+struct SyncT {
   uint64_t* a_ready;
   uint64_t* acc_ready;
   uint32_t acc_par;
   int* status;
+  uint32_t a_leader;   // PAIR: shared::cluster address of the leader CTA's a_ready barrier
+  long long* prof = nullptr;   // debug builds: (tag, clock64) event pairs of one tile iteration
 };
+__device__ __forceinline__ void prof_event(long long*& prof, long long tag) {
+  if (prof) {
+    prof[0] = tag;
+    prof[1] = clock64();
+    prof += 2;
+  }
+}
+using Sync = SyncT<false>;
 
-__device__ __forceinline__ void signal_a(Sync& sy) {
+// "my part of the A operand is written" -> MMA issuer.  Single CTA: every worker thread arrives.  Pair: every thread
+// fences its own writes, one lane per warp arrives on the leader CTA's barrier (8 warps x 2 CTAs).
+template <bool PAIR>
+__device__ __forceinline__ void signal_a(SyncT<PAIR>& sy) {
   fence_proxy_async_smem();
   tc_fence_before();
-  mbar_arrive(sy.a_ready);
+  if (PAIR) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive_cluster(sy.a_leader);
+  } else {
+    mbar_arrive(sy.a_ready);
+  }
+  prof_event(sy.prof, 1);
 }
-__device__ __forceinline__ void wait_acc(Sync& sy, int tag) {
+template <bool PAIR>
+__device__ __forceinline__ void wait_acc(SyncT<PAIR>& sy, int tag) {
   mbar_wait(sy.acc_ready, sy.acc_par, sy.status, tag);
   sy.acc_par ^= 1;
   tc_fence_after();
+  prof_event(sy.prof, 100000 + tag);
 }
 __device__ __forceinline__ void group_sync() {  // the 256 worker threads only
   asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -403,13 +427,17 @@ struct FieldCfg {
 // ---- warp-role loops shared by the forward and backward kernels ------------------------------------------------
 // TMA producer: streams the packed stage images of `plan` once per tile through the slot ring.
 __device__ __forceinline__ void tma_warp_loop(const FieldPlan& plan, const uint8_t* __restrict__ packed, uint8_t* slots,
-                                              uint64_t* full, uint64_t* empty, long long ntiles, int* status, int lane) {
+                                              uint64_t* full, uint64_t* empty, long long ntiles, int* status, int lane,
+                                              long long* prof_base = nullptr) {
   uint32_t slot = 0, phase = 0;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  int iter = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
     uint32_t off = 0;
+    long long* prof = (prof_base && iter == 2 && lane == 0) ? prof_base : nullptr;
     for (int st = 0; st < plan.num_stages; ++st) {
       const uint32_t bytes = (uint32_t)plan.st[st].n8 * 1024u;
       mbar_wait(&empty[slot], phase ^ 1, status, 100);
+      prof_event(prof, 40000 + st);
       if (lane == 0) {
         mbar_arrive_expect_tx(&full[slot], bytes);
         tma_bulk_g2s(slots + slot * kStageSlotBytes, packed + off, bytes, &full[slot]);
@@ -421,42 +449,145 @@ __device__ __forceinline__ void tma_warp_loop(const FieldPlan& plan, const uint8
   }
 }
 
-// MMA issuer: one thread issues tcgen05.mma for every stage; passes are delimited by the a_ready / acc_ready barriers.
-__device__ __forceinline__ void mma_warp_loop(const FieldPlan& plan, uint8_t* X, uint8_t* slots, uint64_t* full,
-                                              uint64_t* empty, uint64_t* a_ready, uint64_t* acc_ready, uint32_t tmem_base,
-                                              long long ntiles, int* status, int lane) {
+// MMA issuer.  All 32 lanes of the warp run the loop converged on warp-uniform values; every tcgen05 instruction is
+// guarded by elect.sync and the barrier waits spin inside asm (mbar_wait_uniform).  ptxas then keeps the whole loop on
+// the uniform datapath (LDCU / UPRMT / UTCHMMA / UTCBAR back to back, no R2UR, no per-thread election loops).  Issued
+// from an `if (lane == 0)` region instead, every tcgen05 instruction is wrapped in an election loop whose back-branch
+// waits for the instruction's operand read: the issuer then runs in lock step with the tensor pipe (measured ~1000
+// cycles per 4-MMA stage instead of 256).  Passes are delimited by the a_ready / acc_ready barriers.
+template <bool PAIR, bool PROF>
+__device__ __forceinline__ void mma_issue_loop(const FieldPlan& plan, uint8_t* X, uint8_t* slots, uint64_t* full,
+                                               uint64_t* pfull, uint64_t* empty, uint64_t* a_ready, uint64_t* acc_ready,
+                                               uint32_t tmem_base, long long first, long long count, long long step,
+                                               int* status, long long* prof_base) {
+  constexpr uint32_t NS = PAIR ? kPairSlots : kSlots;
+  constexpr uint32_t SLOT_BYTES = PAIR ? kPairSlotBytes : kStageSlotBytes;
   uint32_t slot = 0, phase = 0, a_par = 0;
-  const uint32_t x_addr = smem_u32(X), s_addr = smem_u32(slots);
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  const uint64_t a_base = umma_smem_desc_sw128(smem_u32(X));
+  const uint64_t b_base = umma_smem_desc_sw128(smem_u32(slots));
+  int iter = 0;
+  for (long long it = first; it < count; it += step, ++iter) {
+    long long* prof = (PROF && prof_base && iter == 2 && (threadIdx.x & 31) == 0) ? prof_base : nullptr;
     for (int st = 0; st < plan.num_stages; ++st) {
       const StageRec r = plan.st[st];
       const uint32_t flags = r.kflags >> 3, ksteps = r.kflags & 7;
       if (flags & ST_WAIT_A) {
-        mbar_wait(a_ready, a_par, status, 200 + st);
+        mbar_wait_uniform<PAIR>(a_ready, a_par, status, 200 + st);
         a_par ^= 1;
+        if (PROF) prof_event(prof, 10000 + st);
       }
-      mbar_wait(&full[slot], phase, status, 400 + st);
+      mbar_wait_uniform<false>(&full[slot], phase, status, 400 + st);
+      if (PROF) prof_event(prof, 20000 + st);
+      if (PAIR) {
+        mbar_wait_uniform<true>(&pfull[slot], phase, status, 600 + st);
+        if (PROF) prof_event(prof, 25000 + st);
+      }
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t idesc = umma_idesc_m128((uint32_t)r.n8 * 8u, (flags & ST_F16) != 0);
-        const uint64_t a0 = umma_smem_desc_sw128(x_addr + r.a_chunk * kChunkBytes);
-        const uint64_t b0 = umma_smem_desc_sw128(s_addr + slot * kStageSlotBytes);
-        const uint32_t d = tmem_base + (uint32_t)r.d_col8 * 8u;
-        for (uint32_t k = 0; k < ksteps; ++k) {
-          // advancing K by 16 elements = 32 bytes = 2 descriptor address units inside the 128B swizzle atom
-          tc_mma_bf16(d, a0 + 2 * k, b0 + 2 * k, idesc, (k > 0 || !(flags & ST_FRESH)) ? 1u : 0u);
+      const uint32_t n = (uint32_t)r.n8 * 8u;
+      const bool f16 = (flags & ST_F16) != 0;
+      const uint32_t idesc = PAIR ? umma_idesc_m256(n, f16) : umma_idesc_m128(n, f16);
+      // descriptor address field counts 16-byte units; K advances 16 elements = 32 bytes = 2 units per MMA
+      const uint64_t a0 = a_base + (uint64_t)(r.a_chunk * (kChunkBytes >> 4));
+      const uint64_t b0 = b_base + (uint64_t)(slot * (SLOT_BYTES >> 4));
+      const uint32_t d = tmem_base + (uint32_t)r.d_col8 * 8u;
+      const uint32_t acc0 = (flags & ST_FRESH) ? 0u : 1u;
+      auto mma = [&](uint64_t a, uint64_t b, uint32_t acc) {
+        if (elect_one()) {
+          if (PAIR) tc_mma_pair(d, a, b, idesc, acc);
+          else tc_mma_bf16(d, a, b, idesc, acc);
         }
-        if (r.a_chunk2 != 0xFF) {   // split precision: the residual (lo) activations times the same weights
-          const uint64_t a1 = umma_smem_desc_sw128(x_addr + r.a_chunk2 * kChunkBytes);
-          for (uint32_t k = 0; k < ksteps; ++k) tc_mma_bf16(d, a1 + 2 * k, b0 + 2 * k, idesc, 1u);
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (elect_one()) {
+          if (PAIR) tc_commit_pair(bar);
+          else tc_commit(bar);
         }
-        tc_commit(&empty[slot]);
-        if (flags & ST_COMMIT) tc_commit(acc_ready);
+      };
+      mma(a0, b0, acc0);
+      if (ksteps > 1) mma(a0 + 2, b0 + 2, 1u);
+      if (ksteps > 2) mma(a0 + 4, b0 + 4, 1u);
+      if (ksteps > 3) mma(a0 + 6, b0 + 6, 1u);
+      if (r.a_chunk2 != 0xFF) {   // split precision: the residual (lo) activations times the same weights
+        const uint64_t a1 = a_base + (uint64_t)(r.a_chunk2 * (kChunkBytes >> 4));
+        mma(a1, b0, 1u);
+        if (ksteps > 1) mma(a1 + 2, b0 + 2, 1u);
+        if (ksteps > 2) mma(a1 + 4, b0 + 4, 1u);
+        if (ksteps > 3) mma(a1 + 6, b0 + 6, 1u);
       }
-      __syncwarp();
-      if (++slot == kSlots) { slot = 0; phase ^= 1; }
+      commit(&empty[slot]);
+      if (flags & ST_COMMIT) commit(acc_ready);
+      if (PROF) prof_event(prof, 30000 + st);
+      if (++slot == NS) { slot = 0; phase ^= 1; }
     }
   }
+}
+
+template <bool PROF = false>
+__device__ __forceinline__ void mma_warp_loop(const FieldPlan& plan, uint8_t* X, uint8_t* slots, uint64_t* full,
+                                              uint64_t* empty, uint64_t* a_ready, uint64_t* acc_ready, uint32_t tmem_base,
+                                              long long ntiles, int* status, int lane, long long* prof_base = nullptr) {
+  mma_issue_loop<false, PROF>(plan, X, slots, full, nullptr, empty, a_ready, acc_ready, tmem_base, blockIdx.x, ntiles,
+                              gridDim.x, status, prof_base);
+}
+
+// ---- CTA-pair variants ------------------------------------------------------------------------------------
+// Tile schedule: cluster c processes tile pairs c, c + nclusters, ...; CTA `rank` of the pair owns tile 2*pair + rank.
+// TMA producer of one CTA: its half (rows [rank*n/2, (rank+1)*n/2)) of every stage.
+__device__ __forceinline__ void tma_warp_loop_pair(const FieldPlan& plan, const uint8_t* __restrict__ packed,
+                                                   uint8_t* slots, uint64_t* full, uint64_t* empty, long long npairs,
+                                                   uint32_t rank, int* status, int lane, long long* prof_base = nullptr) {
+  uint32_t slot = 0, phase = 0;
+  int iter = 0;
+  const long long pt0 = cluster_id_x(), pt_step = cluster_num_x();
+  for (long long pt = pt0; pt < npairs; pt += pt_step, ++iter) {
+    uint32_t off = 0;
+    long long* prof = (prof_base && iter == 2 && lane == 0) ? prof_base : nullptr;
+    for (int st = 0; st < plan.num_stages; ++st) {
+      const uint32_t half = (uint32_t)plan.st[st].n8 * 512u;
+      mbar_wait_cluster(&empty[slot], phase ^ 1, status, 100);
+      prof_event(prof, 40000 + st);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full[slot], half);
+        tma_bulk_g2s(slots + slot * kPairSlotBytes, packed + off + rank * half, half, &full[slot]);
+      }
+      __syncwarp();
+      off += 2 * half;
+      if (++slot == kPairSlots) { slot = 0; phase ^= 1; }
+    }
+  }
+}
+
+// Peer CTA (rank 1): forwards "my half of the stage has landed" to the leader's pfull barriers.
+__device__ __forceinline__ void relay_warp_loop_pair(const FieldPlan& plan, uint64_t* full, uint64_t* pfull,
+                                                     long long npairs, int* status, int lane) {
+  uint32_t slot = 0, phase = 0;
+  uint32_t remote[kPairSlots];
+#pragma unroll
+  for (int i = 0; i < kPairSlots; ++i) remote[i] = mapa_u32(&pfull[i], 0);
+  const long long pt0 = cluster_id_x(), pt_step = cluster_num_x();
+  for (long long pt = pt0; pt < npairs; pt += pt_step) {
+    for (int st = 0; st < plan.num_stages; ++st) {
+      mbar_wait(&full[slot], phase, status, 500 + st);
+      if (lane == 0) {
+        uint32_t r = remote[0];
+#pragma unroll
+        for (int i = 1; i < kPairSlots; ++i) r = (slot == (uint32_t)i) ? remote[i] : r;
+        mbar_arrive_cluster(r);
+      }
+      __syncwarp();
+      if (++slot == kPairSlots) { slot = 0; phase ^= 1; }
+    }
+  }
+}
+
+// Leader CTA (rank 0): issues the M=256 MMAs of the pair.
+template <bool PROF = false>
+__device__ __forceinline__ void mma_warp_loop_pair(const FieldPlan& plan, uint8_t* X, uint8_t* slots, uint64_t* full,
+                                                   uint64_t* pfull, uint64_t* empty, uint64_t* a_ready,
+                                                   uint64_t* acc_ready, uint32_t tmem_base, long long npairs, int* status,
+                                                   int lane, long long* prof_base = nullptr) {
+  mma_issue_loop<true, PROF>(plan, X, slots, full, pfull, empty, a_ready, acc_ready, tmem_base, cluster_id_x(), npairs,
+                             cluster_num_x(), status, prof_base);
 }
 
 }  // namespace

@@ -17,6 +17,7 @@
 // finer), accumulation is fp32 in TMEM; dx, ambient and sigma heads are evaluated in fp32.  With more than 10
 // encoding octaves the deformation phase runs in split precision (fp16 hi + lo operands, ~fp32 accuracy) because
 // the encoding of the warped point amplifies its error by 2^(L-1).
+#include <stdlib.h>
 #include <string.h>
 #include "field_dev.cuh"
 
@@ -32,7 +33,7 @@ struct TrainOut {
   float* saves;
 };
 
-template <class C, bool DBG, bool TRAIN>
+template <class C, bool DBG, bool TRAIN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 2)
 field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__ NetDims dm,
                  const uint8_t* __restrict__ packed, const float* __restrict__ fc, const float* __restrict__ grid,
@@ -43,43 +44,95 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
   uint8_t* X = smem;
   uint8_t* slots = smem + kSmemX;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
-  uint64_t* full = bars;               // [kSlots]
-  uint64_t* empty = bars + kSlots;     // [kSlots]
-  uint64_t* a_ready = bars + 2 * kSlots;
-  uint64_t* acc_ready = bars + 2 * kSlots + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kSlots + 2);
+  constexpr int NS = PAIR ? kPairSlots : kSlots;
+  uint64_t* full = bars;               // [NS]
+  uint64_t* empty = bars + NS;         // [NS]
+  uint64_t* a_ready = bars + 2 * NS;
+  uint64_t* acc_ready = bars + 2 * NS + 1;
+  uint64_t* pfull = bars + 2 * NS + 2; // [NS], PAIR leader only: the peer's halves of the stages have landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * NS + 2);
+  uint32_t* peer_tmem = tmem_ptr + 1;  // PAIR: the peer reports its TMEM base here (must equal the leader's)
   float* xchg = reinterpret_cast<float*>(smem + kSmemXchg);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the role dispatch convergent and
+  // the MMA issue loop on the uniform datapath (with the plain threadIdx.x >> 5 every tcgen05 instruction below gets a
+  // divergence guard + R2UR moves with scoreboard waits, ~4x slower issue)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const long long ntiles = (P + kTileRows - 1) / kTileRows;
+  const long long npairs = (ntiles + 1) / 2;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) {  // UMMA 128B swizzle needs 1024-byte aligned tiles
       status[0] = 2;
       __trap();
     }
-    for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(a_ready, kWorkerThreads);
+    for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    if (PAIR) {
+      for (int i = 0; i < NS; ++i) mbar_init(&pfull[i], 1);
+      mbar_init(a_ready, 2 * (kWorkerThreads / 32));   // one arrival per worker warp of both CTAs
+    } else {
+      mbar_init(a_ready, kWorkerThreads);
+    }
     mbar_init(acc_ready, 1);
     fence_mbar_init();
   }
-  if (warp == kMmaWarp) tmem_alloc(tmem_ptr, kTmemCols);
+  if (warp == kMmaWarp) {
+    if (PAIR) tmem_alloc_pair(tmem_ptr, kTmemCols);
+    else tmem_alloc(tmem_ptr, kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (PAIR) {
+    // barriers of both CTAs are initialised before anything arrives remotely; the pair's accumulators must sit at
+    // the same TMEM columns in both SMs
+    if (rank == 1 && threadIdx.x == 0) st_cluster_u32(mapa_u32(peer_tmem, 0), tmem_base);
+    cluster_sync_all();
+    if (rank == 0 && threadIdx.x == 0 && *peer_tmem != tmem_base) {
+      status[0] = 3;
+      status[1] = (int)tmem_base;
+      status[2] = (int)*peer_tmem;
+      __threadfence_system();
+      __trap();
+    }
+    __syncthreads();   // reconverge after the single-thread check (keeps the role loops below warp-uniform)
+  }
 
+  // debug builds, dbg_pass == SAHS_DBG_PROF: block 0 records (tag, clock64) event pairs of its third tile into dbg,
+  // 4096 long longs per role: worker thread 0, worker thread 255, MMA issuer, TMA producer
+  long long* prof_buf = (DBG && dbg && dbg_pass == SAHS_DBG_PROF && blockIdx.x == 0) ? reinterpret_cast<long long*>(dbg)
+                                                                                      : nullptr;
   if (warp == kTmaWarp) {
-    tma_warp_loop(plan, packed, slots, full, empty, ntiles, status, lane);
+    long long* pb = prof_buf ? prof_buf + 3 * 4096 : nullptr;
+    if (PAIR) tma_warp_loop_pair(plan, packed, slots, full, empty, npairs, rank, status, lane, pb);
+    else tma_warp_loop(plan, packed, slots, full, empty, ntiles, status, lane, pb);
   } else if (warp == kMmaWarp) {
-    mma_warp_loop(plan, X, slots, full, empty, a_ready, acc_ready, tmem_base, ntiles, status, lane);
+    long long* pb = prof_buf ? prof_buf + 2 * 4096 : nullptr;
+    if (!PAIR) mma_warp_loop<DBG>(plan, X, slots, full, empty, a_ready, acc_ready, tmem_base, ntiles, status, lane, pb);
+    else if (rank == 0) mma_warp_loop_pair<DBG>(plan, X, slots, full, pfull, empty, a_ready, acc_ready, tmem_base, npairs, status, lane, pb);
+    else relay_warp_loop_pair(plan, full, pfull, npairs, status, lane);
   } else {
     // ================================ workers ===================================================
-    Sync sy{a_ready, acc_ready, 0u, status};
+    SyncT<PAIR> sy{a_ready, acc_ready, 0u, status, PAIR ? mapa_u32(a_ready, 0) : 0u};
     const int row = threadIdx.x & (kTileRows - 1);
     const int grp = threadIdx.x >> 7;
     const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // PAIR: `it` walks tile pairs and this CTA owns tile 2*it + rank (possibly past the end: all rows masked)
+    const long long it_end = PAIR ? npairs : ntiles;
+    const long long it_step = PAIR ? (long long)cluster_num_x() : (long long)gridDim.x;
+    int iter = 0;
+    const long long it0 = PAIR ? (long long)cluster_id_x() : (long long)blockIdx.x;
+    for (long long it = it0; it < it_end; it += it_step, ++iter) {
+      const long long tile = PAIR ? 2 * it + rank : it;
+      if (DBG) {
+        sy.prof = nullptr;
+        if (prof_buf && iter == 2 && (threadIdx.x == 0 || threadIdx.x == 255)) {
+          sy.prof = prof_buf + (threadIdx.x == 0 ? 0 : 4096);
+          prof_event(sy.prof, 2);   // tile start
+        }
+      }
       const long long p = tile * kTileRows + row;
       const bool valid = p < P;
       const long long pc = valid ? p : P - 1;
@@ -361,48 +414,72 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       }
       tc_fence_before();
       group_sync();   // xchg[] consumed before the next tile's fc_feat epilogue rewrites it
+      if (DBG) prof_event(sy.prof, 3);   // tile end
     }
   }
+  tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's smem / TMEM / barriers stay alive until both CTAs are done
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
+}
+
+// SAHS_FIELD_PAIR=0 selects the single-CTA kernel (A/B measurements); default is the CTA-pair kernel.
+static bool field_pair_enabled() {
+  const char* e = getenv("SAHS_FIELD_PAIR");
+  return !(e && e[0] == '0');
 }
 
 template <class C>
 int launch_field(const HostPlan& hp, const void* packed, const float* fc, const float* grid, const float* ro,
                  const float* rd, const float* z, int R, int S, float* raw, float* dbg, int dbg_pass,
                  cudaStream_t st, TrainOut tr = TrainOut{nullptr, nullptr, nullptr}) {
-  auto kfn = tr.tape_x ? field_fwd_kernel<C, false, true>
-                       : ((dbg != nullptr) ? field_fwd_kernel<C, true, false> : field_fwd_kernel<C, false, false>);
-  SAHS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
-  int* status = nullptr;
-  SAHS_CUDA(cudaGetSymbolAddress((void**)&status, g_field_status));
+  int* status = sahs_status_words(0);
+  SAHS_CHECK_ARG(status, "cannot allocate the diagnostic word");
   const long long P = (long long)R * S;
   const long long ntiles = (P + kTileRows - 1) / kTileRows;
+  const uint8_t* pk = (const uint8_t*)packed;
+  const bool prof = dbg != nullptr && dbg_pass == SAHS_DBG_PROF;
+  if (!tr.tape_x && (!dbg || prof) && field_pair_enabled()) {
+    // CTA pairs: clusters of 2, two clusters resident per SM pair
+    auto kfn = prof ? field_fwd_kernel<C, true, false, true> : field_fwd_kernel<C, false, false, true>;
+    SAHS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    const long long npairs = (ntiles + 1) / 2;
+    long long nclusters = sahs_num_sms();           // 2 CTAs per SM = one cluster per SM on average
+    if (nclusters > npairs) nclusters = npairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * nclusters));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemTotal;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    SAHS_CUDA(cudaLaunchKernelEx(&cfg, kfn, hp.plan, hp.dims, pk, fc, grid, ro, rd, z, S, P, raw, dbg, dbg_pass,
+                                 status, tr));
+    SAHS_LAUNCH_CHECK();
+    return SAHS_OK;
+  }
+  auto kfn = tr.tape_x ? field_fwd_kernel<C, false, true, false>
+                       : ((dbg != nullptr) ? field_fwd_kernel<C, true, false, false>
+                                           : field_fwd_kernel<C, false, false, false>);
+  SAHS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
   long long grid_dim = 2LL * sahs_num_sms();
   if (grid_dim > ntiles) grid_dim = ntiles;
-  kfn<<<(unsigned)grid_dim, kThreads, kSmemTotal, st>>>(hp.plan, hp.dims, (const uint8_t*)packed, fc, grid, ro, rd, z, S,
+  kfn<<<(unsigned)grid_dim, kThreads, kSmemTotal, st>>>(hp.plan, hp.dims, pk, fc, grid, ro, rd, z, S,
                                                        P, raw, dbg, dbg_pass, status, tr);
   SAHS_LAUNCH_CHECK();
   return SAHS_OK;
 }
 
 }  // namespace
-
-int sahs_bwd_status_internal(int* out4_host);
-int sahs_wgrad_status_internal(int* out4_host);
-
-extern "C" int sahs_field_status(int* out4_host) {
-  SAHS_CUDA(cudaMemcpyFromSymbol(out4_host, g_field_status, sizeof(int) * 4));
-  if (out4_host[0] == 0) {   // forward healthy: report the backward kernel's word
-    int b[4] = {0, 0, 0, 0};
-    if (sahs_bwd_status_internal(b) == 0 && b[0] != 0) memcpy(out4_host, b, sizeof(b));
-    else if (sahs_wgrad_status_internal(b) == 0 && b[0] != 0) memcpy(out4_host, b, sizeof(b));
-  }
-  return SAHS_OK;
-}
 
 static int field_fwd_impl(const sahs_model_spec* spec, int level, const void* packed, const float* frame_const,
                           const float* grid_cl, const float* ro, const float* rd, const float* z, int num_rays,

@@ -39,7 +39,6 @@ struct WUnit {
   WOut g[2];
 };
 
-__device__ int g_wgrad_status[4];
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
   asm volatile(
@@ -73,7 +72,10 @@ field_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   uint64_t* acc_full = bars + 2 * kWStages;
   uint64_t* acc_empty = bars + 2 * kWStages + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kWStages + 2);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the role dispatch convergent and
+  // the MMA issue loop on the uniform datapath (with the plain threadIdx.x >> 5 every tcgen05 instruction below gets a
+  // divergence guard + R2UR moves with scoreboard waits, ~4x slower issue)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) { status[0] = 2; __trap(); }
@@ -117,35 +119,36 @@ field_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
     }
   } else if (warp == 1) {
     // ================= MMA: D[128, 64 nB (+16)] += dY^T [X | 1] over the tile range =================
+    // whole warp converged, waits spin inside asm, elect.sync per instruction: the loop stays on the uniform datapath
     uint32_t stage = 0, phase = 0, acc_par = 0;
     int done = 0;
+    const uint64_t o0 = umma_smem_desc_mn_sw128(smem_u32(ones));
     for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
-      const WUnit& un = units[u];
+      const int t0 = units[u].t0, t1 = units[u].t1, nB = units[u].nB;
       if (done > 0) {   // the previous unit's accumulator must be drained
-        mbar_wait(acc_empty, acc_par, status, 300);
+        mbar_wait_uniform<false>(acc_empty, acc_par, status, 300);
         acc_par ^= 1;
         tc_fence_after();
       }
-      const uint32_t nmain = (uint32_t)un.nB * 64u;
-      for (int t = un.t0; t < un.t1; ++t) {
-        mbar_wait(&full[stage], phase, status, 400);
+      const uint32_t nmain = (uint32_t)nB * 64u;
+      const uint32_t id_main = umma_idesc_mn_f16_m128(nmain), id_one = umma_idesc_mn_f16_m128(16);
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait_uniform<false>(&full[stage], phase, status, 400);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t base = smem_u32(smem + stage * kWStageBytes);
-          const uint64_t a0 = umma_smem_desc_mn_sw128(base);
-          const uint64_t b0 = umma_smem_desc_mn_sw128(base + 2 * kChunkBytes);
-          const uint64_t o0 = umma_smem_desc_mn_sw128(smem_u32(ones));
-          const uint32_t id_main = umma_idesc_mn_f16_m128(nmain), id_one = umma_idesc_mn_f16_m128(16);
-#pragma unroll 1
-          for (uint32_t k = 0; k < 8; ++k) {   // 16 points per step = 2 KB down the panel
-            const uint32_t acc = (t > un.t0 || k > 0) ? 1u : 0u;
-            tc_mma_bf16(tmem_base, a0 + k * 128, b0 + k * 128, id_main, acc);
-            tc_mma_bf16(tmem_base + nmain, a0 + k * 128, o0 + k * 128, id_one, acc);
-          }
-          tc_commit(&empty[stage]);
-          if (t == un.t1 - 1) tc_commit(acc_full);
+        const uint32_t base = smem_u32(smem + stage * kWStageBytes);
+        const uint64_t a0 = umma_smem_desc_mn_sw128(base);
+        const uint64_t b0 = umma_smem_desc_mn_sw128(base + 2 * kChunkBytes);
+        const uint32_t acc_first = (t > t0) ? 1u : 0u;
+#pragma unroll
+        for (uint32_t k = 0; k < 8; ++k) {   // 16 points per step = 2 KB down the panel
+          const uint32_t acc = k > 0 ? 1u : acc_first;
+          if (elect_one()) tc_mma_bf16(tmem_base, a0 + k * 128, b0 + k * 128, id_main, acc);
+          if (elect_one()) tc_mma_bf16(tmem_base + nmain, a0 + k * 128, o0 + k * 128, id_one, acc);
         }
-        __syncwarp();
+        if (elect_one()) tc_commit(&empty[stage]);
+        if (t == t1 - 1) {
+          if (elect_one()) tc_commit(acc_full);
+        }
         if (++stage == kWStages) { stage = 0; phase ^= 1; }
       }
       ++done;
@@ -255,9 +258,6 @@ struct UnitBuilder {
 
 }  // namespace
 
-int sahs_wgrad_status_internal(int* out4_host) {
-  return cudaMemcpyFromSymbol(out4_host, g_wgrad_status, sizeof(int) * 4) == cudaSuccess ? 0 : -1;
-}
 
 // grads: device pointers to zero-initialised fp32 gradient buffers in the canonical parameter order
 // (sahs_param_count entries; [0] = embedding grid, unused here).  Frame-constant input columns are left untouched
@@ -407,8 +407,8 @@ extern "C" int sahs_field_wgrad(const sahs_model_spec* spec, int level, float* c
   rc = make_tape_map(&tm_d, tape_d, num_points, d.td_total);
   if (rc) return rc;
   SAHS_CUDA(cudaFuncSetAttribute(field_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmemTotal));
-  int* status = nullptr;
-  SAHS_CUDA(cudaGetSymbolAddress((void**)&status, g_wgrad_status));
+  int* status = sahs_status_words(2);
+  SAHS_CHECK_ARG(status, "cannot allocate the diagnostic word");
   int grid = nsm < (int)units.size() ? nsm : (int)units.size();
   field_wgrad_kernel<<<grid, kWThreads, kWSmemTotal, st>>>(tm_x, tm_d, (const WUnit*)units_workspace, (int)units.size(),
                                                           status);

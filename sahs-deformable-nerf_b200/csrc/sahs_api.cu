@@ -26,6 +26,36 @@ int sahs_num_sms() {
   return cached;
 }
 
+// Diagnostic words of the field kernels (forward, dgrad, wgrad: 4 ints each) live in mapped pinned host memory, so
+// they stay readable after a kernel trapped and the context is gone.  Allocated once per process.
+static int* g_status_host = nullptr;
+int* sahs_status_words(int which) {
+  static int* dev = [] {
+    int* h = nullptr;
+    int* d = nullptr;
+    if (cudaHostAlloc((void**)&h, 12 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) return (int*)nullptr;
+    for (int i = 0; i < 12; ++i) h[i] = 0;
+    if (cudaHostGetDevicePointer((void**)&d, h, 0) != cudaSuccess) return (int*)nullptr;
+    g_status_host = h;
+    return d;
+  }();
+  return dev ? dev + 4 * which : nullptr;
+}
+
+extern "C" int sahs_field_status(int* out4_host) {
+  for (int i = 0; i < 4; ++i) out4_host[i] = 0;
+  if (!g_status_host) return SAHS_OK;   // no field kernel launched yet
+  for (int k = 0; k < 3; ++k) {
+    const volatile int* w = g_status_host + 4 * k;
+    if (w[0] != 0) {
+      for (int i = 0; i < 4; ++i) out4_host[i] = w[i];
+      out4_host[0] += 100 * k;          // 1xx: dgrad kernel, 2xx: wgrad kernel
+      break;
+    }
+  }
+  return SAHS_OK;
+}
+
 extern "C" int sahs_abi_version(void) { return 1; }
 extern "C" const char* sahs_last_error(void) { return g_err; }
 extern "C" uint64_t sahs_launch_count(void) { return g_sahs_launches.load(std::memory_order_relaxed); }

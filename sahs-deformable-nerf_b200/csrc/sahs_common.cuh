@@ -42,6 +42,7 @@ extern std::atomic<uint64_t> g_sahs_launches;
   } while (0)
 
 int sahs_num_sms();
+int* sahs_status_words(int which);   // device-visible diagnostic word of kernel 0 fwd / 1 dgrad / 2 wgrad
 
 // ------------------------------------------------------------------------------------------------
 // device side
@@ -183,6 +184,173 @@ __device__ __forceinline__ uint32_t umma_idesc_m128(uint32_t n, bool f16) {
 // byte offset of element (row, col) inside one [rows x 64] bf16 K-chunk with 128B swizzle
 __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t col) {
   return (row >> 3) * 1024u + (row & 7u) * 128u + ((((col >> 3) ^ row) & 7u) << 4) + (col & 7u) * 2u;
+}
+
+// ---- warp-converged issue -------------------------------------------------------------------------------
+// tcgen05.mma / tcgen05.commit take uniform-register operands.  Issued from a divergent `if (lane == 0)` region, ptxas
+// wraps each of them in a per-thread election loop whose back-branch waits until the instruction has consumed its
+// operands -- for a commit that is after every earlier MMA has drained, i.e. the issuer runs in lock step with the
+// tensor pipe (measured: ~1000 cycles per commit).  The variants below are called by all 32 lanes of a converged warp
+// with warp-uniform arguments; elect.sync picks the lane that issues.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %2;\n\t"
+      "@px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, rx;\n\t}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFF));
+  return pred != 0;
+}
+// Bounded mbarrier wait whose spin loop lives inside one asm block: the compiler sees straight-line, warp-uniform
+// code around it (a C++ spin loop makes everything after it "possibly divergent" and pushes the MMA issue loop off
+// the uniform datapath).  On timeout: status[0] = 1, status[1] = tag, then trap.  CLUSTER: acquire at cluster scope.
+template <bool CLUSTER>
+__device__ __forceinline__ void mbar_wait_uniform(uint64_t* bar, uint32_t parity, int* status, int tag) {
+  if (CLUSTER) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 c;\n\t"
+        "mov.u32 c, 0;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "add.u32 c, c, 1;\n\t"
+        "setp.lt.u32 p, c, 0x1000000;\n\t"
+        "@p bra WAIT_%=;\n\t"
+        "st.global.u32 [%2], 1;\n\t"
+        "st.global.u32 [%2+4], %3;\n\t"
+        "fence.sc.sys;\n\t"
+        "trap;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity), "l"(status), "r"(tag)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 c;\n\t"
+        "mov.u32 c, 0;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "add.u32 c, c, 1;\n\t"
+        "setp.lt.u32 p, c, 0x1000000;\n\t"
+        "@p bra WAIT_%=;\n\t"
+        "st.global.u32 [%2], 1;\n\t"
+        "st.global.u32 [%2+4], %3;\n\t"
+        "fence.sc.sys;\n\t"
+        "trap;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity), "l"(status), "r"(tag)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tc_mma_f16_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  if (elect_one()) tc_mma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+__device__ __forceinline__ void tc_commit_w(uint64_t* bar) {
+  if (elect_one()) tc_commit(bar);
+}
+
+// ---- CTA pairs (cluster of 2, tcgen05 cta_group::2) ---------------------------------------------------
+// The three getters below must be called by a converged warp: the value goes through a shuffle so that the compiler
+// knows it is warp-uniform (see the note on the warp index in field_fwd.cu).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return __shfl_sync(0xffffffffu, r, 0);
+}
+__device__ __forceinline__ uint32_t cluster_id_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+  return __shfl_sync(0xffffffffu, r, 0);
+}
+__device__ __forceinline__ uint32_t cluster_num_x() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r));
+  return __shfl_sync(0xffffffffu, r, 0);
+}
+__device__ __forceinline__ void cluster_sync_all() {   // every thread of both CTAs
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta pointer of this CTA) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait on a barrier that the peer CTA arrives on (acquire at cluster scope)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* status, int tag) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++spins > (1u << 24)) {
+      if (status) {
+        status[0] = 1;
+        status[1] = tag;
+        status[2] = (int)blockIdx.x;
+        status[3] = (int)threadIdx.x;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {  // one full warp in each CTA
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this smem offset in both CTAs
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+// D[tmem, both CTAs] (+)= A[smem, 128 rows per CTA] * B[smem, N/2 rows per CTA]^T; issued by the leader CTA only
+__device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  if (elect_one()) tc_mma_pair(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+__device__ __forceinline__ void tc_commit_pair_w(uint64_t* bar) {
+  if (elect_one()) tc_commit_pair(bar);
+}
+// kind::f16 instruction descriptor for the pair: M = 256 (128 rows in each CTA)
+__device__ __forceinline__ uint32_t umma_idesc_m256(uint32_t n, bool f16) {
+  const uint32_t fmt = f16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -21,3 +21,15 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """After a GPU session, print the field kernels' diagnostic word (readable even if a kernel trapped)."""
+    mod = sys.modules.get("sahs_b200.lib")
+    if mod is None or getattr(mod, "_lib", None) is None:
+        return
+    import ctypes as C
+    out = (C.c_int * 4)()
+    mod._lib.sahs_field_status(out)
+    if out[0] != 0:
+        print(f"\n[sahs] field kernel status word: code={out[0]} tag={out[1]} block={out[2]} thread={out[3]}")
