@@ -427,10 +427,10 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
   }
 }
 
-// SAHS_FIELD_PAIR=0 selects the single-CTA kernel (A/B measurements); default is the CTA-pair kernel.
+// SAHS_FIELD_PAIR=1 selects the CTA-pair (cta_group::2) kernel; the single-CTA kernel is the default (faster today).
 static bool field_pair_enabled() {
   const char* e = getenv("SAHS_FIELD_PAIR");
-  return !(e && e[0] == '0');
+  return e && e[0] == '1';
 }
 
 template <class C>

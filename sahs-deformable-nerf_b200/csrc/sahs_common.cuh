@@ -205,7 +205,7 @@ __device__ __forceinline__ bool elect_one() {
 }
 // Bounded mbarrier wait whose spin loop lives inside one asm block: the compiler sees straight-line, warp-uniform
 // code around it (a C++ spin loop makes everything after it "possibly divergent" and pushes the MMA issue loop off
-// the uniform datapath).  On timeout: status[0] = 1, status[1] = tag, then trap.  CLUSTER: acquire at cluster scope.
+// the uniform datapath).  On timeout: status[0] = 1, status[1] = tag, then trap.  (CLUSTER marks barriers the peer CTA arrives on; same wait.)
 template <bool CLUSTER>
 __device__ __forceinline__ void mbar_wait_uniform(uint64_t* bar, uint32_t parity, int* status, int tag) {
   if (CLUSTER) {
@@ -213,7 +213,7 @@ __device__ __forceinline__ void mbar_wait_uniform(uint64_t* bar, uint32_t parity
         "{\n\t.reg .pred p;\n\t.reg .u32 c;\n\t"
         "mov.u32 c, 0;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra DONE_%=;\n\t"
         "add.u32 c, c, 1;\n\t"
         "setp.lt.u32 p, c, 0x1000000;\n\t"
@@ -280,8 +280,12 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
 }
+// Remote arrive with the default semantics (what CUTLASS' ClusterBarrier::arrive(cta_id) emits).  The explicit
+// .release.cluster form costs a MEMBAR + ERRBAR per arrive, and waiting with .acquire.cluster makes ptxas emit
+// CCTL.IVALL (a full L1 invalidate) after every wait -- with one wait per weight stage that wiped the L1-resident
+// biases ~140 times per tile.  The data guarded here lives in shared memory and is read by the async proxy only.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
   asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
@@ -290,14 +294,14 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
 }
-// bounded wait on a barrier that the peer CTA arrives on (acquire at cluster scope)
+// bounded wait on a barrier that the peer CTA arrives on
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, int* status, int tag) {
   uint32_t spins = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
