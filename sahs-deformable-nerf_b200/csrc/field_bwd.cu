@@ -83,8 +83,11 @@ __device__ __forceinline__ void bwd_epilogue(uint32_t tmem_row, int cbeg, uint4 
   for (int blk = 0; blk < NBLK; ++blk) {
     const int c0 = cbeg + 16 * blk;
     tmem_ld_wait();
-    if (blk + 1 < NBLK) tmem_ld16(tmem_row + c0 + 16, (blk & 1) ? va : vb);
-    const uint32_t (&v)[16] = (blk & 1) ? vb : va;
+    if (blk + 1 < NBLK) {
+      if (blk & 1) tmem_ld16_prefetch(tmem_row + c0 + 16, va, vb[0]);
+      else tmem_ld16_prefetch(tmem_row + c0 + 16, vb, va[0]);
+    }
+    uint32_t (&v)[16] = (blk & 1) ? vb : va;
     const uint32_t bits = mw[blk >> 1] >> ((blk & 1) * 16);
     uint32_t pk[8];
 #pragma unroll

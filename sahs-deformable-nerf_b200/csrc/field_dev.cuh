@@ -19,9 +19,13 @@ constexpr int kSmemBar = kSmemX + kSmemSlots;                 // barriers after 
 constexpr int kSmemXchg = kSmemBar + 256;                     // 128 floats exchanged between the two groups
 constexpr int kSmemTotal = kSmemXchg + 512;
 // CTA-pair variant (cluster of 2, tcgen05 cta_group::2): every CTA holds half of each weight stage (N/2 rows), so the
-// same 48 KB ring is twice as deep and the L2 -> SM weight traffic per point is halved.
-constexpr int kPairSlots = 6;
+// L2 -> SM weight traffic per point is halved and a 24 KB ring is as deep (3 stages) as the single-CTA 48 KB one ...
+constexpr int kPairSlots = 3;
 constexpr int kPairSlotBytes = kStageSlotBytes / 2;
+// ... and the 24 KB this frees hold the per-frame constant block (folded biases, fp32 head weights) in shared memory:
+// the epilogues' bias reads become LDS instead of global loads through the 28 KB L1 (measured: 18 % of the kernel).
+constexpr int kPairFcFloats = 5632;
+constexpr int kPairSmemTotal = kSmemX + kPairSlots * kPairSlotBytes + kPairFcFloats * 4 + 256 + 512;
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2 };
 
@@ -184,14 +188,31 @@ __device__ __forceinline__ float4 ldg_stream(const float* p) {   // read-once da
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
+// frame-constant loads: FCS = the block lives in shared memory (CTA-pair kernel), else global through L1
+template <bool FCS>
+__device__ __forceinline__ float4 ldc4(const float* p) {
+  if (FCS) return *reinterpret_cast<const float4*>(p);
+  return ldg_keep(p);
+}
+template <bool FCS>
+__device__ __forceinline__ float ldc1(const float* p) {
+  if (FCS) return *p;
+  return ldg_keep1(p);
+}
+template <bool FCS = false>
 __device__ __forceinline__ void load_bias(float4 (&b)[4], const float* __restrict__ bias) {
+#if defined(SAHS_EXP_NOBIAS)   // timing experiment only: no bias traffic (results are wrong)
 #pragma unroll
-  for (int j = 0; j < 4; ++j) b[j] = ldg_keep(bias + 4 * j);
+  for (int j = 0; j < 4; ++j) b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+#else
+#pragma unroll
+  for (int j = 0; j < 4; ++j) b[j] = ldc4<FCS>(bias + 4 * j);
+#endif
 }
 
 // one 16-column block of an epilogue: +bias (FADD2), optional fp32 dot, pack, activation, swizzled store.
 // The bias registers are dead after the adds, so the next block's bias is fetched before the pack/store part.
-template <int ACT, bool F16, bool DOT, bool DBG, bool TRAIN = false>
+template <int ACT, bool F16, bool DOT, bool DBG, bool TRAIN = false, bool FCS = false>
 __device__ __forceinline__ void epi_block(uint32_t (&v)[16], float4 (&b)[4], const float* __restrict__ next_bias, int c0,
                                           uint8_t* rowp, int row, const float* __restrict__ dot_w, float& dot,
                                           float* dbg_row, __half* tape_row = nullptr, uint32_t* mbits = nullptr) {
@@ -203,7 +224,7 @@ __device__ __forceinline__ void epi_block(uint32_t (&v)[16], float4 (&b)[4], con
     add2(f[4 * j + 0], f[4 * j + 1], b[j].x, b[j].y);
     add2(f[4 * j + 2], f[4 * j + 3], b[j].z, b[j].w);
   }
-  if (next_bias) load_bias(b, next_bias);
+  if (next_bias) load_bias<FCS>(b, next_bias);
   if (TRAIN) {
     // training: sign bits for the activation derivative and the activated values (fp16, row-major) for the wgrad
     uint32_t bits = 0;
@@ -227,7 +248,7 @@ __device__ __forceinline__ void epi_block(uint32_t (&v)[16], float4 (&b)[4], con
   for (int j = 0; j < 4; ++j) {
     const float f0 = f[4 * j], f1 = f[4 * j + 1], f2 = f[4 * j + 2], f3 = f[4 * j + 3];
     if (DOT) {
-      const float4 w = ldg_keep(dot_w + c0 + 4 * j);
+      const float4 w = ldc4<FCS>(dot_w + c0 + 4 * j);
       dot += f0 * w.x + f1 * w.y + f2 * w.z + f3 * w.w;
     }
     pk[2 * j] = act2<ACT, F16>(pack2<F16>(f0, f1));
@@ -252,7 +273,7 @@ __device__ __forceinline__ void epi_block(uint32_t (&v)[16], float4 (&b)[4], con
 // Epilogue of one pass for this group's NBLK 16-column blocks starting at column cbeg.  TMEM loads are double
 // buffered against the math of the previous block; `b` arrives pre-loaded with the first block's bias (fetched by
 // the caller before it waited for the accumulator).
-template <int ACT, bool F16, bool DOT, bool DBG, int NBLK, bool TRAIN = false>
+template <int ACT, bool F16, bool DOT, bool DBG, int NBLK, bool TRAIN = false, bool FCS = false>
 __device__ __forceinline__ float epilogue(uint32_t tmem_row, int cbeg, const float* __restrict__ bias, float4 (&b)[4],
                                           uint8_t* X, int row, const float* __restrict__ dot_w, float* dbg_row,
                                           __half* tape_row = nullptr, uint4* mask_out = nullptr) {
@@ -268,11 +289,11 @@ __device__ __forceinline__ float epilogue(uint32_t tmem_row, int cbeg, const flo
     tmem_ld_wait();
     uint32_t bits = 0;
     if (blk & 1) {
-      if (blk + 1 < NBLK) tmem_ld16(tmem_row + c0 + 16, va);
-      epi_block<ACT, F16, DOT, DBG, TRAIN>(vb, b, nb, c0, rowp, row, dot_w, dot, dbg_row, tape_row, &bits);
+      if (blk + 1 < NBLK) tmem_ld16_prefetch(tmem_row + c0 + 16, va, vb[0]);
+      epi_block<ACT, F16, DOT, DBG, TRAIN, FCS>(vb, b, nb, c0, rowp, row, dot_w, dot, dbg_row, tape_row, &bits);
     } else {
-      if (blk + 1 < NBLK) tmem_ld16(tmem_row + c0 + 16, vb);
-      epi_block<ACT, F16, DOT, DBG, TRAIN>(va, b, nb, c0, rowp, row, dot_w, dot, dbg_row, tape_row, &bits);
+      if (blk + 1 < NBLK) tmem_ld16_prefetch(tmem_row + c0 + 16, vb, va[0]);
+      epi_block<ACT, F16, DOT, DBG, TRAIN, FCS>(va, b, nb, c0, rowp, row, dot_w, dot, dbg_row, tape_row, &bits);
     }
     if (TRAIN) mw[blk >> 1] |= bits << ((blk & 1) * 16);
   }
@@ -312,7 +333,7 @@ struct RowStreamSplit {
 };
 
 // relu epilogue writing hi/lo fp16 planes: columns [cbeg, cbeg + 16*NBLK) of the accumulator
-template <bool DBG, int NBLK>
+template <bool DBG, int NBLK, bool FCS = false>
 __device__ __forceinline__ void epilogue_split(uint32_t tmem_row, int cbeg, const float* __restrict__ bias, uint8_t* X,
                                                int row, int lo_off, float* dbg_row, int dbg_col0) {
   uint8_t* rowp = X + (row >> 3) * 1024 + (row & 7) * 128;
@@ -320,7 +341,7 @@ __device__ __forceinline__ void epilogue_split(uint32_t tmem_row, int cbeg, cons
   for (int blk = 0; blk < NBLK; ++blk) {
     const int c0 = cbeg + 16 * blk;
     float4 b[4];
-    load_bias(b, bias + c0);
+    load_bias<FCS>(b, bias + c0);
     uint32_t v[16];
     tmem_ld16(tmem_row + c0, v);
     tmem_ld_wait();
@@ -352,7 +373,7 @@ __device__ __forceinline__ void epilogue_split(uint32_t tmem_row, int cbeg, cons
 }
 
 // fp32 reduction of the last hidden layer against NOUT small-head weight rows: columns [cbeg, cbeg+16*NBLK)
-template <bool DBG, int NBLK, int NOUT>
+template <bool DBG, int NBLK, int NOUT, bool FCS = false>
 __device__ __forceinline__ void final_partial(uint32_t tmem_row, int cbeg, const float* __restrict__ bias,
                                               const float* __restrict__ w, int ld, float (&part)[NOUT], float* dbg_row,
                                               int dbg_col0) {
@@ -364,7 +385,7 @@ __device__ __forceinline__ void final_partial(uint32_t tmem_row, int cbeg, const
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float4 bb = ldg_keep(bias + c0 + 4 * j);
+      const float4 bb = ldc4<FCS>(bias + c0 + 4 * j);
       const float h0 = fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.f), h1 = fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.f);
       const float h2 = fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.f), h3 = fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.f);
       if (DBG && dbg_row) {
@@ -373,7 +394,7 @@ __device__ __forceinline__ void final_partial(uint32_t tmem_row, int cbeg, const
       }
 #pragma unroll
       for (int k = 0; k < NOUT; ++k) {
-        const float4 ww = ldg_keep(w + k * ld + c0 + 4 * j);
+        const float4 ww = ldc4<FCS>(w + k * ld + c0 + 4 * j);
         part[k] += h0 * ww.x + h1 * ww.y + h2 * ww.z + h3 * ww.w;
       }
     }

@@ -43,7 +43,11 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* X = smem;
   uint8_t* slots = smem + kSmemX;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
+  // PAIR: [X 64 KB | 3 x 8 KB slots | frame constants 22 KB | barriers | xchg]; else [X | 3 x 16 KB slots | barriers | xchg]
+  constexpr int kSlotsBytes = PAIR ? kPairSlots * kPairSlotBytes : kSmemSlots;
+  constexpr int kFcBytes = PAIR ? kPairFcFloats * 4 : 0;
+  float* fc_s = reinterpret_cast<float*>(smem + kSmemX + kSlotsBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemX + kSlotsBytes + kFcBytes);
   constexpr int NS = PAIR ? kPairSlots : kSlots;
   uint64_t* full = bars;               // [NS]
   uint64_t* empty = bars + NS;         // [NS]
@@ -52,7 +56,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
   uint64_t* pfull = bars + 2 * NS + 2; // [NS], PAIR leader only: the peer's halves of the stages have landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * NS + 2);
   uint32_t* peer_tmem = tmem_ptr + 1;  // PAIR: the peer reports its TMEM base here (must equal the leader's)
-  float* xchg = reinterpret_cast<float*>(smem + kSmemXchg);
+  float* xchg = reinterpret_cast<float*>(smem + kSmemX + kSlotsBytes + kFcBytes + 256);
 
   // warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the role dispatch convergent and
   // the MMA issue loop on the uniform datapath (with the plain threadIdx.x >> 5 every tcgen05 instruction below gets a
@@ -76,6 +80,9 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
     }
     mbar_init(acc_ready, 1);
     fence_mbar_init();
+  }
+  if (PAIR) {
+    for (int i = threadIdx.x; i < dm.fc_total; i += kThreads) fc_s[i] = __ldg(fc + i);
   }
   if (warp == kMmaWarp) {
     if (PAIR) tmem_alloc_pair(tmem_ptr, kTmemCols);
@@ -115,6 +122,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
     else relay_warp_loop_pair(plan, full, pfull, npairs, status, lane);
   } else {
     // ================================ workers ===================================================
+    const float* fcw = PAIR ? fc_s : fc;   // frame constants: shared-memory copy in the pair kernel
     SyncT<PAIR> sy{a_ready, acc_ready, 0u, status, PAIR ? mapa_u32(a_ready, 0) : 0u};
     const int row = threadIdx.x & (kTileRows - 1);
     const int grp = threadIdx.x >> 7;
@@ -159,7 +167,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
 #pragma unroll
           for (int i = C::E0_DIM; i < C::E0_PAD; ++i) st.put(col++, 0.f);
         };
-        const float* wf = fc + dm.off_wfinal;
+        const float* wf = fcw + dm.off_wfinal;
         const float* bf = wf + 3 * dm.wh;
         const float* wa = bf + 4;
         const float* ba = wa + C::AMB_DIM * dm.hh;
@@ -176,31 +184,31 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
               signal_a(sy);
               wait_acc(sy, 1100 + 16 * net + i);
             }
-            const float* bias = fc + dm.off_wbias + i * dm.whh + boff;
+            const float* bias = fcw + dm.off_wbias + i * dm.whh + boff;
             float* dr = (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) ? dbg_row : nullptr;
             if (i < dm.w_layers - 1) {
-              if (net == 0) epilogue_split<DBG, 4>(tmem_row, grp * 64, bias, X, row, 2, dr, 0);
-              else epilogue_split<DBG, 2>(tmem_row, grp * 32, bias, X, row, 1, dr, dm.wh);
+              if (net == 0) epilogue_split<DBG, 4, PAIR>(tmem_row, grp * 64, bias, X, row, 2, dr, 0);
+              else epilogue_split<DBG, 2, PAIR>(tmem_row, grp * 32, bias, X, row, 1, dr, dm.wh);
               signal_a(sy);
             } else if (net == 0) {
               float part[3] = {0.f, 0.f, 0.f};
-              final_partial<DBG, 4, 3>(tmem_row, grp * 64, bias, wf, dm.wh, part, dr, 0);
+              final_partial<DBG, 4, 3, PAIR>(tmem_row, grp * 64, bias, wf, dm.wh, part, dr, 0);
 #pragma unroll
               for (int k = 0; k < 3; ++k) scratch[(grp * 128 + row) * 8 + k] = part[k];
               group_sync();
 #pragma unroll
               for (int k = 0; k < 3; ++k)
-                mapped[k] = pt[k] + tanhf(scratch[row * 8 + k] + scratch[(128 + row) * 8 + k] + ldg_keep1(bf + k));
+                mapped[k] = pt[k] + tanhf(scratch[row * 8 + k] + scratch[(128 + row) * 8 + k] + ldc1<PAIR>(bf + k));
               group_sync();
             } else {
               float part[C::AMB_DIM > 0 ? C::AMB_DIM : 1] = {};
-              final_partial<DBG, 2, (C::AMB_DIM > 0 ? C::AMB_DIM : 1)>(tmem_row, grp * 32, bias, wa, dm.hh, part, dr, dm.wh);
+              final_partial<DBG, 2, (C::AMB_DIM > 0 ? C::AMB_DIM : 1), PAIR>(tmem_row, grp * 32, bias, wa, dm.hh, part, dr, dm.wh);
 #pragma unroll
               for (int k = 0; k < C::AMB_DIM; ++k) scratch[(grp * 128 + row) * 8 + k] = part[k];
               group_sync();
 #pragma unroll
               for (int k = 0; k < C::AMB_DIM; ++k)
-                amb[k] = scratch[row * 8 + k] + scratch[(128 + row) * 8 + k] + ldg_keep1(ba + k);
+                amb[k] = scratch[row * 8 + k] + scratch[(128 + row) * 8 + k] + ldc1<PAIR>(ba + k);
               group_sync();
             }
           }
@@ -217,19 +225,19 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         write_e0(dm.e0_chunk_base);
         signal_a(sy);
         for (int i = 0; i < dm.w_layers - 1; ++i) {
-          const float* bias = fc + dm.off_wbias + i * dm.whh;
+          const float* bias = fcw + dm.off_wbias + i * dm.whh;
           const bool two_pass = (i == dm.w_skip && !dm.e0_resident);
           float4 b[4];
-          if (!two_pass) load_bias(b, bias + grp * 96);
+          if (!two_pass) load_bias<PAIR>(b, bias + grp * 96);
           wait_acc(sy, 1000 + i);
           if (two_pass) {
             write_e0(0);
             signal_a(sy);
-            load_bias(b, bias + grp * 96);
+            load_bias<PAIR>(b, bias + grp * 96);
             wait_acc(sy, 1100 + i);
           }
           // whh = 192: three 32-column blocks per group
-          epilogue<ACT_RELU, true, false, DBG, 6, TRAIN>(tmem_row, grp * 96, bias, b, X, row, nullptr,
+          epilogue<ACT_RELU, true, false, DBG, 6, TRAIN, PAIR>(tmem_row, grp * 96, bias, b, X, row, nullptr,
                                                          (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) ? dbg_row : nullptr,
                                                          tape ? tape + dm.tx_wh + i * dm.whh : nullptr, mask_slot(i));
           signal_a(sy);
@@ -240,8 +248,8 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
           const int i = dm.w_layers - 1;
           wait_acc(sy, 1000 + i);
           if (i == dm.w_skip && !dm.e0_resident) { write_e0(0); signal_a(sy); wait_acc(sy, 1100 + i); }
-          const float* bias = fc + dm.off_wbias + i * dm.whh;
-          const float* wf = fc + dm.off_wfinal;
+          const float* bias = fcw + dm.off_wbias + i * dm.whh;
+          const float* wf = fcw + dm.off_wfinal;
           const float* bf = wf + 3 * dm.wh;          // [wf 3*wh | bf 4 | wa amb*hh | ba 4], all 16-byte aligned
           const float* wa = bf + 4;
           const float* ba = wa + C::AMB_DIM * dm.hh;
@@ -255,7 +263,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 bb = ldg_keep(bias + c0 + 4 * j);
+              const float4 bb = ldc4<PAIR>(bias + c0 + 4 * j);
               float h[4] = {fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.f), fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.f),
                             fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.f)};
               if (TRAIN) {
@@ -272,13 +280,13 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
               if (c0 < dm.wh) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
-                  const float4 w = ldg_keep(wf + k * dm.wh + c0 + 4 * j);
+                  const float4 w = ldc4<PAIR>(wf + k * dm.wh + c0 + 4 * j);
                   part[k] += h[0] * w.x + h[1] * w.y + h[2] * w.z + h[3] * w.w;
                 }
               } else {
 #pragma unroll
                 for (int k = 0; k < C::AMB_DIM; ++k) {
-                  const float4 w = ldg_keep(wa + k * dm.hh + (c0 + 4 * j - dm.wh));
+                  const float4 w = ldc4<PAIR>(wa + k * dm.hh + (c0 + 4 * j - dm.wh));
                   part[3 + k] += h[0] * w.x + h[1] * w.y + h[2] * w.z + h[3] * w.w;
                 }
               }
@@ -294,10 +302,10 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
           group_sync();
 #pragma unroll
           for (int k = 0; k < 3; ++k)
-            mapped[k] = pt[k] + tanhf(scratch[row * 8 + k] + scratch[(128 + row) * 8 + k] + ldg_keep1(bf + k));
+            mapped[k] = pt[k] + tanhf(scratch[row * 8 + k] + scratch[(128 + row) * 8 + k] + ldc1<PAIR>(bf + k));
 #pragma unroll
           for (int k = 0; k < C::AMB_DIM; ++k)
-            amb[k] = scratch[row * 8 + 3 + k] + scratch[(128 + row) * 8 + 3 + k] + ldg_keep1(ba + k);
+            amb[k] = scratch[row * 8 + 3 + k] + scratch[(128 + row) * 8 + 3 + k] + ldc1<PAIR>(ba + k);
           group_sync();   // scratch is dead before E1 overwrites it
         }
       }
@@ -336,17 +344,17 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       write_e1();
       signal_a(sy);
       for (int i = 0; i < dm.t_layers; ++i) {
-        const float* bias = fc + dm.off_tbias + i * dm.th;
+        const float* bias = fcw + dm.off_tbias + i * dm.th;
         float4 b[4];
-        if (i != dm.t_skip) load_bias(b, bias + grp * 128);
+        if (i != dm.t_skip) load_bias<PAIR>(b, bias + grp * 128);
         wait_acc(sy, 2000 + i);
         if (i == dm.t_skip) {
           write_e1();
           signal_a(sy);
-          load_bias(b, bias + grp * 128);
+          load_bias<PAIR>(b, bias + grp * 128);
           wait_acc(sy, 2100 + i);
         }
-        epilogue<ACT_LEAKY, kTrunkF16, false, DBG, 8, TRAIN>(
+        epilogue<ACT_LEAKY, kTrunkF16, false, DBG, 8, TRAIN, PAIR>(
             tmem_row, grp * 128, bias, b, X, row, nullptr,
             (DBG && dbg_row && dbg_pass == SAHS_DBG_TRUNK(i)) ? dbg_row : nullptr,
             tape ? tape + dm.tx_th + i * dm.th : nullptr, mask_slot((C::USE_W ? dm.w_layers : 0) + i));
@@ -354,10 +362,10 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       }
       // fc_feat (no activation) + sigma = fc_alpha(feat) in fp32 (partial dot per group)
       float4 bfe[4];
-      load_bias(bfe, fc + dm.off_featb + grp * 128);
+      load_bias<PAIR>(bfe, fcw + dm.off_featb + grp * 128);
       wait_acc(sy, 2200);
-      float sigma = epilogue<ACT_NONE, kTrunkF16, true, DBG, 8, TRAIN>(
-          tmem_row, grp * 128, fc + dm.off_featb, bfe, X, row, fc + dm.off_alpha,
+      float sigma = epilogue<ACT_NONE, kTrunkF16, true, DBG, 8, TRAIN, PAIR>(
+          tmem_row, grp * 128, fcw + dm.off_featb, bfe, X, row, fcw + dm.off_alpha,
           (DBG && dbg_row && dbg_pass == SAHS_DBG_TRUNK(dm.t_layers)) ? dbg_row : nullptr,
           tape ? tape + dm.tx_feat : nullptr, nullptr);
       if (grp == 1) xchg[row] = sigma;
@@ -386,11 +394,11 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       }
       signal_a(sy);
       for (int i = 0; i < 4; ++i) {
-        const float* bias = fc + dm.off_hbias + i * 2 * dm.hd;
+        const float* bias = fcw + dm.off_hbias + i * 2 * dm.hd;
         float4 b[4];
-        load_bias(b, bias + grp * 128);
+        load_bias<PAIR>(b, bias + grp * 128);
         wait_acc(sy, 3100 + i);
-        epilogue<ACT_LEAKY, kTrunkF16, false, DBG, 8, TRAIN>(
+        epilogue<ACT_LEAKY, kTrunkF16, false, DBG, 8, TRAIN, PAIR>(
             tmem_row, grp * 128, bias, b, X, row, nullptr,
             (DBG && dbg_row && dbg_pass == SAHS_DBG_HEAD(i)) ? dbg_row : nullptr,
             tape ? tape + dm.tx_hh + i * 2 * dm.hd : nullptr, mask_slot((C::USE_W ? dm.w_layers : 0) + dm.t_layers + i));
@@ -404,8 +412,8 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         tmem_ld_wait();
         float o[16];
 #pragma unroll
-        for (int k = 0; k < 15; ++k) o[k] = __uint_as_float(v[k]) + __ldg(fc + dm.off_outb + k);
-        o[15] = sigma + xchg[row] + __ldg(fc + dm.off_alpha + dm.th);
+        for (int k = 0; k < 15; ++k) o[k] = __uint_as_float(v[k]) + ldc1<PAIR>(fcw + dm.off_outb + k);
+        o[15] = sigma + xchg[row] + ldc1<PAIR>(fcw + dm.off_alpha + dm.th);
         if (valid) {
           float4* dst = reinterpret_cast<float4*>(raw_out + p * SAHS_RAW_CH);
 #pragma unroll
@@ -427,10 +435,11 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
   }
 }
 
-// SAHS_FIELD_PAIR=1 selects the CTA-pair (cta_group::2) kernel; the single-CTA kernel is the default (faster today).
+// The CTA-pair (cta_group::2) kernel is the default render path; SAHS_FIELD_PAIR=0 selects the single-CTA kernel
+// (A/B measurements; also used for debug passes and training, which have no pair variant yet).
 static bool field_pair_enabled() {
   const char* e = getenv("SAHS_FIELD_PAIR");
-  return e && e[0] == '1';
+  return !(e && e[0] == '0');
 }
 
 template <class C>
@@ -443,17 +452,17 @@ int launch_field(const HostPlan& hp, const void* packed, const float* fc, const 
   const long long ntiles = (P + kTileRows - 1) / kTileRows;
   const uint8_t* pk = (const uint8_t*)packed;
   const bool prof = dbg != nullptr && dbg_pass == SAHS_DBG_PROF;
-  if (!tr.tape_x && (!dbg || prof) && field_pair_enabled()) {
+  if (!tr.tape_x && (!dbg || prof) && field_pair_enabled() && hp.dims.fc_total <= kPairFcFloats) {
     // CTA pairs: clusters of 2, two clusters resident per SM pair
     auto kfn = prof ? field_fwd_kernel<C, true, false, true> : field_fwd_kernel<C, false, false, true>;
-    SAHS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
+    SAHS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemTotal));
     const long long npairs = (ntiles + 1) / 2;
     long long nclusters = sahs_num_sms();           // 2 CTAs per SM = one cluster per SM on average
     if (nclusters > npairs) nclusters = npairs;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * nclusters));
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = kSmemTotal;
+    cfg.dynamicSmemBytes = kPairSmemTotal;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;

@@ -154,11 +154,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+#if defined(SAHS_EXP_NOTMEM)
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = taddr + i;
+  return;
+#endif
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// Prefetching variant: `pin` is a register of the block that is processed while this load is in flight.  The fake
+// in/out dependence keeps the compiler from sinking the load below that block's math (which it otherwise does to
+// shorten the destination registers' live ranges, serialising TMEM latency with the epilogue math).
+__device__ __forceinline__ void tmem_ld16_prefetch(uint32_t taddr, uint32_t (&v)[16], uint32_t& pin) {
+#if defined(SAHS_EXP_NOTMEM)   // timing experiment only: no accumulator reads (results are wrong)
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = taddr + i;
+  return;
+#endif
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%17];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "+r"(pin)
       : "r"(taddr)
       : "memory");
 }

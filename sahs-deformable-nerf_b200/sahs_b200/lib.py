@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_PKG), "lib", "libsahs_b200.so")
+LIB_PATH = os.environ.get("SAHS_B200_LIB") or os.path.join(os.path.dirname(_PKG), "lib", "libsahs_b200.so")
 
 _lib: Optional[C.CDLL] = None
 
