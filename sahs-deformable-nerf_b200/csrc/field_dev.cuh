@@ -478,38 +478,34 @@ __device__ __forceinline__ void tma_warp_loop(const FieldPlan& plan, const uint8
 // cycles per 4-MMA stage instead of 256).  Passes are delimited by the a_ready / acc_ready barriers.
 template <bool PAIR, bool PROF>
 __device__ __forceinline__ void mma_issue_loop(const FieldPlan& plan, uint8_t* X, uint8_t* slots, uint64_t* full,
-                                               uint64_t* pfull, uint64_t* empty, uint64_t* a_ready, uint64_t* acc_ready,
+                                               uint64_t* empty, uint64_t* a_ready, uint64_t* acc_ready,
                                                uint32_t tmem_base, long long first, long long count, long long step,
                                                int* status, long long* prof_base) {
   constexpr uint32_t NS = PAIR ? kPairSlots : kSlots;
-  constexpr uint32_t SLOT_BYTES = PAIR ? kPairSlotBytes : kStageSlotBytes;
+  constexpr uint32_t SLOT_UNITS = (PAIR ? kPairSlotBytes : kStageSlotBytes) >> 4;   // descriptor address units (16 B)
   uint32_t slot = 0, phase = 0, a_par = 0;
   const uint64_t a_base = umma_smem_desc_sw128(smem_u32(X));
   const uint64_t b_base = umma_smem_desc_sw128(smem_u32(slots));
+  // software pipeline: the next stage's record is fetched and its `full` barrier peeked while this stage's MMAs run
+  StageRec r = plan.st[0];
+  uint32_t token = 0;
   int iter = 0;
   for (long long it = first; it < count; it += step, ++iter) {
     long long* prof = (PROF && prof_base && iter == 2 && (threadIdx.x & 31) == 0) ? prof_base : nullptr;
     for (int st = 0; st < plan.num_stages; ++st) {
-      const StageRec r = plan.st[st];
       const uint32_t flags = r.kflags >> 3, ksteps = r.kflags & 7;
       if (flags & ST_WAIT_A) {
         mbar_wait_uniform<PAIR>(a_ready, a_par, status, 200 + st);
         a_par ^= 1;
         if (PROF) prof_event(prof, 10000 + st);
       }
-      mbar_wait_uniform<false>(&full[slot], phase, status, 400 + st);
+      mbar_wait_token(&full[slot], phase, token, status, 400 + st);   // PAIR: both halves of the stage have landed
       if (PROF) prof_event(prof, 20000 + st);
-      if (PAIR) {
-        mbar_wait_uniform<true>(&pfull[slot], phase, status, 600 + st);
-        if (PROF) prof_event(prof, 25000 + st);
-      }
       tc_fence_after();
-      const uint32_t n = (uint32_t)r.n8 * 8u;
-      const bool f16 = (flags & ST_F16) != 0;
-      const uint32_t idesc = PAIR ? umma_idesc_m256(n, f16) : umma_idesc_m128(n, f16);
+      const uint32_t idesc = PAIR ? (r.idesc ^ (((128u >> 4) ^ (256u >> 4)) << 24)) : r.idesc;   // M field 128 -> 256
       // descriptor address field counts 16-byte units; K advances 16 elements = 32 bytes = 2 units per MMA
-      const uint64_t a0 = a_base + (uint64_t)(r.a_chunk * (kChunkBytes >> 4));
-      const uint64_t b0 = b_base + (uint64_t)(slot * (SLOT_BYTES >> 4));
+      const uint64_t a0 = a_base + (uint64_t)r.a_off;
+      const uint64_t b0 = b_base + (uint64_t)(slot * SLOT_UNITS);
       const uint32_t d = tmem_base + (uint32_t)r.d_col8 * 8u;
       const uint32_t acc0 = (flags & ST_FRESH) ? 0u : 1u;
       auto mma = [&](uint64_t a, uint64_t b, uint32_t acc) {
@@ -529,7 +525,7 @@ __device__ __forceinline__ void mma_issue_loop(const FieldPlan& plan, uint8_t* X
       if (ksteps > 2) mma(a0 + 4, b0 + 4, 1u);
       if (ksteps > 3) mma(a0 + 6, b0 + 6, 1u);
       if (r.a_chunk2 != 0xFF) {   // split precision: the residual (lo) activations times the same weights
-        const uint64_t a1 = a_base + (uint64_t)(r.a_chunk2 * (kChunkBytes >> 4));
+        const uint64_t a1 = a_base + (uint64_t)r.a2_off;
         mma(a1, b0, 1u);
         if (ksteps > 1) mma(a1 + 2, b0 + 2, 1u);
         if (ksteps > 2) mma(a1 + 4, b0 + 4, 1u);
@@ -539,6 +535,8 @@ __device__ __forceinline__ void mma_issue_loop(const FieldPlan& plan, uint8_t* X
       if (flags & ST_COMMIT) commit(acc_ready);
       if (PROF) prof_event(prof, 30000 + st);
       if (++slot == NS) { slot = 0; phase ^= 1; }
+      r = plan.st[(st + 1 < plan.num_stages) ? st + 1 : 0];
+      token = mbar_peek(&full[slot], phase);
     }
   }
 }
@@ -547,7 +545,7 @@ template <bool PROF = false>
 __device__ __forceinline__ void mma_warp_loop(const FieldPlan& plan, uint8_t* X, uint8_t* slots, uint64_t* full,
                                               uint64_t* empty, uint64_t* a_ready, uint64_t* acc_ready, uint32_t tmem_base,
                                               long long ntiles, int* status, int lane, long long* prof_base = nullptr) {
-  mma_issue_loop<false, PROF>(plan, X, slots, full, nullptr, empty, a_ready, acc_ready, tmem_base, blockIdx.x, ntiles,
+  mma_issue_loop<false, PROF>(plan, X, slots, full, empty, a_ready, acc_ready, tmem_base, blockIdx.x, ntiles,
                               gridDim.x, status, prof_base);
 }
 
@@ -578,13 +576,14 @@ __device__ __forceinline__ void tma_warp_loop_pair(const FieldPlan& plan, const 
   }
 }
 
-// Peer CTA (rank 1): forwards "my half of the stage has landed" to the leader's pfull barriers.
-__device__ __forceinline__ void relay_warp_loop_pair(const FieldPlan& plan, uint64_t* full, uint64_t* pfull,
-                                                     long long npairs, int* status, int lane) {
+// Peer CTA (rank 1): forwards "my half of the stage has landed" to the leader's full barrier of the same slot (which
+// counts two arrivals per phase: the leader's own expect_tx arrive and this one).
+__device__ __forceinline__ void relay_warp_loop_pair(const FieldPlan& plan, uint64_t* full, long long npairs, int* status,
+                                                     int lane) {
   uint32_t slot = 0, phase = 0;
   uint32_t remote[kPairSlots];
 #pragma unroll
-  for (int i = 0; i < kPairSlots; ++i) remote[i] = mapa_u32(&pfull[i], 0);
+  for (int i = 0; i < kPairSlots; ++i) remote[i] = mapa_u32(&full[i], 0);
   const long long pt0 = cluster_id_x(), pt_step = cluster_num_x();
   for (long long pt = pt0; pt < npairs; pt += pt_step) {
     for (int st = 0; st < plan.num_stages; ++st) {
@@ -604,10 +603,10 @@ __device__ __forceinline__ void relay_warp_loop_pair(const FieldPlan& plan, uint
 // Leader CTA (rank 0): issues the M=256 MMAs of the pair.
 template <bool PROF = false>
 __device__ __forceinline__ void mma_warp_loop_pair(const FieldPlan& plan, uint8_t* X, uint8_t* slots, uint64_t* full,
-                                                   uint64_t* pfull, uint64_t* empty, uint64_t* a_ready,
+                                                   uint64_t* empty, uint64_t* a_ready,
                                                    uint64_t* acc_ready, uint32_t tmem_base, long long npairs, int* status,
                                                    int lane, long long* prof_base = nullptr) {
-  mma_issue_loop<true, PROF>(plan, X, slots, full, pfull, empty, a_ready, acc_ready, tmem_base, cluster_id_x(), npairs,
+  mma_issue_loop<true, PROF>(plan, X, slots, full, empty, a_ready, acc_ready, tmem_base, cluster_id_x(), npairs,
                              cluster_num_x(), status, prof_base);
 }
 

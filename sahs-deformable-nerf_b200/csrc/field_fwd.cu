@@ -53,7 +53,6 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
   uint64_t* empty = bars + NS;         // [NS]
   uint64_t* a_ready = bars + 2 * NS;
   uint64_t* acc_ready = bars + 2 * NS + 1;
-  uint64_t* pfull = bars + 2 * NS + 2; // [NS], PAIR leader only: the peer's halves of the stages have landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * NS + 2);
   uint32_t* peer_tmem = tmem_ptr + 1;  // PAIR: the peer reports its TMEM base here (must equal the leader's)
   float* xchg = reinterpret_cast<float*>(smem + kSmemX + kSlotsBytes + kFcBytes + 256);
@@ -71,9 +70,9 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       status[0] = 2;
       __trap();
     }
-    for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    // PAIR leader: a stage is complete when its own half (expect_tx arrive) and the peer's half (relayed arrive) landed
+    for (int i = 0; i < NS; ++i) { mbar_init(&full[i], (PAIR && rank == 0) ? 2 : 1); mbar_init(&empty[i], 1); }
     if (PAIR) {
-      for (int i = 0; i < NS; ++i) mbar_init(&pfull[i], 1);
       mbar_init(a_ready, 2 * (kWorkerThreads / 32));   // one arrival per worker warp of both CTAs
     } else {
       mbar_init(a_ready, kWorkerThreads);
@@ -118,8 +117,8 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
   } else if (warp == kMmaWarp) {
     long long* pb = prof_buf ? prof_buf + 2 * 4096 : nullptr;
     if (!PAIR) mma_warp_loop<DBG>(plan, X, slots, full, empty, a_ready, acc_ready, tmem_base, ntiles, status, lane, pb);
-    else if (rank == 0) mma_warp_loop_pair<DBG>(plan, X, slots, full, pfull, empty, a_ready, acc_ready, tmem_base, npairs, status, lane, pb);
-    else relay_warp_loop_pair(plan, full, pfull, npairs, status, lane);
+    else if (rank == 0) mma_warp_loop_pair<DBG>(plan, X, slots, full, empty, a_ready, acc_ready, tmem_base, npairs, status, lane, pb);
+    else relay_warp_loop_pair(plan, full, npairs, status, lane);
   } else {
     // ================================ workers ===================================================
     const float* fcw = PAIR ? fc_s : fc;   // frame constants: shared-memory copy in the pair kernel

@@ -94,6 +94,17 @@ struct Builder {
   }
 };
 
+// fills the derived StageRec fields the MMA issue loop reads
+void finalize_plan(FieldPlan& plan) {
+  for (int i = 0; i < plan.num_stages; ++i) {
+    StageRec& r = plan.st[i];
+    const uint32_t flags = r.kflags >> 3;
+    r.idesc = sahs_idesc_m128((uint32_t)r.n8 * 8u, (flags & ST_F16) != 0);
+    r.a_off = (uint16_t)(r.a_chunk * (kChunkBytes >> 4));
+    r.a2_off = (uint16_t)((r.a_chunk2 == 0xFF ? 0 : r.a_chunk2) * (kChunkBytes >> 4));
+  }
+}
+
 }  // namespace
 
 extern "C" int sahs_param_count(const sahs_model_spec* spec) {
@@ -264,6 +275,7 @@ int sahs_build_host_plan(const sahs_model_spec& s, const float* const* params, H
   }
   hp.plan.num_stages = b.ns;
   hp.plan.total_bytes = (int32_t)b.off;
+  finalize_plan(hp.plan);
   return SAHS_OK;
 }
 
@@ -329,6 +341,7 @@ int sahs_build_bwd_plan(const sahs_model_spec& s, const float* const* params, Ho
   }
   hp.plan.num_stages = b.ns;
   hp.plan.total_bytes = (int32_t)b.off;
+  finalize_plan(hp.plan);
   return SAHS_OK;
 }
 

@@ -20,14 +20,24 @@ constexpr int kStageSlotBytes = 16384;
 
 enum : uint8_t { ST_WAIT_A = 1, ST_COMMIT = 2, ST_FRESH = 4, ST_F16 = 8 };  // F16: fp16 operands (else bf16)
 
-struct StageRec {   // 8 bytes, lives in kernel parameter space
+struct StageRec {   // 16 bytes, lives in kernel parameter space
   uint8_t n8;       // N / 8
   uint8_t kflags;   // ksteps (low 3 bits) | flags << 3
   uint8_t a_chunk;  // which X chunk is the A operand
   uint8_t d_col8;   // accumulator column offset / 8
   uint8_t a_chunk2; // second A chunk multiplied by the same stage (split precision: the lo part), 0xFF = none
   uint8_t pad[3];
+  // derived on the host (sahs_finalize_plan) so that the MMA issue loop decodes a stage with one 16-byte load:
+  uint32_t idesc;   // tcgen05 instruction descriptor for M = 128 (the pair kernel ORs in M = 256)
+  uint16_t a_off;   // a_chunk  * kChunkBytes / 16: offset of the A descriptor's address field
+  uint16_t a2_off;  // a_chunk2 * kChunkBytes / 16 (unused when a_chunk2 == 0xFF)
 };
+
+// kind::f16 instruction descriptor (D fp32, A/B both fp16 (format 0) or bf16 (1), K-major): N at bit 17, M at bit 24
+inline uint32_t sahs_idesc_m128(uint32_t n, bool f16) {
+  const uint32_t fmt = f16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
 
 struct FieldPlan {
   int32_t num_stages;

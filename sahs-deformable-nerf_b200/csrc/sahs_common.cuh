@@ -274,6 +274,41 @@ __device__ __forceinline__ void tc_commit_w(uint64_t* bar) {
   if (elect_one()) tc_commit(bar);
 }
 
+// Non-blocking look at a barrier phase (1 = complete).  Issued right after a stage's MMAs for the NEXT stage's
+// barrier, so that the wait at the top of the next iteration is normally a register test (CUTLASS' peek / token idiom).
+__device__ __forceinline__ uint32_t mbar_peek(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+// mbar_wait_uniform that is skipped when the peeked token already saw the phase complete
+__device__ __forceinline__ void mbar_wait_token(uint64_t* bar, uint32_t parity, uint32_t token, int* status, int tag) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .u32 c;\n\t"
+      "setp.ne.u32 p, %4, 0;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "mov.u32 c, 0;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "add.u32 c, c, 1;\n\t"
+      "setp.lt.u32 p, c, 0x1000000;\n\t"
+      "@p bra WAIT_%=;\n\t"
+      "st.global.u32 [%2], 1;\n\t"
+      "st.global.u32 [%2+4], %3;\n\t"
+      "fence.sc.sys;\n\t"
+      "trap;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity), "l"(status), "r"(tag), "r"(token)
+      : "memory");
+}
+
 // ---- CTA pairs (cluster of 2, tcgen05 cta_group::2) ---------------------------------------------------
 // The three getters below must be called by a converged warp: the value goes through a shuffle so that the compiler
 // knows it is warp-uniform (see the note on the warp index in field_fwd.cu).
