@@ -105,8 +105,10 @@ int sahs_field_fwd(const sahs_model_spec* spec, int level, const void* packed, c
 /* Layout of the training tapes for this spec (40 ints: tx_e0, e0_k, tx_wh, whh, w_layers, tx_e1, e1_k, tx_th, th,
  * t_layers, tx_feat, tx_xtra, tx_hh, tx_total, td_wh, td_final, td_th, td_feat, td_hh, td_out, td_total,
  * n_mask_layers, e0_dim, e1_dim, xtra_dim, wh, hh, w_skip, t_skip, ct_off, ct_len, use_w, hd, packed_t_bytes,
- * bwd_stages, fc_total, packed_train_bytes, 0, 0, 0).  Tapes are row-major fp16, one row per sample point:
- * activation tape [P, tx_total], gradient tape [P, td_total]; masks are [n_mask_layers][P][2] x 16 bytes; saves [P,8]. */
+ * bwd_stages, fc_total, packed_train_bytes, 0, 0, 0).
+ * Both tapes are tile-major chunk images: tape[ceil(P/128)][total/64][128 points x 64 columns, fp16, 128B-swizzled], i.e.
+ * ceil(P/128)*128 x total fp16 values (tx_total / td_total columns, every item starts at a multiple of 64);
+ * masks are [n_mask_layers][P][2] x 16 bytes; saves [P,8]. */
 int sahs_train_layout(const sahs_model_spec* spec, int32_t* out, int max_out);
 /* Packed forward image used by training (always the merged fp16 deformation phase) and the transposed fp16 image
  * consumed by sahs_field_bwd. */
@@ -129,7 +131,7 @@ int sahs_field_bwd(const sahs_model_spec* spec, int level, const void* packed_t,
 
 /* dW_l = dY_l^T X_{l-1} and db_l = sum_p dY_l for every layer, accumulated (atomically) into the caller's
  * zero-initialised fp32 gradient buffers `grads_host_array` (device pointers in the canonical parameter order; entry 0,
- * the embedding grid, is not touched).  Reads the two tapes with TMA tensor loads.  The frame-constant input columns
+ * the embedding grid, is not touched).  Reads the tape chunks with TMA bulk loads.  The frame-constant input columns
  * of folded layers are left untouched (their gradient is the rank-1 product db x cvec).  `units_workspace`: >= 256 KB
  * of device memory.  Results carry the `scale` factor of sahs_field_bwd. */
 int sahs_field_wgrad(const sahs_model_spec* spec, int level, float* const* grads_host_array, const void* tape_x,

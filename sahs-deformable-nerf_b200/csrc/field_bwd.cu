@@ -5,8 +5,8 @@
 // order of the backward plan (sahs_build_bwd_plan), activations' sign masks recorded by the training forward.
 // d_raw is multiplied by a caller-chosen scale so that fp16 (11-bit significand; bf16's 8 bits give ~8% noise on the
 // gradient of the warped point after the 2^9 gain of the encoding) does not underflow.
-// Every layer's activation gradient is written (fp16, scaled, row-major) to the gradient tape; the weight gradients
-// dW_l = dY_l^T X_{l-1} are plain GEMMs over the two tapes (host side, sahs_b200/train.py).
+// Every layer's activation gradient (fp16, scaled) is an operand chunk in shared memory anyway; those chunks go to the
+// gradient tape with TMA bulk stores (tile-major chunk images) for the wgrad kernel: dW_l = dY_l^T X_{l-1}.
 // ref (what autograd differentiates in the reference): nerf/modules.py:254-295, :371-390, :444-462,
 //      nerf/models.py:301-365, nerf/nerf_helpers.py:305-349.
 #include "field_dev.cuh"
@@ -17,7 +17,7 @@ struct BwdIO {
   const float* d_raw;       // [P,16]
   const uint4* masks;       // [layer][P][2]
   const float* saves;       // [P,8]: warped point (3), ambient (<=2)
-  __half* tape_d;           // [P, dm.td_total] fp16, scaled by *scale
+  __half* tape_d;           // gradient tape: [tiles][td_total / 64][128 x 64] fp16 chunk images, scaled by *scale
   float* grid_grad;         // channel-last [32,32,32,32] fp32, atomically accumulated (may be null)
   const float* scale;       // device scalar: d_raw is multiplied by it (fp16 range management); outputs carry the factor
 };
@@ -71,10 +71,11 @@ __device__ __forceinline__ int pe_backward(TmemCols& rd, int col, const float (&
   return col;
 }
 
-// dgrad epilogue: accumulator (no bias) -> [+ rank-1 sigma term] -> x activation derivative -> bf16 -> X and tape
+// dgrad epilogue: accumulator (no bias) -> [+ rank-1 sigma term] -> x activation derivative -> fp16 -> X (the operand
+// chunks then go to the gradient tape with TMA bulk stores)
 template <int ACT, int NBLK, bool ADD_SIGMA>
 __device__ __forceinline__ void bwd_epilogue(uint32_t tmem_row, int cbeg, uint4 mask, uint8_t* X, int row,
-                                             __half* tape_row, float dsig, const float* __restrict__ w_alpha) {
+                                             float dsig, const float* __restrict__ w_alpha) {
   uint8_t* rowp = X + (row >> 3) * 1024 + (row & 7) * 128;
   const uint32_t mw[4] = {mask.x, mask.y, mask.z, mask.w};
   uint32_t va[16], vb[16];
@@ -110,10 +111,6 @@ __device__ __forceinline__ void bwd_epilogue(uint32_t tmem_row, int cbeg, uint4 
     for (int q = 0; q < 2; ++q)
       *reinterpret_cast<uint4*>(chunk + ((((u0 + q) ^ row) & 7) << 4)) =
           make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-    if (tape_row) {
-      *reinterpret_cast<uint4*>(tape_row + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      *reinterpret_cast<uint4*>(tape_row + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-    }
   }
 }
 
@@ -203,7 +200,21 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       const bool valid = p < P;
       const long long pc = valid ? p : P - 1;
       const long long ray = pc / S;
-      __half* tape = valid ? io.tape_d + p * dm.td_total : nullptr;
+      // gradient tape of this tile: tile-major chunk images (sahs_make_dims), written from X with TMA bulk stores
+      uint8_t* tape_tile = reinterpret_cast<uint8_t*>(io.tape_d) + (size_t)tile * (dm.td_total / 64) * kChunkBytes;
+      auto tape_put = [&](int chunk0, int nch, int col) {   // after every worker fenced its writes (signal_a)
+        group_sync();
+        if (threadIdx.x == 0) {
+          for (int i = 0; i < nch; ++i)
+            tma_bulk_s2g(tape_tile + (size_t)(col / 64 + i) * kChunkBytes, X + (chunk0 + i) * kChunkBytes, kChunkBytes);
+          tma_store_commit();
+        }
+      };
+      auto tape_drain = [&]() {   // before X is overwritten: earlier bulk stores have finished reading it
+        if (threadIdx.x == 0) tma_store_wait_read();
+        group_sync();
+      };
+      tape_drain();
       auto mask_of = [&](int layer) -> uint4 {
         return __ldg(io.masks + ((size_t)layer * P + pc) * 2 + grp);
       };
@@ -226,24 +237,23 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       if (grp == 0) {
         uint32_t pk[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) pk[j] = pack2<true>(dr[2 * j], j == 7 ? 0.f : dr[2 * j + 1]);
+        // column 15 (d sigma) stays in the operand: the transposed output-layer image has a zero row there, and the
+        // tape copy of this chunk feeds the wgrad of fc_alpha
+        for (int j = 0; j < 8; ++j) pk[j] = pack2<true>(dr[2 * j], dr[2 * j + 1]);
         uint8_t* rowp = X + (row >> 3) * 1024 + (row & 7) * 128;
         *reinterpret_cast<uint4*>(rowp + (((0 ^ row) & 7) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         *reinterpret_cast<uint4*>(rowp + (((1 ^ row) & 7) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        if (tape) {
-          pk[7] = pack2<true>(dr[14], dr[15]);    // the tape keeps d sigma (wgrad of fc_alpha)
-          *reinterpret_cast<uint4*>(tape + dm.td_out) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(tape + dm.td_out + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
       }
       signal_a(sy);
+      tape_put(0, 1, dm.td_out);
       // ---- heads ----
       for (int i = 3; i >= 0; --i) {   // pass producing d(head hidden i): output layer for i == 3, layers i+1 otherwise
         const uint4 m = mask_of(wl + dm.t_layers + i);
         wait_acc(sy, 5000 + i);
-        bwd_epilogue<ACT_LEAKY, 8, false>(tmem_row, grp * 128, m, X, row, tape ? tape + dm.td_hh + i * 2 * dm.hd : nullptr,
-                                          0.f, nullptr);
+        tape_drain();
+        bwd_epilogue<ACT_LEAKY, 8, false>(tmem_row, grp * 128, m, X, row, 0.f, nullptr);
         signal_a(sy);
+        tape_put(0, 2 * dm.hd / 64, dm.td_hh + i * 2 * dm.hd);
       }
       // d [PE(dir) | embedding]: only the embedding part carries gradient
       const float* sv = io.saves + pc * 8;
@@ -265,16 +275,18 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       signal_a(sy);
       // d feat = dir/seg contributions + d sigma * fc_alpha
       wait_acc(sy, 5200);
-      bwd_epilogue<ACT_NONE, 8, true>(tmem_row, grp * 128, make_uint4(0, 0, 0, 0), X, row,
-                                      tape ? tape + dm.td_feat : nullptr, dsig, fc + dm.off_alpha);
+      tape_drain();
+      bwd_epilogue<ACT_NONE, 8, true>(tmem_row, grp * 128, make_uint4(0, 0, 0, 0), X, row, dsig, fc + dm.off_alpha);
       signal_a(sy);
+      tape_put(0, dm.th / 64, dm.td_feat);
       // fc_feat^T -> d(trunk hidden L-1)
       {
         const uint4 m = mask_of(wl + dm.t_layers - 1);
         wait_acc(sy, 5300);
-        bwd_epilogue<ACT_LEAKY, 8, false>(tmem_row, grp * 128, m, X, row,
-                                          tape ? tape + dm.td_th + (dm.t_layers - 1) * dm.th : nullptr, 0.f, nullptr);
+        tape_drain();
+        bwd_epilogue<ACT_LEAKY, 8, false>(tmem_row, grp * 128, m, X, row, 0.f, nullptr);
         signal_a(sy);
+        tape_put(0, dm.th / 64, dm.td_th + (dm.t_layers - 1) * dm.th);
       }
       // ---- trunk ----
       for (int i = dm.t_layers - 1; i >= 0; --i) {
@@ -288,9 +300,10 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         if (i > 0) {
           const uint4 m = mask_of(wl + i - 1);
           wait_acc(sy, 5500 + i);
-          bwd_epilogue<ACT_LEAKY, 8, false>(tmem_row, grp * 128, m, X, row,
-                                            tape ? tape + dm.td_th + (i - 1) * dm.th : nullptr, 0.f, nullptr);
+          tape_drain();
+          bwd_epilogue<ACT_LEAKY, 8, false>(tmem_row, grp * 128, m, X, row, 0.f, nullptr);
           signal_a(sy);
+          tape_put(0, dm.th / 64, dm.td_th + (i - 1) * dm.th);
         }
       }
       if (C::USE_W) {
@@ -304,21 +317,23 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
           const float t = mapped[k] - pt[k];
           dpre[k] = dmap[k] * (1.f - t * t);
         }
-        if (grp == 0 && tape) {
+        tape_drain();   // the trunk's last gradient chunks have left X
+        if (grp == 0) {
+          // d(pre-tanh dx, ambient) -> columns 0-15 of chunk 3 (idle during the deformation layers) -> tape item td_final
           float f8[8] = {dpre[0], dpre[1], dpre[2], 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int k = 0; k < C::AMB_DIM; ++k) f8[3 + k] = damb[k];
-          *reinterpret_cast<uint4*>(tape + dm.td_final) =
+          uint8_t* r3 = X + 3 * kChunkBytes + (row >> 3) * 1024 + (row & 7) * 128;
+          *reinterpret_cast<uint4*>(r3 + (((0 ^ row) & 7) << 4)) =
               make_uint4(pack2<true>(f8[0], f8[1]), pack2<true>(f8[2], f8[3]), pack2<true>(f8[4], f8[5]),
                          pack2<true>(f8[6], f8[7]));
-          *reinterpret_cast<uint4*>(tape + dm.td_final + 8) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(r3 + (((1 ^ row) & 7) << 4)) = make_uint4(0u, 0u, 0u, 0u);
         }
         const float* wf = fc + dm.off_wfinal;
         const float* wa = wf + 3 * dm.wh + 4;
         const uint4 m5 = mask_of(dm.w_layers - 1);
         const uint32_t mw[4] = {m5.x, m5.y, m5.z, m5.w};
         uint8_t* rowp = X + (row >> 3) * 1024 + (row & 7) * 128;
-        __half* t5 = tape ? tape + dm.td_wh + (dm.w_layers - 1) * dm.whh : nullptr;
 #pragma unroll
         for (int blk = 0; blk < 6; ++blk) {
           const int c0 = grp * 96 + 16 * blk;
@@ -348,23 +363,24 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
           for (int q = 0; q < 2; ++q)
             *reinterpret_cast<uint4*>(chunk + ((((u0 + q) ^ row) & 7) << 4)) =
                 make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-          if (t5) {
-            *reinterpret_cast<uint4*>(t5 + c0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(t5 + c0 + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          }
         }
         signal_a(sy);
+        tape_put(0, dm.whh / 64, dm.td_wh + (dm.w_layers - 1) * dm.whh);
+        tape_put(3, 1, dm.td_final);
         for (int i = dm.w_layers - 1; i >= 1; --i) {
           const uint4 m = mask_of(i - 1);
           wait_acc(sy, 5600 + i);
-          bwd_epilogue<ACT_RELU, 6, false>(tmem_row, grp * 96, m, X, row, tape ? tape + dm.td_wh + (i - 1) * dm.whh : nullptr,
-                                           0.f, nullptr);
+          tape_drain();
+          bwd_epilogue<ACT_RELU, 6, false>(tmem_row, grp * 96, m, X, row, 0.f, nullptr);
           if (i > 1) signal_a(sy);
+          else fence_proxy_async_smem();   // the last gradient chunk is only stored, not multiplied
+          tape_put(0, dm.whh / 64, dm.td_wh + (i - 1) * dm.whh);
         }
       }
       tc_fence_before();
       group_sync();
     }
+    if (threadIdx.x == 0) tma_store_wait_all();   // tape stores complete before the CTA exits
   }
   __syncthreads();
   if (warp == kMmaWarp) {

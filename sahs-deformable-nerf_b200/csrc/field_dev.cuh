@@ -115,7 +115,6 @@ template <bool F16, int NUNITS, bool SPLIT = true>
 struct RowStream {
   uint8_t* rowp;   // X + row offset inside a chunk
   int chunk0, row, grp;
-  __half* tape = nullptr;          // training: this row's slice of the activation tape (fp16, row-major)
   float buf[8];
   __device__ __forceinline__ RowStream(uint8_t* X, int chunk0_, int row_, int grp_)
       : rowp(X + (row_ >> 3) * 1024 + (row_ & 7) * 128), chunk0(chunk0_), row(row_), grp(grp_) {}
@@ -131,10 +130,6 @@ struct RowStream {
         q.z = pack2<F16>(buf[4], buf[5]);
         q.w = pack2<F16>(buf[6], buf[7]);
         *reinterpret_cast<uint4*>(rowp + (chunk0 + (u >> 3)) * kChunkBytes + ((((u & 7) ^ row) & 7) << 4)) = q;
-        if (tape)
-          *reinterpret_cast<uint4*>(tape + 8 * u) =
-              make_uint4(pack2<true>(buf[0], buf[1]), pack2<true>(buf[2], buf[3]), pack2<true>(buf[4], buf[5]),
-                         pack2<true>(buf[6], buf[7]));
       }
     }
   }
@@ -215,7 +210,7 @@ __device__ __forceinline__ void load_bias(float4 (&b)[4], const float* __restric
 template <int ACT, bool F16, bool DOT, bool DBG, bool TRAIN = false, bool FCS = false>
 __device__ __forceinline__ void epi_block(uint32_t (&v)[16], float4 (&b)[4], const float* __restrict__ next_bias, int c0,
                                           uint8_t* rowp, int row, const float* __restrict__ dot_w, float& dot,
-                                          float* dbg_row, __half* tape_row = nullptr, uint32_t* mbits = nullptr) {
+                                          float* dbg_row, uint32_t* mbits = nullptr) {
   float f[16];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -226,22 +221,11 @@ __device__ __forceinline__ void epi_block(uint32_t (&v)[16], float4 (&b)[4], con
   }
   if (next_bias) load_bias<FCS>(b, next_bias);
   if (TRAIN) {
-    // training: sign bits for the activation derivative and the activated values (fp16, row-major) for the wgrad
+    // training: sign bits of the pre-activations (the activated values reach the tape as whole operand chunks)
     uint32_t bits = 0;
-    uint32_t tp[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float a0 = f[2 * j], a1 = f[2 * j + 1];
-      bits |= (a0 > 0.f ? 1u : 0u) << (2 * j);
-      bits |= (a1 > 0.f ? 1u : 0u) << (2 * j + 1);
-      const float lk = ACT == ACT_LEAKY ? 0.01f : 0.f;
-      tp[j] = (ACT == ACT_NONE) ? pack2<true>(a0, a1) : pack2<true>(fmaxf(a0, lk * a0), fmaxf(a1, lk * a1));
-    }
+    for (int j = 0; j < 16; ++j) bits |= (f[j] > 0.f ? 1u : 0u) << j;
     if (mbits) *mbits = bits;
-    if (tape_row) {
-      *reinterpret_cast<uint4*>(tape_row + c0) = make_uint4(tp[0], tp[1], tp[2], tp[3]);
-      *reinterpret_cast<uint4*>(tape_row + c0 + 8) = make_uint4(tp[4], tp[5], tp[6], tp[7]);
-    }
   }
   uint32_t pk[8];
 #pragma unroll
@@ -276,7 +260,7 @@ __device__ __forceinline__ void epi_block(uint32_t (&v)[16], float4 (&b)[4], con
 template <int ACT, bool F16, bool DOT, bool DBG, int NBLK, bool TRAIN = false, bool FCS = false>
 __device__ __forceinline__ float epilogue(uint32_t tmem_row, int cbeg, const float* __restrict__ bias, float4 (&b)[4],
                                           uint8_t* X, int row, const float* __restrict__ dot_w, float* dbg_row,
-                                          __half* tape_row = nullptr, uint4* mask_out = nullptr) {
+                                          uint4* mask_out = nullptr) {
   float dot = 0.f;
   uint32_t mw[4] = {0u, 0u, 0u, 0u};
   uint8_t* rowp = X + (row >> 3) * 1024 + (row & 7) * 128;
@@ -290,10 +274,10 @@ __device__ __forceinline__ float epilogue(uint32_t tmem_row, int cbeg, const flo
     uint32_t bits = 0;
     if (blk & 1) {
       if (blk + 1 < NBLK) tmem_ld16_prefetch(tmem_row + c0 + 16, va, vb[0]);
-      epi_block<ACT, F16, DOT, DBG, TRAIN, FCS>(vb, b, nb, c0, rowp, row, dot_w, dot, dbg_row, tape_row, &bits);
+      epi_block<ACT, F16, DOT, DBG, TRAIN, FCS>(vb, b, nb, c0, rowp, row, dot_w, dot, dbg_row, &bits);
     } else {
       if (blk + 1 < NBLK) tmem_ld16_prefetch(tmem_row + c0 + 16, vb, va[0]);
-      epi_block<ACT, F16, DOT, DBG, TRAIN, FCS>(va, b, nb, c0, rowp, row, dot_w, dot, dbg_row, tape_row, &bits);
+      epi_block<ACT, F16, DOT, DBG, TRAIN, FCS>(va, b, nb, c0, rowp, row, dot_w, dot, dbg_row, &bits);
     }
     if (TRAIN) mw[blk >> 1] |= bits << ((blk & 1) * 16);
   }

@@ -24,8 +24,8 @@
 
 namespace {
 
-// TRAIN: additionally records what the backward pass needs -- every layer's activated output (fp16, row-major
-// "activation tape" [P, dm.tx_total]), the sign bits of the pre-activations ([layer][P][2] x 128 bit) and the warped
+// TRAIN: additionally records what the backward pass needs -- every layer's activated output (fp16 "activation tape",
+// tile-major chunk images written with TMA bulk stores, layout in sahs_make_dims), the sign bits of the pre-activations ([layer][P][2] x 128 bit) and the warped
 // point / ambient coordinates ([P,8] fp32).
 struct TrainOut {
   __half* tape_x;
@@ -150,8 +150,28 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
 #pragma unroll
       for (int k = 0; k < 3; ++k) pt[k] = __fadd_rn(ro[ray * 3 + k], __fmul_rn(dir[k], zz));
       float* dbg_row = (DBG && dbg && tile == 0) ? dbg + row * 256 : nullptr;
-      // training tape slices of this row (null for padding rows of the last tile)
-      __half* tape = (TRAIN && valid) ? tr.tape_x + p * dm.tx_total : nullptr;
+      // training: activation tape of this tile, tile-major chunk images (sahs_make_dims); operand chunks go there
+      // straight from shared memory with TMA bulk stores
+      uint8_t* tape_tile = TRAIN ? reinterpret_cast<uint8_t*>(tr.tape_x) + (size_t)tile * (dm.tx_total / 64) * kChunkBytes
+                                 : nullptr;
+      // X chunks [chunk0, chunk0 + nch) -> tape columns [col, col + 64 nch).  Every worker has fenced its writes
+      // (signal_a or an explicit fence.proxy.async) before calling.
+      auto tape_put = [&](int chunk0, int nch, int col) {
+        if (!TRAIN) return;
+        group_sync();
+        if (threadIdx.x == 0) {
+          for (int i = 0; i < nch; ++i)
+            tma_bulk_s2g(tape_tile + (size_t)(col / 64 + i) * kChunkBytes, X + (chunk0 + i) * kChunkBytes, kChunkBytes);
+          tma_store_commit();
+        }
+      };
+      // before X is overwritten: the bulk stores issued so far have finished reading shared memory
+      auto tape_drain = [&]() {
+        if (!TRAIN) return;
+        if (threadIdx.x == 0) tma_store_wait_read();
+        group_sync();
+      };
+      tape_drain();
       auto mask_slot = [&](int layer) -> uint4* {
         return (TRAIN && valid) ? tr.masks + ((size_t)layer * P + p) * 2 + grp : nullptr;
       };
@@ -216,19 +236,20 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         // -------- deformation phase: warp | hyper-sheet merged (fp16 operands) --------
         auto write_e0 = [&](int chunk0) {
           RowStream<true, C::E0_PAD / 8> st(X, chunk0, row, grp);
-          if (TRAIN && tape) st.tape = tape + dm.tx_e0;
           int col = pe_stream<C::XYZ_L, true, 3>(st, 0, pt);
 #pragma unroll
           for (int i = C::E0_DIM; i < C::E0_PAD; ++i) st.put(col++, 0.f);
         };
         write_e0(dm.e0_chunk_base);
         signal_a(sy);
+        tape_put(dm.e0_chunk_base, dm.e0_chunks, dm.tx_e0);
         for (int i = 0; i < dm.w_layers - 1; ++i) {
           const float* bias = fcw + dm.off_wbias + i * dm.whh;
           const bool two_pass = (i == dm.w_skip && !dm.e0_resident);
           float4 b[4];
           if (!two_pass) load_bias<PAIR>(b, bias + grp * 96);
           wait_acc(sy, 1000 + i);
+          tape_drain();
           if (two_pass) {
             write_e0(0);
             signal_a(sy);
@@ -238,15 +259,18 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
           // whh = 192: three 32-column blocks per group
           epilogue<ACT_RELU, true, false, DBG, 6, TRAIN, PAIR>(tmem_row, grp * 96, bias, b, X, row, nullptr,
                                                          (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) ? dbg_row : nullptr,
-                                                         tape ? tape + dm.tx_wh + i * dm.whh : nullptr, mask_slot(i));
+                                                         mask_slot(i));
           signal_a(sy);
+          tape_put(0, dm.whh / 64, dm.tx_wh + i * dm.whh);
         }
         {
           // last hidden layer stays in fp32: dx = tanh(fc_final h_w), ambient = fc_ambient h_h.  Group g reduces its
           // 96 columns; the 5 partial sums per row are exchanged through the (idle) X buffer.
           const int i = dm.w_layers - 1;
           wait_acc(sy, 1000 + i);
+          tape_drain();
           if (i == dm.w_skip && !dm.e0_resident) { write_e0(0); signal_a(sy); wait_acc(sy, 1100 + i); }
+          uint8_t* rowp5 = X + (row >> 3) * 1024 + (row & 7) * 128;
           const float* bias = fcw + dm.off_wbias + i * dm.whh;
           const float* wf = fcw + dm.off_wfinal;
           const float* bf = wf + 3 * dm.wh;          // [wf 3*wh | bf 4 | wa amb*hh | ba 4], all 16-byte aligned
@@ -268,9 +292,10 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
               if (TRAIN) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) hmask[blk] |= (h[q] > 0.f ? 1u : 0u) << (4 * j + q);
-                if (tape)
-                  *reinterpret_cast<uint2*>(tape + dm.tx_wh + i * dm.whh + c0 + 4 * j) =
-                      make_uint2(pack2<true>(h[0], h[1]), pack2<true>(h[2], h[3]));
+                // the tape needs this layer's output as an operand chunk too (X chunks 0-2 are free here)
+                const int col = c0 + 4 * j;
+                *reinterpret_cast<uint2*>(rowp5 + (col >> 6) * kChunkBytes + (((((col & 63) >> 3) ^ row) & 7) << 4) +
+                                          (col & 7) * 2) = make_uint2(pack2<true>(h[0], h[1]), pack2<true>(h[2], h[3]));
               }
               if (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) {
 #pragma unroll
@@ -295,7 +320,12 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
             uint4* ms = mask_slot(i);
             if (ms) *ms = make_uint4(hmask[0], hmask[1], hmask[2], 0u);
           }
-          float* scratch = reinterpret_cast<float*>(X);   // [2][128][8]
+          if (TRAIN) {
+            fence_proxy_async_smem();
+            tape_put(0, dm.whh / 64, dm.tx_wh + i * dm.whh);
+          }
+          // [2][128][8] floats; training keeps chunks 0-2 for the tape store above and uses the (now idle) chunk 3
+          float* scratch = reinterpret_cast<float*>(X + (TRAIN ? 3 * kChunkBytes : 0));
 #pragma unroll
           for (int k = 0; k < 3 + C::AMB_DIM; ++k) scratch[(grp * 128 + row) * 8 + k] = part[k];
           group_sync();
@@ -306,6 +336,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
           for (int k = 0; k < C::AMB_DIM; ++k)
             amb[k] = scratch[row * 8 + 3 + k] + scratch[(128 + row) * 8 + 3 + k] + ldc1<PAIR>(ba + k);
           group_sync();   // scratch is dead before E1 overwrites it
+          tape_drain();
         }
       }
       if (TRAIN && valid && grp == 0) {
@@ -334,7 +365,6 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       // -------- trunk (bf16 operands) --------
       auto write_e1 = [&]() {
         RowStream<kTrunkF16, C::E1_PAD / 8> st(X, 0, row, grp);
-        if (TRAIN && tape) st.tape = tape + dm.tx_e1;
         int col = pe_stream<C::XYZ_L, true, 3>(st, 0, mapped);
         if (C::AMB_PE > 0) col = pe_stream<C::AMB_L, C::AMB_INC, (C::AMB_DIM > 0 ? C::AMB_DIM : 1)>(st, col, amb);
 #pragma unroll
@@ -342,11 +372,13 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       };
       write_e1();
       signal_a(sy);
+      tape_put(0, dm.e1_chunks, dm.tx_e1);
       for (int i = 0; i < dm.t_layers; ++i) {
         const float* bias = fcw + dm.off_tbias + i * dm.th;
         float4 b[4];
         if (i != dm.t_skip) load_bias<PAIR>(b, bias + grp * 128);
         wait_acc(sy, 2000 + i);
+        tape_drain();
         if (i == dm.t_skip) {
           write_e1();
           signal_a(sy);
@@ -356,25 +388,28 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         epilogue<ACT_LEAKY, kTrunkF16, false, DBG, 8, TRAIN, PAIR>(
             tmem_row, grp * 128, bias, b, X, row, nullptr,
             (DBG && dbg_row && dbg_pass == SAHS_DBG_TRUNK(i)) ? dbg_row : nullptr,
-            tape ? tape + dm.tx_th + i * dm.th : nullptr, mask_slot((C::USE_W ? dm.w_layers : 0) + i));
+            mask_slot((C::USE_W ? dm.w_layers : 0) + i));
         signal_a(sy);
+        tape_put(0, dm.th / 64, dm.tx_th + i * dm.th);
       }
       // fc_feat (no activation) + sigma = fc_alpha(feat) in fp32 (partial dot per group)
       float4 bfe[4];
       load_bias<PAIR>(bfe, fcw + dm.off_featb + grp * 128);
       wait_acc(sy, 2200);
+      tape_drain();
       float sigma = epilogue<ACT_NONE, kTrunkF16, true, DBG, 8, TRAIN, PAIR>(
           tmem_row, grp * 128, fcw + dm.off_featb, bfe, X, row, fcw + dm.off_alpha,
           (DBG && dbg_row && dbg_pass == SAHS_DBG_TRUNK(dm.t_layers)) ? dbg_row : nullptr,
-          tape ? tape + dm.tx_feat : nullptr, nullptr);
+          nullptr);
       if (grp == 1) xchg[row] = sigma;
       signal_a(sy);
+      tape_put(0, dm.th / 64, dm.tx_feat);
       // -------- heads: layers_dir.0 = [feat | PE(dir) | emb], layers_seg.0 = feat --------
       wait_acc(sy, 3000);
+      tape_drain();
       {
         // extra K-chunk: cols [0,27) PE(dir), [27,59) embedding, zero padding up to 64
         RowStream<kTrunkF16, 8, false> st(X, 0, row, 0);
-        if (TRAIN && tape) st.tape = tape + dm.tx_xtra;
         if (grp == 0) {
           int col = pe_stream<C::DIR_L, true, 3>(st, 0, dir);
 #pragma unroll
@@ -388,20 +423,22 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
           const uint32_t pair = emb_pk[q >> 1];
           const uint16_t hv = (q & 1) ? (uint16_t)(pair >> 16) : (uint16_t)(pair & 0xffffu);
           *reinterpret_cast<uint16_t*>(rowp + ((((col >> 3) ^ row) & 7) << 4) + (col & 7) * 2) = hv;
-          if (TRAIN && tape) tape[dm.tx_xtra + col] = __ushort_as_half(hv);   // for the wgrad of layers_dir.0
         }
       }
       signal_a(sy);
+      tape_put(0, 1, dm.tx_xtra);
       for (int i = 0; i < 4; ++i) {
         const float* bias = fcw + dm.off_hbias + i * 2 * dm.hd;
         float4 b[4];
         load_bias<PAIR>(b, bias + grp * 128);
         wait_acc(sy, 3100 + i);
+        tape_drain();
         epilogue<ACT_LEAKY, kTrunkF16, false, DBG, 8, TRAIN, PAIR>(
             tmem_row, grp * 128, bias, b, X, row, nullptr,
             (DBG && dbg_row && dbg_pass == SAHS_DBG_HEAD(i)) ? dbg_row : nullptr,
-            tape ? tape + dm.tx_hh + i * 2 * dm.hd : nullptr, mask_slot((C::USE_W ? dm.w_layers : 0) + dm.t_layers + i));
+            mask_slot((C::USE_W ? dm.w_layers : 0) + dm.t_layers + i));
         signal_a(sy);
+        tape_put(0, 2 * dm.hd / 64, dm.tx_hh + i * 2 * dm.hd);
       }
       // -------- output layer: cols 0-2 rgb, 3-14 seg (+ sigma) --------
       wait_acc(sy, 3200);
@@ -423,6 +460,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       group_sync();   // xchg[] consumed before the next tile's fc_feat epilogue rewrites it
       if (DBG) prof_event(sy.prof, 3);   // tile end
     }
+    if (TRAIN && threadIdx.x == 0) tma_store_wait_all();   // tape stores complete before the CTA exits
   }
   tc_fence_before();
   __syncthreads();

@@ -91,8 +91,8 @@ struct NetDims {
                                     // one after the other: needed when the encoding has more than 10 octaves
   // frame-constant block offsets (floats)
   int off_wbias, off_wfinal, off_tbias, off_featb, off_alpha, off_hbias, off_outb, fc_total;
-  // training tapes (row-major bf16, one row per point): column offsets of the saved activations (tx_*) and of the
-  // activation gradients (td_*); sign masks are indexed by layer (W i -> i, T i -> w_layers + i, H i -> .. + t_layers + i)
+  // training tapes (fp16 chunk images, see sahs_make_dims): column offsets of the saved activations (tx_*) and of the
+  // activation gradients (td_*), all multiples of 64; sign masks are indexed by layer (W i -> i, T i -> w_layers + i, H i -> .. + t_layers + i)
   int tx_e0, tx_wh, tx_e1, tx_th, tx_feat, tx_xtra, tx_hh, tx_total;
   int td_wh, td_final, td_th, td_feat, td_hh, td_out, td_total;
   int n_mask_layers;
@@ -148,22 +148,27 @@ inline int sahs_make_dims(const sahs_model_spec& s, NetDims& d, bool train = fal
   d.off_hbias = o;  o += 4 * 2 * d.hd;
   d.off_outb = o;   o += 16;
   d.fc_total = o;
+  // Training tapes are stored as tile-major chunk images: tape[tile][slot][128 points x 64 columns, 128B-swizzled] --
+  // exactly the shared-memory operand chunks, written by TMA bulk stores and read back by the wgrad kernel with bulk
+  // loads.  Every item therefore starts at a multiple of 64 columns (slot = column / 64).
+  auto up64 = [](int v) { return (v + 63) / 64 * 64; };
   int t = 0;
-  d.tx_e0 = t;   t += d.use_w ? d.e0_k : 0;
-  d.tx_wh = t;   t += d.use_w ? d.w_layers * d.whh : 0;
-  d.tx_e1 = t;   t += d.e1_k;
+  d.tx_e0 = t;   t += d.use_w ? up64(d.e0_k) : 0;
+  d.tx_wh = t;   t += d.use_w ? d.w_layers * up64(d.whh) : 0;
+  d.tx_e1 = t;   t += up64(d.e1_k);
   d.tx_th = t;   t += d.t_layers * d.th;
   d.tx_feat = t; t += d.th;
   d.tx_xtra = t; t += 64;
   d.tx_hh = t;   t += 4 * 2 * d.hd;
   d.tx_total = t;
   t = 0;
-  d.td_wh = t;    t += d.use_w ? d.w_layers * d.whh : 0;
-  d.td_final = t; t += d.use_w ? 16 : 0;
+  d.td_wh = t;    t += d.use_w ? d.w_layers * up64(d.whh) : 0;
+  d.td_final = t; t += d.use_w ? 64 : 0;
   d.td_th = t;    t += d.t_layers * d.th;
   d.td_feat = t;  t += d.th;
   d.td_hh = t;    t += 4 * 2 * d.hd;
-  d.td_out = t;   t += 16;
+  d.td_out = t;   t += 64;
+  t += 64;        // the wgrad kernel always fetches two dY chunks: one slot of slack after the last item
   d.td_total = t;
   d.n_mask_layers = (d.use_w ? d.w_layers : 0) + d.t_layers + 4;
   return 0;

@@ -1,14 +1,14 @@
 // (2c) Weight gradients of the fused field: dW_l[n,k] = sum_p dY_l[p,n] X_{l-1}[p,k], db_l[n] = sum_p dY_l[p,n],
-// straight from the two training tapes (row-major fp16 [P, cols]) with tcgen05.
+// straight from the two training tapes with tcgen05.
 //
-//   * operands: 128-point x 64-feature boxes fetched by TMA tensor loads (cp.async.bulk.tensor.2d, 128B swizzle) --
-//     a box lands in shared memory as an MN-major UMMA operand tile (features contiguous, K = points);
+//   * operands: the tapes are tile-major chunk images (tape[tile][slot][128 points x 64 features, 128B-swizzled], the
+//     forward / backward kernels' own operand chunks, see sahs_make_dims), so a chunk is one contiguous 16 KB bulk copy
+//     (cp.async.bulk) and lands in shared memory as an MN-major UMMA operand tile (features contiguous, K = points);
 //   * one work unit = (<=128 output rows of one layer, <=4 input chunks, a range of tiles): the accumulator
 //     D[128, 64*nB + 16] stays in TMEM across the whole tile range (the extra 16 columns multiply dY by a constant
 //     "ones" operand, i.e. the bias gradient), then is added to the fp32 gradient buffers with red.global.add;
 //   * 1 CTA per SM: warp 0 TMA, warp 1 MMA issue, warps 2-5 epilogue; two 96 KB operand stages.
 // HBM-bound: every unit streams its dY and X boxes once (about 3 MB per tile over all layers).
-#include <cuda.h>
 #include <string.h>
 #include <vector>
 #include "field_dev.cuh"
@@ -33,19 +33,13 @@ struct WOut {          // where a slice of the accumulator goes
 };
 struct WUnit {
   int32_t t0, t1;      // tile range
-  int32_t a_col;       // first column of dY in the gradient tape (128 columns are loaded)
+  int32_t a_col;       // first column of dY in the gradient tape (two 64-column chunks are loaded), multiple of 64
   int32_t nB;
-  int32_t b_col[4];    // first column of each 64-wide input chunk in the activation tape
+  int32_t b_col[4];    // first column of each 64-wide input chunk in the activation tape, multiples of 64
   WOut g[2];
 };
 
 
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-      : "memory");
-}
 // MN-major SWIZZLE_128B operand: 64-feature panels of [128 points x 128 B], panels 16 KB apart (LBO), 8-point groups
 // 1 KB apart (SBO); cute::UMMA::make_umma_desc<Major::MN> / DeepGEMM make_umma_desc conventions.
 __device__ __forceinline__ uint64_t umma_smem_desc_mn_sw128(uint32_t smem_addr) {
@@ -62,7 +56,7 @@ __device__ __forceinline__ uint32_t umma_idesc_mn_f16_m128(uint32_t n) {   // fp
 }
 
 __global__ void __launch_bounds__(kWThreads, 1)
-field_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_d,
+field_wgrad_kernel(const uint8_t* __restrict__ tape_x, const uint8_t* __restrict__ tape_d, int slots_x, int slots_d,
                    const WUnit* __restrict__ units, int nunits, int* __restrict__ status) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ones = smem + kWSmemOnes;
@@ -108,10 +102,12 @@ field_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
         if (lane == 0) {
           uint8_t* base = smem + stage * kWStageBytes;
           mbar_arrive_expect_tx(&full[stage], (uint32_t)(2 + un.nB) * kChunkBytes);
-          tma_load_2d(base, &tm_d, un.a_col, t * kTileRows, &full[stage]);
-          tma_load_2d(base + kChunkBytes, &tm_d, un.a_col + 64, t * kTileRows, &full[stage]);
+          const uint8_t* dt = tape_d + ((size_t)t * slots_d + (un.a_col >> 6)) * kChunkBytes;
+          tma_bulk_g2s(base, dt, 2 * kChunkBytes, &full[stage]);                  // two adjacent dY chunks
+          const uint8_t* xt = tape_x + (size_t)t * slots_x * kChunkBytes;
           for (int j = 0; j < un.nB; ++j)
-            tma_load_2d(base + (2 + j) * kChunkBytes, &tm_x, un.b_col[j], t * kTileRows, &full[stage]);
+            tma_bulk_g2s(base + (2 + j) * kChunkBytes, xt + (size_t)(un.b_col[j] >> 6) * kChunkBytes, kChunkBytes,
+                         &full[stage]);
         }
         __syncwarp();
         if (++stage == kWStages) { stage = 0; phase ^= 1; }
@@ -203,36 +199,7 @@ field_wgrad_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_consta
   }
 }
 
-// ---- host: tensor maps + unit list -----------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int make_tape_map(CUtensorMap* tm, const void* base, long long rows, int cols) {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) {
-      sahs_set_error("cuTensorMapEncodeTiled entry point not available");
-      return SAHS_ECUDA;
-    }
-    fn = (EncodeTiledFn)p;
-  }
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)kTileRows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    sahs_set_error("cuTensorMapEncodeTiled failed (%d) for a [%lld x %d] tape", (int)r, rows, cols);
-    return SAHS_ECUDA;
-  }
-  return SAHS_OK;
-}
-
+// ---- host: unit list ----------------------------------------------------------------------------------------------
 struct UnitBuilder {
   std::vector<WUnit> blocks;   // one entry per (layer block); tile ranges are split later
   // chunks: list of (activation-tape column, destination column in W, valid columns)
@@ -401,17 +368,18 @@ extern "C" int sahs_field_wgrad(const sahs_model_spec* spec, int level, float* c
   cudaStream_t st = (cudaStream_t)stream;
   SAHS_CUDA(cudaMemcpyAsync(units_workspace, units.data(), units.size() * sizeof(WUnit), cudaMemcpyHostToDevice, st));
   SAHS_CUDA(cudaStreamSynchronize(st));   // the host vector dies at return (pageable source)
-  CUtensorMap tm_x, tm_d;
-  rc = make_tape_map(&tm_x, tape_x, num_points, d.tx_total);
-  if (rc) return rc;
-  rc = make_tape_map(&tm_d, tape_d, num_points, d.td_total);
-  if (rc) return rc;
+  for (auto& u : units) {
+    bool ok = (u.a_col & 63) == 0;
+    for (int j = 0; j < u.nB; ++j) ok = ok && (u.b_col[j] & 63) == 0;
+    SAHS_CHECK_ARG(ok, "tape items must start at multiples of 64 columns");
+  }
   SAHS_CUDA(cudaFuncSetAttribute(field_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmemTotal));
   int* status = sahs_status_words(2);
   SAHS_CHECK_ARG(status, "cannot allocate the diagnostic word");
   int grid = nsm < (int)units.size() ? nsm : (int)units.size();
-  field_wgrad_kernel<<<grid, kWThreads, kWSmemTotal, st>>>(tm_x, tm_d, (const WUnit*)units_workspace, (int)units.size(),
-                                                          status);
+  field_wgrad_kernel<<<grid, kWThreads, kWSmemTotal, st>>>((const uint8_t*)tape_x, (const uint8_t*)tape_d,
+                                                          d.tx_total / 64, d.td_total / 64,
+                                                          (const WUnit*)units_workspace, (int)units.size(), status);
   SAHS_LAUNCH_CHECK();
   return SAHS_OK;
 }

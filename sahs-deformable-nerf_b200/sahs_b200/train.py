@@ -3,13 +3,14 @@ gradients as GEMMs over the tapes.
 
 What the reference gets from autograd through WarpFieldMLP / HyperSheetMLP / NeRFMLP / grid_sample / the positional
 encodings (ref: nerf/modules.py:254-295, :371-390, :444-462, nerf/models.py:301-365) is produced here by
-  * `sahs_field_fwd_train`  -- the fused forward, additionally writing every layer's activated output (fp16,
-                               row-major "activation tape"), the activation sign masks and the warped point;
+  * `sahs_field_fwd_train`  -- the fused forward, additionally writing every layer's activated output (the fp16
+                               "activation tape": tile-major images of the kernel's own operand chunks, TMA bulk
+                               stores), the activation sign masks and the warped point;
   * `sahs_field_bwd`        -- the fused activation-gradient chain (tcgen05, transposed fp16 weights, scaled), writing every
-                               layer's dY to the "gradient tape" and scattering into the embedding-grid gradient;
-  * `sahs_field_wgrad`      -- dW_l = dY_l^T X_{l-1} and db_l for every layer: tcgen05 GEMMs fed by TMA tensor loads of
-                               the two tapes, accumulators in TMEM across a tile range, red.global.add into fp32 grads
-                               (SAHS_WGRAD=library switches to torch.mm over tape slices, kept for cross-checking);
+                               layer's dY to the "gradient tape" (same layout) and scattering into the embedding-grid
+                               gradient;
+  * `sahs_field_wgrad`      -- dW_l = dY_l^T X_{l-1} and db_l for every layer: tcgen05 GEMMs fed by bulk loads of the
+                               tape chunks, accumulators in TMEM across a tile range, red.global.add into fp32 grads;
   * the frame-constant input columns (driving 76 | pose code 36) were folded into biases in the forward, so their
     weight gradient is the rank-1 product db x cvec and d(driving) = W_const^T db.
 """
@@ -35,17 +36,9 @@ def train_layout(cspec) -> Dict[str, int]:
     return dict(zip(_LAYOUT_KEYS, list(out)))
 
 
-import os
-
-USE_LIBRARY_WGRAD = os.environ.get("SAHS_WGRAD", "kernel") == "library"
-
-
-def _mm_t(dy: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
-    """dy^T @ x with fp32 accumulation and fp32 output (fp16 operands)."""
-    try:
-        return torch.mm(dy.t(), x, out_dtype=torch.float32)
-    except (TypeError, RuntimeError):
-        return torch.mm(dy.t().float(), x.float())
+def tape_rows(num_points: int) -> int:
+    """Tapes are tile-major chunk images: whole 128-point tiles are stored."""
+    return (num_points + 127) // 128 * 128
 
 
 class TrainState:
@@ -92,7 +85,7 @@ class FieldTrainFn(torch.autograd.Function):
         dev = z.device
         fc = model.frame_constants(level, driving_vec.detach(), pose_code.detach())
         raw = torch.empty(R, S, 16, dtype=torch.float32, device=dev)
-        tape_x = torch.empty(P, lay["tx_total"], dtype=torch.float16, device=dev)
+        tape_x = torch.empty(tape_rows(P), lay["tx_total"], dtype=torch.float16, device=dev)   # [tiles][slots][128x64]
         masks = torch.empty(lay["n_mask_layers"], P, 2, 4, dtype=torch.int32, device=dev)
         saves = torch.empty(P, 8, dtype=torch.float32, device=dev)
         L.check(lib.sahs_field_fwd_train(C.byref(ts.cspec), lvl, L.ptr(ts.packed_train), L.ptr(fc), L.ptr(ts.grid),
@@ -113,7 +106,7 @@ class FieldTrainFn(torch.autograd.Function):
         P = R * S
         dev = z.device
         d_raw = L.f32c(d_raw)
-        tape_d = torch.empty(P, lay["td_total"], dtype=torch.float16, device=dev)   # every column is written by the kernel
+        tape_d = torch.empty(tape_rows(P), lay["td_total"], dtype=torch.float16, device=dev)  # [tiles][slots][128x64]
         grid_grad = torch.zeros(32, 32, 32, 32, dtype=torch.float32, device=dev)
         # fp16 range management without a host sync: scale d_raw so that its largest entry is 16
         scale = (16.0 / d_raw.abs().amax().clamp_min(1e-30)).reshape(1).float()
@@ -121,10 +114,7 @@ class FieldTrainFn(torch.autograd.Function):
                                    L.ptr(rd), L.ptr(z), R, S, L.ptr(d_raw), L.ptr(scale), L.ptr(masks), L.ptr(saves),
                                    L.ptr(tape_d), L.ptr(grid_grad), L.stream_ptr(dev)), "field_bwd")
         cvec = torch.cat((drv.reshape(-1), pcode.reshape(-1)))
-        if USE_LIBRARY_WGRAD:
-            grads, d_cvec = _weight_grads(model, level, lay, tape_x, tape_d, cvec)
-        else:
-            grads, d_cvec = _weight_grads_kernel(model, level, ts, lay, tape_x, tape_d, cvec, P)
+        grads, d_cvec = _weight_grads_kernel(model, level, ts, lay, tape_x, tape_d, cvec, P)
         inv = 1.0 / scale
         grads = [g * inv if g is not None else None for g in grads]
         d_cvec = d_cvec * inv
@@ -175,87 +165,6 @@ def _weight_grads_kernel(model, level, ts, lay, tx, td, cvec, P):
         elif i == lay["t_skip"]:
             fold(params[k], grads[k], grads[k + 1], th + e1d, lay["ct_off"], lay["ct_len"])
         k += 2
-    return grads, d_cvec
-
-
-def _weight_grads(model, level, lay, tx, td, cvec):
-    """dW / db for every parameter in the canonical order of model._level_params(level)."""
-    s = model.spec
-    X = lambda off, w: tx[:, off:off + w]
-    D = lambda off, w: td[:, off:off + w]
-    d_cvec = torch.zeros(112, dtype=torch.float32, device=tx.device)
-    grads: List[Optional[torch.Tensor]] = [None]                 # slot 0: embedding grid (filled by the caller)
-    db_all = td.sum(dim=0, dtype=torch.float32)                  # every bias gradient in one pass over the tape
-    DB = lambda off, w: db_all[off:off + w]
-
-    def layer(W, dyo, n, parts, const=None):
-        """dyo/n: column offset and width of dY in the gradient tape; parts: list of (col0 in W, input slice);
-        const: (col0, c_off, c_len) of the folded columns."""
-        dY = D(dyo, n)
-        dW = torch.zeros_like(W, dtype=torch.float32)
-        for col0, xin in parts:
-            dW[:, col0:col0 + xin.shape[1]] = _mm_t(dY, xin)
-        db = DB(dyo, n)
-        if const is not None:
-            col0, c_off, c_len = const
-            if c_len > 0:
-                dW[:, col0:col0 + c_len] = torch.outer(db, cvec[c_off:c_off + c_len])
-                d_cvec[c_off:c_off + c_len] += W[:, col0:col0 + c_len].float().t() @ db
-        grads.extend([dW, db])
-
-    wh, hh, whh = lay["wh"], lay["hh"], lay["whh"]
-    e0d, e1d = lay["e0_dim"], lay["e1_dim"]
-    if s.use_warp:
-        for name, lo, n, mod in (("warp", 0, wh, model.warp_field_mlp.layers_xyz),
-                                 ("hyper", wh, hh, model.hyper_sheep_mlp.layers_ambient)):
-            for i, lin in enumerate(mod):
-                dyo = lay["td_wh"] + i * whh + lo
-                e0 = X(lay["tx_e0"], e0d)
-                if i == 0:
-                    layer(lin.weight, dyo, n, [(0, e0)], (e0d, 0, 112))
-                else:
-                    xin = X(lay["tx_wh"] + (i - 1) * whh + lo, n)
-                    if i == lay["w_skip"]:
-                        layer(lin.weight, dyo, n, [(0, xin), (n, e0)], (n + e0d, 0, 112))
-                    else:
-                        layer(lin.weight, dyo, n, [(0, xin)])
-            h5 = X(lay["tx_wh"] + (lay["w_layers"] - 1) * whh + lo, n)
-            if name == "warp":
-                grads.extend([_mm_t(D(lay["td_final"], 3), h5), DB(lay["td_final"], 3)])
-            else:
-                grads.extend([_mm_t(D(lay["td_final"] + 3, s.amb_dim), h5), DB(lay["td_final"] + 3, s.amb_dim)])
-    m = model.nerf_mlps[level]
-    th, hd = lay["th"], lay["hd"]
-    e1 = X(lay["tx_e1"], e1d)
-    for i, lin in enumerate(m.layers_xyz):
-        dyo = lay["td_th"] + i * th
-        if i == 0:
-            layer(lin.weight, dyo, th, [(0, e1)], (e1d, lay["ct_off"], lay["ct_len"]))
-        else:
-            xin = X(lay["tx_th"] + (i - 1) * th, th)
-            if i == lay["t_skip"]:
-                layer(lin.weight, dyo, th, [(0, xin), (th, e1)], (th + e1d, lay["ct_off"], lay["ct_len"]))
-            else:
-                layer(lin.weight, dyo, th, [(0, xin)])
-    feat = X(lay["tx_feat"], th)
-    layer(m.fc_feat.weight, lay["td_feat"], th, [(0, X(lay["tx_th"] + (lay["t_layers"] - 1) * th, th))])
-    grads.extend([_mm_t(D(lay["td_out"] + 15, 1), feat), DB(lay["td_out"] + 15, 1)])
-    xtra = X(lay["tx_xtra"], lay["xtra_dim"])
-    for i, lin in enumerate(m.layers_dir):
-        dyo = lay["td_hh"] + i * 2 * hd
-        if i == 0:
-            layer(lin.weight, dyo, hd, [(0, feat), (th, xtra)])
-        else:
-            layer(lin.weight, dyo, hd, [(0, X(lay["tx_hh"] + (i - 1) * 2 * hd, hd))])
-    h3 = lay["tx_hh"] + 3 * 2 * hd
-    grads.extend([_mm_t(D(lay["td_out"], 3), X(h3, hd)), DB(lay["td_out"], 3)])
-    for i, lin in enumerate(m.layers_seg):
-        dyo = lay["td_hh"] + i * 2 * hd + hd
-        if i == 0:
-            layer(lin.weight, dyo, hd, [(0, feat)])
-        else:
-            layer(lin.weight, dyo, hd, [(0, X(lay["tx_hh"] + (i - 1) * 2 * hd + hd, hd))])
-    grads.extend([_mm_t(D(lay["td_out"] + 3, 12), X(h3 + hd, hd)), DB(lay["td_out"] + 3, 12)])
     return grads, d_cvec
 
 
