@@ -10,6 +10,8 @@
 //   * 1 CTA per SM: warp 0 TMA, warp 1 MMA issue, warps 2-5 epilogue; two 96 KB operand stages.
 // HBM-bound: every unit streams its dY and X boxes once (about 3 MB per tile over all layers).
 #include <string.h>
+#include <map>
+#include <mutex>
 #include <vector>
 #include "field_dev.cuh"
 
@@ -366,8 +368,22 @@ extern "C" int sahs_field_wgrad(const sahs_model_spec* spec, int level, float* c
   }
   SAHS_CHECK_ARG(units.size() * sizeof(WUnit) <= workspace_bytes, "units workspace too small (need 256 KB)");
   cudaStream_t st = (cudaStream_t)stream;
-  SAHS_CUDA(cudaMemcpyAsync(units_workspace, units.data(), units.size() * sizeof(WUnit), cudaMemcpyHostToDevice, st));
-  SAHS_CUDA(cudaStreamSynchronize(st));   // the host vector dies at return (pageable source)
+  {
+    // The unit list depends only on the spec, the point count and the gradient pointers; callers that keep those
+    // stable (persistent gradient buffers, one workspace per level) upload it once.  A changed list is uploaded
+    // synchronously (pageable source), an unchanged one costs no copy and -- more importantly -- no stream sync.
+    static std::mutex mu;
+    static std::map<void*, std::vector<WUnit>> uploaded;
+    std::lock_guard<std::mutex> lock(mu);
+    std::vector<WUnit>& prev = uploaded[units_workspace];
+    const bool same = prev.size() == units.size() &&
+                      (units.empty() || memcmp(prev.data(), units.data(), units.size() * sizeof(WUnit)) == 0);
+    if (!same) {
+      SAHS_CUDA(cudaMemcpyAsync(units_workspace, units.data(), units.size() * sizeof(WUnit), cudaMemcpyHostToDevice, st));
+      SAHS_CUDA(cudaStreamSynchronize(st));
+      prev = units;
+    }
+  }
   for (auto& u : units) {
     bool ok = (u.a_col & 63) == 0;
     for (int j = 0; j < u.nB; ++j) ok = ok && (u.b_col[j] & 63) == 0;

@@ -114,10 +114,14 @@ class FieldTrainFn(torch.autograd.Function):
                                    L.ptr(rd), L.ptr(z), R, S, L.ptr(d_raw), L.ptr(scale), L.ptr(masks), L.ptr(saves),
                                    L.ptr(tape_d), L.ptr(grid_grad), L.stream_ptr(dev)), "field_bwd")
         cvec = torch.cat((drv.reshape(-1), pcode.reshape(-1)))
-        grads, d_cvec = _weight_grads_kernel(model, level, ts, lay, tape_x, tape_d, cvec, P)
+        views, d_cvec, flat, sizes = _weight_grads_kernel(model, level, ts, lay, tape_x, tape_d, cvec, P)
         inv = 1.0 / scale
-        grads = [g * inv if g is not None else None for g in grads]
-        d_cvec = d_cvec * inv
+        out = flat * inv                     # un-scale every parameter gradient of the level in one launch; a fresh
+        d_cvec = d_cvec * inv                # tensor, because autograd may keep what it is handed
+        grads, o = [], 0
+        for g, n in zip(views, sizes):
+            grads.append(None if g is None else out[o:o + n].view(g.shape))
+            o += n
         grads[0] = (grid_grad * inv).permute(3, 0, 1, 2).unsqueeze(0).contiguous() if model.spec.use_grid else None
         d_driving = d_cvec[:76].reshape(drv.shape)
         return (None, None, None, None, None, d_driving, None) + tuple(grads)
@@ -129,14 +133,26 @@ def _weight_grads_kernel(model, level, ts, lay, tx, td, cvec, P):
     lib = L.load()
     params = model._level_params(level)
     dev = tx.device
-    grads: List[Optional[torch.Tensor]] = [None if p is None else torch.zeros_like(p, dtype=torch.float32) for p in params]
-    arr = (C.c_void_p * len(grads))()
-    for i, g in enumerate(grads):
-        arr[i] = g.data_ptr() if g is not None else None
-    ws = model.__dict__.setdefault("_wgrad_ws", None)
-    if ws is None or ws.device != dev:
-        ws = torch.empty(256 * 1024, dtype=torch.uint8, device=dev)
-        model.__dict__["_wgrad_ws"] = ws
+    # persistent flat fp32 gradient buffer of this level (one memset per step, stable pointers -> the wgrad kernel's
+    # unit list is uploaded once) with one view per parameter
+    cache = model.__dict__.setdefault("_wgrad_buffers", {})
+    ent = cache.get(level)
+    sig = tuple((None if p is None else (tuple(p.shape), p.device)) for p in params)
+    if ent is None or ent["sig"] != sig:
+        sizes = [0 if p is None else p.numel() for p in params]
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        views, o = [], 0
+        for p, n in zip(params, sizes):
+            views.append(None if p is None else flat[o:o + n].view(p.shape))
+            o += n
+        arr = (C.c_void_p * len(views))()
+        for i, g in enumerate(views):
+            arr[i] = g.data_ptr() if g is not None else None
+        ent = {"sig": sig, "flat": flat, "views": views, "arr": arr, "sizes": sizes,
+               "ws": torch.empty(256 * 1024, dtype=torch.uint8, device=dev)}
+        cache[level] = ent
+    flat, grads, arr, ws = ent["flat"], list(ent["views"]), ent["arr"], ent["ws"]
+    flat.zero_()
     L.check(lib.sahs_field_wgrad(C.byref(ts.cspec), 0 if level == "coarse" else 1, arr, L.ptr(tx), L.ptr(td), P,
                                  L.ptr(ws), ws.numel(), L.stream_ptr(dev)), "field_wgrad")
     d_cvec = torch.zeros(112, dtype=torch.float32, device=dev)
@@ -165,7 +181,7 @@ def _weight_grads_kernel(model, level, ts, lay, tx, td, cvec, P):
         elif i == lay["t_skip"]:
             fold(params[k], grads[k], grads[k + 1], th + e1d, lay["ct_off"], lay["ct_len"])
         k += 2
-    return grads, d_cvec
+    return grads, d_cvec, flat, ent["sizes"]
 
 
 def field_train(model, level, ro, rd, z, driving_vec, pose_code):
