@@ -309,7 +309,7 @@ def main():
         tmodel = getattr(sahs_b200.models, cfg_t.models.mask.type)(cfg_t)
         tmodel.load_state_dict(sd)
         tmodel = tmodel.to(dev)
-        opt = torch.optim.Adam(tmodel.parameters(), lr=float(cfg_t.optimizer.lr))
+        opt = torch.optim.Adam(tmodel.parameters(), lr=float(cfg_t.optimizer.lr), fused=True)   # one multi-tensor launch
         f0 = dev_frames[0]
         ro_all, rd_all = f0["ro"].reshape(-1, 3), f0["rd"].reshape(-1, 3)
         maskf = f0["mask"].view(-1, 12).float()

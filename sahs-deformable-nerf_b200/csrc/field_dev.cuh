@@ -152,8 +152,10 @@ __device__ __forceinline__ int pe_stream(Stream& st, int col, const float (&x)[D
       if (k % 5 == 0) {
         sincosf(x[d] * (float)(1 << k), &s[d], &c[d]);
       } else {
-        const float s2 = 2.f * s[d] * c[d];
-        c[d] = 1.f - 2.f * s[d] * s[d];
+        // explicit roundings (same reason as grid_gather16): sin 2a = (2 sin a) cos a, cos 2a = 1 - (2 sin a) sin a
+        const float t = __fmul_rn(2.f, s[d]);
+        const float s2 = __fmul_rn(t, c[d]);
+        c[d] = __fmaf_rn(-t, s[d], 1.f);
         s[d] = s2;
       }
     }
@@ -387,17 +389,21 @@ __device__ __forceinline__ void final_partial(uint32_t tmem_row, int cbeg, const
 
 // trilinear gather of 16 of the 32 channels from the channel-last embedding grid, ref: nerf/models.py:346-365
 // (align_corners=True, zero padding, raw warped coordinates; x -> last grid dim, z -> first)
+// Explicit rounding intrinsics: the result must not depend on how a particular kernel instantiation contracts
+// (x + 1) * sc or the weight products into FMAs (the pair and single-CTA kernels are compared bit for bit).
 __device__ __forceinline__ void grid_gather16(const float* __restrict__ g, int ch0, float x, float y, float z,
                                               float (&out)[16]) {
   const float sc = 0.5f * (SAHS_GRID_RES - 1);
-  const float ix = (x + 1.f) * sc, iy = (y + 1.f) * sc, iz = (z + 1.f) * sc;
+  const float ix = __fmul_rn(__fadd_rn(x, 1.f), sc), iy = __fmul_rn(__fadd_rn(y, 1.f), sc),
+              iz = __fmul_rn(__fadd_rn(z, 1.f), sc);
   const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
 #pragma unroll
   for (int c = 0; c < 16; ++c) out[c] = 0.f;
 #pragma unroll
   for (int corner = 0; corner < 8; ++corner) {
     const float xi = fx + (corner & 1), yi = fy + ((corner >> 1) & 1), zi = fz + (corner >> 2);
-    const float w = (1.f - fabsf(ix - xi)) * (1.f - fabsf(iy - yi)) * (1.f - fabsf(iz - zi));
+    const float w = __fmul_rn(__fmul_rn(__fsub_rn(1.f, fabsf(__fsub_rn(ix, xi))), __fsub_rn(1.f, fabsf(__fsub_rn(iy, yi)))),
+                              __fsub_rn(1.f, fabsf(__fsub_rn(iz, zi))));
     const bool ok = xi >= 0.f && xi <= SAHS_GRID_RES - 1 && yi >= 0.f && yi <= SAHS_GRID_RES - 1 && zi >= 0.f &&
                     zi <= SAHS_GRID_RES - 1;
     if (ok) {
@@ -406,7 +412,8 @@ __device__ __forceinline__ void grid_gather16(const float* __restrict__ g, int c
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 v = ldg_stream(reinterpret_cast<const float*>(p + q));
-        out[4 * q + 0] += w * v.x; out[4 * q + 1] += w * v.y; out[4 * q + 2] += w * v.z; out[4 * q + 3] += w * v.w;
+        out[4 * q + 0] = __fmaf_rn(w, v.x, out[4 * q + 0]); out[4 * q + 1] = __fmaf_rn(w, v.y, out[4 * q + 1]);
+        out[4 * q + 2] = __fmaf_rn(w, v.z, out[4 * q + 2]); out[4 * q + 3] = __fmaf_rn(w, v.w, out[4 * q + 3]);
       }
     }
   }

@@ -14,7 +14,7 @@ sd = FX.make_state_dict(spec, seed=42, dense=True)
 H = W = 512
 fr = FX.make_frame_inputs(spec, H, W, seed=0)
 model = sahs_b200.AudioFaceModel(cfg); model.load_state_dict(sd); model = model.to(DEV)
-opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+opt = torch.optim.Adam(model.parameters(), lr=5e-4, fused=True)
 pose = fr["pose"].to(DEV)
 with torch.no_grad():
     ro, rd = sahs_b200.get_ray_bundle(H, W, fr["intrinsics"], pose)
