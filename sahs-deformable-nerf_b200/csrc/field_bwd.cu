@@ -9,6 +9,7 @@
 // gradient tape with TMA bulk stores (tile-major chunk images) for the wgrad kernel: dW_l = dY_l^T X_{l-1}.
 // ref (what autograd differentiates in the reference): nerf/modules.py:254-295, :371-390, :444-462,
 //      nerf/models.py:301-365, nerf/nerf_helpers.py:305-349.
+#include <stdlib.h>
 #include "field_dev.cuh"
 
 namespace {
@@ -73,7 +74,7 @@ __device__ __forceinline__ int pe_backward(TmemCols& rd, int col, const float (&
 
 // dgrad epilogue: accumulator (no bias) -> [+ rank-1 sigma term] -> x activation derivative -> fp16 -> X (the operand
 // chunks then go to the gradient tape with TMA bulk stores)
-template <int ACT, int NBLK, bool ADD_SIGMA>
+template <int ACT, int NBLK, bool ADD_SIGMA, bool FCS = false>
 __device__ __forceinline__ void bwd_epilogue(uint32_t tmem_row, int cbeg, uint4 mask, uint8_t* X, int row,
                                              float dsig, const float* __restrict__ w_alpha) {
   uint8_t* rowp = X + (row >> 3) * 1024 + (row & 7) * 128;
@@ -95,8 +96,8 @@ __device__ __forceinline__ void bwd_epilogue(uint32_t tmem_row, int cbeg, uint4 
     for (int j = 0; j < 8; ++j) {
       float g0 = __uint_as_float(v[2 * j]), g1 = __uint_as_float(v[2 * j + 1]);
       if (ADD_SIGMA) {
-        g0 += dsig * ldg_keep1(w_alpha + c0 + 2 * j);
-        g1 += dsig * ldg_keep1(w_alpha + c0 + 2 * j + 1);
+        g0 += dsig * ldc1<FCS>(w_alpha + c0 + 2 * j);
+        g1 += dsig * ldc1<FCS>(w_alpha + c0 + 2 * j + 1);
       }
       if (ACT != ACT_NONE) {
         const float neg = ACT == ACT_LEAKY ? 0.01f : 0.f;
@@ -151,7 +152,7 @@ __device__ __forceinline__ void grid_backward(const float* __restrict__ g, float
   dxyz[0] = sc * gx; dxyz[1] = sc * gy; dxyz[2] = sc * gz;
 }
 
-template <class C>
+template <class C, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 2)
 field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__ NetDims dm,
                  const uint8_t* __restrict__ packed_t, const float* __restrict__ fc, const float* __restrict__ grid,
@@ -160,42 +161,73 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* X = smem;
   uint8_t* slots = smem + kSmemX;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemBar);
+  // same shared-memory layouts as the forward kernel (PAIR: 3 x 8 KB ring + frame constants in shared memory)
+  constexpr int kSlotsBytes = PAIR ? kPairSlots * kPairSlotBytes : kSmemSlots;
+  constexpr int kFcBytes = PAIR ? kPairFcFloats * 4 : 0;
+  float* fc_s = reinterpret_cast<float*>(smem + kSmemX + kSlotsBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kSmemX + kSlotsBytes + kFcBytes);
+  constexpr int NS = PAIR ? kPairSlots : kSlots;
   uint64_t* full = bars;
-  uint64_t* empty = bars + kSlots;
-  uint64_t* a_ready = bars + 2 * kSlots;
-  uint64_t* acc_ready = bars + 2 * kSlots + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kSlots + 2);
+  uint64_t* empty = bars + NS;
+  uint64_t* a_ready = bars + 2 * NS;
+  uint64_t* acc_ready = bars + 2 * NS + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * NS + 2);
+  uint32_t* peer_tmem = tmem_ptr + 1;
 
   // warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the role dispatch convergent and
-  // the MMA issue loop on the uniform datapath (with the plain threadIdx.x >> 5 every tcgen05 instruction below gets a
-  // divergence guard + R2UR moves with scoreboard waits, ~4x slower issue)
+  // the MMA issue loop on the uniform datapath (see field_fwd.cu)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const long long ntiles = (P + kTileRows - 1) / kTileRows;
+  const long long npairs = (ntiles + 1) / 2;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) { status[0] = 2; __trap(); }
-    for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(a_ready, kWorkerThreads);
+    for (int i = 0; i < NS; ++i) { mbar_init(&full[i], (PAIR && rank == 0) ? 2 : 1); mbar_init(&empty[i], 1); }
+    mbar_init(a_ready, PAIR ? 2 * (kWorkerThreads / 32) : kWorkerThreads);
     mbar_init(acc_ready, 1);
     fence_mbar_init();
   }
-  if (warp == kMmaWarp) tmem_alloc(tmem_ptr, kTmemCols);
+  if (PAIR) {
+    for (int i = threadIdx.x; i < dm.fc_total; i += kThreads) fc_s[i] = __ldg(fc + i);
+  }
+  if (warp == kMmaWarp) {
+    if (PAIR) tmem_alloc_pair(tmem_ptr, kTmemCols);
+    else tmem_alloc(tmem_ptr, kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (PAIR) {
+    if (rank == 1 && threadIdx.x == 0) st_cluster_u32(mapa_u32(peer_tmem, 0), tmem_base);
+    cluster_sync_all();
+    if (rank == 0 && threadIdx.x == 0 && *peer_tmem != tmem_base) {
+      status[0] = 3;
+      __threadfence_system();
+      __trap();
+    }
+    __syncthreads();   // reconverge after the single-thread check
+  }
 
   if (warp == kTmaWarp) {
-    tma_warp_loop(plan, packed_t, slots, full, empty, ntiles, status, lane);
+    if (PAIR) tma_warp_loop_pair(plan, packed_t, slots, full, empty, npairs, rank, status, lane);
+    else tma_warp_loop(plan, packed_t, slots, full, empty, ntiles, status, lane);
   } else if (warp == kMmaWarp) {
-    mma_warp_loop(plan, X, slots, full, empty, a_ready, acc_ready, tmem_base, ntiles, status, lane);
+    if (!PAIR) mma_warp_loop(plan, X, slots, full, empty, a_ready, acc_ready, tmem_base, ntiles, status, lane);
+    else if (rank == 0) mma_warp_loop_pair(plan, X, slots, full, empty, a_ready, acc_ready, tmem_base, npairs, status, lane);
+    else relay_warp_loop_pair(plan, full, npairs, status, lane);
   } else {
-    Sync sy{a_ready, acc_ready, 0u, status};
+    const float* fcw = PAIR ? fc_s : fc;   // frame constants: shared-memory copy in the pair kernel
+    SyncT<PAIR> sy{a_ready, acc_ready, 0u, status, PAIR ? mapa_u32(a_ready, 0) : 0u};
     const int row = threadIdx.x & (kTileRows - 1);
     const int grp = threadIdx.x >> 7;
     const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const int wl = C::USE_W ? dm.w_layers : 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long it_end = PAIR ? npairs : ntiles;
+    const long long it_step = PAIR ? (long long)cluster_num_x() : (long long)gridDim.x;
+    const long long it0 = PAIR ? (long long)cluster_id_x() : (long long)blockIdx.x;
+    for (long long it = it0; it < it_end; it += it_step) {
+      const long long tile = PAIR ? 2 * it + rank : it;   // PAIR: possibly one past the end (all rows masked)
       const long long p = tile * kTileRows + row;
       const bool valid = p < P;
       const long long pc = valid ? p : P - 1;
@@ -204,7 +236,7 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       uint8_t* tape_tile = reinterpret_cast<uint8_t*>(io.tape_d) + (size_t)tile * (dm.td_total / 64) * kChunkBytes;
       auto tape_put = [&](int chunk0, int nch, int col) {   // after every worker fenced its writes (signal_a)
         group_sync();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0 && tile < ntiles) {
           for (int i = 0; i < nch; ++i)
             tma_bulk_s2g(tape_tile + (size_t)(col / 64 + i) * kChunkBytes, X + (chunk0 + i) * kChunkBytes, kChunkBytes);
           tma_store_commit();
@@ -251,7 +283,7 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         const uint4 m = mask_of(wl + dm.t_layers + i);
         wait_acc(sy, 5000 + i);
         tape_drain();
-        bwd_epilogue<ACT_LEAKY, 8, false>(tmem_row, grp * 128, m, X, row, 0.f, nullptr);
+        bwd_epilogue<ACT_LEAKY, 8, false, PAIR>(tmem_row, grp * 128, m, X, row, 0.f, nullptr);
         signal_a(sy);
         tape_put(0, 2 * dm.hd / 64, dm.td_hh + i * 2 * dm.hd);
       }
@@ -276,7 +308,7 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       // d feat = dir/seg contributions + d sigma * fc_alpha
       wait_acc(sy, 5200);
       tape_drain();
-      bwd_epilogue<ACT_NONE, 8, true>(tmem_row, grp * 128, make_uint4(0, 0, 0, 0), X, row, dsig, fc + dm.off_alpha);
+      bwd_epilogue<ACT_NONE, 8, true, PAIR>(tmem_row, grp * 128, make_uint4(0, 0, 0, 0), X, row, dsig, fcw + dm.off_alpha);
       signal_a(sy);
       tape_put(0, dm.th / 64, dm.td_feat);
       // fc_feat^T -> d(trunk hidden L-1)
@@ -284,7 +316,7 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         const uint4 m = mask_of(wl + dm.t_layers - 1);
         wait_acc(sy, 5300);
         tape_drain();
-        bwd_epilogue<ACT_LEAKY, 8, false>(tmem_row, grp * 128, m, X, row, 0.f, nullptr);
+        bwd_epilogue<ACT_LEAKY, 8, false, PAIR>(tmem_row, grp * 128, m, X, row, 0.f, nullptr);
         signal_a(sy);
         tape_put(0, dm.th / 64, dm.td_th + (dm.t_layers - 1) * dm.th);
       }
@@ -301,7 +333,7 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
           const uint4 m = mask_of(wl + i - 1);
           wait_acc(sy, 5500 + i);
           tape_drain();
-          bwd_epilogue<ACT_LEAKY, 8, false>(tmem_row, grp * 128, m, X, row, 0.f, nullptr);
+          bwd_epilogue<ACT_LEAKY, 8, false, PAIR>(tmem_row, grp * 128, m, X, row, 0.f, nullptr);
           signal_a(sy);
           tape_put(0, dm.th / 64, dm.td_th + (i - 1) * dm.th);
         }
@@ -329,7 +361,7 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
                          pack2<true>(f8[6], f8[7]));
           *reinterpret_cast<uint4*>(r3 + (((1 ^ row) & 7) << 4)) = make_uint4(0u, 0u, 0u, 0u);
         }
-        const float* wf = fc + dm.off_wfinal;
+        const float* wf = fcw + dm.off_wfinal;
         const float* wa = wf + 3 * dm.wh + 4;
         const uint4 m5 = mask_of(dm.w_layers - 1);
         const uint32_t mw[4] = {m5.x, m5.y, m5.z, m5.w};
@@ -348,10 +380,10 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
               float v = 0.f;
               if (c < dm.wh) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) v += ldg_keep1(wf + k * dm.wh + c) * dpre[k];
+                for (int k = 0; k < 3; ++k) v += ldc1<PAIR>(wf + k * dm.wh + c) * dpre[k];
               } else {
 #pragma unroll
-                for (int k = 0; k < C::AMB_DIM; ++k) v += ldg_keep1(wa + k * dm.hh + (c - dm.wh)) * damb[k];
+                for (int k = 0; k < C::AMB_DIM; ++k) v += ldc1<PAIR>(wa + k * dm.hh + (c - dm.wh)) * damb[k];
               }
               g[e] = ((bits >> (j + e)) & 1u) ? v : 0.f;
             }
@@ -371,7 +403,7 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
           const uint4 m = mask_of(i - 1);
           wait_acc(sy, 5600 + i);
           tape_drain();
-          bwd_epilogue<ACT_RELU, 6, false>(tmem_row, grp * 96, m, X, row, 0.f, nullptr);
+          bwd_epilogue<ACT_RELU, 6, false, PAIR>(tmem_row, grp * 96, m, X, row, 0.f, nullptr);
           if (i > 1) signal_a(sy);
           else fence_proxy_async_smem();   // the last gradient chunk is only stored, not multiplied
           tape_put(0, dm.whh / 64, dm.td_wh + (i - 1) * dm.whh);
@@ -382,26 +414,58 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
     }
     if (threadIdx.x == 0) tma_store_wait_all();   // tape stores complete before the CTA exits
   }
+  tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's smem / TMEM / barriers stay alive until both CTAs are done
   if (warp == kMmaWarp) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
+}
+
+// The CTA-pair variant of the dgrad kernel is opt-in (SAHS_BWD_PAIR=1): its passes are shorter than the forward's and
+// the pair's lock step costs more than the halved weight traffic saves (measured 1.68 vs 1.56 ms per level).
+static bool bwd_pair_enabled() {
+  const char* e = getenv("SAHS_BWD_PAIR");
+  return e && e[0] == '1';
 }
 
 template <class C>
 int launch_bwd(const HostPlan& hp, const void* packed_t, const float* fc, const float* grid, const float* ro,
                const float* rd, const float* z, int R, int S, BwdIO io, cudaStream_t st) {
-  auto kfn = field_bwd_kernel<C>;
-  SAHS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
   int* status = sahs_status_words(1);
   SAHS_CHECK_ARG(status, "cannot allocate the diagnostic word");
   const long long P = (long long)R * S;
   const long long ntiles = (P + kTileRows - 1) / kTileRows;
+  const uint8_t* pk = (const uint8_t*)packed_t;
+  if (bwd_pair_enabled() && hp.dims.fc_total <= kPairFcFloats) {
+    auto kfn = field_bwd_kernel<C, true>;
+    SAHS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemTotal));
+    const long long npairs = (ntiles + 1) / 2;
+    long long nclusters = sahs_num_sms();
+    if (nclusters > npairs) nclusters = npairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * nclusters));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kPairSmemTotal;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    SAHS_CUDA(cudaLaunchKernelEx(&cfg, kfn, hp.plan, hp.dims, pk, fc, grid, ro, rd, z, S, P, io, status));
+    SAHS_LAUNCH_CHECK();
+    return SAHS_OK;
+  }
+  auto kfn = field_bwd_kernel<C, false>;
+  SAHS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
   long long grid_dim = 2LL * sahs_num_sms();
   if (grid_dim > ntiles) grid_dim = ntiles;
-  kfn<<<(unsigned)grid_dim, kThreads, kSmemTotal, st>>>(hp.plan, hp.dims, (const uint8_t*)packed_t, fc, grid, ro, rd, z, S,
-                                                       P, io, status);
+  kfn<<<(unsigned)grid_dim, kThreads, kSmemTotal, st>>>(hp.plan, hp.dims, pk, fc, grid, ro, rd, z, S, P, io, status);
   SAHS_LAUNCH_CHECK();
   return SAHS_OK;
 }

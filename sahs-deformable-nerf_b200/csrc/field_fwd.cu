@@ -159,7 +159,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       auto tape_put = [&](int chunk0, int nch, int col) {
         if (!TRAIN) return;
         group_sync();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0 && tile < ntiles) {   // (a pair's second CTA may own a tile past the end: nothing to store)
 #if !defined(SAHS_EXP_NOSTORE)   // timing experiment only: keep the synchronisation, skip the bulk stores
           for (int i = 0; i < nch; ++i)
             tma_bulk_s2g(tape_tile + (size_t)(col / 64 + i) * kChunkBytes, X + (chunk0 + i) * kChunkBytes, kChunkBytes);
@@ -475,7 +475,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
 }
 
 // The CTA-pair (cta_group::2) kernel is the default render path; SAHS_FIELD_PAIR=0 selects the single-CTA kernel
-// (A/B measurements; also used for debug passes and training, which have no pair variant yet).
+// (A/B measurements; also used for the per-pass debug outputs).
 static bool field_pair_enabled() {
   const char* e = getenv("SAHS_FIELD_PAIR");
   return !(e && e[0] == '0');
@@ -491,9 +491,10 @@ int launch_field(const HostPlan& hp, const void* packed, const float* fc, const 
   const long long ntiles = (P + kTileRows - 1) / kTileRows;
   const uint8_t* pk = (const uint8_t*)packed;
   const bool prof = dbg != nullptr && dbg_pass == SAHS_DBG_PROF;
-  if (!tr.tape_x && (!dbg || prof) && field_pair_enabled() && hp.dims.fc_total <= kPairFcFloats) {
+  if ((!dbg || prof) && field_pair_enabled() && hp.dims.fc_total <= kPairFcFloats) {
     // CTA pairs: clusters of 2, two clusters resident per SM pair
-    auto kfn = prof ? field_fwd_kernel<C, true, false, true> : field_fwd_kernel<C, false, false, true>;
+    auto kfn = tr.tape_x ? field_fwd_kernel<C, false, true, true>
+                         : (prof ? field_fwd_kernel<C, true, false, true> : field_fwd_kernel<C, false, false, true>);
     SAHS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemTotal));
     const long long npairs = (ntiles + 1) / 2;
     long long nclusters = sahs_num_sms();           // 2 CTAs per SM = one cluster per SM on average
