@@ -24,6 +24,23 @@ POSE_CODE_DIM = 36
 GRID_CH = 32
 
 
+# Packed weight images are cached per model and must be rebuilt after every weight update.  In-place updates through
+# ordinary torch ops bump `Tensor._version`; fused optimizers (Adam(fused=True), ...) do not, so every optimizer step in
+# the process also advances this epoch.  Code that rewrites weights behind torch's back calls model.invalidate_packed().
+_OPT_EPOCH = [0]
+
+
+def _on_optimizer_step(*_args, **_kwargs):
+    _OPT_EPOCH[0] += 1
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_hook
+    _reg_hook(_on_optimizer_step)
+except Exception:  # noqa: BLE001  (very old torch: fall back to the version counters only)
+    pass
+
+
 @dataclass(frozen=True)
 class ModelSpec:
     """Dimensions the reference derives in NeRFaceModel.__init__ (ref: nerf/models.py:189-299)."""
@@ -180,6 +197,7 @@ class NeRFaceModel(torch.nn.Module):
             mlps[lvl] = m
         self.nerf_mlps = torch.nn.ModuleDict(mlps)
         self._packed: Dict[int, dict] = {}
+        self._invalidations = 0
 
     # ---- packing: fp32 master parameters -> bf16 stage images (re-done whenever a parameter changed) ----
     def _level_params(self, level: str) -> List[Optional[torch.Tensor]]:
@@ -205,12 +223,18 @@ class NeRFaceModel(torch.nn.Module):
         out += [m.fc_seg.weight, m.fc_seg.bias]
         return out
 
+    def invalidate_packed(self) -> None:
+        """Force a repack on the next call (for weight updates torch cannot see, e.g. custom kernels)."""
+        self._invalidations += 1
+
     def packed_level(self, level: str) -> dict:
         """Packed weight image + parameter pointer table of one level, rebuilt when parameters changed."""
         lib = L.load()
         lvl = 0 if level == "coarse" else 1
         params = [p.detach() if p is not None else None for p in self._level_params(level)]
-        key = tuple((p.data_ptr(), p._version) for p in params if p is not None)
+        # staleness key: storage + autograd version of every parameter, plus the process-wide optimizer-step epoch
+        # (fused / foreach optimizers update parameters without bumping `_version`)
+        key = (_OPT_EPOCH[0], self._invalidations) + tuple((p.data_ptr(), p._version) for p in params if p is not None)
         st = self._packed.get(lvl)
         if st is not None and st["key"] == key:
             return st

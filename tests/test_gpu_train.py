@@ -93,13 +93,15 @@ def test_train_step_gradients_vs_oracle_autograd(cfg_name):
     assert not bad, bad
 
 
-def test_optimizer_step_repacks_weights():
-    """After an in-place parameter update the packed images are rebuilt (stale-weight guard) and the loss moves."""
+@pytest.mark.parametrize("fused", [False, True])
+def test_optimizer_step_repacks_weights(fused):
+    """After an in-place parameter update the packed images are rebuilt (stale-weight guard) and the loss moves.  Fused
+    optimizers do not bump Tensor._version: the optimizer-step hook in models.py covers them."""
     sahs, cfg, spec, sd, fr, target, mask = _setup("audio/person_2_auto", 4, 8, seed=6)
     model = sahs.AudioFaceModel(cfg)
     model.load_state_dict(sd)
     model = model.to(DEV)
-    opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4, fused=fused)
     pose = fr["pose"].to(DEV)
     with torch.no_grad():
         ro, rd = sahs.get_ray_bundle(4, 8, fr["intrinsics"], pose)
