@@ -117,10 +117,17 @@ __device__ __forceinline__ void bwd_epilogue(uint32_t tmem_row, int cbeg, uint4 
 
 // backward of the trilinear embedding gather: scatter w_c * d_emb into the grid gradient and return the gradient
 // w.r.t. the (raw, un-normalised) warped coordinate.  ref: nerf/models.py:346-365 (grid_sample, align_corners=True).
-__device__ __forceinline__ void grid_backward(const float* __restrict__ g, float* __restrict__ gg, bool scatter, float x,
-                                              float y, float z, const float (&de)[32], float (&dxyz)[3]) {
+// The scatter is split between the two worker groups (`half` = 16 of the 32 channels each) and uses 16-byte vector
+// reductions (REDG.ADD.F32x4): 32 of them per point instead of 256 scalar atomics by half of the threads -- the scalar
+// version was 60 % of the dgrad kernel.
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void grid_backward(const float* __restrict__ g, float* __restrict__ gg, bool scatter, int half,
+                                              float x, float y, float z, const float (&de)[32], float (&dxyz)[3]) {
   const float sc = 0.5f * (SAHS_GRID_RES - 1);
-  const float ix = (x + 1.f) * sc, iy = (y + 1.f) * sc, iz = (z + 1.f) * sc;
+  const float ix = __fmul_rn(__fadd_rn(x, 1.f), sc), iy = __fmul_rn(__fadd_rn(y, 1.f), sc),
+              iz = __fmul_rn(__fadd_rn(z, 1.f), sc);   // same roundings as grid_gather16
   const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
   float gx = 0.f, gy = 0.f, gz = 0.f;
 #pragma unroll 1
@@ -138,12 +145,12 @@ __device__ __forceinline__ void grid_backward(const float* __restrict__ g, float
     for (int q = 0; q < 8; ++q) {
       const float4 v = ldg_stream(g + off + 4 * q);
       dot += v.x * de[4 * q] + v.y * de[4 * q + 1] + v.z * de[4 * q + 2] + v.w * de[4 * q + 3];
-      if (scatter) {
-        atomicAdd(gg + off + 4 * q + 0, w * de[4 * q + 0]);
-        atomicAdd(gg + off + 4 * q + 1, w * de[4 * q + 1]);
-        atomicAdd(gg + off + 4 * q + 2, w * de[4 * q + 2]);
-        atomicAdd(gg + off + 4 * q + 3, w * de[4 * q + 3]);
-      }
+    }
+    if (scatter) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if ((q >> 2) == half)
+          red_add_v4(gg + off + 4 * q, w * de[4 * q], w * de[4 * q + 1], w * de[4 * q + 2], w * de[4 * q + 3]);
     }
     gx += (bx ? 1.f : -1.f) * wy * wz * dot;
     gy += (by ? 1.f : -1.f) * wx * wz * dot;
@@ -301,8 +308,11 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         float de[32];
 #pragma unroll
         for (int q = 0; q < 32; ++q) de[q] = rdc.get(C::DIR_DIM + q);
-        grid_backward(grid, io.grid_grad, valid && grp == 0 && io.grid_grad != nullptr, mapped[0], mapped[1], mapped[2],
-                      de, dmap);
+#if defined(SAHS_EXP_NOSCATTER)   // timing experiment only
+        grid_backward(grid, io.grid_grad, false, grp, mapped[0], mapped[1], mapped[2], de, dmap);
+#else
+        grid_backward(grid, io.grid_grad, valid && io.grid_grad != nullptr, grp, mapped[0], mapped[1], mapped[2], de, dmap);
+#endif
       }
       signal_a(sy);
       // d feat = dir/seg contributions + d sigma * fc_alpha
@@ -378,6 +388,9 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
             for (int e = 0; e < 2; ++e) {
               const int c = c0 + j + e;
               float v = 0.f;
+#if defined(SAHS_EXP_NOFINAL)   // timing experiment only
+              v = dpre[0] + damb[0];
+#else
               if (c < dm.wh) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) v += ldc1<PAIR>(wf + k * dm.wh + c) * dpre[k];
@@ -385,6 +398,7 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
 #pragma unroll
                 for (int k = 0; k < C::AMB_DIM; ++k) v += ldc1<PAIR>(wa + k * dm.hh + (c - dm.wh)) * damb[k];
               }
+#endif
               g[e] = ((bits >> (j + e)) & 1u) ? v : 0.f;
             }
             pk[j >> 1] = pack2<true>(g[0], g[1]);

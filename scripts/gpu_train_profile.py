@@ -40,6 +40,8 @@ t0 = time.perf_counter()
 for _ in range(5): step()
 torch.cuda.synchronize()
 print("wall ms/step", (time.perf_counter() - t0) / 5 * 1e3)
+if os.environ.get("SAHS_NO_TORCH_PROFILER") == "1":   # under ncu: CUPTI cannot serve both
+    sys.exit(0)
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(3): step()
