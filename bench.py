@@ -284,7 +284,11 @@ def main():
                                 else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"),
                 "frac_of_burst_peak": achieved / float(peaks.get("bf16_tflops", 1590.0)),
                 "algorithmic_flop_per_point": flops_per_point, "points_per_launch": fine[0][0],
-                "avg_launch_ms": fine_ms, "field_share_of_step": all_field_ms / ms_step, "traffic": None}
+                "avg_launch_ms": fine_ms, "field_share_of_step": all_field_ms / ms_step,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed `ncu --set full`
+                # capture (profiles/r1_render_ncu_summary.txt): 0.17 GB read + 2.10 GB written = the raw[.,16] store
+                "traffic": 2.27e9 if (args.config == "audio/person_2_auto") else None,
+                "traffic_unit": "bytes of DRAM traffic per launch (the kernel is tensor-bound; weights stay in L2)"}
 
     # ------------------------------ end-to-end arm (host buffers) -------------------------------
     host = [dict(pose=fr["pose"].pin_memory(), driving=fr["driving"].pin_memory(), mask=fr["mask"].pin_memory())

@@ -73,8 +73,13 @@ def allreduce_gradients(params, group=None, average: bool = True) -> None:
     dist.all_reduce(flat, group=group)
     if average:
         flat /= dist.get_world_size(group)
-    off = 0
+    views, off = [], 0
     for g in grads:
         n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
+        views.append(flat[off:off + n].view_as(g))
         off += n
+    if hasattr(torch, "_foreach_copy_"):
+        torch._foreach_copy_(grads, views)          # one multi-tensor launch instead of one copy per parameter
+    else:
+        for g, v in zip(grads, views):
+            g.copy_(v)
