@@ -308,11 +308,7 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         float de[32];
 #pragma unroll
         for (int q = 0; q < 32; ++q) de[q] = rdc.get(C::DIR_DIM + q);
-#if defined(SAHS_EXP_NOSCATTER)   // timing experiment only
-        grid_backward(grid, io.grid_grad, false, grp, mapped[0], mapped[1], mapped[2], de, dmap);
-#else
         grid_backward(grid, io.grid_grad, valid && io.grid_grad != nullptr, grp, mapped[0], mapped[1], mapped[2], de, dmap);
-#endif
       }
       signal_a(sy);
       // d feat = dir/seg contributions + d sigma * fc_alpha
@@ -388,9 +384,6 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
             for (int e = 0; e < 2; ++e) {
               const int c = c0 + j + e;
               float v = 0.f;
-#if defined(SAHS_EXP_NOFINAL)   // timing experiment only
-              v = dpre[0] + damb[0];
-#else
               if (c < dm.wh) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) v += ldc1<PAIR>(wf + k * dm.wh + c) * dpre[k];
@@ -398,7 +391,6 @@ field_bwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
 #pragma unroll
                 for (int k = 0; k < C::AMB_DIM; ++k) v += ldc1<PAIR>(wa + k * dm.hh + (c - dm.wh)) * damb[k];
               }
-#endif
               g[e] = ((bits >> (j + e)) & 1u) ? v : 0.f;
             }
             pk[j >> 1] = pack2<true>(g[0], g[1]);

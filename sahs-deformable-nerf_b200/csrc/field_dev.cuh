@@ -198,13 +198,8 @@ __device__ __forceinline__ float ldc1(const float* p) {
 }
 template <bool FCS = false>
 __device__ __forceinline__ void load_bias(float4 (&b)[4], const float* __restrict__ bias) {
-#if defined(SAHS_EXP_NOBIAS)   // timing experiment only: no bias traffic (results are wrong)
-#pragma unroll
-  for (int j = 0; j < 4; ++j) b[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-#else
 #pragma unroll
   for (int j = 0; j < 4; ++j) b[j] = ldc4<FCS>(bias + 4 * j);
-#endif
 }
 
 // one 16-column block of an epilogue: +bias (FADD2), optional fp32 dot, pack, activation, swizzled store.

@@ -160,11 +160,9 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         if (!TRAIN) return;
         group_sync();
         if (threadIdx.x == 0 && tile < ntiles) {   // (a pair's second CTA may own a tile past the end: nothing to store)
-#if !defined(SAHS_EXP_NOSTORE)   // timing experiment only: keep the synchronisation, skip the bulk stores
           for (int i = 0; i < nch; ++i)
             tma_bulk_s2g(tape_tile + (size_t)(col / 64 + i) * kChunkBytes, X + (chunk0 + i) * kChunkBytes, kChunkBytes);
           tma_store_commit();
-#endif
         }
       };
       // before X is overwritten: the bulk stores issued so far have finished reading shared memory

@@ -168,11 +168,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-#if defined(SAHS_EXP_NOTMEM)
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = taddr + i;
-  return;
-#endif
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -185,11 +180,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 // in/out dependence keeps the compiler from sinking the load below that block's math (which it otherwise does to
 // shorten the destination registers' live ranges, serialising TMEM latency with the epilogue math).
 __device__ __forceinline__ void tmem_ld16_prefetch(uint32_t taddr, uint32_t (&v)[16], uint32_t& pin) {
-#if defined(SAHS_EXP_NOTMEM)   // timing experiment only: no accumulator reads (results are wrong)
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = taddr + i;
-  return;
-#endif
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%17];"
