@@ -114,9 +114,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
 // shared -> global bulk copy by the TMA unit (bulk async-group completion).  Used for the training tapes: an
 // operand chunk the epilogue has just written to shared memory goes to HBM as one 16 KB burst instead of 128 x 8
 // scattered 16-byte stores.
+// The stores carry an L2 evict-first policy: the tapes are written once and read much later, and as ordinary
+// write-allocate traffic the 3.6 GB per step kept pushing the (L2-resident) weight image and frame constants out of L2
+// (training forward 0.88 -> 0.69 ms per level with the hint).
 __device__ __forceinline__ void tma_bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
-               "r"(bytes)
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(gmem_dst),
+               "r"(smem_u32(smem_src)), "r"(bytes), "l"(pol)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
