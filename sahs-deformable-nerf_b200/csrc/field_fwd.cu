@@ -269,6 +269,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
           const int i = dm.w_layers - 1;
           wait_acc(sy, 1000 + i);
           tape_drain();
+          if (DBG) prof_event(sy.prof, 201);
           if (i == dm.w_skip && !dm.e0_resident) { write_e0(0); signal_a(sy); wait_acc(sy, 1100 + i); }
           uint8_t* rowp5 = X + (row >> 3) * 1024 + (row & 7) * 128;
           const float* bias = fcw + dm.off_wbias + i * dm.whh;
@@ -320,6 +321,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
             uint4* ms = mask_slot(i);
             if (ms) *ms = make_uint4(hmask[0], hmask[1], hmask[2], 0u);
           }
+          if (DBG) prof_event(sy.prof, 202);   // fp32 last deformation layer done
           if (TRAIN) {
             fence_proxy_async_smem();
             tape_put(0, dm.whh / 64, dm.tx_wh + i * dm.whh);
@@ -337,6 +339,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
             amb[k] = scratch[row * 8 + 3 + k] + scratch[(128 + row) * 8 + 3 + k] + ldc1<PAIR>(ba + k);
           group_sync();   // scratch is dead before E1 overwrites it
           tape_drain();
+          if (DBG) prof_event(sy.prof, 203);   // tanh / ambient exchange done
         }
       }
       if (TRAIN && valid && grp == 0) {
@@ -362,6 +365,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
           }
         }
       }
+      if (DBG) prof_event(sy.prof, 204);   // embedding gather done
       // -------- trunk (bf16 operands) --------
       auto write_e1 = [&]() {
         RowStream<kTrunkF16, C::E1_PAD / 8> st(X, 0, row, grp);
@@ -371,6 +375,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         for (int i = C::E1_DIM; i < C::E1_PAD; ++i) st.put(col++, 0.f);
       };
       write_e1();
+      if (DBG) prof_event(sy.prof, 205);   // E1 written
       signal_a(sy);
       tape_put(0, dm.e1_chunks, dm.tx_e1);
       for (int i = 0; i < dm.t_layers; ++i) {

@@ -70,6 +70,10 @@ def main(pair, R):
     issued = {int(t) - 30000: rel(c) for t, c in mma if 30000 <= t < 40000}
     free = {int(t) - 40000: rel(c) for t, c in tma if 40000 <= t < 50000}
     nst = max(issued) + 1 if issued else 0
+    marks = [(int(t), rel(c)) for t, c in w0 if 200 < t < 300]
+    if marks:
+        print("mid-tile worker phase (worker 0): " + ", ".join(f"{t}@{c}" for t, c in marks) +
+              "  [201 acc wake, 202 fp32 last deformation layer, 203 tanh/exchange, 204 embedding gather, 205 E1 written]")
     print(f"passes: signals {len(sig0)}, acc wakes {len(acc0)}, mma wakes {len(wake)}, stages {nst}")
     tot_epi = tot_mma = tot_wake = 0
     print(" pass  tag  st0 nst | sig0 sig255 | mmawake (+lat) | issue_end | acc0 acc255 | mma_phase  epilogue(next sig - acc)")
