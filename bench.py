@@ -376,6 +376,43 @@ def main():
                  "what": "fwd + bwd (hand-written compositing, dgrad-chain and wgrad kernels) + grad all-reduce + Adam, "
                          "semantic-weighted batch of 2048 rays per GPU, perturb + noise 0.1"}
 
+    # ------------------------------ 3DMM-conditioned render (BASELINE config 4) -------------------
+    config4 = None
+    if not args.no_train and args.config == "audio/person_2_auto":
+        cfg4 = FX.load_cfg("expression/person_2")
+        cfg4.nerf.validation.perturb = False
+        ospec4 = O.spec_from_cfg(cfg4)
+        model4 = getattr(sahs_b200.models, cfg4.models.mask.type)(cfg4)
+        model4.load_state_dict(FX.make_state_dict(ospec4, seed=42, dense=True))
+        model4 = model4.to(dev)
+        fr4 = FX.make_frame_inputs(ospec4, H, W, seed=300 + rank)
+        pose4 = fr4["pose"].to(dev)
+        ro4, rd4 = sahs_b200.get_ray_bundle(H, W, fr4["intrinsics"], pose4)
+        drv4, mask4, bg4 = fr4["driving"].to(dev), fr4["mask"].to(dev), fr4["background"].view(-1, 15).to(dev)
+
+        def step4():
+            with torch.no_grad():
+                return sahs_b200.run_one_iter_of_nerf(H, W, 1200.0, model4, ro4, rd4, cfg4, mode="validation",
+                                                      driving=drv4, pose=pose4, background_prior=bg4, inHead=mask4)
+
+        for _ in range(2):
+            step4()
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n4 = max(2, min(args.steps, 5))
+        c0.record()
+        for _ in range(n4):
+            step4()
+        c1.record()
+        barrier()
+        ms4 = torch.tensor([c0.elapsed_time(c1) / n4], device=dev)
+        if world > 1:
+            dist.all_reduce(ms4, op=dist.ReduceOp.MAX)
+        config4 = {"workload": "Stage-I 512x512 render, expression/person_2 (3DMM-conditioned, 15 octaves: split-precision "
+                               "deformation phase), device resident", "ms_per_frame": float(ms4),
+                   "value": world * R / (float(ms4) / 1e3), "unit": "rays/s"}
+        del model4
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rps, dt, cores = cpu_port_rays_per_s(args.config, args.cpu_rays)
@@ -396,6 +433,7 @@ def main():
                     "ms_per_frame": 1e3 * float(e2e_s) / args.steps},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
             "train": train,
+            "config4": config4,
         }
         _emit(json.dumps(line))
     if world > 1:
