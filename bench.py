@@ -341,11 +341,14 @@ def main():
         gen = torch.Generator(device=dev).manual_seed(42 + rank)
         target_all = torch.rand(R, 3, device=dev, generator=gen)
         sample_prob = torch.ones(12, device=dev)
+        mask_i32 = f0["mask"].view(-1, 12).to(torch.int32).contiguous()
+        step_no = [0]
 
         def train_step():
             nonlocal sample_prob
-            probs = (maskf * sample_prob).sum(-1)            # semantic-weighted ray batch (train script :390-420)
-            sel = torch.multinomial(probs / probs.sum(), nrays, replacement=False, generator=gen)
+            # semantic-weighted ray batch on the device (train script :390-420; sahs_weighted_sample)
+            step_no[0] += 1
+            sel = sahs_b200.weighted_sample(mask_i32, sample_prob, nrays, seed=(42 + rank) * 1000003 + step_no[0])
             out = sahs_b200.run_one_iter_of_nerf(H, W, 1200.0, tmodel, ro_all[sel], rd_all[sel], cfg_t, mode="train",
                                                  driving=f0["driving"], pose=f0["pose"], background_prior=bg_dev[sel],
                                                  inHead=f0["mask"].view(-1, 12)[sel])

@@ -175,6 +175,16 @@ int sahs_sample_pdf(const float* bins, const float* weights, const float* u, int
 int sahs_frame_postprocess(const float* map15, int64_t num_rays, uint8_t* rgb_u8, uint8_t* label_u8,
                            uint8_t* seg_color_u8, void* stream);
 
+/* Semantic-weighted ray batch on the device (replaces the host-side np.random.choice(H*W, n, replace=False, p=probs)
+ * of train_stage_rays_auto.py:390-420): weight_i = sum_c class_prob[c] * mask[i, c] (mask: int32 [num_pixels,
+ * num_classes], one-hot in the reference), num_select distinct pixel indices drawn without replacement with
+ * probability proportional to the weights (exponential-clock keys from Philox-4x32-10(seed, pixel), radix select).
+ * The result is reproducible as a set for a given seed; the order of out_indices is unspecified.  At least num_select
+ * pixels must have a positive weight (the reference raises otherwise).  workspace: 2048 + 4 * num_pixels bytes. */
+int sahs_weighted_sample(const int32_t* mask, const float* class_prob, int64_t num_pixels, int num_classes,
+                         int num_select, uint64_t seed, int64_t* out_indices, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
 /* Diagnostic word written by the field kernel when a bounded mbarrier wait times out (0 = healthy):
  * out4_host[0] code (+100 dgrad kernel, +200 wgrad kernel), [1] tag, [2] block, [3] thread.  The words live in mapped
  * host memory, so this works (and issues no CUDA call) after a kernel trapped. */

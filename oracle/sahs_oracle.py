@@ -459,3 +459,17 @@ def frame_postprocess(rgb_map: torch.Tensor):
     label = torch.argmax(rgb_map[..., 3:], dim=-1)
     pal = torch.tensor([c[::-1] for c in _SEG_PALETTE], dtype=torch.uint8)
     return rgb, label.to(torch.uint8), pal[label]
+
+
+def weighted_sample_probs(mask: torch.Tensor, class_prob: torch.Tensor) -> np.ndarray:
+    """probs of the semantic-weighted ray sampler (ref: train_stage_rays_auto.py:390-394):
+    sum_c sample_prob[c] * mask[..., c], normalised."""
+    p = (class_prob.reshape(1, -1) * mask.reshape(-1, mask.shape[-1]).float()).sum(-1).double().numpy()
+    return p / p.sum()
+
+
+def weighted_sample(mask: torch.Tensor, class_prob: torch.Tensor, num_select: int, rng: np.random.Generator) -> np.ndarray:
+    """The reference's draw (ref: train_stage_rays_auto.py:416-418): np.random.choice(N, n, replace=False, p=probs).
+    (A Generator instead of the legacy global RandomState: same sequential without-replacement distribution.)"""
+    p = weighted_sample_probs(mask, class_prob)
+    return rng.choice(p.shape[0], size=num_select, replace=False, p=p)

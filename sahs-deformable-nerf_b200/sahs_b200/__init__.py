@@ -11,4 +11,4 @@ from .nerf_helpers import (cumprod_exclusive, get_embedding_function, get_miniba
                            img2mse, meshgrid_xy, mse2psnr, positional_encoding, sample_pdf, sample_pdf_2)
 from .train_utils import predict_and_render_radiance, run_network, run_one_iter_of_nerf  # noqa: F401
 from .volume_rendering_utils import volume_render_radiance_field  # noqa: F401
-from .ops import frame_postprocess  # noqa: F401,E402
+from .ops import frame_postprocess, weighted_sample  # noqa: F401,E402

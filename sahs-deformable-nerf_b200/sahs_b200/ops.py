@@ -148,6 +148,34 @@ def frame_postprocess(rgb_map: torch.Tensor):
     return rgb, lab, col
 
 
+_SAMPLER_WS = {}
+
+
+def weighted_sample(mask: torch.Tensor, class_prob: torch.Tensor, num_select: int, seed: int) -> torch.Tensor:
+    """Semantic-weighted ray batch: `num_select` distinct pixel indices, drawn without replacement with probability
+    proportional to sum_c class_prob[c] * mask[i, c] -- the device-side replacement of
+    np.random.choice(H*W, n, replace=False, p=probs) (ref: train_stage_rays_auto.py:390-420).
+    mask: int32 [..., C] (one-hot in the reference); returns int64 [num_select] (a set: order unspecified)."""
+    lib = L.load()
+    if not mask.is_cuda:
+        raise RuntimeError("weighted_sample needs CUDA tensors (there is no CPU fallback)")
+    C_ = mask.shape[-1]
+    m = mask.reshape(-1, C_)
+    if m.dtype != torch.int32 or not m.is_contiguous():
+        m = m.to(torch.int32).contiguous()
+    n = m.shape[0]
+    prob = L.f32c(class_prob.to(m.device))
+    key = (m.device, n)
+    ws = _SAMPLER_WS.get(key)
+    if ws is None:
+        ws = torch.empty(2048 + 4 * n, dtype=torch.uint8, device=m.device)
+        _SAMPLER_WS[key] = ws
+    out = torch.empty(num_select, dtype=torch.int64, device=m.device)
+    L.check(lib.sahs_weighted_sample(L.ptr(m), L.ptr(prob), n, C_, int(num_select), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                     L.ptr(out), L.ptr(ws), ws.numel(), L.stream_ptr(m.device)), "weighted_sample")
+    return out
+
+
 def field_status():
     lib = L.load()
     out = (C.c_int * 4)()

@@ -372,3 +372,52 @@ def test_render_is_chunking_invariant(sahs):
         b = sahs.run_one_iter_of_nerf(H, W, 1.0, model, ro[100:], rd[100:], cfg, background_prior=bg[100:], **kw)
     for f, x, y in zip(full, a, b):
         assert torch.equal(f, torch.cat((x, y), 0))
+
+
+# ------------------------------------------------------------------------------------------------------
+# semantic-weighted ray sampler
+# ------------------------------------------------------------------------------------------------------
+def test_weighted_sampler_structure_and_reproducibility(sahs):
+    gen = torch.Generator().manual_seed(5)
+    H = W = 512
+    labels = torch.randint(0, 12, (H * W,), generator=gen)
+    mask = torch.nn.functional.one_hot(labels, 12).to(torch.int32)
+    prob = torch.rand(12, generator=gen) + 0.1
+    prob[3] = 0.0                                              # one class is never sampled
+    a = sahs.weighted_sample(mask.to(DEV), prob.to(DEV), 2048, seed=123).cpu()
+    b = sahs.weighted_sample(mask.to(DEV), prob.to(DEV), 2048, seed=123).cpu()
+    c = sahs.weighted_sample(mask.to(DEV), prob.to(DEV), 2048, seed=124).cpu()
+    assert a.shape == (2048,) and a.dtype == torch.int64
+    assert int(a.min()) >= 0 and int(a.max()) < H * W
+    assert a.unique().numel() == 2048                           # without replacement
+    assert set(a.tolist()) == set(b.tolist())                   # same seed -> same set
+    assert len(set(a.tolist()) & set(c.tolist())) < 200         # another seed -> another draw
+    assert not bool((labels[a] == 3).any())                     # zero-weight pixels are never drawn
+    # class frequencies follow the class weights (each class has ~1/12 of the pixels): 4 sigma
+    counts = torch.bincount(labels[a], minlength=12).double()
+    expect = 2048 * (prob.double() * torch.bincount(labels, minlength=12).double())
+    expect = expect / expect.sum() * 2048
+    sigma = expect.clamp_min(1.0).sqrt()
+    assert bool(((counts - expect).abs() <= 4.5 * sigma + 1).all()), (counts, expect)
+
+
+def test_weighted_sampler_matches_reference_distribution(sahs):
+    """Inclusion probabilities of every item against the reference's sequential np.random.choice(replace=False, p=...)
+    on a case where sampling without replacement differs visibly from independent draws (n is 40 % of N)."""
+    N, n, trials = 20, 8, 4000
+    w = torch.tensor([8.0, 4, 4, 2, 2, 2, 1, 1, 1, 1, 1, 1, 0.5, 0.5, 0.5, 0.5, 0.25, 0.25, 0.25, 0.0])
+    mask = torch.eye(N, dtype=torch.int32)                     # item i belongs to "class" i
+    hits = torch.zeros(N, dtype=torch.float64)
+    m_dev, w_dev = mask.to(DEV), w.to(DEV)
+    for t in range(trials):
+        idx = sahs.weighted_sample(m_dev, w_dev, n, seed=1000 + t)
+        hits[idx.cpu()] += 1
+    ours = hits / trials
+    rng = np.random.default_rng(0)
+    ref_hits = np.zeros(N)
+    for t in range(trials):
+        ref_hits[O.weighted_sample(mask, w, n, rng)] += 1
+    ref = torch.from_numpy(ref_hits / trials)
+    assert ours[-1] == 0 and abs(float(ours.sum()) - n) < 1e-9
+    sigma = (ref * (1 - ref) / trials).sqrt() * (2 ** 0.5)      # both sides are Monte-Carlo estimates
+    assert bool(((ours - ref).abs() <= 4.5 * sigma + 2e-3).all()), (ours, ref)
