@@ -161,3 +161,20 @@ def test_fine_pass_conditioning():
             zp, _ = torch.sort(z_f * (1 + (torch.rand(z_f.shape, generator=gen) * 2 - 1) * 2e-7), -1)
             out[cfg_name] = float((fine(z_f) - fine(zp)).abs().max())
     assert out["expression/person_2"] > 1e-3 and out["audio/person_2_auto"] < 1e-5, out
+
+
+def test_weighted_sampler_reference_semantics():
+    """Oracle restatement of the reference's semantic-weighted draw (train_stage_rays_auto.py:390-418): probabilities
+    are the class weights of each pixel's one-hot label, normalised; the draw is without replacement and never returns
+    a zero-probability pixel."""
+    gen = torch.Generator().manual_seed(3)
+    labels = torch.randint(0, 12, (4096,), generator=gen)
+    mask = torch.nn.functional.one_hot(labels, 12).to(torch.int32)
+    prob = torch.rand(12, generator=gen) + 0.05
+    prob[7] = 0.0
+    p = O.weighted_sample_probs(mask, prob)
+    assert abs(p.sum() - 1.0) < 1e-12 and (p[(labels == 7).numpy()] == 0).all()
+    want = (prob[labels] / prob[labels].sum()).double().numpy()
+    assert np.allclose(p, want, rtol=1e-6, atol=0)
+    idx = O.weighted_sample(mask, prob, 512, np.random.default_rng(0))
+    assert len(set(idx.tolist())) == 512 and not (labels[torch.from_numpy(idx)] == 7).any()
