@@ -19,12 +19,21 @@ constexpr int kWarps = 8;
 constexpr int kMaxS = 256;      // coarse samples per ray
 constexpr int kMaxMerged = 512; // S + n_fine
 
+constexpr int kBlocksPerSm = 4; // 32 resident warps per SM (6 blocks = 40 registers measured no faster: issue bound)
+
+// per-warp scratch in dynamic shared memory, sized for the launch's S and NF (so short rays leave room for more warps)
 struct WarpScratch {
-  float w[kMaxS];        // w[j] = weights[j+1] + 1e-5, j < n = S-2
-  float cdf[kMaxS];      // n+1 entries
-  float bins[kMaxS];     // S-1 mid points
-  float merged[kMaxMerged];
+  float* w;        // w[j] = weights[j+1] + 1e-5, j < n = S-2          [S]
+  float* cdf;      // n+1 entries                                      [S]
+  float* bins;     // S-1 mid points; reused for the 64 sorted samples [max(S, 64)]
+  float* merged;   // cat(z, samples), padded to a power of two        [P]
 };
+__host__ __device__ inline int merged_pow2(int S, int NF) {
+  int P = 1;
+  while (P < S + NF) P <<= 1;
+  return P;
+}
+__host__ __device__ inline int scratch_floats(int S, int NF) { return 2 * S + (S > 64 ? S : 64) + merged_pow2(S, NF); }
 
 __device__ __forceinline__ double shfl_up_double(double v, int o) {
   int lo = __double2loint(v), hi = __double2hiint(v);
@@ -33,13 +42,17 @@ __device__ __forceinline__ double shfl_up_double(double v, int o) {
   return __hiloint2double(hi, lo);
 }
 
-__global__ void __launch_bounds__(kWarps * 32)
+__global__ void __launch_bounds__(kWarps * 32, kBlocksPerSm)
 sample_pdf_merge_kernel(const float* __restrict__ z, const float* __restrict__ bins_in,
                         const float* __restrict__ weights, const float* __restrict__ u, int u_per_ray, int R, int S,
                         int NF, float* __restrict__ z_samples, float* __restrict__ z_merged,
                         int64_t* __restrict__ inds_out) {
-  __shared__ WarpScratch scratch[kWarps];
-  WarpScratch& sm = scratch[threadIdx.x >> 5];
+  extern __shared__ float scratch_all[];
+  WarpScratch sm;
+  sm.w = scratch_all + (size_t)(threadIdx.x >> 5) * scratch_floats(S, NF);
+  sm.cdf = sm.w + S;
+  sm.bins = sm.cdf + S;
+  sm.merged = sm.bins + (S > 64 ? S : 64);
   const int lane = threadIdx.x & 31;
   const int n = S - 2;        // number of pdf entries
   const int nb = S - 1;       // number of bins == number of cdf entries
@@ -124,10 +137,64 @@ sample_pdf_merge_kernel(const float* __restrict__ z, const float* __restrict__ b
     }
     __syncwarp();
     if (bins_in) continue;
-    // ---- sort(cat(z, z_samples)): bitonic network over the next power of two ---------------------
+    // ---- sort(cat(z, z_samples)) (values only, so any correct sort reproduces torch.sort) ---------
     const int tot = S + NF;
-    int P = 1;
-    while (P < tot) P <<= 1;
+    // Fast path (the shapes the renderer uses): the coarse depths are already ascending, so sort the 64 new samples in
+    // registers (bitonic network over warp shuffles, two values per lane) and merge the two sorted lists by rank:
+    // position(z_i) = i + #{samples < z_i}, position(s_j) = j + #{coarse <= s_j}.
+    bool fast = (NF == 64);
+    if (fast) {
+      bool ok = true;
+      for (int j = lane; j + 1 < S; j += 32) ok = ok && !(sm.merged[j] > sm.merged[j + 1]);
+      fast = __all_sync(0xffffffffu, ok);
+    }
+    if (fast) {
+      float v0 = sm.merged[S + lane], v1 = sm.merged[S + 32 + lane];   // element index e = lane (v0), 32 + lane (v1)
+      for (int k = 2; k <= 64; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          if (j == 32) {            // partner is the other register of the same lane (only when k == 64: ascending)
+            const float lo = fminf(v0, v1), hi = fmaxf(v0, v1);
+            v0 = lo; v1 = hi;
+          } else {
+            const float p0 = __shfl_xor_sync(0xffffffffu, v0, j), p1 = __shfl_xor_sync(0xffffffffu, v1, j);
+            const bool lower = (lane & j) == 0;                 // this lane holds the lower index of the pair
+            const bool up0 = (lane & k) == 0, up1 = ((32 + lane) & k) == 0;
+            v0 = (lower == up0) ? fminf(v0, p0) : fmaxf(v0, p0);
+            v1 = (lower == up1) ? fminf(v1, p1) : fmaxf(v1, p1);
+          }
+        }
+      }
+      __syncwarp();
+      sm.bins[lane] = v0;            // sorted samples (bins[] is dead by now and holds at least 64 floats)
+      sm.bins[32 + lane] = v1;
+      __syncwarp();
+      float* outp = z_merged + (size_t)r * tot;
+      // samples: rank among the coarse depths (first index with z > s, i.e. number of coarse <= s)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float sv = h == 0 ? v0 : v1;
+        int lo = 0, hi = S;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (sm.merged[mid] <= sv) lo = mid + 1; else hi = mid;
+        }
+        outp[lane + 32 * h + lo] = sv;
+      }
+      // coarse depths: rank among the samples (number of samples < z)
+      for (int i = lane; i < S; i += 32) {
+        const float zv = sm.merged[i];
+        int lo = 0, hi = 64;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (sm.bins[mid] < zv) lo = mid + 1; else hi = mid;
+        }
+        outp[i + lo] = zv;
+      }
+      __syncwarp();
+      continue;
+    }
+    // general path: bitonic network in shared memory over the next power of two
+    const int P = merged_pow2(S, NF);
     for (int j = tot + lane; j < P; j += 32) sm.merged[j] = __int_as_float(0x7f800000);  // +inf padding
     __syncwarp();
     for (int k = 2; k <= P; k <<= 1) {
@@ -151,6 +218,17 @@ sample_pdf_merge_kernel(const float* __restrict__ z, const float* __restrict__ b
   }
 }
 
+// dynamic shared memory of one block; above 48 KB the kernel attribute is raised once
+size_t scratch_bytes(int S, int NF) {
+  const size_t bytes = (size_t)kWarps * scratch_floats(S, NF) * sizeof(float);
+  static size_t opted = 48 * 1024;
+  if (bytes > opted) {
+    cudaFuncSetAttribute(sample_pdf_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    opted = bytes;
+  }
+  return bytes;
+}
+
 }  // namespace
 
 extern "C" int sahs_sample_pdf_merge(const float* z, const float* weights, const float* u, int u_per_ray,
@@ -162,9 +240,10 @@ extern "C" int sahs_sample_pdf_merge(const float* z, const float* weights, const
   SAHS_CHECK_ARG(num_fine >= 1 && num_samples + num_fine <= kMaxMerged, "num_samples + num_fine must be <= 512");
   if (num_rays == 0) return SAHS_OK;
   int blocks = (num_rays + kWarps - 1) / kWarps;
-  int cap = sahs_num_sms() * 4;
+  int cap = sahs_num_sms() * kBlocksPerSm;
   if (blocks > cap) blocks = cap;
-  sample_pdf_merge_kernel<<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(z, nullptr, weights, u, u_per_ray, num_rays,
+  const size_t smem = scratch_bytes(num_samples, num_fine);
+  sample_pdf_merge_kernel<<<blocks, kWarps * 32, smem, (cudaStream_t)stream>>>(z, nullptr, weights, u, u_per_ray, num_rays,
                                                                           num_samples, num_fine, z_samples, z_merged,
                                                                           inds);
   SAHS_LAUNCH_CHECK();
@@ -179,9 +258,10 @@ extern "C" int sahs_sample_pdf(const float* bins, const float* weights, const fl
   SAHS_CHECK_ARG(num_fine >= 1 && num_fine <= kMaxMerged, "num_fine must be <= 512");
   if (num_rays == 0) return SAHS_OK;
   int blocks = (num_rays + kWarps - 1) / kWarps;
-  int cap = sahs_num_sms() * 4;
+  int cap = sahs_num_sms() * kBlocksPerSm;
   if (blocks > cap) blocks = cap;
-  sample_pdf_merge_kernel<<<blocks, kWarps * 32, 0, (cudaStream_t)stream>>>(nullptr, bins, weights, u, u_per_ray,
+  const size_t smem = scratch_bytes(num_bins + 1, num_fine);
+  sample_pdf_merge_kernel<<<blocks, kWarps * 32, smem, (cudaStream_t)stream>>>(nullptr, bins, weights, u, u_per_ray,
                                                                           num_rays, num_bins + 1, num_fine, samples,
                                                                           nullptr, inds);
   SAHS_LAUNCH_CHECK();

@@ -143,6 +143,28 @@ def test_sample_pdf_properties_full_frame(sahs):
     assert torch.equal(inds[sub].cpu(), i_o) and torch.equal(zs[sub].cpu(), s_o)
 
 
+@pytest.mark.parametrize("S,NF,shuffle", [(64, 48, False), (64, 64, True), (40, 17, False), (128, 64, False)])
+def test_sample_pdf_merge_paths(sahs, S, NF, shuffle):
+    """The merge has two code paths: 64 new samples into ascending coarse depths (register sort + rank merge) and
+    everything else (bitonic network in shared memory, also taken when the coarse depths are not ascending).
+    Both must equal sort(cat(z, samples)) bitwise, and the samples must equal the oracle's."""
+    from sahs_b200 import ops
+    R = 1531
+    gen = torch.Generator().manual_seed(S * 1000 + NF)
+    z, _ = torch.sort(0.48 + 0.6 * torch.rand(R, S, generator=gen), -1)
+    if shuffle:
+        z = z[:, torch.randperm(S, generator=gen)].contiguous()
+    w = torch.rand(R, S, generator=gen) ** 6
+    u = torch.rand(R, NF, generator=gen)
+    zs, zm, inds = ops.sample_pdf_merge(z.to(DEV), w.to(DEV), NF, u.to(DEV), return_inds=True)
+    mids = 0.5 * (z[:, 1:] + z[:, :-1])
+    if not shuffle:     # searchsorted semantics need ascending bins; the shuffled case checks the merge only
+        s_o, i_o = O.sample_pdf(mids, w[:, 1:-1], NF, det=False, u=u, return_inds=True)
+        assert torch.equal(inds.cpu(), i_o) and torch.equal(zs.cpu(), s_o)
+    want, _ = torch.sort(torch.cat((z, zs.cpu()), -1), -1)
+    assert torch.equal(zm.cpu(), want)
+
+
 # ------------------------------------------------------------------------------------------------------
 # (3) compositing
 # ------------------------------------------------------------------------------------------------------
