@@ -185,6 +185,18 @@ int sahs_weighted_sample(const int32_t* mask, const float* class_prob, int64_t n
                          int num_select, uint64_t seed, int64_t* out_indices, void* workspace, size_t workspace_bytes,
                          void* stream);
 
+/* Stage-I training loss and its gradient in one launch (replaces ~75 elementwise/reduction launches per step).
+ * ref: nerf/nerf_helpers.py:14-62 (MaskCrossEntropyLoss, MaskMSELoss), assembled as in train_stage_rays_auto.py:455-468:
+ * per level  l2 + ce_weight * CE + mouth_weight * sum_{k in [mouth_lo, mouth_hi)} (masked_l2[k] + masked_CE[k])
+ * (0.02, 0.005 and classes 7..8 in the script), summed over the coarse and fine maps; the cross entropy's target is
+ * the mask, as at the call site.  map_coarse / map_fine [R,15] (rgb + 12 class probabilities; map_fine may be NULL),
+ * target_rgb [R,3], mask [R,12] float.  Outputs: stats[53] = {loss, l2_c, ce_c, l2_f, ce_f, masked_l2_c[12],
+ * masked_ce_c[12], masked_l2_f[12], masked_ce_f[12]}, sample_prob[12] (the dynamic sampling weights, :466-468) and
+ * d loss / d map for both levels [R,15].  Deterministic (fixed reduction order). */
+int sahs_stage1_loss(const float* map_coarse, const float* map_fine, const float* target_rgb, const float* mask,
+                     int num_rays, int num_classes, float ce_weight, float mouth_weight, int mouth_lo, int mouth_hi,
+                     float* stats, float* sample_prob, float* d_map_coarse, float* d_map_fine, void* stream);
+
 /* Diagnostic word written by the field kernel when a bounded mbarrier wait times out (0 = healthy):
  * out4_host[0] code (+100 dgrad kernel, +200 wgrad kernel), [1] tag, [2] block, [3] thread.  The words live in mapped
  * host memory, so this works (and issues no CUDA call) after a kernel trapped. */

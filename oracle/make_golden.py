@@ -243,10 +243,51 @@ def postprocess_case(nerf, name):
                         ref_label=_np(label))
 
 
+def loss_case(nerf, name, rows, seed):
+    """Stage-I loss assembly (ref: nerf/nerf_helpers.py:14-62 modules, train_stage_rays_auto.py:455-468 assembly),
+    with one class absent from the batch (count 0 -> 1) and autograd gradients w.r.t. both maps."""
+    g = torch.Generator().manual_seed(seed)
+
+    def make_map():
+        m = torch.rand(rows, 15, generator=g)
+        m[:, 3:] = torch.softmax(torch.randn(rows, 12, generator=g) * 2.0, -1)
+        return m.requires_grad_(True)
+
+    map_c, map_f = make_map(), make_map()
+    target = torch.rand(rows, 3, generator=g)
+    cls = torch.randint(0, 11, (rows,), generator=g)            # class 11 never drawn
+    mask = torch.nn.functional.one_hot(cls, 12).float()
+    mse_loss, ce_loss = nerf.MaskMSELoss(), nerf.MaskCrossEntropyLoss()
+    c_l2, m_c_l2, w_c_l2 = mse_loss(mask, map_c[..., :3], target[..., :3])
+    c_ce, m_c_ce, w_c_ce = ce_loss(mask, map_c[..., 3:], mask)
+    coarse = c_l2 + 0.02 * c_ce + 0.005 * torch.sum(m_c_l2[7:9] + m_c_ce[7:9])
+    f_l2, m_f_l2, w_f_l2 = mse_loss(mask, map_f[..., :3], target[..., :3])
+    f_ce, m_f_ce, w_f_ce = ce_loss(mask, map_f[..., 3:], mask)
+    fine = f_l2 + 0.02 * f_ce + 0.005 * torch.sum(m_f_l2[7:9] + m_f_ce[7:9])
+    prob = (w_c_l2 + w_c_ce + w_f_l2 + w_f_ce) / (w_c_l2.sum() + w_c_ce.sum() + w_f_l2.sum() + w_f_ce.sum())
+    loss = coarse + fine
+    loss.backward()
+    oc, of = map_c.detach().clone().requires_grad_(True), map_f.detach().clone().requires_grad_(True)
+    loss_o, prob_o = O.stage1_loss(oc, of, target, mask)
+    loss_o.backward()
+    errs = {"loss": _maxabs(loss.detach(), loss_o.detach()), "prob": _maxabs(prob.detach(), prob_o),
+            "d_coarse": _maxabs(map_c.grad, oc.grad), "d_fine": _maxabs(map_f.grad, of.grad)}
+    print(f"[{name}] oracle vs reference:", errs)
+    assert all(v == 0.0 for v in errs.values()), errs
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), map_c=_np(map_c), map_f=_np(map_f), target=_np(target),
+                        mask=_np(mask), ref_loss=_np(loss), ref_prob=_np(prob), ref_d_coarse=_np(map_c.grad),
+                        ref_d_fine=_np(map_f.grad),
+                        ref_stats=np.concatenate([_np(x).reshape(-1) for x in
+                                                  (loss, c_l2, c_ce, f_l2, f_ce, m_c_l2, m_c_ce, m_f_l2, m_f_ce)]))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     nerf = RH.import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "loss":          # add this one case without regenerating the others
+        loss_case(nerf, "stage1_loss", 777, 31)
+        return
     helpers_case(nerf, "helpers")
     postprocess_case(nerf, "postprocess")
     sample_pdf_case(nerf, "sample_pdf_2048", 2048, 11)
@@ -257,6 +298,7 @@ def main():
     e2e_case(nerf, "e2e_audio_val", "audio/person_2_auto", 16, 16, 0, 0.78, "validation")
     e2e_case(nerf, "e2e_expr2_val", "expression/person_2", 12, 12, 1, 0.5, "validation")
     e2e_case(nerf, "e2e_audio_train_stoch", "audio/person_2_auto", 12, 12, 2, 0.78, "train", stochastic=True)
+    loss_case(nerf, "stage1_loss", 777, 31)
     print("golden vectors written to", GOLD)
 
 

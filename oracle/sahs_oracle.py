@@ -473,3 +473,37 @@ def weighted_sample(mask: torch.Tensor, class_prob: torch.Tensor, num_select: in
     (A Generator instead of the legacy global RandomState: same sequential without-replacement distribution.)"""
     p = weighted_sample_probs(mask, class_prob)
     return rng.choice(p.shape[0], size=num_select, replace=False, p=p)
+
+
+def masked_mse(mask: torch.Tensor, inp: torch.Tensor, target: torch.Tensor):
+    """MaskMSELoss.forward (ref: nerf/nerf_helpers.py:40-62) with weights=None -> (mean, per-class)."""
+    mask = mask.reshape(-1, mask.shape[-1])
+    count = torch.count_nonzero(mask, dim=0)
+    count = torch.where(count == 0, torch.ones_like(count), count)
+    diff = torch.sum(torch.square(inp.reshape(-1, 3) - target.reshape(-1, 3)), dim=-1).unsqueeze(-1)
+    return torch.mean(diff), torch.sum(diff * mask, dim=0) / count
+
+
+def masked_cross_entropy(mask: torch.Tensor, inp: torch.Tensor, target: torch.Tensor):
+    """MaskCrossEntropyLoss.forward (ref: nerf/nerf_helpers.py:14-37) with weights=None -> (mean, per-class)."""
+    mask = mask.reshape(-1, mask.shape[-1])
+    count = torch.count_nonzero(mask, dim=0)
+    count = torch.where(count == 0, torch.ones_like(count), count)
+    ce = -torch.sum(target.reshape(-1, target.shape[-1]) * torch.log(inp.reshape(-1, inp.shape[-1]) + 1e-10),
+                    dim=-1).unsqueeze(-1)
+    return torch.mean(ce), torch.sum(ce * mask, dim=0) / count
+
+
+def stage1_loss(rgb_coarse: torch.Tensor, rgb_fine: torch.Tensor, target_rgb: torch.Tensor, mask: torch.Tensor):
+    """Loss assembly of the training script (ref: train_stage_rays_auto.py:455-468): per level
+    l2 + 0.02 * CE + 0.005 * sum(masked_l2[7:9] + masked_CE[7:9]); sample_prob = normalised sum of the four per-class
+    vectors.  Differentiable torch ops (the gradient tests run autograd through it).  Returns (loss, sample_prob)."""
+    mask = mask.to(rgb_coarse.dtype)
+    total, parts = 0.0, []
+    for rgb in (rgb_coarse, rgb_fine):
+        l2, m_l2 = masked_mse(mask, rgb[..., :3], target_rgb[..., :3])
+        ce, m_ce = masked_cross_entropy(mask, rgb[..., 3:], mask)
+        total = total + (l2 + 0.02 * ce + 0.005 * torch.sum(m_l2[7:9] + m_ce[7:9]))
+        parts += [m_l2, m_ce]
+    s = parts[0] + parts[1] + parts[2] + parts[3]
+    return total, (s / (parts[0].sum() + parts[1].sum() + parts[2].sum() + parts[3].sum())).detach()

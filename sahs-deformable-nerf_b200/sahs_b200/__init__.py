@@ -5,7 +5,7 @@ eval_stage_rays.py:28-39, train_stage_rays_auto.py:21-23) for the hot path."""
 from . import models  # noqa: F401
 from .cfgnode import CfgNode  # noqa: F401
 from .configs import builtin_config  # noqa: F401
-from .losses import MaskCrossEntropyLoss, MaskMSELoss, stage1_loss  # noqa: F401
+from .losses import MaskCrossEntropyLoss, MaskMSELoss, stage1_loss, stage1_loss_modules  # noqa: F401
 from .models import AudioFaceModel, NeRFaceModel  # noqa: F401
 from .nerf_helpers import (cumprod_exclusive, get_embedding_function, get_minibatches, get_ray_bundle,  # noqa: F401
                            img2mse, meshgrid_xy, mse2psnr, positional_encoding, sample_pdf, sample_pdf_2)

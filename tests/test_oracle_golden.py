@@ -178,3 +178,19 @@ def test_weighted_sampler_reference_semantics():
     assert np.allclose(p, want, rtol=1e-6, atol=0)
     idx = O.weighted_sample(mask, prob, 512, np.random.default_rng(0))
     assert len(set(idx.tolist())) == 512 and not (labels[torch.from_numpy(idx)] == 7).any()
+
+
+def test_stage1_loss_oracle_matches_reference_golden():
+    """Loss assembly of the training script (nerf_helpers.py:14-62, train_stage_rays_auto.py:455-468): the oracle
+    reproduces the reference's loss, dynamic sample_prob and autograd gradients bit for bit (one class is absent from
+    the batch, so the count-0 -> 1 rule is exercised)."""
+    g = load("stage1_loss")
+    mc = torch.from_numpy(g["map_c"]).requires_grad_(True)
+    mf = torch.from_numpy(g["map_f"]).requires_grad_(True)
+    mask = torch.from_numpy(g["mask"])
+    assert int(mask[:, 11].sum()) == 0
+    loss, prob = O.stage1_loss(mc, mf, torch.from_numpy(g["target"]), mask)
+    loss.backward()
+    assert float(loss.detach()) == float(g["ref_loss"]) and np.array_equal(prob.numpy(), g["ref_prob"])
+    assert np.array_equal(mc.grad.numpy(), g["ref_d_coarse"]) and np.array_equal(mf.grad.numpy(), g["ref_d_fine"])
+    assert abs(float(prob.sum()) - 1.0) < 1e-6
