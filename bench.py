@@ -124,7 +124,7 @@ def cpu_port_rays_per_s(cfg_name, n_rays, repeats=1):
 def run_reference(args, rank):
     if rank != 0:
         return
-    n_rays = args.cpu_rays
+    n_rays = args.cpu_rays or 4096
     times = []
     for i in range(args.warmup + args.steps):
         rps, dt, cores = cpu_port_rays_per_s(args.config, n_rays)
@@ -175,7 +175,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="audio/person_2_auto")
-    ap.add_argument("--cpu-rays", type=int, default=2048, help="rays per CPU-baseline sample")
+    ap.add_argument("--cpu-rays", type=int, default=0,
+                    help="rays per CPU sample (0 = 16384 for the cpu_baseline leg, about 10 s on 16 cores; "
+                         "4096 per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
     args = ap.parse_args()
@@ -328,13 +330,15 @@ def main():
     # ------------------------------ training step (BASELINE config 3) ----------------------------
     train = None
     if not args.no_train:
-        from sahs_b200 import parallel as PL
         cfg_t = FX.load_cfg(args.config)                     # shipped stochastic settings: perturb, noise 0.1
         nrays = int(cfg_t.nerf.train.num_random_rays)
         tmodel = getattr(sahs_b200.models, cfg_t.models.mask.type)(cfg_t)
         tmodel.load_state_dict(sd)
         tmodel = tmodel.to(dev)
-        opt = torch.optim.Adam(tmodel.parameters(), lr=float(cfg_t.optimizer.lr), fused=True)   # one multi-tensor launch
+        # Adam on one flat buffer: gradient gather + (N > 1) one sum all-reduce + one kernel (sahs_adam_step)
+        opt = sahs_b200.FlatAdam(tmodel.parameters(), lr=float(cfg_t.optimizer.lr))
+        lr0, decay = float(cfg_t.optimizer.lr), float(cfg_t.scheduler.lr_decay_factor)
+        decay_steps = float(cfg_t.scheduler.lr_decay) * 1000.0
         f0 = dev_frames[0]
         ro_all, rd_all = f0["ro"].reshape(-1, 3), f0["rd"].reshape(-1, 3)
         maskf = f0["mask"].view(-1, 12).float()
@@ -355,8 +359,8 @@ def main():
             loss, sample_prob = sahs_b200.stage1_loss(out[0], out[3], target_all[sel], maskf[sel])
             opt.zero_grad(set_to_none=True)
             loss.backward()
-            PL.allreduce_gradients([p for p in tmodel.parameters()])
-            opt.step()
+            opt.step()                                           # includes the data-parallel gradient average
+            opt.param_groups[0]["lr"] = sahs_b200.exp_lr(lr0, decay, decay_steps, step_no[0])   # train script :503-509
             return loss
 
         for _ in range(3):
@@ -376,7 +380,8 @@ def main():
         train = {"metric": "train_rays_per_s", "value": world * nrays / (tms_step / 1e3), "unit": "rays/s",
                  "ms_per_step": tms_step, "rays_per_step_per_gpu": nrays, "loss": float(last.detach()),
                  "our_kernel_launches_per_step": int((lib.sahs_launch_count() - l0) / args.steps),
-                 "what": "fwd + bwd (hand-written compositing, dgrad-chain and wgrad kernels) + grad all-reduce + Adam, "
+                 "what": "device-side ray sampler + fwd + bwd (hand-written compositing, dgrad-chain and wgrad kernels) + "
+                         "one-kernel loss + grad all-reduce + flat Adam with exponential lr decay, "
                          "semantic-weighted batch of 2048 rays per GPU, perturb + noise 0.1"}
 
     # ------------------------------ 3DMM-conditioned render (BASELINE config 4) -------------------
@@ -418,9 +423,10 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rps, dt, cores = cpu_port_rays_per_s(args.config, args.cpu_rays)
+        cpu_rays = args.cpu_rays or 16384
+        rps, dt, cores = cpu_port_rays_per_s(args.config, cpu_rays)
         cpu_baseline = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-                        "sample": f"{args.cpu_rays} evenly spaced rays of one 512x512 frame ({dt:.1f} s), oracle port "
+                        "sample": f"{cpu_rays} evenly spaced rays of one 512x512 frame ({dt:.1f} s), oracle port "
                                   "(reference algorithm in torch-CPU ops), all host threads"}
     if rank == 0:
         line = {

@@ -197,6 +197,14 @@ int sahs_stage1_loss(const float* map_coarse, const float* map_fine, const float
                      int num_rays, int num_classes, float ce_weight, float mouth_weight, int mouth_lo, int mouth_hi,
                      float* stats, float* sample_prob, float* d_map_coarse, float* d_map_fine, void* stream);
 
+/* One Adam step on flat fp32 buffers (parameters, gradients, first and second moments, n elements each, 16-byte
+ * aligned).  ref: train_stage_rays_auto.py:200-210 (torch.optim.Adam, no weight decay / amsgrad) with the decayed
+ * learning rate of :503-509 passed as `lr`.  step counts from 1 (bias correction); grads are multiplied by grad_scale
+ * first (1 / world size after a sum all-reduce).  Same arithmetic as torch.optim.Adam's single-tensor path
+ * (hyper-parameters are doubles because 1 - beta2 must be formed in double, as Python does). */
+int sahs_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                   double beta1, double beta2, double eps, int step, float grad_scale, void* stream);
+
 /* Diagnostic word written by the field kernel when a bounded mbarrier wait times out (0 = healthy):
  * out4_host[0] code (+100 dgrad kernel, +200 wgrad kernel), [1] tag, [2] block, [3] thread.  The words live in mapped
  * host memory, so this works (and issues no CUDA call) after a kernel trapped. */

@@ -12,3 +12,4 @@ from .nerf_helpers import (cumprod_exclusive, get_embedding_function, get_miniba
 from .train_utils import predict_and_render_radiance, run_network, run_one_iter_of_nerf  # noqa: F401
 from .volume_rendering_utils import volume_render_radiance_field  # noqa: F401
 from .ops import frame_postprocess, weighted_sample  # noqa: F401,E402
+from .optim import FlatAdam, exp_lr  # noqa: F401,E402

@@ -1,0 +1,106 @@
+"""Adam on a flat parameter buffer, fused with the data-parallel gradient average.
+
+ref: train_stage_rays_auto.py:200-210 (`torch.optim.Adam([{'params': trainable_parameters}], lr=cfg.optimizer.lr)`),
+     :494-509 (`optimizer.step(); optimizer.zero_grad()`, then lr = lr0 * decay_factor ** (i / (lr_decay * 1000))).
+
+`FlatAdam` is a `torch.optim.Optimizer`: same constructor keywords (lr, betas, eps), `param_groups[..]["lr"]` can be
+overwritten every step as the script does, `state_dict()` holds `exp_avg` / `exp_avg_sq` / `step` per parameter.  On
+construction it re-homes every parameter into ONE flat fp32 buffer (the parameters become views of it), and keeps the
+two moments and a gradient staging buffer in the same layout.  `step()` is then three launches instead of a walk over
+124 tensors: gather the gradients into the flat buffer, (optionally) one sum all-reduce of that buffer, one
+`sahs_adam_step` kernel that folds the 1 / world-size average into its gradient read.
+"""
+from __future__ import annotations
+
+from typing import Iterable, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import lib as L
+
+
+def exp_lr(lr0: float, decay_factor: float, decay_steps: float, iteration: int) -> float:
+    """Learning rate of iteration i (ref: train_stage_rays_auto.py:503-507): lr0 * decay_factor ** (i / decay_steps),
+    decay_steps = cfg.scheduler.lr_decay * 1000."""
+    return lr0 * (decay_factor ** (iteration / decay_steps))
+
+
+class FlatAdam(torch.optim.Optimizer):
+    def __init__(self, params: Iterable, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, group=None):
+        if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1):
+            raise ValueError("bad Adam hyper-parameters")
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps))
+        L.load()                                             # fail loudly without the CUDA library
+        self._group = group
+        self._segments = []                                  # (param_group index, begin, end) in the flat buffers
+        plist = [p for g in self.param_groups for p in g["params"]]
+        if not plist:
+            raise ValueError("no parameters")
+        dev = plist[0].device
+        for p in plist:
+            if p.device != dev or not p.is_cuda or p.dtype != torch.float32:
+                raise RuntimeError("FlatAdam needs fp32 CUDA parameters on one device (there is no CPU path)")
+        # every parameter starts on a 16-byte boundary so the kernel's float4 accesses never straddle two tensors' ends
+        offs, total = [], 0
+        for p in plist:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self._n = total
+        self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._steps = 0
+        self._step_t = torch.tensor(0.0)                     # one counter object shared by every parameter's state
+        self._grad_views = []
+        with torch.no_grad():
+            for p, off in zip(plist, offs):
+                n = p.numel()
+                view = self.flat_param[off:off + n].view(p.shape)
+                view.copy_(p.data)
+                p.data = view                                   # the parameter now lives in the flat buffer
+                self._grad_views.append(self.flat_grad[off:off + n].view(p.shape))
+                self.state[p] = {"step": self._step_t, "exp_avg": self.flat_exp_avg[off:off + n].view(p.shape),
+                                 "exp_avg_sq": self.flat_exp_avg_sq[off:off + n].view(p.shape)}
+        i = 0
+        for gi, g in enumerate(self.param_groups):
+            b = offs[i] if g["params"] else 0
+            i += len(g["params"])
+            e = offs[i] if i < len(offs) else total
+            self._segments.append((gi, b, e))
+        self._params = plist        # (moving the storage changes data_ptr(), which the packed-weight cache keys on)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        lib = L.load()
+        # gradients -> flat staging buffer (absent gradients count as zero, as torch.optim.Adam skips them)
+        have = [(v, p.grad) for v, p in zip(self._grad_views, self._params) if p.grad is not None]
+        if len(have) != len(self._params):
+            self.flat_grad.zero_()
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        scale = 1.0
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self._group) > 1:
+            dist.all_reduce(self.flat_grad, group=self._group)
+            scale = 1.0 / dist.get_world_size(self._group)
+        self._steps += 1
+        stream = L.stream_ptr(self.flat_param.device)
+        for gi, b, e in self._segments:
+            g = self.param_groups[gi]
+            if e <= b:
+                continue
+            L.check(lib.sahs_adam_step(self.flat_param.data_ptr() + 4 * b, self.flat_grad.data_ptr() + 4 * b,
+                                       self.flat_exp_avg.data_ptr() + 4 * b, self.flat_exp_avg_sq.data_ptr() + 4 * b,
+                                       e - b, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
+                                       float(g["eps"]), self._steps, scale, stream), "adam_step")
+        self._step_t += 1
+        return loss
+
+    def averaged_gradients(self) -> Optional[torch.Tensor]:
+        """The flat gradient buffer of the last step (summed over ranks; multiply by 1 / world size for the mean)."""
+        return self.flat_grad
