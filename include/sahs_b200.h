@@ -185,17 +185,19 @@ int sahs_weighted_sample(const int32_t* mask, const float* class_prob, int64_t n
                          int num_select, uint64_t seed, int64_t* out_indices, void* workspace, size_t workspace_bytes,
                          void* stream);
 
-/* Stage-I training loss and its gradient in one launch (replaces ~75 elementwise/reduction launches per step).
+/* Stage-I training loss and its gradient in two small launches (replaces ~75 elementwise/reduction launches per step).
  * ref: nerf/nerf_helpers.py:14-62 (MaskCrossEntropyLoss, MaskMSELoss), assembled as in train_stage_rays_auto.py:455-468:
  * per level  l2 + ce_weight * CE + mouth_weight * sum_{k in [mouth_lo, mouth_hi)} (masked_l2[k] + masked_CE[k])
  * (0.02, 0.005 and classes 7..8 in the script), summed over the coarse and fine maps; the cross entropy's target is
  * the mask, as at the call site.  map_coarse / map_fine [R,15] (rgb + 12 class probabilities; map_fine may be NULL),
  * target_rgb [R,3], mask [R,12] float.  Outputs: stats[53] = {loss, l2_c, ce_c, l2_f, ce_f, masked_l2_c[12],
  * masked_ce_c[12], masked_l2_f[12], masked_ce_f[12]}, sample_prob[12] (the dynamic sampling weights, :466-468) and
- * d loss / d map for both levels [R,15].  Deterministic (fixed reduction order). */
+ * d loss / d map for both levels [R,15].  workspace: 4096 floats (per-CTA partial sums).  Two launches; deterministic
+ * (fixed reduction order). */
 int sahs_stage1_loss(const float* map_coarse, const float* map_fine, const float* target_rgb, const float* mask,
                      int num_rays, int num_classes, float ce_weight, float mouth_weight, int mouth_lo, int mouth_hi,
-                     float* stats, float* sample_prob, float* d_map_coarse, float* d_map_fine, void* stream);
+                     float* stats, float* sample_prob, float* d_map_coarse, float* d_map_fine, float* workspace,
+                     void* stream);
 
 /* One Adam step on flat fp32 buffers (parameters, gradients, first and second moments, n elements each, 16-byte
  * aligned).  ref: train_stage_rays_auto.py:200-210 (torch.optim.Adam, no weight decay / amsgrad) with the decayed

@@ -348,7 +348,8 @@ int sahs_build_bwd_plan(const sahs_model_spec& s, const float* const* params, Ho
 // --------------------------------------------------------------------------------------------------------
 // pack kernel: one block per stage, fp32 -> bf16, written at the 128B-swizzled offset
 // --------------------------------------------------------------------------------------------------------
-constexpr int kPackBatch = 40;
+constexpr int kPackBatch = kMaxStages;   // one launch per image: 160 x 96 B of kernel parameters (limit 32 KB since CUDA 12.1)
+constexpr int kPackSlices = 8;            // CTAs per stage image (a stage is at most 256 x 64 elements)
 struct PackBatch {
   PackStage st[kPackBatch];
 };
@@ -356,7 +357,7 @@ struct PackBatch {
 __global__ void pack_stage_kernel(const __grid_constant__ PackBatch batch, uint8_t* __restrict__ out) {
   const PackStage& ps = batch.st[blockIdx.x];
   const int total = ps.n * 64;
-  for (int e = threadIdx.x; e < total; e += blockDim.x) {
+  for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < total; e += blockDim.x * gridDim.y) {
     int row = e >> 6, col = e & 63;
     float v = 0.f;
 #pragma unroll
@@ -441,7 +442,7 @@ extern "C" int sahs_pack_params(const sahs_model_spec* spec, int level, const fl
     PackBatch pb;
     int cnt = hp.plan.num_stages - s0 < kPackBatch ? hp.plan.num_stages - s0 : kPackBatch;
     memcpy(pb.st, hp.pack + s0, sizeof(PackStage) * cnt);
-    pack_stage_kernel<<<cnt, 256, 0, st>>>(pb, (uint8_t*)packed_out);
+    pack_stage_kernel<<<dim3(cnt, kPackSlices), 256, 0, st>>>(pb, (uint8_t*)packed_out);
     SAHS_LAUNCH_CHECK();
   }
   if (spec->use_grid && grid_out) {
@@ -545,7 +546,7 @@ extern "C" int sahs_pack_params_train(const sahs_model_spec* spec, int level, co
     PackBatch pb;
     int cnt = hp.plan.num_stages - s0 < kPackBatch ? hp.plan.num_stages - s0 : kPackBatch;
     memcpy(pb.st, hp.pack + s0, sizeof(PackStage) * cnt);
-    pack_stage_kernel<<<cnt, 256, 0, (cudaStream_t)stream>>>(pb, (uint8_t*)packed_out);
+    pack_stage_kernel<<<dim3(cnt, kPackSlices), 256, 0, (cudaStream_t)stream>>>(pb, (uint8_t*)packed_out);
     SAHS_LAUNCH_CHECK();
   }
   return SAHS_OK;
@@ -564,7 +565,7 @@ extern "C" int sahs_pack_params_bwd(const sahs_model_spec* spec, int level, cons
     PackBatch pb;
     int cnt = hp.plan.num_stages - s0 < kPackBatch ? hp.plan.num_stages - s0 : kPackBatch;
     memcpy(pb.st, hp.pack + s0, sizeof(PackStage) * cnt);
-    pack_stage_kernel<<<cnt, 256, 0, (cudaStream_t)stream>>>(pb, (uint8_t*)packed_t_out);
+    pack_stage_kernel<<<dim3(cnt, kPackSlices), 256, 0, (cudaStream_t)stream>>>(pb, (uint8_t*)packed_t_out);
     SAHS_LAUNCH_CHECK();
   }
   return SAHS_OK;

@@ -1,4 +1,4 @@
-// Stage-I training loss, forward and backward in one launch.
+// Stage-I training loss, forward and backward in two small launches.
 // ref: nerf/nerf_helpers.py:14-62 (MaskCrossEntropyLoss, MaskMSELoss) and their assembly in
 //      train_stage_rays_auto.py:455-468:
 //   per level (coarse, fine):  diff_i = sum_c (rgb_ic - target_ic)^2,  ce_i = -sum_k mask_ik * log(p_ik + 1e-10)
@@ -7,33 +7,32 @@
 //     level loss = l2 + ce_weight * c + mouth_weight * sum_{k in [mouth_lo, mouth_hi)} (m_l2[k] + m_c[k])
 //   sample_prob = s / sum(s),  s = sum over levels of (m_l2 + m_c)        (the dynamic per-class sampling weight)
 // The reference spends ~75 elementwise/reduction launches and as many autograd nodes on this per step; a 2048-ray
-// batch is 0.6 MB, so the whole thing is launch bound.  One CTA: pass 1 accumulates the 64 sums (per-thread registers ->
-// warp shuffles -> fixed-order sum over the warps, so the result is deterministic), pass 2 re-reads the (L1/L2 resident)
-// rows and writes d loss / d map for both levels.  The cross entropy's target is the mask itself, as at the call site.
+// batch is 0.6 MB, so the whole thing is launch bound.  Two launches: (1) every CTA reduces the 64 sums of its rays
+// (registers -> warp shuffles -> fixed-order sum over the warps) into one row of a small workspace; (2) every CTA adds
+// the rows in order (deterministic result), forms the per-class normalisers, and writes d loss / d map of its rays;
+// CTA 0 also writes the loss, the statistics and sample_prob.  The cross entropy's target is the mask itself, as at
+// the call site.
 #include "sahs_common.cuh"
 
 namespace {
 
 constexpr int kC = 12;                 // semantic classes
 constexpr int kMapCh = 3 + kC;         // rgb + class probabilities per ray
-constexpr int kLossThreads = 512;   // 64 accumulators per thread: 512 threads leave 128 registers each (no spills)
+constexpr int kLossThreads = 256;
+constexpr int kLossMaxBlocks = 64;     // rows of the workspace
 constexpr int kAcc = kC + 2 * (2 + 2 * kC);   // counts, then per level: l2 sum, ce sum, m_l2[12], m_c[12]  (= 64)
 
 __global__ void __launch_bounds__(kLossThreads)
-stage1_loss_kernel(const float* __restrict__ map_c, const float* __restrict__ map_f, const float* __restrict__ target,
-                   const float* __restrict__ mask, int R, float ce_weight, float mouth_weight, int mouth_lo,
-                   int mouth_hi, float* __restrict__ stats, float* __restrict__ sample_prob, float* __restrict__ d_c,
-                   float* __restrict__ d_f) {
+stage1_loss_sums_kernel(const float* __restrict__ map_c, const float* __restrict__ map_f,
+                        const float* __restrict__ target, const float* __restrict__ mask, int R,
+                        float* __restrict__ partial) {
   __shared__ float part[kLossThreads / 32][kAcc];
-  __shared__ float tot[kAcc];
-  __shared__ float inv_count[kC];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int levels = map_f ? 2 : 1;
   float acc[kAcc];
 #pragma unroll
   for (int a = 0; a < kAcc; ++a) acc[a] = 0.f;
-  // ---- pass 1: sums ------------------------------------------------------------------------------------------
-  for (int i = tid; i < R; i += kLossThreads) {
+  for (int i = blockIdx.x * kLossThreads + tid; i < R; i += gridDim.x * kLossThreads) {
     float m[kC];
 #pragma unroll
     for (int k = 0; k < kC; ++k) {
@@ -72,14 +71,32 @@ stage1_loss_kernel(const float* __restrict__ map_c, const float* __restrict__ ma
   __syncthreads();
   if (tid < kAcc) {
     float v = 0.f;
+#pragma unroll
     for (int w = 0; w < kLossThreads / 32; ++w) v += part[w][tid];
+    partial[blockIdx.x * kAcc + tid] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+stage1_loss_grad_kernel(const float* __restrict__ map_c, const float* __restrict__ map_f,
+                        const float* __restrict__ target, const float* __restrict__ mask, int R, float ce_weight,
+                        float mouth_weight, int mouth_lo, int mouth_hi, const float* __restrict__ partial,
+                        float* __restrict__ stats, float* __restrict__ sample_prob, float* __restrict__ d_c,
+                        float* __restrict__ d_f) {
+  __shared__ float tot[kAcc];
+  __shared__ float inv_count[kC];
+  const int tid = threadIdx.x;
+  const int levels = map_f ? 2 : 1;
+  if (tid < kAcc) {
+    float v = 0.f;
+    for (int b = 0; b < (int)gridDim.x; ++b) v += partial[b * kAcc + tid];     // same order in every CTA
     tot[tid] = v;
   }
   __syncthreads();
   if (tid < kC) inv_count[tid] = 1.f / fmaxf(tot[tid], 1.f);
   __syncthreads();
   const float inv_r = 1.f / (float)R;
-  if (tid == 0) {
+  if (blockIdx.x == 0 && tid == 0) {
     // stats: [0] total loss, per level l: [1+2l] l2, [2+2l] ce, then m_l2 / m_c per level at 5 + l*24
     float loss = 0.f, s[kC], ssum = 0.f;
     for (int k = 0; k < kC; ++k) s[k] = 0.f;
@@ -102,8 +119,7 @@ stage1_loss_kernel(const float* __restrict__ map_c, const float* __restrict__ ma
     for (int k = 0; k < kC; ++k) ssum += s[k];
     for (int k = 0; k < kC; ++k) sample_prob[k] = s[k] / ssum;
   }
-  // ---- pass 2: d loss / d map ----------------------------------------------------------------------------------
-  for (int i = tid; i < R; i += kLossThreads) {
+  for (int i = blockIdx.x * kLossThreads + tid; i < R; i += gridDim.x * kLossThreads) {
     float m[kC], mouth = 0.f;
 #pragma unroll
     for (int k = 0; k < kC; ++k) {
@@ -132,15 +148,20 @@ stage1_loss_kernel(const float* __restrict__ map_c, const float* __restrict__ ma
 extern "C" int sahs_stage1_loss(const float* map_coarse, const float* map_fine, const float* target_rgb,
                                 const float* mask, int num_rays, int num_classes, float ce_weight, float mouth_weight,
                                 int mouth_lo, int mouth_hi, float* stats, float* sample_prob, float* d_map_coarse,
-                                float* d_map_fine, void* stream) {
+                                float* d_map_fine, float* workspace, void* stream) {
   SAHS_CHECK_ARG(num_rays >= 1, "at least one ray");
   SAHS_CHECK_ARG(num_classes == kC, "the maps carry 3 colour + 12 class channels");
-  SAHS_CHECK_ARG(map_coarse && target_rgb && mask && stats && sample_prob && d_map_coarse, "null pointer");
+  SAHS_CHECK_ARG(map_coarse && target_rgb && mask && stats && sample_prob && d_map_coarse && workspace, "null pointer");
   SAHS_CHECK_ARG(!map_fine || d_map_fine, "a fine map needs a fine gradient buffer");
   SAHS_CHECK_ARG(mouth_lo >= 0 && mouth_hi <= kC && mouth_lo <= mouth_hi, "bad mouth class range");
-  stage1_loss_kernel<<<1, kLossThreads, 0, (cudaStream_t)stream>>>(map_coarse, map_fine, target_rgb, mask, num_rays,
-                                                                  ce_weight, mouth_weight, mouth_lo, mouth_hi, stats,
-                                                                  sample_prob, d_map_coarse, d_map_fine);
+  int blocks = (num_rays + kLossThreads - 1) / kLossThreads;
+  if (blocks > kLossMaxBlocks) blocks = kLossMaxBlocks;
+  cudaStream_t st = (cudaStream_t)stream;
+  stage1_loss_sums_kernel<<<blocks, kLossThreads, 0, st>>>(map_coarse, map_fine, target_rgb, mask, num_rays, workspace);
+  SAHS_LAUNCH_CHECK();
+  stage1_loss_grad_kernel<<<blocks, kLossThreads, 0, st>>>(map_coarse, map_fine, target_rgb, mask, num_rays, ce_weight,
+                                                         mouth_weight, mouth_lo, mouth_hi, workspace, stats,
+                                                         sample_prob, d_map_coarse, d_map_fine);
   SAHS_LAUNCH_CHECK();
   return SAHS_OK;
 }

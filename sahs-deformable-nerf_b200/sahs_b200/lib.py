@@ -75,7 +75,7 @@ def load() -> C.CDLL:
         "sahs_weighted_sample": (C.c_int, [vp, vp, i64, i32, i32, C.c_uint64, vp, vp, C.c_size_t, vp]),
         "sahs_adam_step": (C.c_int, [vp, vp, vp, vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, i32, C.c_float,
                            vp]),
-        "sahs_stage1_loss": (C.c_int, [vp, vp, vp, vp, i32, i32, C.c_float, C.c_float, i32, i32, vp, vp, vp, vp, vp]),
+        "sahs_stage1_loss": (C.c_int, [vp, vp, vp, vp, i32, i32, C.c_float, C.c_float, i32, i32, vp, vp, vp, vp, vp, vp]),
         "sahs_field_status": (C.c_int, [C.POINTER(C.c_int)]),
     }
     for name, (res, args) in sigs.items():

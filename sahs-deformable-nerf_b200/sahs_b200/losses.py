@@ -4,7 +4,7 @@ ref: nerf/nerf_helpers.py:14-62 (MaskCrossEntropyLoss, MaskMSELoss), train_stage
 
 `MaskMSELoss` / `MaskCrossEntropyLoss` mirror the reference's modules (same constructor, same 3-tuple result) for
 callers that use them one at a time.  `stage1_loss` is what the training step calls: the whole assembly -- both
-levels, the mouth term, the dynamic `sample_prob` and the gradient w.r.t. both maps -- in ONE kernel launch
+levels, the mouth term, the dynamic `sample_prob` and the gradient w.r.t. both maps -- in two small launches
 (csrc/loss.cu, `sahs_stage1_loss`) behind a torch.autograd.Function.
 """
 from __future__ import annotations
@@ -71,7 +71,7 @@ def stage1_loss_modules(rgb_coarse, rgb_fine, target_rgb, mask, mse=None, ce=Non
 
 
 class _Stage1LossFn(torch.autograd.Function):
-    """One launch computes the loss, its statistics, sample_prob and d loss / d map; backward only scales."""
+    """The forward call computes the loss, its statistics, sample_prob and d loss / d map; backward only scales."""
 
     @staticmethod
     def forward(ctx, map_c, map_f, target, mask):
@@ -83,12 +83,13 @@ class _Stage1LossFn(torch.autograd.Function):
         R = mc.shape[0]
         if mf.shape[0] != R or tg.shape[0] != R or mk.shape[0] != R:
             raise RuntimeError("stage1_loss: maps, target and mask must cover the same rays")
-        buf = torch.empty(53 + 12, dtype=torch.float32, device=dev)     # one allocation: statistics, then sample_prob
-        stats, prob = buf[:53], buf[53:]
+        # one allocation: statistics [53], sample_prob [12], pad to 16 B, per-CTA partial sums [4096]
+        buf = torch.empty(68 + 4096, dtype=torch.float32, device=dev)
+        stats, prob, work = buf[:53], buf[53:65], buf[68:]
         d_c, d_f = torch.empty_like(mc), torch.empty_like(mf)
         L.check(lib.sahs_stage1_loss(L.ptr(mc), L.ptr(mf), L.ptr(tg), L.ptr(mk), R, 12, CE_WEIGHT, MOUTH_WEIGHT,
                                      MOUTH_CLASSES[0], MOUTH_CLASSES[1], L.ptr(stats), L.ptr(prob), L.ptr(d_c),
-                                     L.ptr(d_f), L.stream_ptr(dev)), "stage1_loss")
+                                     L.ptr(d_f), L.ptr(work), L.stream_ptr(dev)), "stage1_loss")
         ctx.save_for_backward(d_c, d_f)
         ctx.shapes = (map_c.shape, map_f.shape)
         ctx.mark_non_differentiable(prob, stats)
@@ -102,7 +103,7 @@ class _Stage1LossFn(torch.autograd.Function):
 
 def stage1_loss(rgb_coarse, rgb_fine, target_rgb, mask, return_stats: bool = False):
     """coarse + fine: l2 + 0.02 * CE + 0.005 * (mouth classes 7..8), ref: train_stage_rays_auto.py:455-465, and the
-    dynamic per-class sampling weight `sample_prob` (:466-468), fused into one kernel (forward and gradient).
+    dynamic per-class sampling weight `sample_prob` (:466-468), fused into two small kernels (sums, then gradients).
     rgb_* [R,15] maps from run_one_iter_of_nerf, target_rgb [R,>=3], mask [R,12].  Returns (loss, sample_prob)
     (+ the 53 statistics of include/sahs_b200.h when return_stats).  CUDA tensors only: there is no CPU path."""
     if not rgb_coarse.is_cuda:

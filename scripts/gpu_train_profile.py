@@ -14,7 +14,7 @@ sd = FX.make_state_dict(spec, seed=42, dense=True)
 H = W = 512
 fr = FX.make_frame_inputs(spec, H, W, seed=0)
 model = sahs_b200.AudioFaceModel(cfg); model.load_state_dict(sd); model = model.to(DEV)
-opt = torch.optim.Adam(model.parameters(), lr=5e-4, fused=True)
+opt = sahs_b200.FlatAdam(model.parameters(), lr=5e-4)
 pose = fr["pose"].to(DEV)
 with torch.no_grad():
     ro, rd = sahs_b200.get_ray_bundle(H, W, fr["intrinsics"], pose)
@@ -23,13 +23,12 @@ bg = fr["background"].view(-1, 15).to(DEV)
 maskf = fr["mask"].view(-1, 12).float().to(DEV)
 target = torch.rand(H * W, 3, device=DEV)
 drv = fr["driving"].to(DEV)
-try:
-    a = torch.randn(64, 32, device=DEV, dtype=torch.float16); b = torch.randn(64, 48, device=DEV, dtype=torch.float16)
-    r = torch.mm(a.t(), b, out_dtype=torch.float32); print("torch.mm out_dtype OK", r.dtype)
-except Exception as e:
-    print("torch.mm out_dtype NOT supported:", repr(e)[:200])
+mask_i32 = fr["mask"].view(-1, 12).to(torch.int32).to(DEV).contiguous()
+prob = torch.ones(12, device=DEV)
+it = [0]
 def step():
-    sel = torch.randint(0, H * W, (2048,), device=DEV)
+    it[0] += 1
+    sel = sahs_b200.weighted_sample(mask_i32, prob, 2048, seed=it[0])
     out = sahs_b200.run_one_iter_of_nerf(H, W, 1200.0, model, ro[sel], rd[sel], cfg, mode="train", driving=drv, pose=pose,
                                          background_prior=bg[sel])
     loss, _ = sahs_b200.stage1_loss(out[0], out[3], target[sel], maskf[sel])
