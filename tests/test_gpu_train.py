@@ -115,7 +115,7 @@ def test_optimizer_step_repacks_weights(fused):
         opt.zero_grad()
         loss.backward()
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert losses[2] < losses[0], losses
 
 
