@@ -240,3 +240,15 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
     assert lib.sahs_abi_version() == 1
+
+
+def test_exp_lr_matches_training_script_schedule():
+    """lr_new = lr * decay_factor ** (i / (lr_decay * 1000)) (ref: train_stage_rays_auto.py:503-507), shipped values."""
+    from sahs_b200 import exp_lr
+    cfg = FX.load_cfg("audio/person_2_auto")
+    lr0, f, steps = float(cfg.optimizer.lr), float(cfg.scheduler.lr_decay_factor), float(cfg.scheduler.lr_decay) * 1000
+    assert exp_lr(lr0, f, steps, 0) == lr0
+    assert abs(exp_lr(lr0, f, steps, int(steps)) - lr0 * f) < 1e-15
+    assert abs(exp_lr(lr0, f, steps, 125000) - lr0 * f ** 0.5) < 1e-15
+    vals = [exp_lr(lr0, f, steps, i) for i in range(0, 400000, 50000)]
+    assert all(a > b for a, b in zip(vals, vals[1:]))
