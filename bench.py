@@ -421,6 +421,35 @@ def main():
                    "value": world * R / (float(ms4) / 1e3), "unit": "rays/s"}
         del model4
 
+    # ------------------------------ clip rendering over ranks (BASELINE config 5) ----------------
+    clip = None
+    if world > 1 and not args.no_train:
+        from sahs_b200 import parallel as PL
+        n_clip = 4 * world                                   # frames of the clip (whole frames per rank, round robin)
+
+        def clip_frame(f):
+            fr = dev_frames[f % len(dev_frames)]
+            with torch.no_grad():
+                out = sahs_b200.run_one_iter_of_nerf(H, W, 1200.0, model, fr["ro"], fr["rd"], cfg, mode="validation",
+                                                     driving=fr["driving"], pose=fr["pose"], background_prior=bg_dev,
+                                                     inHead=fr["mask"])
+                rgb8, lab8, _ = sahs_b200.frame_postprocess(out[3])
+            return torch.cat((rgb8.view(-1, 3), lab8.view(-1, 1)), -1)          # [R, 4] uint8: 1 MB per frame
+
+        PL.render_clip(clip_frame, world)                    # warm-up: one frame per rank + the gather
+        barrier()
+        c0 = time.perf_counter()
+        got = PL.render_clip(clip_frame, n_clip)
+        barrier()
+        clip_s = torch.tensor([time.perf_counter() - c0], device=dev)
+        dist.all_reduce(clip_s, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            assert got.shape == (n_clip, R, 4)
+        clip = {"workload": f"{n_clip}-frame clip, frame f on rank f mod {world}, uint8 rgb + argmax label gathered to "
+                            "rank 0 once at the end (sahs_b200.parallel.render_clip)",
+                "frames_per_s": n_clip / float(clip_s), "ms_per_frame": 1e3 * float(clip_s) / n_clip,
+                "gathered_bytes_per_frame": 4 * R}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_rays = args.cpu_rays or 16384
@@ -441,7 +470,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_frame": 1e3 * float(e2e_s) / args.steps},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
-            "train": train,
+            "train": train, "clip": clip,
             "config4": config4,
         }
         _emit(json.dumps(line))

@@ -62,6 +62,41 @@ def render_sharded(render_fn, ro: torch.Tensor, rd: torch.Tensor, background=Non
     return gather_rays(list(outs), R, group)
 
 
+def render_clip(render_frame_fn, num_frames: int, group=None):
+    """Clip rendering (BASELINE config 5): frame f is rendered entirely by rank `frame_owner(f, world)` with
+    `render_frame_fn(f)`, which returns the frame as ONE uint8 tensor (e.g. `cat(frame_postprocess(rgb_map)[0:2])`:
+    uint8 rgb + argmax label, 4 B/pixel instead of the 76 B/pixel fp32 maps).  No collective runs while frames are being
+    rendered; at the end the frames are gathered once.  Returns the clip `[num_frames, ...]` in frame order on rank 0
+    and None on the other ranks (single process: the clip)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mine = [render_frame_fn(f) for f in range(num_frames) if frame_owner(f, world) == rank]
+    if world == 1:
+        return torch.stack(mine) if mine else None
+    per_rank = (num_frames + world - 1) // world
+    shape = [None]
+    if mine:
+        shape[0] = (tuple(mine[0].shape), mine[0].dtype)
+    shapes = [None] * world
+    dist.all_gather_object(shapes, shape[0], group=group)
+    ref = next((sh for sh in shapes if sh is not None), None)
+    if ref is None:
+        return None
+    fshape, dtype = ref
+    if mine:
+        dev = mine[0].device
+    else:       # a rank without a frame (fewer frames than ranks) still takes part in the gather
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    local = torch.zeros((per_rank,) + fshape, dtype=dtype, device=dev)      # padded to the largest share
+    for i, fr in enumerate(mine):
+        local[i] = fr
+    bufs = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(bufs, local, group=group)
+    if rank != 0:
+        return None
+    return torch.stack([bufs[frame_owner(f, world)][f // world] for f in range(num_frames)])
+
+
 def allreduce_gradients(params, group=None, average: bool = True) -> None:
     """Data-parallel training: one all-reduce of a flat fp32 gradient buffer per step."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

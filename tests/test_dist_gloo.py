@@ -47,6 +47,34 @@ def _worker(rank, world, port, R):
         dist.destroy_process_group()
 
 
+def _clip_worker(rank, world, port, num_frames):
+    from sahs_b200 import parallel as PL
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rendered = []
+
+        def fake_frame(f):                   # stands in for render + frame_postprocess: uint8 [pixels, 4]
+            rendered.append(f)
+            return (torch.arange(24, dtype=torch.int32).view(6, 4) * (f + 1) % 251).to(torch.uint8)
+
+        clip = PL.render_clip(fake_frame, num_frames)
+        assert rendered == [f for f in range(num_frames) if f % world == rank]       # whole frames, round robin
+        if rank == 0:
+            assert clip.shape == (num_frames, 6, 4) and clip.dtype == torch.uint8
+            for f in range(num_frames):
+                assert torch.equal(clip[f], (torch.arange(24, dtype=torch.int32).view(6, 4) * (f + 1) % 251).to(torch.uint8))
+        else:
+            assert clip is None
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("num_frames", [5, 4, 1])
+def test_clip_frames_round_robin_and_gather_world2(num_frames):
+    mp.spawn(_clip_worker, args=(2, _free_port(), num_frames), nprocs=2, join=True)
+
+
 @pytest.mark.parametrize("R", [1000, 128, 5])
 def test_sharded_render_and_allreduce_world2(R):
     mp.spawn(_worker, args=(2, _free_port(), R), nprocs=2, join=True)
