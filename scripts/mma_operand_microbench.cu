@@ -1,6 +1,6 @@
 // Micro-benchmark: tcgen05.mma completion time for N = 128 vs N = 256 with the B operand in different shared-memory
-// layouts, with and without a concurrent st.shared stream from the other warps (an epilogue's stores), at 1 and 2 CTAs
-// per SM.  Question (experiment (d)): does N = 256 (A tile read once instead of twice) pay, and in
+// layouts, alone, with a concurrent st.shared stream (an epilogue's stores, stores=1) or a concurrent tcgen05.ld stream
+// (an epilogue's accumulator reads, stores=2) from the other four warps, at 1 and 2 CTAs per SM.  Question (experiment (d)): does N = 256 (A tile read once instead of twice) pay, and in
 // which layout?  layout 0: K-major SWIZZLE_128B rows of 64 k (N x 128 B);  1: K-major SWIZZLE_64B rows of 32 k;
 // 2: K-major no swizzle (core matrices 128 B apart in k, 8-row groups 512 B apart);  3: MN-major SWIZZLE_128B panels of
 // [32 k x 128 B].  Operand data is zero (timing only).  Diagnostic only; build:
@@ -138,6 +138,21 @@ __global__ void __launch_bounds__(192, 2) bench(int n, int nmma, int per_commit,
       for (int rep = 0; rep < 3; ++rep) mbar_wait(bar, rep & 1, nullptr, 0);
       *stop = 1;
     }
+  } else if (stores == 2 && warp >= 2) {
+    // an epilogue's other half: tcgen05.ld of the accumulator columns (each warp its own lane quarter), back to back
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t v[16], acc = 0;
+    int it = 0;
+    while (!*stop) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        tmem_ld16(trow + ((it * 8 + j) & 15) * 16, v);
+        tmem_ld_wait();
+        acc += v[0] ^ v[15];
+      }
+      ++it;
+    }
+    if (acc == 0x12345678u) *stop = 2;
   } else if (stores && warp >= 2) {
     uint4 v = make_uint4(threadIdx.x, 1, 2, 3);
     int it = 0;
@@ -207,7 +222,7 @@ void run(int n, int nmma, int per_commit, int stores, int ctas_per_sm, int layou
 
 int main() {
   for (int cps = 1; cps <= 2; ++cps)
-    for (int stores = 0; stores <= 1; ++stores) {
+    for (int stores = 0; stores <= 2; ++stores) {   // 0: MMAs only, 1: + st.shared stream, 2: + tcgen05.ld stream
       run<1, 2>(128, 128, 1, stores, cps, 0);
       for (int layout = 0; layout < 4; ++layout) run<1, 2>(256, 128, 1, stores, cps, layout);
       run<0, 2>(128, 128, 1, stores, cps, 0);
