@@ -20,7 +20,10 @@ constexpr int kSmemXchg = kSmemBar + 256;                     // 128 floats exch
 constexpr int kSmemTotal = kSmemXchg + 512;
 // CTA-pair variant (cluster of 2, tcgen05 cta_group::2): every CTA holds half of each weight stage (N/2 rows), so the
 // L2 -> SM weight traffic per point is halved and a 24 KB ring is as deep (3 stages) as the single-CTA 48 KB one ...
-constexpr int kPairSlots = 3;
+#ifndef SAHS_PAIR_SLOTS
+#define SAHS_PAIR_SLOTS 3
+#endif
+constexpr int kPairSlots = SAHS_PAIR_SLOTS;
 constexpr int kPairSlotBytes = kStageSlotBytes / 2;
 // ... and the 24 KB this frees hold the per-frame constant block (folded biases, fp32 head weights) in shared memory:
 // the epilogues' bias reads become LDS instead of global loads through the 28 KB L1 (measured: 18 % of the kernel).

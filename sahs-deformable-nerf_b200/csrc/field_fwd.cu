@@ -498,14 +498,18 @@ int launch_field(const HostPlan& hp, const void* packed, const float* fc, const 
     // CTA pairs: clusters of 2, two clusters resident per SM pair
     auto kfn = tr.tape_x ? field_fwd_kernel<C, false, true, true>
                          : (prof ? field_fwd_kernel<C, true, false, true> : field_fwd_kernel<C, false, false, true>);
-    SAHS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemTotal));
+    // measurement switch: SAHS_FIELD_ONE_PER_SM=1 pads the shared-memory request so that only one CTA fits per SM
+    // (one cluster per SM pair): shows a CTA's MMA phases without a co-resident CTA sharing the tensor pipe
+    static const bool one_per_sm = [] { const char* e = getenv("SAHS_FIELD_ONE_PER_SM"); return e && e[0] == '1'; }();
+    const int smem_bytes = one_per_sm ? 160 * 1024 : kPairSmemTotal;
+    SAHS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     const long long npairs = (ntiles + 1) / 2;
-    long long nclusters = sahs_num_sms();           // 2 CTAs per SM = one cluster per SM on average
+    long long nclusters = one_per_sm ? sahs_num_sms() / 2 : sahs_num_sms();   // 2 CTAs per SM = one cluster per SM
     if (nclusters > npairs) nclusters = npairs;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * nclusters));
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = kPairSmemTotal;
+    cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
