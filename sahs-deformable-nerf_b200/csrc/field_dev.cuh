@@ -460,7 +460,8 @@ __device__ __forceinline__ void tma_warp_loop(const FieldPlan& plan, const uint8
   int iter = 0;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++iter) {
     uint32_t off = 0;
-    long long* prof = (prof_base && iter == 2 && lane == 0) ? prof_base : nullptr;
+    // (bit 0 of prof_base set: per-pass events only, so this per-stage producer records nothing)
+    long long* prof = (prof_base && !(reinterpret_cast<uintptr_t>(prof_base) & 1) && iter == 2 && lane == 0) ? prof_base : nullptr;
     for (int st = 0; st < plan.num_stages; ++st) {
       const uint32_t bytes = (uint32_t)plan.st[st].n8 * 1024u;
       mbar_wait(&empty[slot], phase ^ 1, status, 100);
@@ -497,7 +498,9 @@ __device__ __forceinline__ void mma_issue_loop(const FieldPlan& plan, uint8_t* X
   uint32_t token = 0;
   int iter = 0;
   for (long long it = first; it < count; it += step, ++iter) {
-    long long* prof = (PROF && prof_base && iter == 2 && (threadIdx.x & 31) == 0) ? prof_base : nullptr;
+    const bool light = PROF && (reinterpret_cast<uintptr_t>(prof_base) & 1);     // per-pass events only
+    long long* prof = (PROF && prof_base && iter == 2 && (threadIdx.x & 31) == 0)
+                          ? reinterpret_cast<long long*>(reinterpret_cast<uintptr_t>(prof_base) & ~(uintptr_t)1) : nullptr;
     for (int st = 0; st < plan.num_stages; ++st) {
       const uint32_t flags = r.kflags >> 3, ksteps = r.kflags & 7;
       if (flags & ST_WAIT_A) {
@@ -506,7 +509,7 @@ __device__ __forceinline__ void mma_issue_loop(const FieldPlan& plan, uint8_t* X
         if (PROF) prof_event(prof, 10000 + st);
       }
       mbar_wait_token(&full[slot], phase, token, status, 400 + st);   // PAIR: both halves of the stage have landed
-      if (PROF) prof_event(prof, 20000 + st);
+      if (PROF && !light) prof_event(prof, 20000 + st);
       tc_fence_after();
       const uint32_t idesc = PAIR ? (r.idesc ^ (((128u >> 4) ^ (256u >> 4)) << 24)) : r.idesc;   // M field 128 -> 256
       // descriptor address field counts 16-byte units; K advances 16 elements = 32 bytes = 2 units per MMA
@@ -539,7 +542,7 @@ __device__ __forceinline__ void mma_issue_loop(const FieldPlan& plan, uint8_t* X
       }
       commit(&empty[slot]);
       if (flags & ST_COMMIT) commit(acc_ready);
-      if (PROF) prof_event(prof, 30000 + st);
+      if (PROF && (!light || (flags & ST_COMMIT))) prof_event(prof, 30000 + st);
       if (++slot == NS) { slot = 0; phase ^= 1; }
       r = plan.st[(st + 1 < plan.num_stages) ? st + 1 : 0];
       token = mbar_peek(&full[slot], phase);
@@ -566,7 +569,8 @@ __device__ __forceinline__ void tma_warp_loop_pair(const FieldPlan& plan, const 
   const long long pt0 = cluster_id_x(), pt_step = cluster_num_x();
   for (long long pt = pt0; pt < npairs; pt += pt_step, ++iter) {
     uint32_t off = 0;
-    long long* prof = (prof_base && iter == 2 && lane == 0) ? prof_base : nullptr;
+    // (bit 0 of prof_base set: per-pass events only, so this per-stage producer records nothing)
+    long long* prof = (prof_base && !(reinterpret_cast<uintptr_t>(prof_base) & 1) && iter == 2 && lane == 0) ? prof_base : nullptr;
     for (int st = 0; st < plan.num_stages; ++st) {
       const uint32_t half = (uint32_t)plan.st[st].n8 * 512u;
       mbar_wait_cluster(&empty[slot], phase ^ 1, status, 100);

@@ -108,14 +108,16 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
 
   // debug builds, dbg_pass == SAHS_DBG_PROF: block 0 records (tag, clock64) event pairs of its third tile into dbg,
   // 4096 long longs per role: worker thread 0, worker thread 255, MMA issuer, TMA producer
-  long long* prof_buf = (DBG && dbg && dbg_pass == SAHS_DBG_PROF && blockIdx.x == 0) ? reinterpret_cast<long long*>(dbg)
-                                                                                      : nullptr;
+  const bool prof_on = DBG && dbg && (dbg_pass == SAHS_DBG_PROF || dbg_pass == SAHS_DBG_PROF_LIGHT) && blockIdx.x == 0;
+  long long* prof_buf = prof_on ? reinterpret_cast<long long*>(dbg) : nullptr;
+  // SAHS_DBG_PROF_LIGHT: bit 0 of the pointers handed to the TMA / MMA loops asks for per-pass events only
+  const uintptr_t prof_light = (dbg_pass == SAHS_DBG_PROF_LIGHT) ? 1u : 0u;
   if (warp == kTmaWarp) {
-    long long* pb = prof_buf ? prof_buf + 3 * 4096 : nullptr;
+    long long* pb = prof_buf ? reinterpret_cast<long long*>(reinterpret_cast<uintptr_t>(prof_buf + 3 * 4096) | prof_light) : nullptr;
     if (PAIR) tma_warp_loop_pair(plan, packed, slots, full, empty, npairs, rank, status, lane, pb);
     else tma_warp_loop(plan, packed, slots, full, empty, ntiles, status, lane, pb);
   } else if (warp == kMmaWarp) {
-    long long* pb = prof_buf ? prof_buf + 2 * 4096 : nullptr;
+    long long* pb = prof_buf ? reinterpret_cast<long long*>(reinterpret_cast<uintptr_t>(prof_buf + 2 * 4096) | prof_light) : nullptr;
     if (!PAIR) mma_warp_loop<DBG>(plan, X, slots, full, empty, a_ready, acc_ready, tmem_base, ntiles, status, lane, pb);
     else if (rank == 0) mma_warp_loop_pair<DBG>(plan, X, slots, full, empty, a_ready, acc_ready, tmem_base, npairs, status, lane, pb);
     else relay_warp_loop_pair(plan, full, npairs, status, lane);
@@ -493,7 +495,7 @@ int launch_field(const HostPlan& hp, const void* packed, const float* fc, const 
   const long long P = (long long)R * S;
   const long long ntiles = (P + kTileRows - 1) / kTileRows;
   const uint8_t* pk = (const uint8_t*)packed;
-  const bool prof = dbg != nullptr && dbg_pass == SAHS_DBG_PROF;
+  const bool prof = dbg != nullptr && (dbg_pass == SAHS_DBG_PROF || dbg_pass == SAHS_DBG_PROF_LIGHT);
   if ((!dbg || prof) && field_pair_enabled() && hp.dims.fc_total <= kPairFcFloats) {
     // CTA pairs: clusters of 2, two clusters resident per SM pair
     auto kfn = tr.tape_x ? field_fwd_kernel<C, false, true, true>

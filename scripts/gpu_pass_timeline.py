@@ -1,6 +1,9 @@
 """Per-pass timeline of one tile of the field kernel (debug build, SAHS_DBG_PROF): where a CTA's cycles go.
 
-    python scripts/gpu_pass_timeline.py [pair: 0|1] [R]
+    python scripts/gpu_pass_timeline.py [pair: 0|1] [R] [light: 0|1]
+
+light = 1 records per-pass events only (SAHS_DBG_PROF_LIGHT): the per-stage events of the full mode cost about 250
+cycles per stage in the issuer's loop and inflate a tile by ~50 %.
 
 Block 0 records clock64 events of its third tile for worker threads 0 and 255, the MMA issuer and the TMA
 producer.  Diagnostic only.
@@ -30,7 +33,7 @@ def events(buf, role):
     return a[:n]
 
 
-def main(pair, R):
+def main(pair, R, light=0):
     os.environ["SAHS_FIELD_PAIR"] = "1" if pair else "0"
     cfg = FX.load_cfg("audio/person_2_auto")
     ospec = O.spec_from_cfg(cfg)
@@ -49,7 +52,7 @@ def main(pair, R):
     dbg = torch.zeros(128, 256, device=dev)
     for _ in range(2):
         dbg.zero_()
-        model.field("fine", ro, rd, z, drv, pcode, frame_const=fc, debug=dbg, debug_pass=99)
+        model.field("fine", ro, rd, z, drv, pcode, frame_const=fc, debug=dbg, debug_pass=98 if light else 99)
         torch.cuda.synchronize()
     buf = dbg.cpu().numpy().view(np.int64).reshape(-1)
     w0, w255, mma, tma = (events(buf, r) for r in range(4))
@@ -110,4 +113,5 @@ def main(pair, R):
 
 
 if __name__ == "__main__":
-    main(int(sys.argv[1]) if len(sys.argv) > 1 else 0, int(sys.argv[2]) if len(sys.argv) > 2 else 16384)
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 0, int(sys.argv[2]) if len(sys.argv) > 2 else 16384,
+         int(sys.argv[3]) if len(sys.argv) > 3 else 0)
