@@ -33,6 +33,14 @@ struct TrainOut {
   float* saves;
 };
 
+// SAHS_DBG_PROF_PROD (per-pass worker events from the production instantiation, true speed) costs the production kernel
+// a null check per pass (~1 % measured), so it is compiled in only with -DSAHS_PROF_PROD=1
+// (profiles/r1_pass_timeline_production_*.txt were taken with such a build).
+#ifndef SAHS_PROF_PROD
+#define SAHS_PROF_PROD 0
+#endif
+constexpr bool kProfProd = SAHS_PROF_PROD != 0;
+
 template <class C, bool DBG, bool TRAIN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 2)
 field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__ NetDims dm,
@@ -108,7 +116,11 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
 
   // debug builds, dbg_pass == SAHS_DBG_PROF: block 0 records (tag, clock64) event pairs of its third tile into dbg,
   // 4096 long longs per role: worker thread 0, worker thread 255, MMA issuer, TMA producer
-  const bool prof_on = DBG && dbg && (dbg_pass == SAHS_DBG_PROF || dbg_pass == SAHS_DBG_PROF_LIGHT) && blockIdx.x == 0;
+  // (SAHS_DBG_PROF_PROD: the production instantiation records the workers' per-pass events -- signal and accumulator
+  // wake-up, already compiled into signal_a / wait_acc behind a null check -- so a tile can be timed at true speed)
+  const bool prof_on = dbg && blockIdx.x == 0 &&
+                       ((DBG && (dbg_pass == SAHS_DBG_PROF || dbg_pass == SAHS_DBG_PROF_LIGHT)) ||
+                        (kProfProd && !DBG && dbg_pass == SAHS_DBG_PROF_PROD));
   long long* prof_buf = prof_on ? reinterpret_cast<long long*>(dbg) : nullptr;
   // SAHS_DBG_PROF_LIGHT: bit 0 of the pointers handed to the TMA / MMA loops asks for per-pass events only
   const uintptr_t prof_light = (dbg_pass == SAHS_DBG_PROF_LIGHT) ? 1u : 0u;
@@ -135,7 +147,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
     const long long it0 = PAIR ? (long long)cluster_id_x() : (long long)blockIdx.x;
     for (long long it = it0; it < it_end; it += it_step, ++iter) {
       const long long tile = PAIR ? 2 * it + rank : it;
-      if (DBG) {
+      if (DBG || (kProfProd && prof_buf)) {
         sy.prof = nullptr;
         if (prof_buf && iter == 2 && (threadIdx.x == 0 || threadIdx.x == 255)) {
           sy.prof = prof_buf + (threadIdx.x == 0 ? 0 : 4096);
@@ -465,7 +477,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
       }
       tc_fence_before();
       group_sync();   // xchg[] consumed before the next tile's fc_feat epilogue rewrites it
-      if (DBG) prof_event(sy.prof, 3);   // tile end
+      if (DBG || kProfProd) prof_event(sy.prof, 3);   // tile end
     }
     if (TRAIN && threadIdx.x == 0) tma_store_wait_all();   // tape stores complete before the CTA exits
   }
@@ -495,8 +507,9 @@ int launch_field(const HostPlan& hp, const void* packed, const float* fc, const 
   const long long P = (long long)R * S;
   const long long ntiles = (P + kTileRows - 1) / kTileRows;
   const uint8_t* pk = (const uint8_t*)packed;
+  const bool prof_prod = dbg != nullptr && dbg_pass == SAHS_DBG_PROF_PROD;   // production kernel + per-pass events
   const bool prof = dbg != nullptr && (dbg_pass == SAHS_DBG_PROF || dbg_pass == SAHS_DBG_PROF_LIGHT);
-  if ((!dbg || prof) && field_pair_enabled() && hp.dims.fc_total <= kPairFcFloats) {
+  if ((!dbg || prof || prof_prod) && field_pair_enabled() && hp.dims.fc_total <= kPairFcFloats) {
     // CTA pairs: clusters of 2, two clusters resident per SM pair
     auto kfn = tr.tape_x ? field_fwd_kernel<C, false, true, true>
                          : (prof ? field_fwd_kernel<C, true, false, true> : field_fwd_kernel<C, false, false, true>);
@@ -526,7 +539,7 @@ int launch_field(const HostPlan& hp, const void* packed, const float* fc, const 
     return SAHS_OK;
   }
   auto kfn = tr.tape_x ? field_fwd_kernel<C, false, true, false>
-                       : ((dbg != nullptr) ? field_fwd_kernel<C, true, false, false>
+                       : ((dbg != nullptr && !prof_prod) ? field_fwd_kernel<C, true, false, false>
                                            : field_fwd_kernel<C, false, false, false>);
   SAHS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal));
   long long grid_dim = 2LL * sahs_num_sms();

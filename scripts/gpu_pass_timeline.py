@@ -1,9 +1,11 @@
 """Per-pass timeline of one tile of the field kernel (debug build, SAHS_DBG_PROF): where a CTA's cycles go.
 
-    python scripts/gpu_pass_timeline.py [pair: 0|1] [R] [light: 0|1]
+    python scripts/gpu_pass_timeline.py [pair: 0|1] [R] [light: 0|1|2]
 
 light = 1 records per-pass events only (SAHS_DBG_PROF_LIGHT): the per-stage events of the full mode cost about 250
 cycles per stage in the issuer's loop and inflate a tile by ~50 %.
+light = 2 (SAHS_DBG_PROF_PROD) records the workers' per-pass events from the PRODUCTION instantiation: true speed
+(needs a library built with -DSAHS_PROF_PROD=1; the default build records nothing in this mode).
 
 Block 0 records clock64 events of its third tile for worker threads 0 and 255, the MMA issuer and the TMA
 producer.  Diagnostic only.
@@ -52,7 +54,7 @@ def main(pair, R, light=0):
     dbg = torch.zeros(128, 256, device=dev)
     for _ in range(2):
         dbg.zero_()
-        model.field("fine", ro, rd, z, drv, pcode, frame_const=fc, debug=dbg, debug_pass=98 if light else 99)
+        model.field("fine", ro, rd, z, drv, pcode, frame_const=fc, debug=dbg, debug_pass={0: 99, 1: 98, 2: 97}[light])
         torch.cuda.synchronize()
     buf = dbg.cpu().numpy().view(np.int64).reshape(-1)
     w0, w255, mma, tma = (events(buf, r) for r in range(4))
@@ -78,6 +80,19 @@ def main(pair, R, light=0):
         print("mid-tile worker phase (worker 0): " + ", ".join(f"{t}@{c}" for t, c in marks) +
               "  [201 acc wake, 202 fp32 last deformation layer, 203 tanh/exchange, 204 embedding gather, 205 E1 written]")
     print(f"passes: signals {len(sig0)}, acc wakes {len(acc0)}, mma wakes {len(wake)}, stages {nst}")
+    if not wake:          # production instantiation: worker-side events only
+        tot_m = tot_e = 0
+        print(" pass  tag |    sig0  sig255 |    acc0  acc255 | mma_phase  worker phase (next sig - acc)")
+        for i in range(min(len(sig0), len(acc0))):
+            s0, s255 = sig0[i], sig255[i] if i < len(sig255) else -1
+            tag, a0 = acc0[i]
+            a255 = acc255[i] if i < len(acc255) else -1
+            nxt = sig0[i + 1] if i + 1 < len(sig0) else rel(w0[-1, 1])
+            tot_m += a0 - max(s0, s255)
+            tot_e += nxt - a0
+            print(f"{i:5d} {tag:5d} | {s0:7d} {s255:7d} | {a0:7d} {a255:7d} | {a0 - max(s0, s255):6d}  {nxt - a0:6d}")
+        print(f"sum: waiting for MMA (signal -> acc wake) {tot_m}; worker phases {tot_e}; first signal at {sig0[0]}")
+        return 0
     tot_epi = tot_mma = tot_wake = 0
     print(" pass  tag  st0 nst | sig0 sig255 | mmawake (+lat) | issue_end | acc0 acc255 | mma_phase  epilogue(next sig - acc)")
     for i in range(min(len(sig0), len(acc0), len(wake))):
