@@ -44,13 +44,18 @@ def build_reference_model(nerf, rcfg, sd):
     return model
 
 
-def e2e_case(nerf, name, cfg_name, H, W, seed, pose_z, mode, stochastic=False, keep_rays=24):
-    """End-to-end run_one_iter_of_nerf (ref: nerf/train_utils.py:209-321) vs oracle.run_one_iter."""
+def e2e_case(nerf, name, cfg_name, H, W, seed, pose_z, mode, stochastic=False, keep_rays=24, trained_like=True,
+             bg_mode="prior"):
+    """End-to-end run_one_iter_of_nerf (ref: nerf/train_utils.py:209-321) vs oracle.run_one_iter.
+    bg_mode: "prior" (background_prior given, the shipped eval/train scripts), "none" (background_prior=None: every
+    channel of every sample goes through the sigmoid, ref: nerf/volume_rendering_utils.py:35) or "white" (none +
+    white_background=True, ref: :75-76)."""
     rcfg = RH.load_reference_cfg(f"config/{cfg_name}.yml")
     spec = O.spec_from_cfg(rcfg)
-    sd = FX.make_state_dict(spec, seed=42, dense=True)
+    sd = FX.make_state_dict(spec, seed=42, dense=True, trained_like=trained_like)
     fr = FX.make_frame_inputs(spec, H, W, seed=seed, pose_z=pose_z)
     node = getattr(rcfg.nerf, mode)
+    node.white_background = (bg_mode == "white")
     if not stochastic:
         node.perturb = False
         node.radiance_field_noise_std = 0.0
@@ -60,7 +65,7 @@ def e2e_case(nerf, name, cfg_name, H, W, seed, pose_z, mode, stochastic=False, k
     model = build_reference_model(nerf, rcfg, sd)
     pose = fr["pose"]
     ro, rd = nerf.get_ray_bundle(H, W, np.array(fr["intrinsics"]), pose)
-    bg = fr["background"].view(-1, 15)
+    bg = fr["background"].view(-1, 15) if bg_mode == "prior" else None
     R = H * W
     draws = {}
     with torch.no_grad():
@@ -87,6 +92,14 @@ def e2e_case(nerf, name, cfg_name, H, W, seed, pose_z, mode, stochastic=False, k
     names = ["rgb_c", "disp_c", "acc_c", "rgb_f", "disp_f", "acc_f", "w_last_f", "depth_f"]
     errs = {n: _maxabs(a, b) for n, a, b in zip(names, out, ref)}
     print(f"[{name}] oracle vs reference max-abs:", {k: f"{v:.2e}" for k, v in errs.items()})
+    sig_c = aux["raw_c"][:, :-1, -1]
+    frac_pos, w_last_c = float((sig_c > 0).float().mean()), float(aux["w_c"][:, -1].mean())
+    print(f"[{name}] coarse pass: {100 * frac_pos:.0f} % of samples with sigma > 0, mean background weight "
+          f"{w_last_c:.3f}, depth_c in [{float(aux['depth_c'].min()):.3f}, {float(aux['depth_c'].max()):.3f}], "
+          f"rgb_f in [{float(out[3][:, :3].min()):.2f}, {float(out[3][:, :3].max()):.2f}]")
+    if trained_like and bg_mode == "prior":
+        # the fixture must exercise the coarse pass (the old audio fixture rendered pure background)
+        assert frac_pos > 0.5 and w_last_c < 0.9, (name, frac_pos, w_last_c)
     tol = dict(rgb_c=3e-5, rgb_f=3e-5, acc_c=1e-5, acc_f=1e-5, w_last_f=3e-5, depth_c=3e-5, depth_f=3e-5)
     for k, v in errs.items():
         if k.startswith("disp"):
@@ -98,6 +111,7 @@ def e2e_case(nerf, name, cfg_name, H, W, seed, pose_z, mode, stochastic=False, k
     k = keep_rays
     save = dict(
         cfg_name=cfg_name, H=H, W=W, seed=seed, pose_z=pose_z, mode=mode, stochastic=int(stochastic),
+        trained_like=int(trained_like), bg_mode=bg_mode, coarse_frac_pos=frac_pos, coarse_w_last=w_last_c,
         state_checksum=FX.state_checksum(sd), pose=_np(pose), driving_vec=_np(drv),
         **{"ref_" + n: _np(r) for n, r in zip(names, ref)},
         z_c=_np(aux["z_c"][:k]), w_c=_np(aux["w_c"]), z_s=_np(aux["z_s"]), z_f=_np(aux["z_f"]),
@@ -296,8 +310,14 @@ def main():
     field_case(nerf, "field_audio", "audio/person_2_auto", 512, 1)
     field_case(nerf, "field_expr2", "expression/person_2", 512, 2)
     e2e_case(nerf, "e2e_audio_val", "audio/person_2_auto", 16, 16, 0, 0.78, "validation")
-    e2e_case(nerf, "e2e_expr2_val", "expression/person_2", 12, 12, 1, 0.5, "validation")
+    # white-noise weights + 15 octaves: the reference itself is ill-conditioned here (stress case, fine pass is checked
+    # fed the reference's fine depths); the trained-like fixture below is held to the free-running bar
+    e2e_case(nerf, "e2e_expr2_val", "expression/person_2", 12, 12, 1, 0.5, "validation", trained_like=False)
+    e2e_case(nerf, "e2e_expr2_trained_val", "expression/person_2", 12, 12, 1, 0.5, "validation")
+    e2e_case(nerf, "e2e_expr1_val", "expression/person_1", 12, 12, 3, 0.5, "validation")
     e2e_case(nerf, "e2e_audio_train_stoch", "audio/person_2_auto", 12, 12, 2, 0.78, "train", stochastic=True)
+    e2e_case(nerf, "e2e_audio_nobg_val", "audio/person_2_auto", 8, 8, 5, 0.78, "validation", bg_mode="none")
+    e2e_case(nerf, "e2e_audio_white_val", "audio/person_2_auto", 8, 8, 6, 0.78, "validation", bg_mode="white")
     loss_case(nerf, "stage1_loss", 777, 31)
     print("golden vectors written to", GOLD)
 

@@ -69,52 +69,84 @@ def train_state(model, level: str) -> TrainState:
     return ts
 
 
+def field_forward_tapes(model, level, ro, rd, z, driving_vec, pose_code):
+    """Training forward of one level: raw[R,S,16] plus everything the backward needs (activation tape, sign masks,
+    warped points).  Returns (raw, saved) -- `saved` is what FieldTrainFn keeps for backward; tests decode the tapes."""
+    lib = L.load()
+    ts = train_state(model, level)
+    lay = ts.lay
+    lvl = 0 if level == "coarse" else 1
+    ro, rd, z = L.f32c(ro.detach()), L.f32c(rd.detach()), L.f32c(z.detach())
+    R, S = z.shape
+    P = R * S
+    dev = z.device
+    fc = model.frame_constants(level, driving_vec.detach(), pose_code.detach())
+    raw = torch.empty(R, S, 16, dtype=torch.float32, device=dev)
+    tape_x = torch.empty(tape_rows(P), lay["tx_total"], dtype=torch.float16, device=dev)   # [tiles][slots][128x64]
+    masks = torch.empty(lay["n_mask_layers"], P, 2, 4, dtype=torch.int32, device=dev)
+    saves = torch.empty(P, 8, dtype=torch.float32, device=dev)
+    L.check(lib.sahs_field_fwd_train(C.byref(ts.cspec), lvl, L.ptr(ts.packed_train), L.ptr(fc), L.ptr(ts.grid),
+                                     L.ptr(ro), L.ptr(rd), L.ptr(z), R, S, L.ptr(raw), L.ptr(tape_x), L.ptr(masks),
+                                     L.ptr(saves), L.stream_ptr(dev)), "field_fwd_train")
+    return raw, dict(ts=ts, level=level, ro=ro, rd=rd, z=z, fc=fc, tape_x=tape_x, masks=masks, saves=saves)
+
+
+def field_backward_tapes(saved, d_raw):
+    """Activation-gradient chain of one level.  Returns (tape_d, grid_grad, scale): every layer's dY (fp16, multiplied
+    by `scale`) as tile-major chunk images, the channel-last embedding-grid gradient (scaled) and the device scalar."""
+    lib = L.load()
+    ts = saved["ts"]
+    lay = ts.lay
+    lvl = 0 if saved["level"] == "coarse" else 1
+    ro, rd, z = saved["ro"], saved["rd"], saved["z"]
+    R, S = z.shape
+    P = R * S
+    dev = z.device
+    d_raw = L.f32c(d_raw)
+    tape_d = torch.empty(tape_rows(P), lay["td_total"], dtype=torch.float16, device=dev)  # [tiles][slots][128x64]
+    grid_grad = torch.zeros(32, 32, 32, 32, dtype=torch.float32, device=dev)
+    # fp16 range management without a host sync: scale d_raw so that its largest entry is 16
+    scale = (16.0 / d_raw.abs().amax().clamp_min(1e-30)).reshape(1).float()
+    L.check(lib.sahs_field_bwd(C.byref(ts.cspec), lvl, L.ptr(ts.packed_t), L.ptr(saved["fc"]), L.ptr(ts.grid), L.ptr(ro),
+                               L.ptr(rd), L.ptr(z), R, S, L.ptr(d_raw), L.ptr(scale), L.ptr(saved["masks"]),
+                               L.ptr(saved["saves"]), L.ptr(tape_d), L.ptr(grid_grad), L.stream_ptr(dev)), "field_bwd")
+    return tape_d, grid_grad, scale
+
+
+def decode_tape(tape: torch.Tensor, num_points: int) -> torch.Tensor:
+    """Tile-major chunk images ([tiles][slots][128 rows x 64 columns, 128B-swizzled]) -> plain [num_points, columns]
+    (diagnostics and tests; the kernels never need this form)."""
+    cols = tape.shape[1]
+    tiles, slots = tape.shape[0] // 128, cols // 64
+    t = tape.reshape(tiles, slots, 16, 8, 8, 8)             # [tile][slot][row>>3][row&7][16-byte unit][8 halves]
+    unit = torch.arange(8, device=tape.device)
+    src = (unit[None, :] ^ unit[:, None])                    # logical unit u of row r sits at physical unit u ^ (r & 7)
+    t = torch.gather(t, 4, src[None, None, None, :, :, None].expand(tiles, slots, 16, 8, 8, 8))
+    return t.reshape(tiles, slots, 128, 64).permute(0, 2, 1, 3).reshape(tiles * 128, cols)[:num_points]
+
+
 class FieldTrainFn(torch.autograd.Function):
     """raw = field(level, ro + rd z, rd; driving_vec, params).  Gradients: params of that level (incl. the shared
     deformation nets and the embedding grid) and driving_vec."""
 
     @staticmethod
     def forward(ctx, model, level, ro, rd, z, driving_vec, pose_code, *params):
-        lib = L.load()
-        ts = train_state(model, level)
-        lay = ts.lay
-        lvl = 0 if level == "coarse" else 1
-        ro, rd, z = L.f32c(ro.detach()), L.f32c(rd.detach()), L.f32c(z.detach())
-        R, S = z.shape
-        P = R * S
-        dev = z.device
-        fc = model.frame_constants(level, driving_vec.detach(), pose_code.detach())
-        raw = torch.empty(R, S, 16, dtype=torch.float32, device=dev)
-        tape_x = torch.empty(tape_rows(P), lay["tx_total"], dtype=torch.float16, device=dev)   # [tiles][slots][128x64]
-        masks = torch.empty(lay["n_mask_layers"], P, 2, 4, dtype=torch.int32, device=dev)
-        saves = torch.empty(P, 8, dtype=torch.float32, device=dev)
-        L.check(lib.sahs_field_fwd_train(C.byref(ts.cspec), lvl, L.ptr(ts.packed_train), L.ptr(fc), L.ptr(ts.grid),
-                                         L.ptr(ro), L.ptr(rd), L.ptr(z), R, S, L.ptr(raw), L.ptr(tape_x), L.ptr(masks),
-                                         L.ptr(saves), L.stream_ptr(dev)), "field_fwd_train")
-        ctx.model, ctx.level, ctx.ts = model, level, ts
-        ctx.save_for_backward(ro, rd, z, fc, tape_x, masks, saves, driving_vec.detach(), pose_code.detach())
+        raw, saved = field_forward_tapes(model, level, ro, rd, z, driving_vec, pose_code)
+        ctx.model, ctx.saved = model, saved
+        ctx.cond = (driving_vec.detach(), pose_code.detach())
         return raw
 
     @staticmethod
     def backward(ctx, d_raw):
-        lib = L.load()
-        model, level, ts = ctx.model, ctx.level, ctx.ts
+        model, saved = ctx.model, ctx.saved
+        ts, level = saved["ts"], saved["level"]
         lay = ts.lay
-        lvl = 0 if level == "coarse" else 1
-        ro, rd, z, fc, tape_x, masks, saves, drv, pcode = ctx.saved_tensors
-        R, S = z.shape
+        drv, pcode = ctx.cond
+        R, S = saved["z"].shape
         P = R * S
-        dev = z.device
-        d_raw = L.f32c(d_raw)
-        tape_d = torch.empty(tape_rows(P), lay["td_total"], dtype=torch.float16, device=dev)  # [tiles][slots][128x64]
-        grid_grad = torch.zeros(32, 32, 32, 32, dtype=torch.float32, device=dev)
-        # fp16 range management without a host sync: scale d_raw so that its largest entry is 16
-        scale = (16.0 / d_raw.abs().amax().clamp_min(1e-30)).reshape(1).float()
-        L.check(lib.sahs_field_bwd(C.byref(ts.cspec), lvl, L.ptr(ts.packed_t), L.ptr(fc), L.ptr(ts.grid), L.ptr(ro),
-                                   L.ptr(rd), L.ptr(z), R, S, L.ptr(d_raw), L.ptr(scale), L.ptr(masks), L.ptr(saves),
-                                   L.ptr(tape_d), L.ptr(grid_grad), L.stream_ptr(dev)), "field_bwd")
+        tape_d, grid_grad, scale = field_backward_tapes(saved, d_raw)
         cvec = torch.cat((drv.reshape(-1), pcode.reshape(-1)))
-        views, d_cvec, flat, sizes = _weight_grads_kernel(model, level, ts, lay, tape_x, tape_d, cvec, P)
+        views, d_cvec, flat, sizes = _weight_grads_kernel(model, level, ts, lay, saved["tape_x"], tape_d, cvec, P)
         inv = 1.0 / scale
         out = flat * inv                     # un-scale every parameter gradient of the level in one launch; a fresh
         d_cvec = d_cvec * inv                # tensor, because autograd may keep what it is handed
@@ -124,6 +156,7 @@ class FieldTrainFn(torch.autograd.Function):
             o += n
         grads[0] = (grid_grad * inv).permute(3, 0, 1, 2).unsqueeze(0).contiguous() if model.spec.use_grid else None
         d_driving = d_cvec[:76].reshape(drv.shape)
+        ctx.saved = None                     # release the tapes
         return (None, None, None, None, None, d_driving, None) + tuple(grads)
 
 

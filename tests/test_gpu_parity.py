@@ -21,6 +21,15 @@ G = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
 C = lambda a: torch.from_numpy(np.ascontiguousarray(a))
 
 
+def _report(line: str) -> None:
+    """Measured numbers go to gpurun_out/test_report.txt (when run through gpurun)."""
+    print(line)
+    d = os.path.join(FX.REPO, "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "test_report.txt"), "a") as f:
+            f.write(line + "\n")
+
+
 def maxabs(a, b):
     return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
 
@@ -38,10 +47,10 @@ def sahs():
     return sahs_b200
 
 
-def _model(sahs, cfg_name):
+def _model(sahs, cfg_name, trained_like=False):
     cfg = FX.load_cfg(cfg_name)
     spec = O.spec_from_cfg(cfg)
-    sd = FX.make_state_dict(spec, seed=42, dense=True)
+    sd = FX.make_state_dict(spec, seed=42, dense=True, trained_like=trained_like)
     model = getattr(sahs.models, cfg.models.mask.type)(cfg)
     model.load_state_dict(sd, strict=True)
     return cfg, spec, sd, model.to(DEV)
@@ -261,6 +270,66 @@ def test_field_forward_vs_reference_golden(sahs, name):
                 assert maxabs(raw[:, sl], ref[:, sl]) <= tol * scale, (level, sl, maxabs(raw[:, sl], ref[:, sl]), scale)
     from sahs_b200 import ops
     assert ops.field_status()[0] == 0
+    # the reference's own intermediates stored with the golden (first tile): warped point, ambient coordinates,
+    # trilinear embedding.  fp32 tails of the kernel: the only fp16 content is the deformation nets' hidden layers
+    # (split precision for 15 octaves).
+    dbg = torch.zeros(128, 256, device=DEV)
+    with torch.no_grad():
+        dvec, pcode = model.driving_vector(fr["driving"].to(DEV)), model.pose_code(G(g["pose"]))
+        z0 = torch.zeros(n, 1, device=DEV)
+        model.field("coarse", G(g["xyz"]), G(g["dirs"]), z0, dvec, pcode, debug=dbg, debug_pass=16)   # SAHS_DBG_MAPPED
+    d = dbg.cpu()
+    tol_map = 2e-4 if spec.xyz_L <= 10 else 2e-6        # merged fp16 deformation phase | split precision
+    assert maxabs(d[:, :3], C(g["mapped"])[:128]) <= tol_map, maxabs(d[:, :3], C(g["mapped"])[:128])
+    assert maxabs(d[:, 3:3 + spec.amb_dim], C(g["amb"])[:128]) <= 50 * tol_map
+    emb_ref = C(g["emb"])[:128]
+    assert maxabs(d[:, 8:40], emb_ref) <= 2e-3 * float(emb_ref.abs().max()) + 10 * tol_map * 30
+
+
+@pytest.mark.parametrize("cfg_name", ["audio/person_2_auto", "expression/person_2", "expression/person_1"])
+def test_field_intermediates_vs_oracle(sahs, cfg_name):
+    """Every pass of the render kernel against the oracle's intermediates on the trained-like fixture (first tile):
+    deformation layers, warped point, trunk layers, fc_feat, both heads.  16-bit operands: 4e-3 of the layer's range."""
+    cfg, spec, sd, model = _model(sahs, cfg_name, trained_like=True)
+    fr = FX.make_frame_inputs(spec, 8, 8, seed=2, pose_z=FX.probe_pose_z(spec))
+    gen = torch.Generator().manual_seed(17)
+    n = 128
+    xyz = (torch.rand(n, 3, generator=gen) * 2 - 1) * 0.3
+    dirs = torch.randn(n, 3, generator=gen) * 0.3 + torch.tensor([0.0, 0.0, -1.0])
+    with torch.no_grad():
+        drv = O.driving_vector(sd, spec, fr["driving"])
+        ref, inter = O.field_forward(sd, spec, "fine", xyz, dirs, drv, fr["pose"], return_intermediates=True)
+        dvec, pcode = model.driving_vector(fr["driving"].to(DEV)), model.pose_code(fr["pose"].to(DEV))
+        z0 = torch.zeros(n, 1, device=DEV)
+        dbg = torch.zeros(128, 256, device=DEV)
+
+        def run(dbg_pass):
+            dbg.zero_()
+            model.field("fine", xyz.to(DEV), dirs.to(DEV), z0, dvec, pcode, debug=dbg, debug_pass=dbg_pass)
+            torch.cuda.synchronize()
+            return dbg.cpu().clone()
+
+        checks = []
+        if spec.use_warp:
+            for i in range(spec.warp_layers):
+                want = torch.cat((inter[f"warp{i}"], inter[f"hyper{i}"]), 1)
+                checks.append((f"deform{i}", run(i)[:, :want.shape[1]], want))
+            d = run(16)
+            checks.append(("mapped", d[:, :3], inter["mapped"]))
+            checks.append(("amb", d[:, 3:3 + spec.amb_dim], inter["amb"]))
+        checks.append(("emb", run(16)[:, 8:40], inter["emb"]))
+        for i in range(spec.trunk_layers):
+            checks.append((f"trunk{i}", run(32 + i), inter[f"trunk{i}"]))
+        checks.append(("feat", run(32 + spec.trunk_layers), inter["feat"]))
+        for i in range(4):
+            checks.append((f"head{i}", run(64 + i), torch.cat((inter[f"dir{i}"], inter[f"seg{i}"]), 1)))
+    bad = []
+    for name, got, want in checks:
+        err, rng = maxabs(got, want), max(float(want.abs().max()), 1e-6)
+        if err > 4e-3 * rng + 2e-4:
+            bad.append((name, err, rng))
+    assert not bad, bad
+    assert sahs.ops.field_status()[0] == 0
 
 
 def test_field_forward_no_deformation_config(sahs):
@@ -317,10 +386,19 @@ def test_field_pair_kernel_matches_single_cta_kernel(sahs, cfg_name, monkeypatch
 # ------------------------------------------------------------------------------------------------------
 # end to end: run_one_iter_of_nerf
 # ------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["e2e_audio_val", "e2e_expr2_val", "e2e_audio_train_stoch"])
+E2E_CASES = ["e2e_audio_val", "e2e_expr2_val", "e2e_expr2_trained_val", "e2e_expr1_val", "e2e_audio_train_stoch",
+             "e2e_audio_nobg_val", "e2e_audio_white_val"]
+
+
+@pytest.mark.parametrize("name", E2E_CASES)
 def test_run_one_iter_vs_reference_golden(sahs, name):
+    """run_one_iter_of_nerf, free running (coarse pass -> sample_pdf -> fine pass, nothing fed from the reference),
+    against the live reference's outputs: the three config families, validation and stochastic train mode (replayed
+    draws), with a background prior, without one, and with white_background."""
     g = load(name)
-    cfg, spec, sd, model = _model(sahs, str(g["cfg_name"]))
+    trained_like = bool(int(g["trained_like"]))
+    cfg, spec, sd, model = _model(sahs, str(g["cfg_name"]), trained_like)
+    assert abs(FX.state_checksum(sd) - float(g["state_checksum"])) <= 1e-9 * float(g["state_checksum"])
     H, W, mode = int(g["H"]), int(g["W"]), str(g["mode"])
     fr = FX.make_frame_inputs(spec, H, W, seed=int(g["seed"]), pose_z=float(g["pose_z"]))
     node = getattr(cfg.nerf, mode)
@@ -330,40 +408,47 @@ def test_run_one_iter_vs_reference_golden(sahs, name):
         draws = {k: G(g["draw_" + k]) for k in ("t_rand", "noise_c", "u", "noise_f")}
     else:
         node.perturb, node.radiance_field_noise_std = False, 0.0
+    bg_mode = str(g["bg_mode"])
+    node.white_background = bg_mode == "white"
+    bg = fr["background"].view(-1, 15).to(DEV) if bg_mode == "prior" else None
     pose = fr["pose"].to(DEV)
     with torch.no_grad():
         ro, rd = sahs.get_ray_bundle(H, W, fr["intrinsics"], pose)
         out = sahs.run_one_iter_of_nerf(H, W, fr["intrinsics"][0], model, ro, rd, cfg, mode=mode,
                                         driving=fr["driving"].to(DEV), pose=pose, pose_c=None,
-                                        background_prior=fr["background"].view(-1, 15).to(DEV),
-                                        inHead=fr["mask"].to(DEV), _draws=draws)
+                                        background_prior=bg, inHead=fr["mask"].to(DEV), _draws=draws)
     assert len(out) == 8
     if mode == "validation":
         assert out[0].shape == (H, W, 15) and out[3].shape == (H, W, 15) and out[7].shape == (H, W)
     names = ["rgb_c", "disp_c", "acc_c", "rgb_f", "disp_f", "acc_f", "w_last_f", "depth_f"]
     flat = {n: (o.reshape(-1, 15) if o.shape[-1] == 15 and o.dim() > 1 else o.reshape(-1)) for n, o in zip(names, out)}
     # north-star tolerance: max-abs 1e-2 on rgb (and the semantic channels) and depth, PSNR >= 50 dB.
-    ill_conditioned = spec.xyz_L > 10
+    stress = spec.xyz_L > 10 and not trained_like
     for n in ("rgb_c", "rgb_f"):
         assert psnr(flat[n][:, :3], C(g["ref_" + n])[:, :3]) >= 50.0
     assert maxabs(flat["rgb_c"], C(g["ref_rgb_c"])) <= 1e-2
-    assert maxabs(flat["acc_f"], C(g["ref_acc_f"])) <= 1e-4
-    if not ill_conditioned:
-        assert maxabs(flat["rgb_f"], C(g["ref_rgb_f"])) <= 1e-2
-        assert maxabs(flat["depth_f"], C(g["ref_depth_f"])) <= 1e-2
-        assert maxabs(flat["w_last_f"], C(g["ref_w_last_f"])) <= 1e-2
+    assert maxabs(flat["acc_c"], C(g["ref_acc_c"])) <= 1e-2
+    assert maxabs(flat["acc_f"], C(g["ref_acc_f"])) <= (1e-4 if bg_mode == "prior" else 1e-2)
+    errs = {n: maxabs(flat[n], C(g["ref_" + n])) for n in ("rgb_c", "rgb_f", "depth_f", "w_last_f")}
+    _report(f"[e2e] {name}: " + " ".join(f"{k} {v:.2e}" for k, v in errs.items())
+            + f" psnr_f {psnr(flat['rgb_f'][:, :3], C(g['ref_rgb_f'])[:, :3]):.1f} dB")
+    if not stress:
+        assert errs["rgb_f"] <= 1e-2 and errs["depth_f"] <= 1e-2 and errs["w_last_f"] <= 1e-2, errs
         rel = float(((flat["disp_f"].cpu() - C(g["ref_disp_f"])).abs() / C(g["ref_disp_f"]).abs()).max())
         assert rel <= 2e-2
+        rel = float(((flat["disp_c"].cpu() - C(g["ref_disp_c"])).abs() / C(g["ref_disp_c"]).abs()).max())
+        assert rel <= 2e-2
     else:
-        # 15 encoding octaves (expression/person_2,3): the *reference algorithm itself* moves by ~8e-3 (rgb) when the
-        # fine depths are jittered by one fp32 ulp (tests/test_oracle_golden.py::test_fine_pass_conditioning), so a
-        # free-running comparison cannot meet 1e-2 unless the coarse pass is bit-identical.  The fine pass is
-        # therefore checked the way the sample_pdf criterion is worded: fed the reference's own fine depths.
-        assert maxabs(flat["rgb_f"], C(g["ref_rgb_f"])) <= 6e-2 and maxabs(flat["depth_f"], C(g["ref_depth_f"])) <= 6e-2
+        # STRESS CASE -- white-noise weights with 15 encoding octaves (expression/person_2,3): the field is spiky far
+        # below the sample spacing and the *reference algorithm itself* moves by ~8e-3 (rgb) when the fine depths are
+        # jittered by one fp32 ulp (tests/test_oracle_golden.py::test_fine_pass_conditioning), so a free-running
+        # comparison cannot meet 1e-2 unless the coarse pass is bit-identical (the trained-like case of the same config,
+        # e2e_expr2_trained_val, is held to the free-running bar above).  Here the fine pass is checked the way the
+        # sample_pdf criterion is worded: fed the reference's own fine depths.
+        assert errs["rgb_f"] <= 6e-2 and errs["depth_f"] <= 6e-2
         from sahs_b200 import ops
         with torch.no_grad():
             ro_f, rd_f = ro.reshape(-1, 3), rd.reshape(-1, 3)
-            bg = fr["background"].view(-1, 15).to(DEV)
             z_f = G(g["z_f"])
             raw_f = model.field("fine", ro_f, rd_f, z_f, model.driving_vector(fr["driving"].to(DEV)), model.pose_code(pose))
             rgb_f, disp_f, acc_f, w_f, depth_f = ops.composite_fwd(raw_f, z_f, rd_f, None, bg, True, False)
@@ -378,7 +463,7 @@ def test_run_one_iter_vs_reference_golden(sahs, name):
 
 def test_render_is_chunking_invariant(sahs):
     """Rays are independent: rendering a ray set in one call or in two halves gives identical bits."""
-    cfg, spec, sd, model = _model(sahs, "audio/person_2_auto")
+    cfg, spec, sd, model = _model(sahs, "audio/person_2_auto", trained_like=True)
     cfg.nerf.validation.perturb = False
     H, W = 8, 24
     fr = FX.make_frame_inputs(spec, H, W, seed=3)

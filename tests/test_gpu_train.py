@@ -1,17 +1,15 @@
 """GPU gradient-parity tests (-m gpu): one Stage-I training step (forward with tapes, hand-written compositing and
 field backward kernels, tape GEMMs) against torch autograd through the CPU oracle on the same rays and loss.
 
-Tolerances (per parameter tensor, cosine similarity with the fp32 autograd gradient and norm ratio).  The CUDA path
+Fixture: the trained-like weights (tests/sahs_fixtures.py: spectral decay, signal-preserving trunk gain, coarse and
+fine networks that agree on the density), on which the coarse pass sees surfaces -- every parameter of BOTH levels has
+a non-zero reference gradient and none is skipped (the round-1 fixture rendered pure background in the coarse pass of
+the audio config, so its coarse-level gradients were exactly zero).
+
+Tolerances (per parameter tensor: cosine similarity with the fp32 autograd gradient, and norm ratio).  The CUDA path
 returns the exact gradient of *its own* forward (fp16 operands); against the fp32 reference the difference is
-dominated by ReLU / LeakyReLU units whose pre-activation sign flips under the forward's ~1e-3 rounding, an error
-that grows layer by layer going down the backward chain (measured with scripts/gpu_dmap_debug.py: cos 0.9999 at the
-last trunk layer -> 0.9963 at the first -> 0.997 in the deformation nets; switching the gradient chain from bf16
-to fp16 operands did not change it).
-  audio config (10 octaves): heads / trunk / hyper / grid >= 0.999, everything >= 0.99, norm ratio within 10 %.
-  expression/person_2 (15 octaves): the encoding of the warped point is ill-conditioned (2^14 gain, see
-  tests/test_oracle_golden.py::test_fine_pass_conditioning) and training uses the merged fp16 deformation phase, so
-  only the radiance MLPs are held to a bar (heads >= 0.98, trunk >= 0.9); the deformation nets must stay positively
-  correlated (>= 0.5) -- a documented limitation."""
+dominated by ReLU / LeakyReLU units whose pre-activation sign flips under the forward's ~1e-3 rounding, an error that
+grows layer by layer going down the backward chain."""
 import os
 
 import numpy as np
@@ -25,22 +23,36 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _setup(cfg_name, H, W, seed):
+def _report(line: str) -> None:
+    """Measured numbers go to gpurun_out/test_report.txt (when run through gpurun) so that bars can be set from data."""
+    print(line)
+    d = os.path.join(FX.REPO, "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "test_report.txt"), "a") as f:
+            f.write(line + "\n")
+
+
+def _setup(cfg_name, H, W, seed, trained_like=True):
     import sahs_b200
     cfg = FX.load_cfg(cfg_name)
     cfg.nerf.train.perturb, cfg.nerf.train.radiance_field_noise_std = False, 0.0
     spec = O.spec_from_cfg(cfg)
-    sd = FX.make_state_dict(spec, seed=42, dense=True)
-    fr = FX.make_frame_inputs(spec, H, W, seed=seed)
+    sd = FX.make_state_dict(spec, seed=42, dense=True, trained_like=trained_like)
+    fr = FX.make_frame_inputs(spec, H, W, seed=seed, pose_z=FX.probe_pose_z(spec))
     gen = torch.Generator().manual_seed(77)
     target = torch.rand(H * W, 3, generator=gen)
     mask = fr["mask"].view(-1, 12).float()
     return sahs_b200, cfg, spec, sd, fr, target, mask
 
 
-@pytest.mark.parametrize("cfg_name", ["audio/person_2_auto", "expression/person_2"])
-def test_train_step_gradients_vs_oracle_autograd(cfg_name):
-    H, W = 6, 8
+# (config, H, W): 48 rays = 72 tiles per fine launch; 2048 rays = the reference's batch (config/audio/person_2_auto.yml:171),
+# 3072 fine tiles: many tiles per wgrad unit; 7 x 9 rays: 63 * 64 and 63 * 128 points, P not a multiple of the tile
+GRAD_CASES = [("audio/person_2_auto", 6, 8), ("audio/person_2_auto", 7, 9), ("audio/person_2_auto", 32, 64),
+              ("expression/person_2", 6, 8), ("expression/person_1", 6, 8)]
+
+
+@pytest.mark.parametrize("cfg_name,H,W", GRAD_CASES)
+def test_train_step_gradients_vs_oracle_autograd(cfg_name, H, W):
     sahs, cfg, spec, sd, fr, target, mask = _setup(cfg_name, H, W, seed=4)
     # ---- oracle: autograd through the CPU restatement ----
     sd_ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
@@ -67,32 +79,138 @@ def test_train_step_gradients_vs_oracle_autograd(cfg_name):
     assert ops.field_status()[0] == 0
     assert abs(float(loss.detach()) - float(loss_ref.detach())) <= 2e-3 * max(1.0, abs(float(loss_ref.detach())))
     assert sample_prob.shape == (12,)
-    bad = {}
-    ill = spec.xyz_L > 10
+    bad, worst = {}, {}
     for name, p in model.named_parameters():
         g_ref = sd_ref[name].grad
         assert p.grad is not None and g_ref is not None, name
         g = p.grad.detach().cpu().double().reshape(-1)
         r = g_ref.double().reshape(-1)
-        if float(r.abs().max()) < 1e-12:
-            assert float(g.abs().max()) < 1e-9, name       # e.g. a coarse net that only sees empty space
-            continue
+        # no parameter is skipped: on this fixture every tensor of both levels has a gradient to compare
+        assert float(r.abs().max()) > 1e-9, (name, "reference gradient is zero: vacuous fixture")
         cos = float(torch.dot(g, r) / (g.norm() * r.norm() + 1e-30))
         ratio = float(g.norm() / r.norm())
-        head = any(t in name for t in ("layers_dir", "layers_seg", "fc_rgb", "fc_seg"))
-        if not ill:
-            need = 0.999 if ("nerf_mlps" in name or "hyper" in name or "spatial" in name) else 0.99
-            if p.numel() <= 16 and need < 0.999:
-                # a 3-element deformation-head bias summed over this test's 48 rays: a handful of ReLU sign flips
-                # (forward rounding) moves its direction by ~1e-2; measured 0.989-0.996 across builds
-                need = 0.98
-            ok = cos >= need and 0.9 <= ratio <= 1.12
-        else:
-            need = 0.98 if head else (0.9 if "nerf_mlps" in name else 0.5)
-            ok = cos >= need
-        if not ok:
-            bad[name] = (cos, ratio, need)
+        deform = name.startswith("warp_field_mlp") or name.startswith("hyper_sheep_mlp") or name.startswith("audNet")
+        need = 0.99 if deform else 0.999
+        if p.numel() <= 16 and deform:
+            # a 3-element deformation-head bias summed over a small batch: a handful of ReLU sign flips (forward
+            # rounding) moves its direction by ~1e-2
+            need = 0.98
+        fam = name.split(".")[0] + ("." + name.split(".")[1] if name.startswith("nerf_mlps") else "")
+        worst[fam] = min(worst.get(fam, (1.0, 1.0)), (cos, ratio))
+        if not (cos >= need and 0.9 <= ratio <= 1.12):
+            bad[name] = (round(cos, 5), round(ratio, 4), need)
+    _report(f"[grad] {cfg_name} {H}x{W}: loss {float(loss.detach()):.6f} (ref {float(loss_ref.detach()):.6f}); worst cos/ratio "
+            + ", ".join(f"{k} {v[0]:.5f}/{v[1]:.3f}" for k, v in sorted(worst.items())))
     assert not bad, bad
+
+
+@pytest.mark.parametrize("cfg_name", ["audio/person_2_auto", "expression/person_2", "expression/person_1"])
+def test_field_tapes_per_layer_vs_oracle(cfg_name):
+    """Per-layer check of the training kernels' tapes (what the wgrad GEMMs consume) against the oracle's intermediates:
+    X_l = every layer's activated output (activation tape written by field_fwd<TRAIN>), dY_l = every layer's
+    pre-activation gradient (gradient tape written by field_bwd), for loss = sum(raw * G).  300 points: three tiles,
+    ragged tail."""
+    import sahs_b200
+    from sahs_b200 import train as TR
+    sahs, cfg, spec, sd, fr, _, _ = _setup(cfg_name, 8, 8, seed=1)
+    gen = torch.Generator().manual_seed(21)
+    n = 300
+    xyz = (torch.rand(n, 3, generator=gen) * 2 - 1) * 0.3
+    dirs = torch.randn(n, 3, generator=gen) * 0.3 + torch.tensor([0.0, 0.0, -1.0])
+    G = torch.randn(n, 16, generator=gen)
+    G[:, 15] *= 0.05
+    model = getattr(sahs.models, cfg.models.mask.type)(cfg)
+    model.load_state_dict(sd)
+    model = model.to(DEV)
+    for level in ("coarse", "fine"):
+        # ---- oracle with autograd taps ----
+        sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        drv = O.driving_vector(sdr, spec, fr["driving"])
+        raw_ref, inter = O.field_forward(sdr, spec, level, xyz, dirs, drv, fr["pose"], return_intermediates=True)
+        for v in inter.values():
+            if v.requires_grad:
+                v.retain_grad()
+        (raw_ref * G).sum().backward()
+        # ---- ours ----
+        with torch.no_grad():
+            dvec = model.driving_vector(fr["driving"].to(DEV))
+            pcode = model.pose_code(fr["pose"].to(DEV))
+            z0 = torch.zeros(n, 1, device=DEV)
+            raw, saved = TR.field_forward_tapes(model, level, xyz.to(DEV), dirs.to(DEV), z0, dvec, pcode)
+            tape_d, grid_grad, scale = TR.field_backward_tapes(saved, G.to(DEV).reshape(n, 1, 16))
+            torch.cuda.synchronize()
+            lay = saved["ts"].lay
+            X = TR.decode_tape(saved["tape_x"], n).float().cpu()
+            D = TR.decode_tape(tape_d, n).float().cpu() / float(scale)
+        assert sahs_b200.ops.field_status()[0] == 0
+
+        def act_grad(key, slope):
+            h = inter[key]
+            return h.grad * torch.where(h > 0, torch.ones_like(h), torch.full_like(h, slope))
+
+        checks_x, checks_d = [], []
+        wh, hh = lay["wh"], lay["hh"]
+        if spec.use_warp:
+            checks_x.append(("e0", X[:, lay["tx_e0"]:lay["tx_e0"] + lay["e0_dim"]],
+                             O.positional_encoding(xyz, spec.xyz_L, spec.xyz_inc)))
+            for i in range(lay["w_layers"]):
+                c = lay["tx_wh"] + i * lay["whh"]
+                want = torch.cat((inter[f"warp{i}"], inter[f"hyper{i}"]), 1).detach()
+                checks_x.append((f"deform{i}", X[:, c:c + wh + hh], want))
+                cd = lay["td_wh"] + i * lay["whh"]
+                checks_d.append((f"d_deform{i}", D[:, cd:cd + wh + hh],
+                                 torch.cat((act_grad(f"warp{i}", 0.0), act_grad(f"hyper{i}", 0.0)), 1)))
+            dx = inter["dx"]
+            want = torch.cat((dx.grad * (1 - dx.detach() ** 2), inter["amb"].grad), 1)
+            checks_d.append(("d_final", D[:, lay["td_final"]:lay["td_final"] + want.shape[1]], want))
+        # the warped point / ambient coordinates the kernel saved (fp32) against the oracle's, then the encoding of the
+        # kernel's own values (the encoding multiplies the fp16 deformation nets' ~5e-5 error by 2^(L-1); that
+        # conditioning is the forward parity tests' subject, not this layout check's)
+        sv = saved["saves"].cpu()
+        tol_map = 3e-4
+        assert float((sv[:, :3] - inter["mapped"].detach()).abs().max()) <= tol_map
+        e1 = O.positional_encoding(sv[:, :3], spec.xyz_L, spec.xyz_inc)
+        if spec.use_ambient:
+            assert float((sv[:, 3:3 + spec.amb_dim] - inter["amb"].detach()).abs().max()) <= 5e-3
+            e1 = torch.cat((e1, O.positional_encoding(sv[:, 3:3 + spec.amb_dim], spec.amb_L, spec.amb_inc)), 1)
+        checks_x.append(("e1", X[:, lay["tx_e1"]:lay["tx_e1"] + lay["e1_dim"]], e1))
+        th = lay["th"]
+        for i in range(lay["t_layers"]):
+            checks_x.append((f"trunk{i}", X[:, lay["tx_th"] + i * th:lay["tx_th"] + (i + 1) * th], inter[f"trunk{i}"].detach()))
+            checks_d.append((f"d_trunk{i}", D[:, lay["td_th"] + i * th:lay["td_th"] + (i + 1) * th], act_grad(f"trunk{i}", 0.01)))
+        checks_x.append(("feat", X[:, lay["tx_feat"]:lay["tx_feat"] + th], inter["feat"].detach()))
+        checks_d.append(("d_feat", D[:, lay["td_feat"]:lay["td_feat"] + th], inter["feat"].grad))
+        xtra = torch.cat((O.positional_encoding(dirs, spec.dir_L, spec.dir_inc), inter["emb"].detach()), 1)
+        checks_x.append(("xtra", X[:, lay["tx_xtra"]:lay["tx_xtra"] + xtra.shape[1]], xtra))
+        hd = lay["hd"]
+        for i in range(4):
+            c = lay["tx_hh"] + i * 2 * hd
+            checks_x.append((f"head{i}", X[:, c:c + 2 * hd], torch.cat((inter[f"dir{i}"], inter[f"seg{i}"]), 1).detach()))
+            cd = lay["td_hh"] + i * 2 * hd
+            checks_d.append((f"d_head{i}", D[:, cd:cd + 2 * hd], torch.cat((act_grad(f"dir{i}", 0.01), act_grad(f"seg{i}", 0.01)), 1)))
+        checks_d.append(("d_out", D[:, lay["td_out"]:lay["td_out"] + 16], G))
+        lines, bad = [], []
+        for name, got, want in checks_x:
+            err = float((got - want).abs().max())
+            ref = max(float(want.abs().max()), 1e-6)
+            lines.append(f"{name} {err / ref:.1e}")
+            if err > 4e-3 * ref + 1e-3:
+                bad.append((name, err, ref))
+        ill = spec.xyz_L > 10
+        for name, got, want in checks_d:
+            g, r = got.double().reshape(-1), want.double().reshape(-1)
+            cos = float(torch.dot(g, r) / (g.norm() * r.norm() + 1e-30))
+            ratio = float(g.norm() / (r.norm() + 1e-30))
+            lines.append(f"{name} {cos:.5f}/{ratio:.3f}")
+            need = 0.999 if name.startswith(("d_head", "d_out", "d_feat")) else (0.995 if name.startswith("d_trunk") else 0.99)
+            if not (cos >= need and 0.95 <= ratio <= 1.05):
+                bad.append((name, cos, ratio, need))
+        _report(f"[tapes] {cfg_name} {level}: " + " ".join(lines))
+        assert not bad, (level, bad)
+        # forward output of the training kernel = oracle raw
+        for sl in (slice(0, 3), slice(3, 15), slice(15, 16)):
+            scale_ = max(1.0, float(raw_ref.detach()[:, sl].abs().max()))
+            assert float((raw.reshape(n, 16).cpu() - raw_ref.detach())[:, sl].abs().max()) <= 3e-2 * scale_
 
 
 @pytest.mark.parametrize("fused", [False, True])
