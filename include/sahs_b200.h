@@ -80,12 +80,12 @@ int sahs_positional_encoding(const float* x, int64_t n, int d, int num_freqs, in
                              void* stream);
 
 /* ---- (2) fused deformation + hyper-sheet + grid gather + radiance MLP (tcgen05/TMEM, TMA-fed) ---- */
-/* Bytes of the packed bf16 weight image of one level (warp+hyper+trunk+heads, UMMA 128B-swizzled stage
+/* Bytes of the packed 16-bit (fp16 operands) weight image of one level (warp+hyper+trunk+heads, UMMA 128B-swizzled stage
  * images in consumption order) and of the per-frame constant block (fp32 biases with the frame-constant
  * driving/pose columns folded in + the small fp32 head weights). */
 int sahs_field_sizes(const sahs_model_spec* spec, size_t* packed_bytes, size_t* frame_const_bytes,
                      size_t* grid_bytes);
-/* fp32 state_dict -> packed bf16 image for `level` (0 coarse, 1 fine); also re-lays the embedding grid
+/* fp32 state_dict -> packed fp16 image for `level` (0 coarse, 1 fine); also re-lays the embedding grid
  * channel-last (grid_out may be NULL when !use_grid).  Replaces nothing in the reference (new layout step);
  * must be re-run after every optimizer step. */
 int sahs_pack_params(const sahs_model_spec* spec, int level, const float* const* params_host_array,
@@ -133,9 +133,14 @@ int sahs_field_bwd(const sahs_model_spec* spec, int level, const void* packed_t,
  * zero-initialised fp32 gradient buffers `grads_host_array` (device pointers in the canonical parameter order; entry 0,
  * the embedding grid, is not touched).  Reads the tape chunks with TMA bulk loads.  The frame-constant input columns
  * of folded layers are left untouched (their gradient is the rank-1 product db x cvec).  `units_workspace`: >= 256 KB
- * of device memory.  Results carry the `scale` factor of sahs_field_bwd. */
+ * of device memory that receives the kernel's work-unit list.  `upload_token` (host memory owned by the caller, one
+ * per workspace, set to 0 whenever the workspace is (re)allocated or may have been overwritten) lets steady-state
+ * steps skip the upload: the library stores a fingerprint of the list it last uploaded INTO THIS WORKSPACE there and
+ * uploads (synchronously) only when the fingerprint changes.  NULL: upload on every call.  Results carry the `scale`
+ * factor of sahs_field_bwd. */
 int sahs_field_wgrad(const sahs_model_spec* spec, int level, float* const* grads_host_array, const void* tape_x,
-                     const void* tape_d, int num_points, void* units_workspace, size_t workspace_bytes, void* stream);
+                     const void* tape_d, int num_points, void* units_workspace, size_t workspace_bytes,
+                     unsigned long long* upload_token, void* stream);
 
 /* ---- (3) alpha compositing ---------------------------------------------------------------------- */
 /* volume_render_radiance_field, ref: nerf/volume_rendering_utils.py:7-78 (+ cumprod_exclusive,

@@ -114,6 +114,20 @@ def get_ray_bundle(height: int, width: int, intrinsics, c2w: torch.Tensor):
     return ro, rd
 
 
+def get_ray_bundle_by_mask(height: int, width: int, intrinsics, c2w: torch.Tensor, mask: torch.Tensor):
+    """ref: nerf/nerf_helpers.py:122-176: world-space rays where mask == 1, camera-frame direction and zero origin
+    where mask == 0 (blended as mask * a + (1 - mask) * b)."""
+    fx, fy, cx, cy = [float(v) for v in intrinsics]
+    dt = c2w.dtype
+    cols = torch.arange(width, dtype=dt).view(1, width).expand(height, width)
+    rows = torch.arange(height, dtype=dt).view(height, 1).expand(height, width)
+    d = torch.stack(((cols - width * cx) / fx, -(rows - height * cy) / fy, -torch.ones_like(cols)), dim=-1)
+    m = mask.to(dt)[..., None].expand(height, width, 3)
+    rd = (1 - m) * d + m * (d[..., None, :] * c2w[:3, :3]).sum(dim=-1)
+    ro = (1 - m) * torch.zeros(1, 1, 3, dtype=dt) + m * c2w[:3, -1].expand(rd.shape)
+    return ro, rd
+
+
 def positional_encoding(x: torch.Tensor, num_freqs: int, include_input: bool = True) -> torch.Tensor:
     """[x, sin(2^0 x), cos(2^0 x), ..., sin(2^(L-1) x), cos(2^(L-1) x)], whole-vector blocks.
     ref: nerf/nerf_helpers.py:305-349 (log_sampling=True is the only mode the configs use)."""

@@ -380,7 +380,7 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
         }
       }
       if (DBG) prof_event(sy.prof, 204);   // embedding gather done
-      // -------- trunk (bf16 operands) --------
+      // -------- trunk (fp16 operands, kTrunkF16) --------
       auto write_e1 = [&]() {
         RowStream<kTrunkF16, C::E1_PAD / 8> st(X, 0, row, grp);
         int col = pe_stream<C::XYZ_L, true, 3>(st, 0, mapped);

@@ -1,4 +1,4 @@
-// Host side of the fused field path: plan construction, weight packing (fp32 state_dict -> bf16 swizzled stage
+// Host side of the fused field path: plan construction, weight packing (fp32 state_dict -> 16-bit (fp16; bf16 when a stage is not flagged f16) swizzled stage
 // images), per-frame constant folding.  See field_plan.cuh for the layout.
 #include <string.h>
 #include <vector>
@@ -346,7 +346,7 @@ int sahs_build_bwd_plan(const sahs_model_spec& s, const float* const* params, Ho
 }
 
 // --------------------------------------------------------------------------------------------------------
-// pack kernel: one block per stage, fp32 -> bf16, written at the 128B-swizzled offset
+// pack kernel: one block per stage, fp32 -> fp16 / bf16 (PackStage::f16), written at the 128B-swizzled offset
 // --------------------------------------------------------------------------------------------------------
 constexpr int kPackBatch = kMaxStages;   // one launch per image: 160 x 96 B of kernel parameters (limit 32 KB since CUDA 12.1)
 constexpr int kPackSlices = 8;            // CTAs per stage image (a stage is at most 256 x 64 elements)

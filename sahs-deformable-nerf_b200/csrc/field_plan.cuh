@@ -2,9 +2,9 @@
 // NeRFMLP; ref: nerf/modules.py:168-295, :323-390, :401-462) are cut into tensor-core "stages".
 //
 // Data layout
-//   * activation buffer X (shared memory): 4 K-chunks of [128 points x 64 features] bf16, each chunk a UMMA
+//   * activation buffer X (shared memory): 4 K-chunks of [128 points x 64 features] 16-bit (fp16), each chunk a UMMA
 //     K-major SWIZZLE_128B operand tile (16 KB).  Chunk c holds features 64c..64c+63.
-//   * a stage = one B operand block [n rows (outputs) x 64 inputs] bf16 in the same swizzled layout
+//   * a stage = one B operand block [n rows (outputs) x 64 inputs] fp16 in the same swizzled layout
 //     (n*128 bytes), streamed by the TMA unit from the packed weight image in consumption order.
 //   * accumulators: TMEM columns 0..255 (fp32), row i of the tile <-> TMEM lane i.
 //   * a pass = the stages issued between two worker phases (epilogue / encoding writes).
@@ -185,5 +185,5 @@ struct HostPlan {
   int num_copy;
 };
 int sahs_build_host_plan(const sahs_model_spec& spec, const float* const* params, HostPlan& hp, bool train = false);
-// dgrad plan: stages hold transposed bf16 weight blocks in the order the backward kernel consumes them
+// dgrad plan: stages hold transposed fp16 weight blocks in the order the backward kernel consumes them
 int sahs_build_bwd_plan(const sahs_model_spec& spec, const float* const* params, HostPlan& hp);

@@ -10,8 +10,6 @@
 //   * 1 CTA per SM: warp 0 TMA, warp 1 MMA issue, warps 2-5 epilogue; two 96 KB operand stages.
 // HBM-bound: every unit streams its dY and X boxes once (about 3 MB per tile over all layers).
 #include <string.h>
-#include <map>
-#include <mutex>
 #include <vector>
 #include "field_dev.cuh"
 
@@ -233,7 +231,7 @@ struct UnitBuilder {
 // (rank-1 terms db x cvec, done by the caller).
 extern "C" int sahs_field_wgrad(const sahs_model_spec* spec, int level, float* const* grads, const void* tape_x,
                                 const void* tape_d, int num_points, void* units_workspace, size_t workspace_bytes,
-                                void* stream) {
+                                unsigned long long* upload_token, void* stream) {
   SAHS_CHECK_ARG(spec && grads && units_workspace, "null pointer");
   if (num_points == 0) return SAHS_OK;
   SAHS_CHECK_ARG(tape_x && tape_d, "null tape");
@@ -369,19 +367,19 @@ extern "C" int sahs_field_wgrad(const sahs_model_spec* spec, int level, float* c
   SAHS_CHECK_ARG(units.size() * sizeof(WUnit) <= workspace_bytes, "units workspace too small (need 256 KB)");
   cudaStream_t st = (cudaStream_t)stream;
   {
-    // The unit list depends only on the spec, the point count and the gradient pointers; callers that keep those
-    // stable (persistent gradient buffers, one workspace per level) upload it once.  A changed list is uploaded
-    // synchronously (pageable source), an unchanged one costs no copy and -- more importantly -- no stream sync.
-    static std::mutex mu;
-    static std::map<void*, std::vector<WUnit>> uploaded;
-    std::lock_guard<std::mutex> lock(mu);
-    std::vector<WUnit>& prev = uploaded[units_workspace];
-    const bool same = prev.size() == units.size() &&
-                      (units.empty() || memcmp(prev.data(), units.data(), units.size() * sizeof(WUnit)) == 0);
-    if (!same) {
+    // The unit list depends only on the spec, the point count and the gradient pointers.  Whether the workspace still
+    // holds it is the CALLER's knowledge (it owns the memory): `upload_token` carries the fingerprint of the list last
+    // uploaded into this workspace, and the caller zeroes it when the workspace is reallocated.  (A process-global
+    // cache keyed on the workspace address would go stale when the allocator hands the address to another tensor.)
+    unsigned long long h = 1469598103934665603ull;   // FNV-1a over the list
+    const unsigned char* bytes = reinterpret_cast<const unsigned char*>(units.data());
+    for (size_t i = 0; i < units.size() * sizeof(WUnit); ++i) h = (h ^ bytes[i]) * 1099511628211ull;
+    h ^= (unsigned long long)units.size() << 1;
+    if (h == 0) h = 1;
+    if (!upload_token || *upload_token != h) {
       SAHS_CUDA(cudaMemcpyAsync(units_workspace, units.data(), units.size() * sizeof(WUnit), cudaMemcpyHostToDevice, st));
-      SAHS_CUDA(cudaStreamSynchronize(st));
-      prev = units;
+      SAHS_CUDA(cudaStreamSynchronize(st));   // pageable source: the vector dies with this call
+      if (upload_token) *upload_token = h;
     }
   }
   for (auto& u : units) {

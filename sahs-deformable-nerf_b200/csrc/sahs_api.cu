@@ -56,6 +56,6 @@ extern "C" int sahs_field_status(int* out4_host) {
   return SAHS_OK;
 }
 
-extern "C" int sahs_abi_version(void) { return 1; }
+extern "C" int sahs_abi_version(void) { return 2; }   // 2: sahs_field_wgrad takes an upload token
 extern "C" const char* sahs_last_error(void) { return g_err; }
 extern "C" uint64_t sahs_launch_count(void) { return g_sahs_launches.load(std::memory_order_relaxed); }

@@ -70,7 +70,7 @@ def load() -> C.CDLL:
         "sahs_pack_params_bwd": (C.c_int, [spec_p, i32, C.POINTER(vp), vp, vp]),
         "sahs_field_fwd_train": (C.c_int, [spec_p, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]),
         "sahs_field_bwd": (C.c_int, [spec_p, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
-        "sahs_field_wgrad": (C.c_int, [spec_p, i32, C.POINTER(vp), vp, vp, i32, vp, C.c_size_t, vp]),
+        "sahs_field_wgrad": (C.c_int, [spec_p, i32, C.POINTER(vp), vp, vp, i32, vp, C.c_size_t, C.POINTER(C.c_uint64), vp]),
         "sahs_frame_postprocess": (C.c_int, [vp, i64, vp, vp, vp, vp]),
         "sahs_weighted_sample": (C.c_int, [vp, vp, i64, i32, i32, C.c_uint64, vp, vp, C.c_size_t, vp]),
         "sahs_adam_step": (C.c_int, [vp, vp, vp, vp, i64, C.c_double, C.c_double, C.c_double, C.c_double, i32, C.c_float,

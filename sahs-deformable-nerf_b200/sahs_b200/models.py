@@ -199,7 +199,7 @@ class NeRFaceModel(torch.nn.Module):
         self._packed: Dict[int, dict] = {}
         self._invalidations = 0
 
-    # ---- packing: fp32 master parameters -> bf16 stage images (re-done whenever a parameter changed) ----
+    # ---- packing: fp32 master parameters -> fp16 stage images (re-done whenever a parameter changed) ----
     def _level_params(self, level: str) -> List[Optional[torch.Tensor]]:
         s = self.spec
         out: List[Optional[torch.Tensor]] = [self.spatial_embeddings if s.use_grid else None]
@@ -252,7 +252,9 @@ class NeRFaceModel(torch.nn.Module):
         arr = L.param_ptr_array(params)
         L.check(lib.sahs_pack_params(C.byref(cspec), lvl, arr, L.ptr(packed), L.ptr(grid), L.stream_ptr(dev)),
                 "pack_params")
-        st = dict(key=key, cspec=cspec, params=params, arr=arr, packed=packed, grid=grid, fc_floats=fb.value // 4)
+        from .custom_ops import spec_ints
+        st = dict(key=key, cspec=cspec, spec_ints=spec_ints(cspec), params=params, arr=arr, packed=packed, grid=grid,
+                  fc_floats=fb.value // 4)
         self._packed[lvl] = st
         return st
 
@@ -287,13 +289,12 @@ class NeRFaceModel(torch.nn.Module):
             return field_train(self, level, ro, rd, z, driving_vec, pose_code)
         st = self.packed_level(level)
         fc = frame_const if frame_const is not None else self.frame_constants(level, driving_vec, pose_code)
-        ro, rd, z = L.f32c(ro), L.f32c(rd), L.f32c(z)
-        R, S = z.shape
-        raw = torch.empty(R, S, 16, dtype=torch.float32, device=z.device)
-        L.check(lib.sahs_field_fwd(C.byref(st["cspec"]), 0 if level == "coarse" else 1, L.ptr(st["packed"]), L.ptr(fc),
-                                   L.ptr(st["grid"]), L.ptr(ro), L.ptr(rd), L.ptr(z), R, S, L.ptr(raw), L.ptr(debug),
-                                   int(debug_pass), L.stream_ptr(z.device)), "field_fwd")
-        return raw
+        lvl = 0 if level == "coarse" else 1
+        if debug is not None:          # diagnostics (per-pass outputs, timelines): straight through the C ABI
+            return ops.field_fwd(st["cspec"], lvl, st["packed"], fc, st["grid"], ro, rd, z, debug, debug_pass)
+        if not z.is_cuda:
+            raise RuntimeError("sahs_b200 ops need CUDA tensors (there is no CPU path)")
+        return torch.ops.sahs_b200.field_fwd(st["spec_ints"], lvl, st["packed"], fc, st["grid"], ro, rd, z)
 
     def forward(self, level, x, driving=None, pose=None, pose_c=None, latent_code=None, **kwargs):
         """Reference call signature (ref: nerf/models.py:367-380): x[...,:3] points, x[...,3:6] view directions;

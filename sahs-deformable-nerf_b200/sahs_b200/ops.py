@@ -12,9 +12,21 @@ MAP_CH = 15
 RAW_CH = 16
 
 
-def _linspace_dev(steps: int, device) -> torch.Tensor:
-    # made on the host so the values are bit-identical to the reference's CPU torch.linspace
-    return torch.linspace(0.0, 1.0, steps, dtype=torch.float32).to(device)
+_LINSPACE = {}
+
+
+def linspace_dev(steps: int, device) -> torch.Tensor:
+    """torch.linspace(0, 1, steps) made on the HOST (bit-identical to the reference's CPU linspace) and
+    cached per device: one upload per process instead of one pageable H2D copy per call."""
+    key = (int(steps), str(torch.device(device)))
+    t = _LINSPACE.get(key)
+    if t is None:
+        t = torch.linspace(0.0, 1.0, steps, dtype=torch.float32).to(device)
+        _LINSPACE[key] = t
+    return t
+
+
+_linspace_dev = linspace_dev
 
 
 def get_ray_bundle(height: int, width: int, intrinsics, c2w: torch.Tensor):
@@ -30,10 +42,11 @@ def get_ray_bundle(height: int, width: int, intrinsics, c2w: torch.Tensor):
 
 
 def coarse_z(num_rays: int, num_samples: int, near: float, far: float, lindisp: bool, device,
-             t_rand: Optional[torch.Tensor] = None) -> torch.Tensor:
+             t_rand: Optional[torch.Tensor] = None, t_vals: Optional[torch.Tensor] = None) -> torch.Tensor:
     """ref: nerf/train_utils.py:93-113."""
     lib = L.load()
-    t_vals = _linspace_dev(num_samples, device)
+    if t_vals is None:
+        t_vals = _linspace_dev(num_samples, device)
     z = torch.empty(num_rays, num_samples, dtype=torch.float32, device=device)
     tr = L.f32c(t_rand) if t_rand is not None else None
     L.check(lib.sahs_coarse_z(num_rays, num_samples, float(near), float(far), int(bool(lindisp)), L.ptr(t_vals),
@@ -54,6 +67,54 @@ def positional_encoding(x: torch.Tensor, num_freqs: int, include_input: bool = T
     L.check(lib.sahs_positional_encoding(L.ptr(xc), n, d, num_freqs, int(include_input), L.ptr(out),
                                          L.stream_ptr(xc.device)), "positional_encoding")
     return out
+
+
+def field_fwd(cspec, level: int, packed, frame_const, grid, ro, rd, z, debug=None, debug_pass: int = -1):
+    """raw[R,S,16] of the points ro + rd * z (the fused field kernel).  ref: nerf/train_utils.py:9-50 and everything
+    below it (nerf/models.py:367-380, :514-528)."""
+    lib = L.load()
+    ro, rd, z = L.f32c(ro), L.f32c(rd), L.f32c(z)
+    R, S = z.shape
+    raw = torch.empty(R, S, RAW_CH, dtype=torch.float32, device=z.device)
+    L.check(lib.sahs_field_fwd(C.byref(cspec), int(level), L.ptr(packed), L.ptr(frame_const), L.ptr(grid), L.ptr(ro),
+                               L.ptr(rd), L.ptr(z), R, S, L.ptr(raw), L.ptr(debug), int(debug_pass),
+                               L.stream_ptr(z.device)), "field_fwd")
+    return raw
+
+
+def tape_rows(num_points: int) -> int:
+    """Tapes are tile-major chunk images: whole 128-point tiles are stored."""
+    return (num_points + 127) // 128 * 128
+
+
+def field_fwd_train(cspec, level: int, packed_train, frame_const, grid, ro, rd, z, tx_total: int, n_mask_layers: int):
+    """Training forward: (raw, activation tape, sign masks, saves), see sahs_b200/train.py."""
+    lib = L.load()
+    ro, rd, z = L.f32c(ro), L.f32c(rd), L.f32c(z)
+    R, S = z.shape
+    P, dev = R * S, z.device
+    raw = torch.empty(R, S, RAW_CH, dtype=torch.float32, device=dev)
+    tape_x = torch.empty(tape_rows(P), tx_total, dtype=torch.float16, device=dev)     # [tiles][slots][128x64]
+    masks = torch.empty(n_mask_layers, P, 2, 4, dtype=torch.int32, device=dev)
+    saves = torch.empty(P, 8, dtype=torch.float32, device=dev)
+    L.check(lib.sahs_field_fwd_train(C.byref(cspec), int(level), L.ptr(packed_train), L.ptr(frame_const), L.ptr(grid),
+                                     L.ptr(ro), L.ptr(rd), L.ptr(z), R, S, L.ptr(raw), L.ptr(tape_x), L.ptr(masks),
+                                     L.ptr(saves), L.stream_ptr(dev)), "field_fwd_train")
+    return raw, tape_x, masks, saves
+
+
+def field_bwd(cspec, level: int, packed_t, frame_const, grid, ro, rd, z, d_raw, scale, masks, saves, td_total: int):
+    """Activation-gradient chain: (gradient tape, channel-last grid gradient), both multiplied by `scale`."""
+    lib = L.load()
+    ro, rd, z, d_raw = L.f32c(ro), L.f32c(rd), L.f32c(z), L.f32c(d_raw)
+    R, S = z.shape
+    P, dev = R * S, z.device
+    tape_d = torch.empty(tape_rows(P), td_total, dtype=torch.float16, device=dev)      # [tiles][slots][128x64]
+    grid_grad = torch.zeros(32, 32, 32, 32, dtype=torch.float32, device=dev)
+    L.check(lib.sahs_field_bwd(C.byref(cspec), int(level), L.ptr(packed_t), L.ptr(frame_const), L.ptr(grid), L.ptr(ro),
+                               L.ptr(rd), L.ptr(z), R, S, L.ptr(d_raw), L.ptr(scale), L.ptr(masks), L.ptr(saves),
+                               L.ptr(tape_d), L.ptr(grid_grad), L.stream_ptr(dev)), "field_bwd")
+    return tape_d, grid_grad
 
 
 def composite_fwd(raw, z, rd, noise=None, bg=None, apply_bg_overwrite=False, white_background=False):
@@ -149,13 +210,18 @@ def frame_postprocess(rgb_map: torch.Tensor):
 
 
 _SAMPLER_WS = {}
+_SEL_POSITIVE_OFFSET = 4 * (256 + 6)      # byte offset of SelState::positive (csrc/sampler.cu)
 
 
-def weighted_sample(mask: torch.Tensor, class_prob: torch.Tensor, num_select: int, seed: int) -> torch.Tensor:
+def weighted_sample(mask: torch.Tensor, class_prob: torch.Tensor, num_select: int, seed: int,
+                    validate: bool = False) -> torch.Tensor:
     """Semantic-weighted ray batch: `num_select` distinct pixel indices, drawn without replacement with probability
     proportional to sum_c class_prob[c] * mask[i, c] -- the device-side replacement of
     np.random.choice(H*W, n, replace=False, p=probs) (ref: train_stage_rays_auto.py:390-420).
-    mask: int32 [..., C] (one-hot in the reference); returns int64 [num_select] (a set: order unspecified)."""
+    mask: int32 [..., C] (one-hot in the reference); returns int64 [num_select] (a set: order unspecified).
+    With fewer positive-weight pixels than `num_select`, np.random.choice raises ("Fewer non-zero entries in p than
+    size"); the kernel instead fills the remainder with zero-weight pixels.  `validate=True` reads the kernel's count of
+    positive-weight pixels back (one device sync) and raises ValueError like numpy; the training loop leaves it off."""
     lib = L.load()
     if not mask.is_cuda:
         raise RuntimeError("weighted_sample needs CUDA tensors (there is no CPU fallback)")
@@ -173,6 +239,10 @@ def weighted_sample(mask: torch.Tensor, class_prob: torch.Tensor, num_select: in
     out = torch.empty(num_select, dtype=torch.int64, device=m.device)
     L.check(lib.sahs_weighted_sample(L.ptr(m), L.ptr(prob), n, C_, int(num_select), int(seed) & 0xFFFFFFFFFFFFFFFF,
                                      L.ptr(out), L.ptr(ws), ws.numel(), L.stream_ptr(m.device)), "weighted_sample")
+    if validate:
+        positive = int(ws[_SEL_POSITIVE_OFFSET:_SEL_POSITIVE_OFFSET + 4].view(torch.int32).item())
+        if positive < num_select:
+            raise ValueError(f"Fewer non-zero entries in p than size ({positive} < {num_select})")
     return out
 
 

@@ -70,6 +70,36 @@ class FlatAdam(torch.optim.Optimizer):
             e = offs[i] if i < len(offs) else total
             self._segments.append((gi, b, e))
         self._params = plist        # (moving the storage changes data_ptr(), which the packed-weight cache keys on)
+        self._offs = offs
+
+    def load_state_dict(self, state_dict) -> None:
+        """Resume (ref: train_stage_rays_auto.py:253, :705 `optimizer.load_state_dict(checkpoint["optimizer_state_dict"])`;
+        the checkpoint may come from this class or from the reference's torch.optim.Adam -- same per-parameter layout).
+        The base class replaces `state[p]` with fresh tensors; the moments are copied back into the flat buffers the
+        kernel reads, the per-parameter entries are re-pointed at views of them and the step counter is restored."""
+        super().load_state_dict(state_dict)
+        steps = 0
+        with torch.no_grad():
+            for p, off in zip(self._params, self._offs):
+                st = self.state.get(p)
+                n = p.numel()
+                views = {"exp_avg": self.flat_exp_avg[off:off + n].view(p.shape),
+                         "exp_avg_sq": self.flat_exp_avg_sq[off:off + n].view(p.shape)}
+                if not st:                                   # no state saved for this parameter: starts from zero
+                    for v in views.values():
+                        v.zero_()
+                    self.state[p] = {"step": self._step_t, **views}
+                    continue
+                for name, v in views.items():
+                    if name in st:
+                        v.copy_(st[name].to(v.device, torch.float32))
+                    else:
+                        v.zero_()
+                    st[name] = v
+                steps = max(steps, int(float(st.get("step", 0))))
+                st["step"] = self._step_t
+        self._steps = steps
+        self._step_t.fill_(float(steps))
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -78,10 +108,13 @@ class FlatAdam(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         lib = L.load()
-        # gradients -> flat staging buffer (absent gradients count as zero, as torch.optim.Adam skips them)
+        # gradients -> flat staging buffer.  A parameter without a gradient is SKIPPED, as torch.optim.Adam does (no
+        # moment decay, no update): the kernel then runs over the contiguous runs of parameters that have one.  (One
+        # difference remains: the bias-correction step count is shared by all parameters, torch keeps one per parameter.)
         have = [(v, p.grad) for v, p in zip(self._grad_views, self._params) if p.grad is not None]
-        if len(have) != len(self._params):
-            self.flat_grad.zero_()
+        partial = len(have) != len(self._params)
+        if partial:
+            self.flat_grad.zero_()                              # (all-reduced with the other ranks' buffers below)
         if have:
             torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
         scale = 1.0
@@ -90,7 +123,7 @@ class FlatAdam(torch.optim.Optimizer):
             scale = 1.0 / dist.get_world_size(self._group)
         self._steps += 1
         stream = L.stream_ptr(self.flat_param.device)
-        for gi, b, e in self._segments:
+        for gi, b, e in (self._live_runs() if partial else self._segments):
             g = self.param_groups[gi]
             if e <= b:
                 continue
@@ -100,6 +133,24 @@ class FlatAdam(torch.optim.Optimizer):
                                        float(g["eps"]), self._steps, scale, stream), "adam_step")
         self._step_t += 1
         return loss
+
+    def _live_runs(self):
+        """(group, begin, end) for every maximal run of consecutive parameters that have a gradient."""
+        runs, i = [], 0
+        for gi, g in enumerate(self.param_groups):
+            cur = None
+            for _ in g["params"]:
+                p, off = self._params[i], self._offs[i]
+                end = self._offs[i + 1] if i + 1 < len(self._offs) else self._n
+                if p.grad is not None:
+                    cur = [gi, off, end] if cur is None else [gi, cur[1], end]
+                elif cur is not None:
+                    runs.append(tuple(cur))
+                    cur = None
+                i += 1
+            if cur is not None:
+                runs.append(tuple(cur))
+        return runs
 
     def averaged_gradients(self) -> Optional[torch.Tensor]:
         """The flat gradient buffer of the last step (summed over ranks; multiply by 1 / world size for the mean)."""

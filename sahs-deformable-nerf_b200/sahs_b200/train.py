@@ -36,9 +36,7 @@ def train_layout(cspec) -> Dict[str, int]:
     return dict(zip(_LAYOUT_KEYS, list(out)))
 
 
-def tape_rows(num_points: int) -> int:
-    """Tapes are tile-major chunk images: whole 128-point tiles are stored."""
-    return (num_points + 127) // 128 * 128
+from .ops import tape_rows  # noqa: E402,F401  (tapes are tile-major chunk images: whole 128-point tiles)
 
 
 class TrainState:
@@ -49,6 +47,7 @@ class TrainState:
         lvl = 0 if level == "coarse" else 1
         st = model.packed_level(level)                      # inference image also gives the pointer table + grid
         self.cspec, self.arr, self.params, self.grid = st["cspec"], st["arr"], st["params"], st["grid"]
+        self.spec_ints = st["spec_ints"]
         self.key = st["key"]
         self.lay = train_layout(self.cspec)
         dev = st["packed"].device
@@ -72,44 +71,27 @@ def train_state(model, level: str) -> TrainState:
 def field_forward_tapes(model, level, ro, rd, z, driving_vec, pose_code):
     """Training forward of one level: raw[R,S,16] plus everything the backward needs (activation tape, sign masks,
     warped points).  Returns (raw, saved) -- `saved` is what FieldTrainFn keeps for backward; tests decode the tapes."""
-    lib = L.load()
     ts = train_state(model, level)
     lay = ts.lay
     lvl = 0 if level == "coarse" else 1
     ro, rd, z = L.f32c(ro.detach()), L.f32c(rd.detach()), L.f32c(z.detach())
-    R, S = z.shape
-    P = R * S
-    dev = z.device
     fc = model.frame_constants(level, driving_vec.detach(), pose_code.detach())
-    raw = torch.empty(R, S, 16, dtype=torch.float32, device=dev)
-    tape_x = torch.empty(tape_rows(P), lay["tx_total"], dtype=torch.float16, device=dev)   # [tiles][slots][128x64]
-    masks = torch.empty(lay["n_mask_layers"], P, 2, 4, dtype=torch.int32, device=dev)
-    saves = torch.empty(P, 8, dtype=torch.float32, device=dev)
-    L.check(lib.sahs_field_fwd_train(C.byref(ts.cspec), lvl, L.ptr(ts.packed_train), L.ptr(fc), L.ptr(ts.grid),
-                                     L.ptr(ro), L.ptr(rd), L.ptr(z), R, S, L.ptr(raw), L.ptr(tape_x), L.ptr(masks),
-                                     L.ptr(saves), L.stream_ptr(dev)), "field_fwd_train")
+    raw, tape_x, masks, saves = torch.ops.sahs_b200.field_fwd_train(ts.spec_ints, lvl, ts.packed_train, fc, ts.grid, ro, rd,
+                                                                    z, lay["tx_total"], lay["n_mask_layers"])
     return raw, dict(ts=ts, level=level, ro=ro, rd=rd, z=z, fc=fc, tape_x=tape_x, masks=masks, saves=saves)
 
 
 def field_backward_tapes(saved, d_raw):
     """Activation-gradient chain of one level.  Returns (tape_d, grid_grad, scale): every layer's dY (fp16, multiplied
     by `scale`) as tile-major chunk images, the channel-last embedding-grid gradient (scaled) and the device scalar."""
-    lib = L.load()
     ts = saved["ts"]
-    lay = ts.lay
     lvl = 0 if saved["level"] == "coarse" else 1
-    ro, rd, z = saved["ro"], saved["rd"], saved["z"]
-    R, S = z.shape
-    P = R * S
-    dev = z.device
     d_raw = L.f32c(d_raw)
-    tape_d = torch.empty(tape_rows(P), lay["td_total"], dtype=torch.float16, device=dev)  # [tiles][slots][128x64]
-    grid_grad = torch.zeros(32, 32, 32, 32, dtype=torch.float32, device=dev)
     # fp16 range management without a host sync: scale d_raw so that its largest entry is 16
     scale = (16.0 / d_raw.abs().amax().clamp_min(1e-30)).reshape(1).float()
-    L.check(lib.sahs_field_bwd(C.byref(ts.cspec), lvl, L.ptr(ts.packed_t), L.ptr(saved["fc"]), L.ptr(ts.grid), L.ptr(ro),
-                               L.ptr(rd), L.ptr(z), R, S, L.ptr(d_raw), L.ptr(scale), L.ptr(saved["masks"]),
-                               L.ptr(saved["saves"]), L.ptr(tape_d), L.ptr(grid_grad), L.stream_ptr(dev)), "field_bwd")
+    tape_d, grid_grad = torch.ops.sahs_b200.field_bwd(ts.spec_ints, lvl, ts.packed_t, saved["fc"], ts.grid, saved["ro"],
+                                                      saved["rd"], saved["z"], d_raw, scale, saved["masks"],
+                                                      saved["saves"], ts.lay["td_total"])
     return tape_d, grid_grad, scale
 
 
@@ -182,12 +164,13 @@ def _weight_grads_kernel(model, level, ts, lay, tx, td, cvec, P):
         for i, g in enumerate(views):
             arr[i] = g.data_ptr() if g is not None else None
         ent = {"sig": sig, "flat": flat, "views": views, "arr": arr, "sizes": sizes,
-               "ws": torch.empty(256 * 1024, dtype=torch.uint8, device=dev)}
+               "ws": torch.empty(256 * 1024, dtype=torch.uint8, device=dev),
+               "ws_token": C.c_uint64(0)}      # fingerprint of the unit list this workspace holds (0: unknown)
         cache[level] = ent
     flat, grads, arr, ws = ent["flat"], list(ent["views"]), ent["arr"], ent["ws"]
     flat.zero_()
     L.check(lib.sahs_field_wgrad(C.byref(ts.cspec), 0 if level == "coarse" else 1, arr, L.ptr(tx), L.ptr(td), P,
-                                 L.ptr(ws), ws.numel(), L.stream_ptr(dev)), "field_wgrad")
+                                 L.ptr(ws), ws.numel(), C.byref(ent["ws_token"]), L.stream_ptr(dev)), "field_wgrad")
     d_cvec = torch.zeros(112, dtype=torch.float32, device=dev)
     s = model.spec
     e0d, e1d, wh, hh, th = lay["e0_dim"], lay["e1_dim"], lay["wh"], lay["hh"], lay["th"]

@@ -47,7 +47,10 @@ def _render_chunk(model, nerf_opts, ro, rd, near, far, driving_vec, pose_code, b
         n = draws.get(key)
         return n if n is not None else torch.randn(R, S, dtype=torch.float32, device=dev) * noise_std
 
-    z_c = ops.coarse_z(R, nc, near, far, bool(nerf_opts.lindisp), dev, t_rand)
+    if not ro.is_cuda:
+        raise RuntimeError("sahs_b200 ops need CUDA tensors (there is no CPU path)")
+    T = torch.ops.sahs_b200
+    z_c = T.coarse_z(R, nc, near, far, bool(nerf_opts.lindisp), ops.linspace_dev(nc, dev), t_rand)
     raw_c = model.field("coarse", ro, rd, z_c, driving_vec, pose_code)
     rgb_c, disp_c, acc_c, w_c, depth_c = composite(raw_c, z_c, rd, noise_for("noise_c", nc), bg, bg is not None, white)
     if nf <= 0:
@@ -58,7 +61,7 @@ def _render_chunk(model, nerf_opts, ro, rd, near, far, driving_vec, pose_code, b
         u = draws.get("u")
         if u is None:
             u = torch.rand(R, nf, dtype=torch.float32, device=dev)
-    z_s, z_f = ops.sample_pdf_merge(z_c, w_c.detach(), nf, u)      # z_samples.detach(), ref: :164
+    z_s, z_f = T.sample_pdf_merge(z_c, w_c.detach(), nf, u)        # z_samples.detach(), ref: :164
     raw_f = model.field("fine", ro, rd, z_f, driving_vec, pose_code)
     rgb_f, disp_f, acc_f, w_f, depth_f = composite(raw_f, z_f, rd, noise_for("noise_f", nc + nf), bg, bg is not None,
                                                    white)
@@ -104,3 +107,33 @@ def run_one_iter_of_nerf(height, width, focal_length, model, ray_origins, ray_di
         shp = tuple(ray_directions.shape[:-1])
         images = [im.view(*shp, im.shape[-1]) if im.dim() == 2 else im.view(shp) for im in images]
     return tuple(images)
+
+
+class GaussianSmoothing(torch.nn.Module):
+    """Depthwise Gaussian filter over 1-3 trailing dims, the module the training script builds for its (optional) mask
+    smoothing (ref: nerf/train_utils.py:409-473): per-dimension kernel
+    exp(-((i - mean) / (2 sigma))^2) / (sigma sqrt(2 pi)) -- the reference's own (non-standard) exponent --, product
+    over dimensions, normalised to sum 1, applied with `padding=5`."""
+
+    def __init__(self, channels, kernel_size, sigma, dim=2):
+        super().__init__()
+        import math
+        import numbers
+        sizes = [kernel_size] * dim if isinstance(kernel_size, numbers.Number) else list(kernel_size)
+        sigmas = [sigma] * dim if isinstance(sigma, numbers.Number) else list(sigma)
+        if dim not in (1, 2, 3):
+            raise RuntimeError("Only 1, 2 and 3 dimensions are supported. Received {}.".format(dim))
+        kernel = torch.ones([int(s) for s in sizes], dtype=torch.float32)
+        for axis, (size, std) in enumerate(zip(sizes, sigmas)):
+            i = torch.arange(int(size), dtype=torch.float32)
+            g = torch.exp(-((i - (size - 1) / 2) / (2 * std)) ** 2) / (std * math.sqrt(2 * math.pi))
+            shape = [1] * dim
+            shape[axis] = int(size)
+            kernel = kernel * g.view(shape)
+        kernel = kernel / kernel.sum()
+        self.register_buffer("weight", kernel.expand(channels, 1, *kernel.shape).clone())
+        self.groups = channels
+        self.conv = (torch.nn.functional.conv1d, torch.nn.functional.conv2d, torch.nn.functional.conv3d)[dim - 1]
+
+    def forward(self, input):
+        return self.conv(input, weight=self.weight, groups=self.groups, padding=5)

@@ -354,3 +354,61 @@ def test_flat_adam_training_loop_repacks_and_descends():
     assert losses[-1] < losses[0], losses
     sd2 = model.state_dict()
     assert all(torch.isfinite(v).all() for v in sd2.values())
+
+
+def test_flat_adam_state_dict_round_trip_resumes_bit_exactly():
+    """Checkpoint resume (ref: train_stage_rays_auto.py:253, :705): step N times, save, load into a FRESH FlatAdam, step
+    again -- parameters and moments must equal an uninterrupted run bit for bit.  Also: a state_dict written by the
+    reference's torch.optim.Adam loads (same per-parameter layout)."""
+    import copy
+    import sahs_b200
+    gen = torch.Generator().manual_seed(5)
+    shapes = [(64, 37), (5,), (3, 128), (1,)]
+    init = [torch.randn(s, generator=gen) for s in shapes]
+    grads = [[torch.randn(s, generator=gen) for s in shapes] for _ in range(7)]
+
+    def make():
+        ps = [t.clone().to(DEV).requires_grad_(True) for t in init]
+        return ps, sahs_b200.FlatAdam(ps, lr=3e-4)
+
+    def run(ps, opt, its):
+        for it in its:
+            for p, g in zip(ps, grads[it]):
+                p.grad = g.to(DEV)
+            opt.step()
+            opt.param_groups[0]["lr"] = sahs_b200.exp_lr(3e-4, 0.1, 5.0, it + 1)
+
+    pa, oa = make()
+    run(pa, oa, range(7))                                        # uninterrupted
+    pb, ob = make()
+    run(pb, ob, range(4))
+    saved = copy.deepcopy(ob.state_dict())
+    saved_params = [p.detach().clone() for p in pb]
+    pc = [t.clone().requires_grad_(True) for t in saved_params]   # "model.load_state_dict" of the checkpoint
+    oc = sahs_b200.FlatAdam(pc, lr=3e-4)
+    oc.load_state_dict(saved)
+    assert float(oc.state[pc[0]]["step"]) == 4.0 and oc._steps == 4
+    assert oc.state[pc[0]]["exp_avg"].data_ptr() >= oc.flat_exp_avg.data_ptr()      # re-pointed at the flat buffer
+    run(pc, oc, range(4, 7))
+    torch.cuda.synchronize()
+    for a, c in zip(pa, pc):
+        assert torch.equal(a.detach(), c.detach())
+        assert torch.equal(oa.state[a]["exp_avg"], oc.state[c]["exp_avg"])
+        assert torch.equal(oa.state[a]["exp_avg_sq"], oc.state[c]["exp_avg_sq"])
+    # a checkpoint written by torch.optim.Adam (what the reference saves)
+    pr = [t.clone().to(DEV).requires_grad_(True) for t in init]
+    orf = torch.optim.Adam(pr, lr=3e-4, foreach=False, fused=False)
+    for it in range(4):
+        for p, g in zip(pr, grads[it]):
+            p.grad = g.to(DEV)
+        orf.step()
+    pd = [p.detach().clone().requires_grad_(True) for p in pr]
+    od = sahs_b200.FlatAdam(pd, lr=3e-4)
+    od.load_state_dict(orf.state_dict())
+    for p, g, pref in zip(pd, grads[4], pr):
+        p.grad = g.to(DEV)
+        pref.grad = g.to(DEV)
+    od.step()
+    orf.step()
+    for p, pref in zip(pd, pr):
+        assert float((p.detach() - pref.detach()).abs().max()) <= 2e-6 * float(pref.detach().abs().max()) + 1e-7

@@ -239,7 +239,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
-    assert lib.sahs_abi_version() == 1
+    assert lib.sahs_abi_version() == 2
 
 
 def test_exp_lr_matches_training_script_schedule():
