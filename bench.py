@@ -4,7 +4,8 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config audio/person_2_auto]
 
 A step = one Stage-I render of a 512x512 frame (262,144 rays, 64 coarse + 128 fine samples per ray) of the
-named config with random-init ("dense" fixture) weights and synthetic per-frame inputs.
+named config with random-init weights (the trained-like fixture of tests/sahs_fixtures.py: a non-empty scene, so the
+frame is also compared with the CPU oracle -- `parity`) and synthetic per-frame inputs.
   value   rays/s with rays and per-frame inputs already resident in HBM (CUDA events, max over ranks)
   e2e     the same through the public API with HOST inputs: per frame H2D of pose/audio/mask from pinned memory,
           get_ray_bundle, run_one_iter_of_nerf, D2H of the fine rgb+semantic map, depth and acc
@@ -97,28 +98,100 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_port_rays_per_s(cfg_name, n_rays, repeats=1):
-    """The oracle port (reference algorithm, torch-CPU ops, all host threads) on a bounded ray sample."""
+def bench_case(cfg_name):
+    """Config, oracle spec and weights of the benchmarked case (shared by the GPU arm, the CPU port and the torch-on-GPU
+    baseline)."""
     import sahs_fixtures as FX
     from oracle import sahs_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
     cfg = FX.load_cfg(cfg_name)
+    cfg.nerf.validation.perturb = False            # deterministic sampling, as for the parity runs
     spec = O.spec_from_cfg(cfg)
-    sd = FX.make_state_dict(spec, seed=42, dense=True)
-    fr = FX.make_frame_inputs(spec, H, W, seed=0)
+    sd = FX.make_state_dict(spec, seed=42, dense=True, trained_like=True)
+    return cfg, spec, sd
+
+
+def bench_frame(spec, seed):
+    import sahs_fixtures as FX
+    return FX.make_frame_inputs(spec, H, W, seed=seed, pose_z=FX.probe_pose_z(spec))
+
+
+def cpu_port_rays_per_s(cfg_name, n_rays, repeats=1, frame_seed=100):
+    """The oracle port (reference algorithm, torch-CPU ops, all host threads) on a bounded ray sample of the
+    benchmark's frame.  Returns (rays/s, seconds, threads, ray indices, the 8 outputs)."""
+    from oracle import sahs_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg, spec, sd = bench_case(cfg_name)
+    fr = bench_frame(spec, frame_seed)
     opts = O.opts_from_cfg(cfg, "validation")
     opts.perturb, opts.noise_std = False, 0.0
     ro, rd = O.get_ray_bundle(H, W, fr["intrinsics"], fr["pose"])
     sel = torch.linspace(0, H * W - 1, n_rays).long()
     ro, rd, bg = ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel], fr["background"].view(-1, 15)[sel]
-    best = None
+    best, out = None, None
     with torch.no_grad():
         for _ in range(repeats):
             t0 = time.perf_counter()
-            O.run_one_iter(sd, spec, opts, ro, rd, fr["driving"], fr["pose"], bg)
+            out = O.run_one_iter(sd, spec, opts, ro, rd, fr["driving"], fr["pose"], bg)
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
-    return n_rays / best, best, torch.get_num_threads()
+    return n_rays / best, best, torch.get_num_threads(), sel, out
+
+
+def torch_gpu_rays_per_s(cfg_name, dev, n_rays, frame_seed=100):
+    """BASELINE config 2's stated comparison: the reference algorithm as plain PyTorch fp32 ops ON THE SAME GPU (the
+    oracle port with its tensors on `dev`, TF32 off, the reference's 131072-ray / 131072-point chunking), full frame or
+    a bounded ray sample.  Library kernels only -- none of ours."""
+    from oracle import sahs_oracle as O
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        cfg, spec, sd = bench_case(cfg_name)
+        sd = {k: v.to(dev) for k, v in sd.items()}
+        fr = bench_frame(spec, frame_seed)
+        opts = O.opts_from_cfg(cfg, "validation")
+        opts.perturb, opts.noise_std = False, 0.0
+        ro, rd = O.get_ray_bundle(H, W, fr["intrinsics"], fr["pose"])
+        sel = torch.linspace(0, H * W - 1, n_rays).long()
+        ro, rd = ro.reshape(-1, 3)[sel].to(dev), rd.reshape(-1, 3)[sel].to(dev)
+        bg, drv, pose = fr["background"].view(-1, 15)[sel].to(dev), fr["driving"].to(dev), fr["pose"].to(dev)
+        times = []
+        with torch.no_grad():
+            for i in range(2):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = O.run_one_iter(sd, spec, opts, ro, rd, drv, pose, bg)
+                e1.record()
+                torch.cuda.synchronize()
+                times.append(e0.elapsed_time(e1))
+        ms = times[-1]                                              # second run (allocator and cuBLAS warm)
+        return n_rays / (ms / 1e3), ms, sel, out
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+
+
+def cpu_train_step_rays_per_s(cfg_name, n_rays, frame_seed=100):
+    """one fwd+bwd training step of the oracle port on the host cores (autograd through the
+    reference algorithm, Stage-I loss), deterministic sampling."""
+    import sahs_fixtures as FX
+    from oracle import sahs_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg, spec, sd = bench_case(cfg_name)
+    fr = bench_frame(spec, frame_seed)
+    opts = O.opts_from_cfg(cfg, "train")
+    opts.perturb, opts.noise_std = False, 0.0
+    ro, rd = O.get_ray_bundle(H, W, fr["intrinsics"], fr["pose"])
+    sel = torch.linspace(0, H * W - 1, n_rays).long()
+    ro, rd, bg = ro.reshape(-1, 3)[sel], rd.reshape(-1, 3)[sel], fr["background"].view(-1, 15)[sel]
+    target = torch.rand(n_rays, 3, generator=torch.Generator().manual_seed(1))
+    mask = fr["mask"].view(-1, 12)[sel].float()
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    t0 = time.perf_counter()
+    out = O.run_one_iter(sdr, spec, opts, ro, rd, fr["driving"], fr["pose"], bg)
+    loss, _ = O.stage1_loss(out[0], out[3], target, mask)
+    loss.backward()
+    dt = time.perf_counter() - t0
+    return n_rays / dt, dt, torch.get_num_threads()
 
 
 def run_reference(args, rank):
@@ -127,7 +200,7 @@ def run_reference(args, rank):
     n_rays = args.cpu_rays or 4096
     times = []
     for i in range(args.warmup + args.steps):
-        rps, dt, cores = cpu_port_rays_per_s(args.config, n_rays)
+        rps, dt, cores, _, _ = cpu_port_rays_per_s(args.config, n_rays)
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * sum(times) / len(times)
@@ -137,7 +210,8 @@ def run_reference(args, rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"Stage-I 512x512 render, {args.config}, 64 coarse + 128 fine samples/ray",
-                   "sample": f"{n_rays} rays of the frame per step (CPU)", "weights": "random-init dense fixture"},
+                   "sample": f"{n_rays} rays of the frame per step (CPU)",
+                   "weights": "random-init, trained-like fixture (seed 42)"},
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
                          "sample": f"{n_rays} evenly spaced rays of one 512x512 frame per step, oracle port "
                                    "(reference algorithm in torch-CPU ops), all host threads"},
@@ -168,6 +242,16 @@ def _emit(text):
         os.write(_REAL_STDOUT, (text + "\n").encode())
 
 
+def _maxabs(a, b):
+    return float((a.double().cpu() - b.double().cpu()).abs().max())
+
+
+def _psnr(a, b):
+    import math
+    mse = float(((a.double().cpu() - b.double().cpu()) ** 2).mean())
+    return 99.0 if mse == 0 else -10.0 * math.log10(mse)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -179,7 +263,9 @@ def main():
                     help="rays per CPU sample (0 = 16384 for the cpu_baseline leg, about 10 s on 16 cores; "
                          "4096 per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step / config-4 / clip measurements")
+    ap.add_argument("--no-torch-gpu", action="store_true", help="skip the PyTorch-fp32-on-this-GPU baseline leg")
+    ap.add_argument("--clip-frames", type=int, default=0, help="frames of the clip (0: 1000 at 8 GPUs, else 16 per GPU)")
     args = ap.parse_args()
     _capture_stdout()
     rank = int(os.environ.get("RANK", "0"))
@@ -192,8 +278,9 @@ def main():
     import torch.distributed as dist
     import sahs_b200
     import sahs_fixtures as FX
-    from oracle import sahs_oracle as O          # fixture generator + CPU baseline only; never on the timed path
+    from oracle import sahs_oracle as O          # fixture generator + CPU/torch baselines + parity check; never timed as ours
     from sahs_b200 import lib as L
+    from sahs_b200 import train_utils as TU
     from sahs_b200.models import ModelSpec
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
@@ -204,19 +291,29 @@ def main():
     lib = L.load()
     warmup = max(args.warmup, 3)
 
-    cfg = FX.load_cfg(args.config)
-    cfg.nerf.validation.perturb = False            # deterministic sampling, as for the parity runs
-    ospec = O.spec_from_cfg(cfg)
+    cfg, ospec, sd = bench_case(args.config)
     mspec = ModelSpec.from_cfg(cfg)
-    sd = FX.make_state_dict(ospec, seed=42, dense=True)
     model = getattr(sahs_b200.models, cfg.models.mask.type)(cfg)
     model.load_state_dict(sd)
     model = model.to(dev)
-    nsteps_total = warmup + args.steps
-    frames = [FX.make_frame_inputs(ospec, H, W, seed=100 + rank + world * i) for i in range(2)]
+    FRAME0 = 100                                   # frame seeds: rank r renders 100 + r, 100 + r + world, ...
+    frames = [bench_frame(ospec, FRAME0 + rank + world * i) for i in range(2)]
     bg_dev = frames[0]["background"].view(-1, 15).to(dev)
     R = H * W
     flops_per_point = 2.0 * algorithmic_macs_per_point(mspec)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_hbm = float(peaks.get("hbm_gbs", 6500.0))
+    peak_src = "MEASURED_PEAKS.json" if peaks else "fallback of B200_PROFILING.md (1.4 PFLOP/s sustained, 6.5 TB/s)"
+    traffic = {}
+    try:        # dram__bytes_read.sum + dram__bytes_write.sum per launch, extracted from the committed ncu --set full capture
+        traffic = json.load(open(os.path.join(REPO, "profiles", "ncu_traffic.json")))
+    except (OSError, ValueError):
+        pass
 
     # ------------------------------ device-resident arm -----------------------------------------
     dev_frames = []
@@ -225,15 +322,14 @@ def main():
         ro, rd = sahs_b200.get_ray_bundle(H, W, fr["intrinsics"], pose)
         dev_frames.append(dict(pose=pose, driving=fr["driving"].to(dev), ro=ro, rd=rd, mask=fr["mask"].to(dev)))
 
-    field_events = []
-    orig_field = model.field
+    stage_events = []
 
-    def timed_field(level, ro, rd, z, *a, **k):
+    def stage_hook(name, fn):                     # CUDA events on the launching (current) stream around every stage
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        out = orig_field(level, ro, rd, z, *a, **k)
+        out = fn()
         e1.record()
-        field_events.append((level, z.numel(), e0, e1))
+        stage_events.append((name, e0, e1))
         return out
 
     def step_resident(i):
@@ -251,7 +347,7 @@ def main():
     for i in range(warmup):
         step_resident(i)
     barrier()
-    model.field = timed_field
+    TU.STAGE_HOOK = stage_hook
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = lib.sahs_launch_count()
@@ -263,34 +359,52 @@ def main():
     barrier()
     launches = lib.sahs_launch_count() - launches0
     clocks = sampler.stop()
-    model.field = orig_field
+    TU.STAGE_HOOK = None
     ms_total = torch.tensor([t0.elapsed_time(t1)], device=dev)
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
     ms_step = float(ms_total) / args.steps
     value = world * R / (ms_step / 1e3)
 
-    fine = [(n, a.elapsed_time(b)) for lvl, n, a, b in field_events if lvl == "fine"]
-    fine_ms = sum(t for _, t in fine) / len(fine)
-    all_field_ms = sum(a.elapsed_time(b) for _, _, a, b in field_events) / args.steps
-    achieved = fine[0][0] * flops_per_point / (fine_ms / 1e3) / 1e12
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    roofline = {"bound": "tensor", "kernel": "field_fwd_kernel (fine level, 262144 rays x 128 samples per launch)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks
-                                else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"),
+    stage_ms = {}
+    for name, a, b in stage_events:
+        stage_ms.setdefault(name, []).append(a.elapsed_time(b))
+    stage_ms = {k: sum(v) / len(v) for k, v in stage_ms.items()}      # per launch (the frame is one ray chunk)
+    nc, nf = int(cfg.nerf.validation.num_coarse), int(cfg.nerf.validation.num_fine)
+    pts_fine, pts_coarse = R * (nc + nf), R * nc
+    fine_ms = stage_ms["field_fine"]
+    achieved = pts_fine * flops_per_point / (fine_ms / 1e3) / 1e12
+    all_field_ms = stage_ms["field_fine"] + stage_ms["field_coarse"]
+    roofline = {"bound": "tensor", "kernel": f"field_fwd_kernel (fine level, {R} rays x {nc + nf} samples per launch)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                 "frac_of_burst_peak": achieved / float(peaks.get("bf16_tflops", 1590.0)),
-                "algorithmic_flop_per_point": flops_per_point, "points_per_launch": fine[0][0],
+                "algorithmic_flop_per_point": flops_per_point, "points_per_launch": pts_fine,
                 "avg_launch_ms": fine_ms, "field_share_of_step": all_field_ms / ms_step,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed `ncu --set full`
-                # capture (profiles/r1_render_ncu_summary.txt): 0.17 GB read + 2.10 GB written = the raw[.,16] store
-                "traffic": 2.27e9 if (args.config == "audio/person_2_auto") else None,
-                "traffic_unit": "bytes of DRAM traffic per launch (the kernel is tensor-bound; weights stay in L2)"}
+                "traffic": traffic.get("field_fwd_kernel_fine"),
+                "traffic_source": "profiles/ncu_traffic.json (dram bytes read + written per launch, ncu --set full)"
+                                  if traffic else None}
+
+    def hbm_entry(kernel, stage, bytes_per_ray, what):
+        ms = stage_ms[stage]
+        gbs = R * bytes_per_ray / (ms / 1e3) / 1e9
+        return {"bound": "hbm", "kernel": kernel, "achieved": gbs, "peak": peak_hbm, "unit": "GB/s", "frac": gbs / peak_hbm,
+                "avg_launch_ms": ms, "algorithmic_bytes_per_ray": bytes_per_ray, "what": what,
+                "traffic": traffic.get(stage)}
+
+    cf = pts_coarse * flops_per_point / (stage_ms["field_coarse"] / 1e3) / 1e12
+    kernels = [
+        {"bound": "tensor", "kernel": f"field_fwd_kernel (coarse level, {R} rays x {nc} samples)", "achieved": cf,
+         "peak": peak_tf, "unit": "TFLOP/s", "frac": cf / peak_tf, "avg_launch_ms": stage_ms["field_coarse"]},
+        hbm_entry("composite_fwd_kernel (coarse, S=64)", "composite_coarse", 72 * nc + 144,
+                  "reads raw[S,16] + z[S] + rd + bg, writes weights[S] + 18 outputs: 72 S + 144 B per ray (SURVEY 8d)"),
+        hbm_entry("composite_fwd_kernel (fine, S=128)", "composite_fine", 72 * (nc + nf) + 144, "as above, S = 128"),
+        hbm_entry("sample_pdf_merge_kernel", "sample_pdf_merge", 4 * (nc + nc + nf + nc + nf),
+                  "reads z[64] + w[64], writes z_samples[64] + merged z[128]: 1,280 B per ray"),
+    ]
+    composite_frame = {"ms": stage_ms["composite_coarse"] + stage_ms["composite_fine"],
+                       "bytes": R * (72 * nc + 144 + 72 * (nc + nf) + 144)}
+    composite_frame["frac_of_hbm_peak"] = composite_frame["bytes"] / (composite_frame["ms"] / 1e3) / 1e9 / peak_hbm
 
     # ------------------------------ end-to-end arm (host buffers) -------------------------------
     host = [dict(pose=fr["pose"].pin_memory(), driving=fr["driving"].pin_memory(), mask=fr["mask"].pin_memory())
@@ -314,6 +428,7 @@ def main():
         out_depth.copy_(out[7], non_blocking=True)
         out_acc.copy_(out[5], non_blocking=True)
         torch.cuda.current_stream().synchronize()     # the frame is on the host before the next one starts
+        return out
 
     for i in range(2):
         step_e2e(i)
@@ -348,11 +463,11 @@ def main():
         mask_i32 = f0["mask"].view(-1, 12).to(torch.int32).contiguous()
         step_no = [0]
 
-        def train_step():
+        def train_step(n=nrays):
             nonlocal sample_prob
             # semantic-weighted ray batch on the device (train script :390-420; sahs_weighted_sample)
             step_no[0] += 1
-            sel = sahs_b200.weighted_sample(mask_i32, sample_prob, nrays, seed=(42 + rank) * 1000003 + step_no[0])
+            sel = sahs_b200.weighted_sample(mask_i32, sample_prob, n, seed=(42 + rank) * 1000003 + step_no[0])
             out = sahs_b200.run_one_iter_of_nerf(H, W, 1200.0, tmodel, ro_all[sel], rd_all[sel], cfg_t, mode="train",
                                                  driving=f0["driving"], pose=f0["pose"], background_prior=bg_dev[sel],
                                                  inHead=f0["mask"].view(-1, 12)[sel])
@@ -363,37 +478,64 @@ def main():
             opt.param_groups[0]["lr"] = sahs_b200.exp_lr(lr0, decay, decay_steps, step_no[0])   # train script :503-509
             return loss
 
-        for _ in range(3):
-            train_step()
-        barrier()
-        l0 = lib.sahs_launch_count()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(args.steps):
-            last = train_step()
-        a1.record()
-        barrier()
-        tms = torch.tensor([a0.elapsed_time(a1)], device=dev)
-        if world > 1:
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        tms_step = float(tms) / args.steps
+        def time_train(n):
+            for _ in range(3):
+                train_step(n)
+            barrier()
+            l0 = lib.sahs_launch_count()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(args.steps):
+                last = train_step(n)
+            a1.record()
+            barrier()
+            tms = torch.tensor([a0.elapsed_time(a1)], device=dev)
+            if world > 1:
+                dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            return float(tms) / args.steps, last, int((lib.sahs_launch_count() - l0) / args.steps)
+
+        tms_step, last, nl = time_train(nrays)
+        pts_step = nrays * (2 * nc + nf)
+        tflop_step = 3.0 * pts_step * flops_per_point / 1e12       # forward + dgrad + wgrad
+        tl = tmodel._train_states["fine"].lay
+        tape_bytes = 0
+        for lvl_pts in (nrays * nc, nrays * (nc + nf)):            # written once forward / by dgrad, read once by wgrad
+            rows = (lvl_pts + 127) // 128 * 128
+            tape_bytes += 2 * rows * 2 * (tl["tx_total"] + tl["td_total"])
         train = {"metric": "train_rays_per_s", "value": world * nrays / (tms_step / 1e3), "unit": "rays/s",
                  "ms_per_step": tms_step, "rays_per_step_per_gpu": nrays, "loss": float(last.detach()),
-                 "our_kernel_launches_per_step": int((lib.sahs_launch_count() - l0) / args.steps),
+                 "our_kernel_launches_per_step": nl,
+                 "roofline": {"bound": "tensor", "achieved": tflop_step / (tms_step / 1e3), "peak": peak_tf,
+                              "unit": "TFLOP/s", "frac": tflop_step / (tms_step / 1e3) / peak_tf,
+                              "algorithmic_tflop_per_step": tflop_step,
+                              "tape_bytes_per_step": tape_bytes,
+                              "tape_ms_at_hbm_peak": tape_bytes / (peak_hbm * 1e9) * 1e3,
+                              "what": "whole step (all kernels + host gaps) against the tensor peak; the tapes' HBM "
+                                      "floor is tape_ms_at_hbm_peak"},
                  "what": "device-side ray sampler + fwd + bwd (hand-written compositing, dgrad-chain and wgrad kernels) + "
                          "one-kernel loss + grad all-reduce + flat Adam with exponential lr decay, "
                          "semantic-weighted batch of 2048 rays per GPU, perturb + noise 0.1"}
+        if world > 1:
+            # strong scaling of the training step: a fixed GLOBAL batch of 16,384 rays
+            gl = 16384
+            sms, _, _ = time_train(gl // world)
+            train["strong"] = {"global_rays_per_step": gl, "rays_per_gpu": gl // world, "ms_per_step": sms,
+                               "value": gl / (sms / 1e3), "unit": "rays/s",
+                               "collective": "one NCCL all-reduce of the flat fp32 gradient buffer per step"}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            rps, dt, cores = cpu_train_step_rays_per_s(args.config, nrays)
+            train["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
+                                     "sample": f"one {nrays}-ray fwd+bwd step of the oracle port under autograd ({dt:.1f} s), "
+                                               "deterministic sampling, all host threads"}
 
     # ------------------------------ 3DMM-conditioned render (BASELINE config 4) -------------------
     config4 = None
     if not args.no_train and args.config == "audio/person_2_auto":
-        cfg4 = FX.load_cfg("expression/person_2")
-        cfg4.nerf.validation.perturb = False
-        ospec4 = O.spec_from_cfg(cfg4)
+        cfg4, ospec4, sd4 = bench_case("expression/person_2")
         model4 = getattr(sahs_b200.models, cfg4.models.mask.type)(cfg4)
-        model4.load_state_dict(FX.make_state_dict(ospec4, seed=42, dense=True))
+        model4.load_state_dict(sd4)
         model4 = model4.to(dev)
-        fr4 = FX.make_frame_inputs(ospec4, H, W, seed=300 + rank)
+        fr4 = bench_frame(ospec4, 300 + rank)
         pose4 = fr4["pose"].to(dev)
         ro4, rd4 = sahs_b200.get_ray_bundle(H, W, fr4["intrinsics"], pose4)
         drv4, mask4, bg4 = fr4["driving"].to(dev), fr4["mask"].to(dev), fr4["background"].view(-1, 15).to(dev)
@@ -421,11 +563,52 @@ def main():
                    "value": world * R / (float(ms4) / 1e3), "unit": "rays/s"}
         del model4
 
+    # ------------------------------ one frame over all ranks: strong scaling ---------------------
+    strong = None
+    if world > 1:
+        from sahs_b200 import parallel as PL
+        f0 = dev_frames[0] if rank == 0 else None
+        fr_s = bench_frame(ospec, FRAME0)                       # every rank renders its tile range of rank 0's frame
+        pose_s = fr_s["pose"].to(dev)
+        ro_s, rd_s = sahs_b200.get_ray_bundle(H, W, fr_s["intrinsics"], pose_s)
+        ro_s, rd_s = ro_s.reshape(-1, 3), rd_s.reshape(-1, 3)
+        drv_s, bg_s = fr_s["driving"].to(dev), fr_s["background"].view(-1, 15).to(dev)
+
+        def render_part(ro_p, rd_p, bg_p):
+            with torch.no_grad():
+                o = sahs_b200.run_one_iter_of_nerf(H, W, 1200.0, model, ro_p, rd_p, cfg, mode="train", driving=drv_s,
+                                                   pose=pose_s, background_prior=bg_p)
+            # one [n, 19] tensor per rank: fine map (15) + disparity + acc + background weight + depth
+            return (torch.cat((o[3], o[4][:, None], o[5][:, None], o[6][:, None], o[7][:, None]), -1),)
+
+        cfg.nerf.train.perturb, cfg.nerf.train.radiance_field_noise_std = False, 0.0
+        for _ in range(2):
+            got = PL.render_sharded(render_part, ro_s, rd_s, bg_s)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ns = max(3, min(args.steps, 10))
+        s0.record()
+        for _ in range(ns):
+            got = PL.render_sharded(render_part, ro_s, rd_s, bg_s)
+        s1.record()
+        barrier()
+        sms = torch.tensor([s0.elapsed_time(s1) / ns], device=dev)
+        dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        same = None
+        if rank == 0:                                            # the sharded frame equals the single-GPU frame bit for bit
+            whole = render_part(ro_s, rd_s, bg_s)[0]
+            same = bool(torch.equal(whole, got[0]))
+        strong = {"workload": f"ONE 512x512 frame, rays split into {world} tile-aligned ranges "
+                              "(sahs_b200.parallel.render_sharded), one all-gather of [R/n, 19] fp32 per frame",
+                  "ms_per_frame": float(sms), "value": R / (float(sms) / 1e3), "unit": "rays/s", "scaling": "strong",
+                  "gathered_bytes_per_frame": R * 19 * 4, "bitwise_equal_to_single_gpu": same,
+                  "collective": "NCCL all_gather (19.9 MB per frame)"}
+
     # ------------------------------ clip rendering over ranks (BASELINE config 5) ----------------
     clip = None
-    if world > 1 and not args.no_train:
+    if not args.no_train:
         from sahs_b200 import parallel as PL
-        n_clip = 4 * world                                   # frames of the clip (whole frames per rank, round robin)
+        n_clip = args.clip_frames or (1000 if world >= 8 else 16 * world)
 
         def clip_frame(f):
             fr = dev_frames[f % len(dev_frames)]
@@ -442,21 +625,46 @@ def main():
         got = PL.render_clip(clip_frame, n_clip)
         barrier()
         clip_s = torch.tensor([time.perf_counter() - c0], device=dev)
-        dist.all_reduce(clip_s, op=dist.ReduceOp.MAX)
+        if world > 1:
+            dist.all_reduce(clip_s, op=dist.ReduceOp.MAX)
         if rank == 0:
             assert got.shape == (n_clip, R, 4)
-        clip = {"workload": f"{n_clip}-frame clip, frame f on rank f mod {world}, uint8 rgb + argmax label gathered to "
-                            "rank 0 once at the end (sahs_b200.parallel.render_clip)",
-                "frames_per_s": n_clip / float(clip_s), "ms_per_frame": 1e3 * float(clip_s) / n_clip,
-                "gathered_bytes_per_frame": 4 * R}
+        del got
+        clip = {"workload": f"{n_clip}-frame clip (BASELINE config 5), frame f on rank f mod {world}, uint8 rgb + argmax "
+                            "label gathered to rank 0 once at the end (sahs_b200.parallel.render_clip)",
+                "frames": n_clip, "frames_per_s": n_clip / float(clip_s), "ms_per_frame": 1e3 * float(clip_s) / n_clip,
+                "seconds_per_1000_frames": 1000.0 * float(clip_s) / n_clip, "gathered_bytes_per_frame": 4 * R}
 
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_rays = args.cpu_rays or 16384
-        rps, dt, cores = cpu_port_rays_per_s(args.config, cpu_rays)
-        cpu_baseline = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-                        "sample": f"{cpu_rays} evenly spaced rays of one 512x512 frame ({dt:.1f} s), oracle port "
-                                  "(reference algorithm in torch-CPU ops), all host threads"}
+    # ------------------------------ baselines + parity at bench scale (rank 0, N = 1) -------------
+    cpu_baseline = parity = torch_gpu = None
+    if rank == 0 and world == 1:
+        with torch.no_grad():
+            ours = step_resident(0)                              # frame seed FRAME0, the one the baselines render
+        ours_f, ours_d = ours[3].reshape(-1, 15), ours[7].reshape(-1)
+        ours_c = ours[0].reshape(-1, 15)
+        if not args.no_cpu_baseline:
+            cpu_rays = args.cpu_rays or 16384
+            rps, dt, cores, sel, ref = cpu_port_rays_per_s(args.config, cpu_rays, frame_seed=FRAME0)
+            cpu_baseline = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
+                            "sample": f"{cpu_rays} evenly spaced rays of one 512x512 frame ({dt:.1f} s), oracle port "
+                                      "(reference algorithm in torch-CPU ops), all host threads"}
+            # the same rays of the frame the GPU arm rendered, against the oracle (north-star bars: 1e-2, 50 dB)
+            parity = {"rays": cpu_rays, "against": "oracle port on the host (fp32), free running",
+                      "rgb_maxabs": _maxabs(ours_f[sel], ref[3]), "rgb_coarse_maxabs": _maxabs(ours_c[sel], ref[0]),
+                      "depth_maxabs": _maxabs(ours_d[sel], ref[7]), "psnr": _psnr(ours_f[sel][:, :3], ref[3][:, :3]),
+                      "mean_opacity_fine": float(1.0 - ours[6].reshape(-1)[sel.to(dev)].mean())}
+            parity["ok"] = bool(parity["rgb_maxabs"] <= 1e-2 and parity["depth_maxabs"] <= 1e-2 and parity["psnr"] >= 50.0)
+        if not args.no_torch_gpu:
+            del ours
+            torch.cuda.empty_cache()
+            rps_t, ms_t, sel_t, ref_t = torch_gpu_rays_per_s(args.config, dev, R, frame_seed=FRAME0)
+            torch_gpu = {"value": rps_t, "unit": "rays/s", "ms_per_frame": ms_t, "kind": "port",
+                         "what": "the reference algorithm as plain PyTorch fp32 ops on this GPU (oracle port, TF32 off, "
+                                 "131072-ray / 131072-point chunks, full 512x512 frame): BASELINE config 2's comparison",
+                         "speedup_ours": (R / (ms_step / 1e3)) / rps_t,
+                         "rgb_maxabs_vs_ours": _maxabs(ours_f, ref_t[3]), "depth_maxabs_vs_ours": _maxabs(ours_d, ref_t[7])}
+            del ref_t
+            torch.cuda.empty_cache()
     if rank == 0:
         line = {
             "metric": "render_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
@@ -464,14 +672,15 @@ def main():
             "dtype": "f16", "data": "synthetic",
             "config": {"workload": f"Stage-I 512x512 render (BASELINE config 2), {args.config}, 64 coarse + 128 fine "
                                    "samples/ray, deterministic sampling", "rays_per_step_per_gpu": R,
-                       "weights": "random-init dense fixture (seed 42)", "parallelism": f"frames over {world} GPU(s)",
+                       "weights": "random-init, trained-like fixture (seed 42; tests/sahs_fixtures.py)",
+                       "parallelism": f"frames over {world} GPU(s)",
                        "l2": "working set per step (raw 3.2 GB) exceeds the 126 MB L2; no flush needed"},
             "ms_per_frame": ms_step,
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_frame": 1e3 * float(e2e_s) / args.steps},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
-            "train": train, "clip": clip,
-            "config4": config4,
+            "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels, "composite_per_frame": composite_frame,
+            "stage_ms": stage_ms, "cpu_baseline": cpu_baseline, "torch_gpu_baseline": torch_gpu, "parity": parity,
+            "clocks": clocks, "train": train, "strong": strong, "clip": clip, "config4": config4,
         }
         _emit(json.dumps(line))
     if world > 1:

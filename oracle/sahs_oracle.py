@@ -188,7 +188,7 @@ def grid_sample_trilinear(grid: torch.Tensor, pts: torch.Tensor) -> torch.Tensor
     iy = (pts[:, 1] + 1.0) * (0.5 * (H - 1))
     iz = (pts[:, 2] + 1.0) * (0.5 * (D - 1))
     x0, y0, z0 = torch.floor(ix), torch.floor(iy), torch.floor(iz)
-    out = torch.zeros(pts.shape[0], C, dtype=pts.dtype)
+    out = torch.zeros(pts.shape[0], C, dtype=pts.dtype, device=pts.device)
     for dz in (0, 1):
         for dy in (0, 1):
             for dx in (0, 1):
@@ -336,7 +336,11 @@ def linspace_f32(steps: int) -> np.ndarray:
 
 def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, num_samples: int, det: bool = True,
                u: Optional[torch.Tensor] = None, return_inds: bool = False):
-    """Inverse-CDF importance sampling, ref: nerf/nerf_helpers.py:454-497 (sample_pdf_2)."""
+    """Inverse-CDF importance sampling, ref: nerf/nerf_helpers.py:454-497 (sample_pdf_2).
+    CPU tensors: ATen's CPU summation orders emulated in numpy (host independent, bit-exact vs the reference on CPU).
+    CUDA tensors (bench.py's torch-on-GPU baseline leg only): the reference's own torch ops on the device."""
+    if bins.is_cuda:
+        return _sample_pdf_torch(bins, weights, num_samples, det, u, return_inds)
     w = (weights.detach().numpy().astype(np.float32) + np.float32(1e-5)).astype(np.float32)
     total = _aten_inner_sum_f32(np.ascontiguousarray(w))
     pdf = (w / total[:, None]).astype(np.float32)
@@ -364,6 +368,26 @@ def sample_pdf(bins: torch.Tensor, weights: torch.Tensor, num_samples: int, det:
     return out
 
 
+def _sample_pdf_torch(bins, weights, num_samples, det, u, return_inds):
+    """sample_pdf_2 with the reference's torch ops (ref: nerf/nerf_helpers.py:454-497), any device."""
+    w = weights + 1e-5
+    pdf = w / torch.sum(w, dim=-1, keepdim=True)
+    cdf = torch.cat((torch.zeros_like(pdf[..., :1]), torch.cumsum(pdf, dim=-1)), dim=-1)
+    if u is None:
+        assert det, "stochastic mode needs the caller's uniform draws"
+        u = torch.linspace(0.0, 1.0, steps=num_samples, dtype=w.dtype, device=w.device).expand(w.shape[0], num_samples)
+    u = u.contiguous()
+    inds = torch.searchsorted(cdf.contiguous(), u, right=True)
+    below = torch.clamp(inds - 1, min=0)
+    above = torch.clamp(inds, max=cdf.shape[-1] - 1)
+    cdf_b, cdf_a = torch.gather(cdf, 1, below), torch.gather(cdf, 1, above)
+    bin_b, bin_a = torch.gather(bins, 1, below), torch.gather(bins, 1, above)
+    denom = cdf_a - cdf_b
+    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
+    samples = bin_b + (u - cdf_b) / denom * (bin_a - bin_b)
+    return (samples, inds) if return_inds else samples
+
+
 # --------------------------------------------------------------------------------------------
 # L3 pipeline
 # --------------------------------------------------------------------------------------------
@@ -388,11 +412,11 @@ def opts_from_cfg(cfg, mode: str) -> RenderOpts:
                       far=float(cfg.dataset.far))
 
 
-def coarse_z(opts: RenderOpts, num_rays: int, t_rand: Optional[torch.Tensor] = None) -> torch.Tensor:
+def coarse_z(opts: RenderOpts, num_rays: int, t_rand: Optional[torch.Tensor] = None, device=None) -> torch.Tensor:
     """ref: nerf/train_utils.py:93-113."""
-    near = torch.full((num_rays, 1), opts.near, dtype=torch.float32)
-    far = torch.full((num_rays, 1), opts.far, dtype=torch.float32)
-    t = torch.linspace(0.0, 1.0, opts.num_coarse, dtype=torch.float32)
+    near = torch.full((num_rays, 1), opts.near, dtype=torch.float32, device=device)
+    far = torch.full((num_rays, 1), opts.far, dtype=torch.float32, device=device)
+    t = torch.linspace(0.0, 1.0, opts.num_coarse, dtype=torch.float32).to(near.device)
     if not opts.lindisp:
         z = near * (1.0 - t) + far * t
     else:
@@ -424,7 +448,7 @@ def render_rays(sd, spec: ModelSpec, opts: RenderOpts, ro, rd, driving, pose, ba
             raw[:, -1, :-1] = background_prior
         return raw
 
-    z_c = coarse_z(opts, R, t_rand)
+    z_c = coarse_z(opts, R, t_rand, device=ro.device)
     raw_c = run_field("coarse", z_c)
     rgb_c, disp_c, acc_c, w_c, depth_c = composite(raw_c, z_c, rd, noise_c, opts.white_background, background_prior)
     z_mid = 0.5 * (z_c[:, 1:] + z_c[:, :-1])

@@ -17,6 +17,14 @@ from .volume_rendering_utils import composite
 # rays per internal chunk: raw_fine is [rays, 128, 16] fp32 = 8 KB/ray -> 4 GB at 512k rays
 MAX_RAYS_PER_CHUNK = 1 << 19
 
+# Measurement hook (bench.py): when set, called as hook(stage_name, fn) around every kernel stage of a ray chunk and
+# must return fn().  None in production: a stage is then a plain call.
+STAGE_HOOK = None
+
+
+def _stage(name, fn):
+    return fn() if STAGE_HOOK is None else STAGE_HOOK(name, fn)
+
 
 def run_network(level, network_fn, pts, ray_batch, chunksize, use_viewdirs, driving=None, pose=None, pose_c=None,
                 latent_code=None, spatial_embeddings=None):
@@ -51,8 +59,10 @@ def _render_chunk(model, nerf_opts, ro, rd, near, far, driving_vec, pose_code, b
         raise RuntimeError("sahs_b200 ops need CUDA tensors (there is no CPU path)")
     T = torch.ops.sahs_b200
     z_c = T.coarse_z(R, nc, near, far, bool(nerf_opts.lindisp), ops.linspace_dev(nc, dev), t_rand)
-    raw_c = model.field("coarse", ro, rd, z_c, driving_vec, pose_code)
-    rgb_c, disp_c, acc_c, w_c, depth_c = composite(raw_c, z_c, rd, noise_for("noise_c", nc), bg, bg is not None, white)
+    raw_c = _stage("field_coarse", lambda: model.field("coarse", ro, rd, z_c, driving_vec, pose_code))
+    n_c = noise_for("noise_c", nc)
+    rgb_c, disp_c, acc_c, w_c, depth_c = _stage("composite_coarse",
+                                                lambda: composite(raw_c, z_c, rd, n_c, bg, bg is not None, white))
     if nf <= 0:
         raise RuntimeError("num_fine == 0 is a dead branch in the reference (depth_fine undefined, "
                            "ref: nerf/train_utils.py:205-206); not supported")
@@ -61,10 +71,11 @@ def _render_chunk(model, nerf_opts, ro, rd, near, far, driving_vec, pose_code, b
         u = draws.get("u")
         if u is None:
             u = torch.rand(R, nf, dtype=torch.float32, device=dev)
-    z_s, z_f = T.sample_pdf_merge(z_c, w_c.detach(), nf, u)        # z_samples.detach(), ref: :164
-    raw_f = model.field("fine", ro, rd, z_f, driving_vec, pose_code)
-    rgb_f, disp_f, acc_f, w_f, depth_f = composite(raw_f, z_f, rd, noise_for("noise_f", nc + nf), bg, bg is not None,
-                                                   white)
+    z_s, z_f = _stage("sample_pdf_merge", lambda: T.sample_pdf_merge(z_c, w_c.detach(), nf, u))   # .detach(), ref: :164
+    raw_f = _stage("field_fine", lambda: model.field("fine", ro, rd, z_f, driving_vec, pose_code))
+    n_f = noise_for("noise_f", nc + nf)
+    rgb_f, disp_f, acc_f, w_f, depth_f = _stage("composite_fine",
+                                                lambda: composite(raw_f, z_f, rd, n_f, bg, bg is not None, white))
     return rgb_c, disp_c, acc_c, rgb_f, disp_f, acc_f, w_f[:, -1], depth_f
 
 
@@ -73,7 +84,13 @@ def predict_and_render_radiance(ray_batch, model, options, mode="train", driving
                                 _draws=None):
     """ref: nerf/train_utils.py:72-206.  ray_batch[r] = (ro 3 | rd 3 | near | far | mask...)."""
     ro, rd = ray_batch[..., :3], ray_batch[..., 3:6]
-    near, far = float(ray_batch[0, 6]), float(ray_batch[0, 7])
+    # near / far ride in columns 6-7 of every ray (ref: :255-256) but are the config's two scalars: read them from the
+    # options (no device sync); callers that really carry other bounds per batch pass them in the rays and set
+    # options.dataset.near / far = None
+    near, far = getattr(options.dataset, "near", None), getattr(options.dataset, "far", None)
+    if near is None or far is None:
+        near, far = float(ray_batch[0, 6]), float(ray_batch[0, 7])
+    near, far = float(near), float(far)
     dvec = model.driving_vector(driving)
     pcode = model.pose_code(pose)
     return _render_chunk(model, getattr(options.nerf, mode), ro, rd, near, far, dvec, pcode, background_prior, _draws)
