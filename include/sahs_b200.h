@@ -230,6 +230,7 @@ int sahs_debug_plan(const sahs_model_spec* spec, int param_count, int32_t* stage
 #define SAHS_DBG_HEAD(i) (64 + (i))     /* cols 0-127 dir hidden i, 128-255 seg hidden i                */
 #define SAHS_DBG_PROF 99                /* debug buffer receives (tag, clock64) event pairs of one tile */
 #define SAHS_DBG_PROF_LIGHT 98          /* same, per-pass events only */
+#define SAHS_DBG_PROF_DUO 96            /* two-tile render kernel: (tag, clock64) events of both sets' 4th tile + the issuer */
 #define SAHS_DBG_PROF_PROD 97           /* per-pass worker events from the PRODUCTION instantiation; needs a -DSAHS_PROF_PROD=1 build */
 
 #ifdef __cplusplus

@@ -71,8 +71,8 @@ __device__ __forceinline__ void wait_acc(SyncT<PAIR>& sy, int tag) {
   tc_fence_after();
   prof_event(sy.prof, 100000 + tag);
 }
-__device__ __forceinline__ void group_sync() {  // the 256 worker threads only
-  asm volatile("bar.sync 1, 256;" ::: "memory");
+__device__ __forceinline__ void group_sync(int bar_id = 1) {  // the 256 worker threads of one tile set only
+  asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
 }
 
 // fp32 pair -> packed 16-bit pair.  fp16 conversions saturate to +-65504 instead of producing inf.
@@ -463,7 +463,7 @@ __device__ __forceinline__ void tma_warp_loop(const FieldPlan& plan, const uint8
     // (bit 0 of prof_base set: per-pass events only, so this per-stage producer records nothing)
     long long* prof = (prof_base && !(reinterpret_cast<uintptr_t>(prof_base) & 1) && iter == 2 && lane == 0) ? prof_base : nullptr;
     for (int st = 0; st < plan.num_stages; ++st) {
-      const uint32_t bytes = (uint32_t)plan.st[st].n8 * 1024u;
+      const uint32_t bytes = sahs_stage_bytes(plan.st[st]);
       mbar_wait(&empty[slot], phase ^ 1, status, 100);
       prof_event(prof, 40000 + st);
       if (lane == 0) {
@@ -474,6 +474,42 @@ __device__ __forceinline__ void tma_warp_loop(const FieldPlan& plan, const uint8
       off += bytes;
       if (++slot == kSlots) { slot = 0; phase ^= 1; }
     }
+  }
+}
+
+// The MMAs of one stage.  The issuer is a single warp on the uniform datapath and is itself ISSUE-BOUND: the generic
+// form below costs ~12 uniform instructions per MMA (descriptor moves, k-step tests, branches), ~90 per stage, and one
+// warp retires about one dependent instruction every 4 cycles -- 362 cycles per 4-MMA stage against 256-272 of tensor
+// time (measured with one tile set alone, no contention: profiles/r2_duo_timeline_oneset.txt).  Nearly every stage is
+// the full K = 64 without a split-precision partner, so that case is straight-line code: four MMAs, descriptor += 2.
+template <bool PAIR>
+__device__ __forceinline__ void issue_stage_mmas(const StageRec& r, uint32_t flags, uint32_t ksteps, uint64_t a_base,
+                                                 uint64_t b0, uint32_t d, uint32_t idesc) {
+  const uint64_t a0 = a_base + (uint64_t)r.a_off;
+  const uint32_t acc0 = (flags & ST_FRESH) ? 0u : 1u;
+  auto mma = [&](uint64_t a, uint64_t b, uint32_t acc) {
+    if (elect_one()) {
+      if (PAIR) tc_mma_pair(d, a, b, idesc, acc);
+      else tc_mma_bf16(d, a, b, idesc, acc);
+    }
+  };
+  if (ksteps == 4 && r.a_chunk2 == 0xFF) {
+    mma(a0, b0, acc0);
+    mma(a0 + 2, b0 + 2, 1u);
+    mma(a0 + 4, b0 + 4, 1u);
+    mma(a0 + 6, b0 + 6, 1u);
+    return;
+  }
+  mma(a0, b0, acc0);
+  if (ksteps > 1) mma(a0 + 2, b0 + 2, 1u);
+  if (ksteps > 2) mma(a0 + 4, b0 + 4, 1u);
+  if (ksteps > 3) mma(a0 + 6, b0 + 6, 1u);
+  if (r.a_chunk2 != 0xFF) {   // split precision: the residual (lo) activations times the same weights
+    const uint64_t a1 = a_base + (uint64_t)r.a2_off;
+    mma(a1, b0, 1u);
+    if (ksteps > 1) mma(a1 + 2, b0 + 2, 1u);
+    if (ksteps > 2) mma(a1 + 4, b0 + 4, 1u);
+    if (ksteps > 3) mma(a1 + 6, b0 + 6, 1u);
   }
 }
 
@@ -493,6 +529,7 @@ __device__ __forceinline__ void mma_issue_loop(const FieldPlan& plan, uint8_t* X
   uint32_t slot = 0, phase = 0, a_par = 0;
   const uint64_t a_base = umma_smem_desc_sw128(smem_u32(X));
   const uint64_t b_base = umma_smem_desc_sw128(smem_u32(slots));
+  const uint64_t b_base_wide = umma_smem_desc_sw64(smem_u32(slots));   // ST_WIDE stages: [256 x 32], 64-byte rows
   // software pipeline: the next stage's record is fetched and its `full` barrier peeked while this stage's MMAs run
   StageRec r = plan.st[0];
   uint32_t token = 0;
@@ -511,10 +548,17 @@ __device__ __forceinline__ void mma_issue_loop(const FieldPlan& plan, uint8_t* X
       mbar_wait_token(&full[slot], phase, token, status, 400 + st);   // PAIR: both halves of the stage have landed
       if (PROF && !light) prof_event(prof, 20000 + st);
       tc_fence_after();
+      // An mbarrier wait costs ~200 cycles even when the phase completed long ago, so the NEXT stage's `full` barrier
+      // is peeked (non-blocking) BEFORE this stage's MMAs are issued: the peek's latency hides under the MMA issue and
+      // the wait at the top of the next iteration is a register test whenever the weights were already there
+      // (round 1 peeked after the MMAs, with nothing left to hide the latency under; profiles/r2_duo_timeline_*.txt).
+      const uint32_t cur = slot;
+      if (++slot == NS) { slot = 0; phase ^= 1; }
+      token = mbar_peek(&full[slot], phase);
       const uint32_t idesc = PAIR ? (r.idesc ^ (((128u >> 4) ^ (256u >> 4)) << 24)) : r.idesc;   // M field 128 -> 256
       // descriptor address field counts 16-byte units; K advances 16 elements = 32 bytes = 2 units per MMA
       const uint64_t a0 = a_base + (uint64_t)r.a_off;
-      const uint64_t b0 = b_base + (uint64_t)(slot * SLOT_UNITS);
+      const uint64_t b0 = ((flags & ST_WIDE) ? b_base_wide : b_base) + (uint64_t)(cur * SLOT_UNITS);
       const uint32_t d = tmem_base + (uint32_t)r.d_col8 * 8u;
       const uint32_t acc0 = (flags & ST_FRESH) ? 0u : 1u;
       auto mma = [&](uint64_t a, uint64_t b, uint32_t acc) {
@@ -540,12 +584,10 @@ __device__ __forceinline__ void mma_issue_loop(const FieldPlan& plan, uint8_t* X
         if (ksteps > 2) mma(a1 + 4, b0 + 4, 1u);
         if (ksteps > 3) mma(a1 + 6, b0 + 6, 1u);
       }
-      commit(&empty[slot]);
+      commit(&empty[cur]);
       if (flags & ST_COMMIT) commit(acc_ready);
       if (PROF && (!light || (flags & ST_COMMIT))) prof_event(prof, 30000 + st);
-      if (++slot == NS) { slot = 0; phase ^= 1; }
       r = plan.st[(st + 1 < plan.num_stages) ? st + 1 : 0];
-      token = mbar_peek(&full[slot], phase);
     }
   }
 }
@@ -572,7 +614,7 @@ __device__ __forceinline__ void tma_warp_loop_pair(const FieldPlan& plan, const 
     // (bit 0 of prof_base set: per-pass events only, so this per-stage producer records nothing)
     long long* prof = (prof_base && !(reinterpret_cast<uintptr_t>(prof_base) & 1) && iter == 2 && lane == 0) ? prof_base : nullptr;
     for (int st = 0; st < plan.num_stages; ++st) {
-      const uint32_t half = (uint32_t)plan.st[st].n8 * 512u;
+      const uint32_t half = sahs_stage_bytes(plan.st[st]) / 2;
       mbar_wait_cluster(&empty[slot], phase ^ 1, status, 100);
       prof_event(prof, 40000 + st);
       if (lane == 0) {
@@ -618,6 +660,244 @@ __device__ __forceinline__ void mma_warp_loop_pair(const FieldPlan& plan, uint8_
                                                    int lane, long long* prof_base = nullptr) {
   mma_issue_loop<true, PROF>(plan, X, slots, full, empty, a_ready, acc_ready, tmem_base, cluster_id_x(), npairs,
                              cluster_num_x(), status, prof_base);
+}
+
+
+// ---- two-tile ("duo") variants ---------------------------------------------------------------------------
+// One cluster (CTA pair, cta_group::2) per SM pair owns TWO tile pairs at a time, "set 0" and "set 1": each set has its
+// own 256 worker threads, activation buffer X, 256 TMEM columns, weight ring and a_ready / acc_ready barriers, and ONE
+// issuer thread serves both sets pass by pass, first come first served.  A pass then runs at the full tensor rate and
+// the two sets settle into anti-phase -- one set's epilogue under the other set's MMAs -- instead of the lock step two
+// independent co-resident CTAs fall into (both in their MMA phase at half rate each, then both in their epilogue with the
+// pipe idle).  Set k of cluster c processes tile pairs c + (2 j + k) * nclusters.
+constexpr int kDuoThreads = 640;                 // 16 worker warps + 2 TMA + MMA / relay + relay
+#ifndef SAHS_DUO_SLOTS
+#define SAHS_DUO_SLOTS 4
+#endif
+constexpr int kDuoSlots = SAHS_DUO_SLOTS;
+constexpr int kDuoTmemCols = 512;
+constexpr int kDuoTmaWarp0 = 16, kDuoMmaWarp = 18, kDuoRelayWarp1 = 19;
+constexpr int kDuoRingBytes = kDuoSlots * kPairSlotBytes;                                 // 32 KB per set
+constexpr int kDuoOffSlots = 2 * kSmemX;                                                   // [X0 | X1 | ring0 | ring1 | fc | bars | xchg]
+constexpr int kDuoOffFc = kDuoOffSlots + 2 * kDuoRingBytes;
+constexpr int kDuoOffBars = kDuoOffFc + kPairFcFloats * 4;
+constexpr int kDuoOffXchg = kDuoOffBars + 512;
+constexpr int kDuoSmemTotal = kDuoOffXchg + 2 * 512;
+constexpr int kDuoBarsPerSet = 2 * kDuoSlots + 2;   // full[NS], empty[NS], a_ready, acc_ready
+
+// TMA producer of one set: this CTA's half of every stage, once per tile pair of the set
+__device__ __forceinline__ void tma_warp_loop_duo(const FieldPlan& plan, const uint8_t* __restrict__ packed, uint8_t* slots,
+                                                  uint64_t* full, uint64_t* empty, long long first, long long npairs,
+                                                  long long step, uint32_t rank, int* status, int lane) {
+  uint32_t slot = 0, phase = 0;
+  for (long long pt = first; pt < npairs; pt += step) {
+    uint32_t off = 0;
+    for (int st = 0; st < plan.num_stages; ++st) {
+      const uint32_t half = sahs_stage_bytes(plan.st[st]) / 2;
+      mbar_wait_cluster(&empty[slot], phase ^ 1, status, 100);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full[slot], half);
+        tma_bulk_g2s(slots + slot * kPairSlotBytes, packed + off + rank * half, half, &full[slot]);
+      }
+      __syncwarp();
+      off += 2 * half;
+      if (++slot == kDuoSlots) { slot = 0; phase ^= 1; }
+    }
+  }
+}
+
+// peer CTA: forwards "my half of the stage has landed" to the leader's full barrier of the same slot
+__device__ __forceinline__ void relay_warp_loop_duo(const FieldPlan& plan, uint64_t* full, long long first, long long npairs,
+                                                    long long step, int* status, int lane) {
+  uint32_t slot = 0, phase = 0;
+  uint32_t remote[kDuoSlots];
+#pragma unroll
+  for (int i = 0; i < kDuoSlots; ++i) remote[i] = mapa_u32(&full[i], 0);
+  for (long long pt = first; pt < npairs; pt += step) {
+    for (int st = 0; st < plan.num_stages; ++st) {
+      mbar_wait(&full[slot], phase, status, 500 + st);
+      if (lane == 0) {
+        uint32_t r = remote[0];
+#pragma unroll
+        for (int i = 1; i < kDuoSlots; ++i) r = (slot == (uint32_t)i) ? remote[i] : r;
+        mbar_arrive_cluster(r);
+      }
+      __syncwarp();
+      if (++slot == kDuoSlots) { slot = 0; phase ^= 1; }
+    }
+  }
+}
+
+// Which set may issue its next pass: polls the two a_ready barriers (starting with `prefer`) until one of the sets that
+// still has work has its operand ready.  The spin lives in one asm block so that the surrounding issue loop stays
+// warp-uniform straight-line code (see mbar_wait_uniform).  live0 / live1: the set still has passes to issue.
+__device__ __forceinline__ uint32_t duo_pick(uint64_t* a_ready0, uint32_t par0, uint32_t live0, uint64_t* a_ready1,
+                                             uint32_t par1, uint32_t live1, uint32_t prefer, int* status) {
+  uint32_t k;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .u32 c;\n\t"
+      "mov.u32 c, 0;\n\t"
+      "mov.u32 %0, %7;\n\t"
+      "PICK_%=:\n\t"
+      "setp.eq.u32 q, %0, 0;\n\t"
+      "@!q bra TRY1_%=;\n\t"
+      "setp.eq.u32 p, %3, 0;\n\t"
+      "@p bra NEXT_%=;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra NEXT_%=;\n\t"
+      "TRY1_%=:\n\t"
+      "setp.eq.u32 p, %6, 0;\n\t"
+      "@p bra NEXT_%=;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%4], %5;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "NEXT_%=:\n\t"
+      "xor.b32 %0, %0, 1;\n\t"
+      "add.u32 c, c, 1;\n\t"
+      "setp.lt.u32 p, c, 0x4000000;\n\t"
+      "@p bra PICK_%=;\n\t"
+      "st.global.u32 [%8], 1;\n\t"
+      "st.global.u32 [%8+4], 777;\n\t"
+      "fence.sc.sys;\n\t"
+      "trap;\n\t"
+      "DONE_%=:\n\t}"
+      : "=&r"(k)
+      : "r"(smem_u32(a_ready0)), "r"(par0), "r"(live0), "r"(smem_u32(a_ready1)), "r"(par1), "r"(live1), "r"(prefer),
+        "l"(status)
+      : "memory");
+  return __shfl_sync(0xffffffffu, k, 0);
+}
+
+// A stage record decoded into what the issue path needs (descriptors, accumulator address, flags).  Decoding is a
+// constant-bank load plus a dependent chain of ~25 uniform-datapath instructions (~100 cycles): done at the top of a
+// stage it sits between the previous stage's last MMA and this stage's first one and drains the tensor pipe's queue --
+// measured 362 cycles per 4-MMA stage with one tile set alone, against 270 of MMA time.  So the NEXT stage is decoded
+// right after the current stage's MMAs and commit have been issued, while they execute.
+struct StageDec {
+  uint64_t a0, a1;          // A descriptors (a1: split-precision partner chunk)
+  uint32_t d, idesc, flags, ksteps;
+  uint32_t fast;            // 1: K = 64, no partner: four straight MMAs; 2: ST_WIDE K = 32: two straight MMAs
+  uint32_t wide;
+};
+__device__ __forceinline__ StageDec duo_decode(const FieldPlan& plan, int st, uint64_t a_base, uint32_t tmem_set) {
+  // two 8-byte constant loads (records sit at 8 + 16 i in the kernel parameter block: 8-byte aligned)
+  const uint2 lo = reinterpret_cast<const uint2*>(&plan.st[st])[0], hi = reinterpret_cast<const uint2*>(&plan.st[st])[1];
+  const uint4 q = make_uint4(lo.x, lo.y, hi.x, hi.y);
+  // StageRec: n8 | kflags | a_chunk | d_col8 || a_chunk2 | pad[3] || idesc || a_off | a2_off
+  StageDec s;
+  const uint32_t kflags = (q.x >> 8) & 0xffu, a_chunk2 = q.y & 0xffu;
+  s.flags = kflags >> 3;
+  s.ksteps = kflags & 7u;
+  s.d = tmem_set + ((q.x >> 24) & 0xffu) * 8u;
+  s.idesc = q.z ^ (((128u >> 4) ^ (256u >> 4)) << 24);   // M field 128 -> 256
+  s.a0 = a_base + (uint64_t)(q.w & 0xffffu);
+  s.a1 = a_base + (uint64_t)(q.w >> 16);
+  s.wide = (s.flags & ST_WIDE) ? 1u : 0u;
+  s.fast = (a_chunk2 != 0xffu) ? 0u : ((s.ksteps == 4u && !s.wide) ? 1u : ((s.ksteps == 2u && s.wide) ? 2u : 0u));
+  if (a_chunk2 == 0xffu) s.a1 = 0;
+  return s;
+}
+
+// per-set issue state of the duo issuer
+struct DuoSet {
+  uint32_t slot = 0, phase = 0, a_par = 0;
+  int st = 0;
+  long long it;
+  StageDec next;            // the set's next stage, already decoded
+};
+
+// One pass (the stages up to and including the one flagged ST_COMMIT) of set K; the set's a_ready phase has completed.
+// An mbarrier wait costs ~200 cycles even when the phase completed long ago (measured: profiles/r2_duo_timeline_*.txt --
+// 201 cycles per stage, every stage).  So the NEXT stage's `full` barrier is peeked (non-blocking test_wait) BEFORE this
+// stage's MMAs are issued: the peek's latency hides under the MMA issue, and the wait at the top of the next iteration
+// is a register test whenever the weights were already there (CUTLASS' consumer_try_wait token idiom, one stage
+// earlier than round 1 had it).
+template <int K, bool PROF>
+__device__ __forceinline__ void duo_issue_pass(const FieldPlan& plan, DuoSet& s, uint64_t a_base, uint64_t b_base,
+                                               uint64_t b_base_wide, uint64_t* full, uint64_t* empty, uint64_t* acc_ready, uint32_t tmem_set,
+                                               long long step, int* status, long long*& prof, bool rec) {
+  constexpr uint32_t SLOT_UNITS = kPairSlotBytes >> 4;
+  s.a_par ^= 1;
+  tc_fence_after();
+  uint32_t flags;
+  uint32_t token = mbar_peek(&full[s.slot], s.phase);
+  do {
+    const StageDec c = s.next;
+    flags = c.flags;
+    if (PROF && rec) prof_event(prof, 25000 + 1000 * K + s.st);
+    mbar_wait_token(&full[s.slot], s.phase, token, status, 400 + s.st);   // both halves of the stage have landed
+    if (PROF && rec) prof_event(prof, 20000 + 1000 * K + s.st);
+    const uint32_t slot = s.slot;
+    const uint64_t b0 = (c.wide ? b_base_wide : b_base) + (uint64_t)(slot * SLOT_UNITS);
+    const uint32_t acc0 = (flags & ST_FRESH) ? 0u : 1u;
+    auto mma = [&](uint64_t a, uint64_t b, uint32_t acc) {
+      if (elect_one()) tc_mma_pair(c.d, a, b, c.idesc, acc);
+    };
+    if (c.fast == 2u) {
+      mma(c.a0, b0, acc0);
+      mma(c.a0 + 2, b0 + 2, 1u);
+    } else if (c.fast == 1u) {
+      mma(c.a0, b0, acc0);
+      mma(c.a0 + 2, b0 + 2, 1u);
+      mma(c.a0 + 4, b0 + 4, 1u);
+      mma(c.a0 + 6, b0 + 6, 1u);
+    } else {
+      mma(c.a0, b0, acc0);
+      if (c.ksteps > 1) mma(c.a0 + 2, b0 + 2, 1u);
+      if (c.ksteps > 2) mma(c.a0 + 4, b0 + 4, 1u);
+      if (c.ksteps > 3) mma(c.a0 + 6, b0 + 6, 1u);
+      if (c.a1 != 0) {   // split precision: the residual (lo) activations times the same weights
+        mma(c.a1, b0, 1u);
+        if (c.ksteps > 1) mma(c.a1 + 2, b0 + 2, 1u);
+        if (c.ksteps > 2) mma(c.a1 + 4, b0 + 4, 1u);
+        if (c.ksteps > 3) mma(c.a1 + 6, b0 + 6, 1u);
+      }
+    }
+    if (elect_one()) tc_commit_pair(&empty[slot]);
+    if (flags & ST_COMMIT) {
+      if (elect_one()) tc_commit_pair(acc_ready);
+    }
+    // ---- off the critical path (the MMAs above are executing): next stage's weights peeked, its record decoded ----
+    if (++s.slot == kDuoSlots) { s.slot = 0; s.phase ^= 1; }
+    token = mbar_peek(&full[s.slot], s.phase);
+    if (++s.st == plan.num_stages) { s.st = 0; s.it += step; }
+    s.next = duo_decode(plan, s.st, a_base, tmem_set);
+  } while (!(flags & ST_COMMIT));
+}
+
+// Leader CTA: the single in-order issuer of both sets.
+template <bool PROF>
+__device__ __forceinline__ void mma_warp_loop_duo(const FieldPlan& plan, uint8_t* X0, uint8_t* X1, uint8_t* slots0,
+                                                  uint8_t* slots1, uint64_t* bars0, uint64_t* bars1, uint32_t tmem_base,
+                                                  long long first0, long long first1, long long step, long long npairs,
+                                                  int* status, long long* prof_in = nullptr) {
+  // bit 0 of prof_in: per-stage events too (before / after the wait for the weights)
+  const bool prof_stages = (reinterpret_cast<uintptr_t>(prof_in) & 1) != 0;
+  long long* prof = reinterpret_cast<long long*>(reinterpret_cast<uintptr_t>(prof_in) & ~(uintptr_t)1);
+  DuoSet s0, s1;
+  s0.it = first0;
+  s1.it = first1;
+  const uint64_t a0 = umma_smem_desc_sw128(smem_u32(X0)), a1 = umma_smem_desc_sw128(smem_u32(X1));
+  const uint64_t b0 = umma_smem_desc_sw128(smem_u32(slots0)), b1 = umma_smem_desc_sw128(smem_u32(slots1));
+  const uint64_t bw0 = umma_smem_desc_sw64(smem_u32(slots0)), bw1 = umma_smem_desc_sw64(smem_u32(slots1));
+  uint64_t *full0 = bars0, *empty0 = bars0 + kDuoSlots, *a_rdy0 = bars0 + 2 * kDuoSlots, *acc0 = bars0 + 2 * kDuoSlots + 1;
+  uint64_t *full1 = bars1, *empty1 = bars1 + kDuoSlots, *a_rdy1 = bars1 + 2 * kDuoSlots, *acc1 = bars1 + 2 * kDuoSlots + 1;
+  s0.next = duo_decode(plan, 0, a0, tmem_base);
+  s1.next = duo_decode(plan, 0, a1, tmem_base + 256u);
+  uint32_t prefer = 0;
+  for (;;) {
+    const uint32_t live0 = s0.it < npairs ? 1u : 0u, live1 = s1.it < npairs ? 1u : 0u;
+    if (!(live0 | live1)) break;
+    const uint32_t k = duo_pick(a_rdy0, s0.a_par, live0, a_rdy1, s1.a_par, live1, prefer, status);
+    // SAHS_DBG_PROF_DUO: pass start / issue end of both sets' 4th tile (tags 10000 / 30000 + 1000 set + first stage)
+    const bool rec = PROF && prof && ((k == 0 && s0.it == first0 + 3 * step) || (k == 1 && s1.it == first1 + 3 * step));
+    const long long tag = 1000 * k + (k == 0 ? s0.st : s1.st);
+    if (PROF && rec) prof_event(prof, 10000 + tag);
+    if (k == 0) duo_issue_pass<0, PROF>(plan, s0, a0, b0, bw0, full0, empty0, acc0, tmem_base, step, status, prof, rec && prof_stages);
+    else duo_issue_pass<1, PROF>(plan, s1, a1, b1, bw1, full1, empty1, acc1, tmem_base + 256u, step, status, prof, rec && prof_stages);
+    if (PROF && rec) prof_event(prof, 30000 + tag);
+    prefer = k ^ 1u;
+  }
 }
 
 }  // namespace

@@ -41,6 +41,352 @@ struct TrainOut {
 #endif
 constexpr bool kProfProd = SAHS_PROF_PROD != 0;
 
+// One 128-point tile, start to finish, as executed by the 256 worker threads of a tile set (`tid` = 0..255 inside the
+// set, named barrier `bar_id` belongs to the set): encodings, epilogues of all passes, fp32 tails, embedding gather,
+// final store.  Shared by the one-tile-per-CTA kernels below and by the two-tile ("duo") kernel.
+template <class C, bool DBG, bool TRAIN, bool PAIR>
+__device__ __forceinline__ void field_tile_program(const NetDims& dm, SyncT<PAIR>& sy, uint8_t* X, const float* fcw,
+                                                   float* xchg, const float* __restrict__ grid,
+                                                   const float* __restrict__ ro, const float* __restrict__ rd,
+                                                   const float* __restrict__ zv, int S, long long P, long long ntiles,
+                                                   float* __restrict__ raw_out, float* __restrict__ dbg, int dbg_pass,
+                                                   TrainOut tr, long long tile, int tid, int bar_id, uint32_t tmem_row,
+                                                   long long* prof_buf, int iter) {
+  const int row = tid & (kTileRows - 1);
+  const int grp = tid >> 7;
+    if (DBG || (kProfProd && prof_buf)) {
+      sy.prof = nullptr;
+      if (prof_buf && iter == 2 && (tid == 0 || tid == 255)) {
+        sy.prof = prof_buf + (tid == 0 ? 0 : 4096);
+        prof_event(sy.prof, 2);   // tile start
+      }
+    }
+    const long long p = tile * kTileRows + row;
+    const bool valid = p < P;
+    const long long pc = valid ? p : P - 1;
+    const long long ray = pc / S;
+    const float zz = zv[pc];
+    const float dir[3] = {rd[ray * 3 + 0], rd[ray * 3 + 1], rd[ray * 3 + 2]};
+    float pt[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pt[k] = __fadd_rn(ro[ray * 3 + k], __fmul_rn(dir[k], zz));
+    float* dbg_row = (DBG && dbg && tile == 0) ? dbg + row * 256 : nullptr;
+    // training: activation tape of this tile, tile-major chunk images (sahs_make_dims); operand chunks go there
+    // straight from shared memory with TMA bulk stores
+    uint8_t* tape_tile = TRAIN ? reinterpret_cast<uint8_t*>(tr.tape_x) + (size_t)tile * (dm.tx_total / 64) * kChunkBytes
+                               : nullptr;
+    // X chunks [chunk0, chunk0 + nch) -> tape columns [col, col + 64 nch).  Every worker has fenced its writes
+    // (signal_a or an explicit fence.proxy.async) before calling.
+    auto tape_put = [&](int chunk0, int nch, int col) {
+      if (!TRAIN) return;
+      group_sync(bar_id);
+      if (tid == 0 && tile < ntiles) {   // (a pair's second CTA may own a tile past the end: nothing to store)
+        for (int i = 0; i < nch; ++i)
+          tma_bulk_s2g(tape_tile + (size_t)(col / 64 + i) * kChunkBytes, X + (chunk0 + i) * kChunkBytes, kChunkBytes);
+        tma_store_commit();
+      }
+    };
+    // before X is overwritten: the bulk stores issued so far have finished reading shared memory
+    auto tape_drain = [&]() {
+      if (!TRAIN) return;
+      if (tid == 0) tma_store_wait_read();
+      group_sync(bar_id);
+    };
+    tape_drain();
+    auto mask_slot = [&](int layer) -> uint4* {
+      return (TRAIN && valid) ? tr.masks + ((size_t)layer * P + p) * 2 + grp : nullptr;
+    };
+    float mapped[3] = {pt[0], pt[1], pt[2]};
+    float amb[C::AMB_DIM > 0 ? C::AMB_DIM : 1] = {};
+
+    if (C::USE_W && dm.w_split) {
+      // -------- deformation phase in split precision: warp net, then hyper-sheet net --------
+      auto write_e0s = [&]() {
+        RowStreamSplit<C::E0_PAD / 8> st(X, 0, 2, row, grp);
+        int col = pe_stream<C::XYZ_L, true, 3>(st, 0, pt);
+#pragma unroll
+        for (int i = C::E0_DIM; i < C::E0_PAD; ++i) st.put(col++, 0.f);
+      };
+      const float* wf = fcw + dm.off_wfinal;
+      const float* bf = wf + 3 * dm.wh;
+      const float* wa = bf + 4;
+      const float* ba = wa + C::AMB_DIM * dm.hh;
+      float* scratch = reinterpret_cast<float*>(X);   // [2][128][8]
+#pragma unroll 1
+      for (int net = 0; net < 2; ++net) {
+        const int boff = net == 0 ? 0 : dm.wh;
+        write_e0s();
+        signal_a(sy);
+        for (int i = 0; i < dm.w_layers; ++i) {
+          wait_acc(sy, 1000 + 16 * net + i);
+          if (i == dm.w_skip) {
+            write_e0s();
+            signal_a(sy);
+            wait_acc(sy, 1100 + 16 * net + i);
+          }
+          const float* bias = fcw + dm.off_wbias + i * dm.whh + boff;
+          float* dr = (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) ? dbg_row : nullptr;
+          if (i < dm.w_layers - 1) {
+            if (net == 0) epilogue_split<DBG, 4, PAIR>(tmem_row, grp * 64, bias, X, row, 2, dr, 0);
+            else epilogue_split<DBG, 2, PAIR>(tmem_row, grp * 32, bias, X, row, 1, dr, dm.wh);
+            signal_a(sy);
+          } else if (net == 0) {
+            float part[3] = {0.f, 0.f, 0.f};
+            final_partial<DBG, 4, 3, PAIR>(tmem_row, grp * 64, bias, wf, dm.wh, part, dr, 0);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) scratch[(grp * 128 + row) * 8 + k] = part[k];
+            group_sync(bar_id);
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+              mapped[k] = pt[k] + tanhf(scratch[row * 8 + k] + scratch[(128 + row) * 8 + k] + ldc1<PAIR>(bf + k));
+            group_sync(bar_id);
+          } else {
+            float part[C::AMB_DIM > 0 ? C::AMB_DIM : 1] = {};
+            final_partial<DBG, 2, (C::AMB_DIM > 0 ? C::AMB_DIM : 1), PAIR>(tmem_row, grp * 32, bias, wa, dm.hh, part, dr, dm.wh);
+#pragma unroll
+            for (int k = 0; k < C::AMB_DIM; ++k) scratch[(grp * 128 + row) * 8 + k] = part[k];
+            group_sync(bar_id);
+#pragma unroll
+            for (int k = 0; k < C::AMB_DIM; ++k)
+              amb[k] = scratch[row * 8 + k] + scratch[(128 + row) * 8 + k] + ldc1<PAIR>(ba + k);
+            group_sync(bar_id);
+          }
+        }
+      }
+    } else if (C::USE_W) {
+      // -------- deformation phase: warp | hyper-sheet merged (fp16 operands) --------
+      auto write_e0 = [&](int chunk0) {
+        RowStream<true, C::E0_PAD / 8> st(X, chunk0, row, grp);
+        int col = pe_stream<C::XYZ_L, true, 3>(st, 0, pt);
+#pragma unroll
+        for (int i = C::E0_DIM; i < C::E0_PAD; ++i) st.put(col++, 0.f);
+      };
+      write_e0(dm.e0_chunk_base);
+      signal_a(sy);
+      tape_put(dm.e0_chunk_base, dm.e0_chunks, dm.tx_e0);
+      for (int i = 0; i < dm.w_layers - 1; ++i) {
+        const float* bias = fcw + dm.off_wbias + i * dm.whh;
+        const bool two_pass = (i == dm.w_skip && !dm.e0_resident);
+        float4 b[4];
+        if (!two_pass) load_bias<PAIR>(b, bias + grp * 96);
+        wait_acc(sy, 1000 + i);
+        tape_drain();
+        if (two_pass) {
+          write_e0(0);
+          signal_a(sy);
+          load_bias<PAIR>(b, bias + grp * 96);
+          wait_acc(sy, 1100 + i);
+        }
+        // whh = 192: three 32-column blocks per group
+        epilogue<ACT_RELU, true, false, DBG, 6, TRAIN, PAIR>(tmem_row, grp * 96, bias, b, X, row, nullptr,
+                                                       (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) ? dbg_row : nullptr,
+                                                       mask_slot(i));
+        signal_a(sy);
+        tape_put(0, dm.whh / 64, dm.tx_wh + i * dm.whh);
+      }
+      {
+        // last hidden layer stays in fp32: dx = tanh(fc_final h_w), ambient = fc_ambient h_h.  Group g reduces its
+        // 96 columns; the 5 partial sums per row are exchanged through the (idle) X buffer.
+        const int i = dm.w_layers - 1;
+        wait_acc(sy, 1000 + i);
+        tape_drain();
+        if (DBG) prof_event(sy.prof, 201);
+        if (i == dm.w_skip && !dm.e0_resident) { write_e0(0); signal_a(sy); wait_acc(sy, 1100 + i); }
+        uint8_t* rowp5 = X + (row >> 3) * 1024 + (row & 7) * 128;
+        const float* bias = fcw + dm.off_wbias + i * dm.whh;
+        const float* wf = fcw + dm.off_wfinal;
+        const float* bf = wf + 3 * dm.wh;          // [wf 3*wh | bf 4 | wa amb*hh | ba 4], all 16-byte aligned
+        const float* wa = bf + 4;
+        const float* ba = wa + C::AMB_DIM * dm.hh;
+        float part[3 + (C::AMB_DIM > 0 ? C::AMB_DIM : 1)] = {};
+        uint32_t hmask[3] = {0u, 0u, 0u};
+#pragma unroll
+        for (int blk = 0; blk < 3; ++blk) {
+          const int c0 = grp * 96 + 32 * blk;
+          uint32_t v[32];
+          tmem_ld32(tmem_row + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = ldc4<PAIR>(bias + c0 + 4 * j);
+            float h[4] = {fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.f), fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.f),
+                          fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.f)};
+            if (TRAIN) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) hmask[blk] |= (h[q] > 0.f ? 1u : 0u) << (4 * j + q);
+              // the tape needs this layer's output as an operand chunk too (X chunks 0-2 are free here)
+              const int col = c0 + 4 * j;
+              *reinterpret_cast<uint2*>(rowp5 + (col >> 6) * kChunkBytes + (((((col & 63) >> 3) ^ row) & 7) << 4) +
+                                        (col & 7) * 2) = make_uint2(pack2<true>(h[0], h[1]), pack2<true>(h[2], h[3]));
+            }
+            if (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) dbg_row[c0 + 4 * j + q] = h[q];
+            }
+            if (c0 < dm.wh) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                const float4 w = ldc4<PAIR>(wf + k * dm.wh + c0 + 4 * j);
+                part[k] += h[0] * w.x + h[1] * w.y + h[2] * w.z + h[3] * w.w;
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < C::AMB_DIM; ++k) {
+                const float4 w = ldc4<PAIR>(wa + k * dm.hh + (c0 + 4 * j - dm.wh));
+                part[3 + k] += h[0] * w.x + h[1] * w.y + h[2] * w.z + h[3] * w.w;
+              }
+            }
+          }
+        }
+        if (TRAIN) {
+          uint4* ms = mask_slot(i);
+          if (ms) *ms = make_uint4(hmask[0], hmask[1], hmask[2], 0u);
+        }
+        if (DBG) prof_event(sy.prof, 202);   // fp32 last deformation layer done
+        if (TRAIN) {
+          fence_proxy_async_smem();
+          tape_put(0, dm.whh / 64, dm.tx_wh + i * dm.whh);
+        }
+        // [2][128][8] floats; training keeps chunks 0-2 for the tape store above and uses the (now idle) chunk 3
+        float* scratch = reinterpret_cast<float*>(X + (TRAIN ? 3 * kChunkBytes : 0));
+#pragma unroll
+        for (int k = 0; k < 3 + C::AMB_DIM; ++k) scratch[(grp * 128 + row) * 8 + k] = part[k];
+        group_sync(bar_id);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          mapped[k] = pt[k] + tanhf(scratch[row * 8 + k] + scratch[(128 + row) * 8 + k] + ldc1<PAIR>(bf + k));
+#pragma unroll
+        for (int k = 0; k < C::AMB_DIM; ++k)
+          amb[k] = scratch[row * 8 + 3 + k] + scratch[(128 + row) * 8 + 3 + k] + ldc1<PAIR>(ba + k);
+        group_sync(bar_id);   // scratch is dead before E1 overwrites it
+        tape_drain();
+        if (DBG) prof_event(sy.prof, 203);   // tanh / ambient exchange done
+      }
+    }
+    if (TRAIN && valid && grp == 0) {
+      float* sv = tr.saves + p * 8;
+      sv[0] = mapped[0]; sv[1] = mapped[1]; sv[2] = mapped[2];
+#pragma unroll
+      for (int k = 0; k < C::AMB_DIM; ++k) sv[3 + k] = amb[k];
+    }
+    // -------- spatial embedding gather: each group keeps its 16 channels packed until layers_dir.0 --------
+    uint32_t emb_pk[8];
+    {
+      float emb[16];
+      grid_gather16(grid, grp * 16, mapped[0], mapped[1], mapped[2], emb);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) emb_pk[q] = pack2<kTrunkF16>(emb[2 * q], emb[2 * q + 1]);
+      if (DBG && dbg_row && dbg_pass == SAHS_DBG_MAPPED) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) dbg_row[8 + grp * 16 + q] = emb[q];
+        if (grp == 0) {
+          dbg_row[0] = mapped[0]; dbg_row[1] = mapped[1]; dbg_row[2] = mapped[2];
+#pragma unroll
+          for (int k = 0; k < C::AMB_DIM; ++k) dbg_row[3 + k] = amb[k];
+        }
+      }
+    }
+    if (DBG) prof_event(sy.prof, 204);   // embedding gather done
+    // -------- trunk (fp16 operands, kTrunkF16) --------
+    auto write_e1 = [&]() {
+      RowStream<kTrunkF16, C::E1_PAD / 8> st(X, 0, row, grp);
+      int col = pe_stream<C::XYZ_L, true, 3>(st, 0, mapped);
+      if (C::AMB_PE > 0) col = pe_stream<C::AMB_L, C::AMB_INC, (C::AMB_DIM > 0 ? C::AMB_DIM : 1)>(st, col, amb);
+#pragma unroll
+      for (int i = C::E1_DIM; i < C::E1_PAD; ++i) st.put(col++, 0.f);
+    };
+    write_e1();
+    if (DBG) prof_event(sy.prof, 205);   // E1 written
+    signal_a(sy);
+    tape_put(0, dm.e1_chunks, dm.tx_e1);
+    for (int i = 0; i < dm.t_layers; ++i) {
+      const float* bias = fcw + dm.off_tbias + i * dm.th;
+      float4 b[4];
+      if (i != dm.t_skip) load_bias<PAIR>(b, bias + grp * 128);
+      wait_acc(sy, 2000 + i);
+      tape_drain();
+      if (i == dm.t_skip) {
+        write_e1();
+        signal_a(sy);
+        load_bias<PAIR>(b, bias + grp * 128);
+        wait_acc(sy, 2100 + i);
+      }
+      epilogue<ACT_LEAKY, kTrunkF16, false, DBG, 8, TRAIN, PAIR>(
+          tmem_row, grp * 128, bias, b, X, row, nullptr,
+          (DBG && dbg_row && dbg_pass == SAHS_DBG_TRUNK(i)) ? dbg_row : nullptr,
+          mask_slot((C::USE_W ? dm.w_layers : 0) + i));
+      signal_a(sy);
+      tape_put(0, dm.th / 64, dm.tx_th + i * dm.th);
+    }
+    // fc_feat (no activation) + sigma = fc_alpha(feat) in fp32 (partial dot per group)
+    float4 bfe[4];
+    load_bias<PAIR>(bfe, fcw + dm.off_featb + grp * 128);
+    wait_acc(sy, 2200);
+    tape_drain();
+    float sigma = epilogue<ACT_NONE, kTrunkF16, true, DBG, 8, TRAIN, PAIR>(
+        tmem_row, grp * 128, fcw + dm.off_featb, bfe, X, row, fcw + dm.off_alpha,
+        (DBG && dbg_row && dbg_pass == SAHS_DBG_TRUNK(dm.t_layers)) ? dbg_row : nullptr,
+        nullptr);
+    if (grp == 1) xchg[row] = sigma;
+    signal_a(sy);
+    tape_put(0, dm.th / 64, dm.tx_feat);
+    // -------- heads: layers_dir.0 = [feat | PE(dir) | emb], layers_seg.0 = feat --------
+    wait_acc(sy, 3000);
+    tape_drain();
+    {
+      // extra K-chunk: cols [0,27) PE(dir), [27,59) embedding, zero padding up to 64
+      RowStream<kTrunkF16, 8, false> st(X, 0, row, 0);
+      if (grp == 0) {
+        int col = pe_stream<C::DIR_L, true, 3>(st, 0, dir);
+#pragma unroll
+        for (int i = C::DIR_DIM; i < 64; ++i) st.put(col++, 0.f);
+      }
+      group_sync(bar_id);     // group 0's zero fill precedes the scalar embedding stores of both groups
+      uint8_t* rowp = X + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int col = C::DIR_DIM + grp * 16 + q;
+        const uint32_t pair = emb_pk[q >> 1];
+        const uint16_t hv = (q & 1) ? (uint16_t)(pair >> 16) : (uint16_t)(pair & 0xffffu);
+        *reinterpret_cast<uint16_t*>(rowp + ((((col >> 3) ^ row) & 7) << 4) + (col & 7) * 2) = hv;
+      }
+    }
+    signal_a(sy);
+    tape_put(0, 1, dm.tx_xtra);
+    for (int i = 0; i < 4; ++i) {
+      const float* bias = fcw + dm.off_hbias + i * 2 * dm.hd;
+      float4 b[4];
+      load_bias<PAIR>(b, bias + grp * 128);
+      wait_acc(sy, 3100 + i);
+      tape_drain();
+      epilogue<ACT_LEAKY, kTrunkF16, false, DBG, 8, TRAIN, PAIR>(
+          tmem_row, grp * 128, bias, b, X, row, nullptr,
+          (DBG && dbg_row && dbg_pass == SAHS_DBG_HEAD(i)) ? dbg_row : nullptr,
+          mask_slot((C::USE_W ? dm.w_layers : 0) + dm.t_layers + i));
+      signal_a(sy);
+      tape_put(0, 2 * dm.hd / 64, dm.tx_hh + i * 2 * dm.hd);
+    }
+    // -------- output layer: cols 0-2 rgb, 3-14 seg (+ sigma) --------
+    wait_acc(sy, 3200);
+    if (grp == 0) {
+      uint32_t v[16];
+      tmem_ld16(tmem_row, v);
+      tmem_ld_wait();
+      float o[16];
+#pragma unroll
+      for (int k = 0; k < 15; ++k) o[k] = __uint_as_float(v[k]) + ldc1<PAIR>(fcw + dm.off_outb + k);
+      o[15] = sigma + xchg[row] + ldc1<PAIR>(fcw + dm.off_alpha + dm.th);
+      if (valid) {
+        float4* dst = reinterpret_cast<float4*>(raw_out + p * SAHS_RAW_CH);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      }
+    }
+    tc_fence_before();
+    group_sync(bar_id);   // xchg[] consumed before the next tile's fc_feat epilogue rewrites it
+    if (DBG || kProfProd) prof_event(sy.prof, 3);   // tile end
+}
+
 template <class C, bool DBG, bool TRAIN, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 2)
 field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__ NetDims dm,
@@ -137,8 +483,6 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
     // ================================ workers ===================================================
     const float* fcw = PAIR ? fc_s : fc;   // frame constants: shared-memory copy in the pair kernel
     SyncT<PAIR> sy{a_ready, acc_ready, 0u, status, PAIR ? mapa_u32(a_ready, 0) : 0u};
-    const int row = threadIdx.x & (kTileRows - 1);
-    const int grp = threadIdx.x >> 7;
     const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     // PAIR: `it` walks tile pairs and this CTA owns tile 2*it + rank (possibly past the end: all rows masked)
     const long long it_end = PAIR ? npairs : ntiles;
@@ -147,337 +491,8 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
     const long long it0 = PAIR ? (long long)cluster_id_x() : (long long)blockIdx.x;
     for (long long it = it0; it < it_end; it += it_step, ++iter) {
       const long long tile = PAIR ? 2 * it + rank : it;
-      if (DBG || (kProfProd && prof_buf)) {
-        sy.prof = nullptr;
-        if (prof_buf && iter == 2 && (threadIdx.x == 0 || threadIdx.x == 255)) {
-          sy.prof = prof_buf + (threadIdx.x == 0 ? 0 : 4096);
-          prof_event(sy.prof, 2);   // tile start
-        }
-      }
-      const long long p = tile * kTileRows + row;
-      const bool valid = p < P;
-      const long long pc = valid ? p : P - 1;
-      const long long ray = pc / S;
-      const float zz = zv[pc];
-      const float dir[3] = {rd[ray * 3 + 0], rd[ray * 3 + 1], rd[ray * 3 + 2]};
-      float pt[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) pt[k] = __fadd_rn(ro[ray * 3 + k], __fmul_rn(dir[k], zz));
-      float* dbg_row = (DBG && dbg && tile == 0) ? dbg + row * 256 : nullptr;
-      // training: activation tape of this tile, tile-major chunk images (sahs_make_dims); operand chunks go there
-      // straight from shared memory with TMA bulk stores
-      uint8_t* tape_tile = TRAIN ? reinterpret_cast<uint8_t*>(tr.tape_x) + (size_t)tile * (dm.tx_total / 64) * kChunkBytes
-                                 : nullptr;
-      // X chunks [chunk0, chunk0 + nch) -> tape columns [col, col + 64 nch).  Every worker has fenced its writes
-      // (signal_a or an explicit fence.proxy.async) before calling.
-      auto tape_put = [&](int chunk0, int nch, int col) {
-        if (!TRAIN) return;
-        group_sync();
-        if (threadIdx.x == 0 && tile < ntiles) {   // (a pair's second CTA may own a tile past the end: nothing to store)
-          for (int i = 0; i < nch; ++i)
-            tma_bulk_s2g(tape_tile + (size_t)(col / 64 + i) * kChunkBytes, X + (chunk0 + i) * kChunkBytes, kChunkBytes);
-          tma_store_commit();
-        }
-      };
-      // before X is overwritten: the bulk stores issued so far have finished reading shared memory
-      auto tape_drain = [&]() {
-        if (!TRAIN) return;
-        if (threadIdx.x == 0) tma_store_wait_read();
-        group_sync();
-      };
-      tape_drain();
-      auto mask_slot = [&](int layer) -> uint4* {
-        return (TRAIN && valid) ? tr.masks + ((size_t)layer * P + p) * 2 + grp : nullptr;
-      };
-      float mapped[3] = {pt[0], pt[1], pt[2]};
-      float amb[C::AMB_DIM > 0 ? C::AMB_DIM : 1] = {};
-
-      if (C::USE_W && dm.w_split) {
-        // -------- deformation phase in split precision: warp net, then hyper-sheet net --------
-        auto write_e0s = [&]() {
-          RowStreamSplit<C::E0_PAD / 8> st(X, 0, 2, row, grp);
-          int col = pe_stream<C::XYZ_L, true, 3>(st, 0, pt);
-#pragma unroll
-          for (int i = C::E0_DIM; i < C::E0_PAD; ++i) st.put(col++, 0.f);
-        };
-        const float* wf = fcw + dm.off_wfinal;
-        const float* bf = wf + 3 * dm.wh;
-        const float* wa = bf + 4;
-        const float* ba = wa + C::AMB_DIM * dm.hh;
-        float* scratch = reinterpret_cast<float*>(X);   // [2][128][8]
-#pragma unroll 1
-        for (int net = 0; net < 2; ++net) {
-          const int boff = net == 0 ? 0 : dm.wh;
-          write_e0s();
-          signal_a(sy);
-          for (int i = 0; i < dm.w_layers; ++i) {
-            wait_acc(sy, 1000 + 16 * net + i);
-            if (i == dm.w_skip) {
-              write_e0s();
-              signal_a(sy);
-              wait_acc(sy, 1100 + 16 * net + i);
-            }
-            const float* bias = fcw + dm.off_wbias + i * dm.whh + boff;
-            float* dr = (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) ? dbg_row : nullptr;
-            if (i < dm.w_layers - 1) {
-              if (net == 0) epilogue_split<DBG, 4, PAIR>(tmem_row, grp * 64, bias, X, row, 2, dr, 0);
-              else epilogue_split<DBG, 2, PAIR>(tmem_row, grp * 32, bias, X, row, 1, dr, dm.wh);
-              signal_a(sy);
-            } else if (net == 0) {
-              float part[3] = {0.f, 0.f, 0.f};
-              final_partial<DBG, 4, 3, PAIR>(tmem_row, grp * 64, bias, wf, dm.wh, part, dr, 0);
-#pragma unroll
-              for (int k = 0; k < 3; ++k) scratch[(grp * 128 + row) * 8 + k] = part[k];
-              group_sync();
-#pragma unroll
-              for (int k = 0; k < 3; ++k)
-                mapped[k] = pt[k] + tanhf(scratch[row * 8 + k] + scratch[(128 + row) * 8 + k] + ldc1<PAIR>(bf + k));
-              group_sync();
-            } else {
-              float part[C::AMB_DIM > 0 ? C::AMB_DIM : 1] = {};
-              final_partial<DBG, 2, (C::AMB_DIM > 0 ? C::AMB_DIM : 1), PAIR>(tmem_row, grp * 32, bias, wa, dm.hh, part, dr, dm.wh);
-#pragma unroll
-              for (int k = 0; k < C::AMB_DIM; ++k) scratch[(grp * 128 + row) * 8 + k] = part[k];
-              group_sync();
-#pragma unroll
-              for (int k = 0; k < C::AMB_DIM; ++k)
-                amb[k] = scratch[row * 8 + k] + scratch[(128 + row) * 8 + k] + ldc1<PAIR>(ba + k);
-              group_sync();
-            }
-          }
-        }
-      } else if (C::USE_W) {
-        // -------- deformation phase: warp | hyper-sheet merged (fp16 operands) --------
-        auto write_e0 = [&](int chunk0) {
-          RowStream<true, C::E0_PAD / 8> st(X, chunk0, row, grp);
-          int col = pe_stream<C::XYZ_L, true, 3>(st, 0, pt);
-#pragma unroll
-          for (int i = C::E0_DIM; i < C::E0_PAD; ++i) st.put(col++, 0.f);
-        };
-        write_e0(dm.e0_chunk_base);
-        signal_a(sy);
-        tape_put(dm.e0_chunk_base, dm.e0_chunks, dm.tx_e0);
-        for (int i = 0; i < dm.w_layers - 1; ++i) {
-          const float* bias = fcw + dm.off_wbias + i * dm.whh;
-          const bool two_pass = (i == dm.w_skip && !dm.e0_resident);
-          float4 b[4];
-          if (!two_pass) load_bias<PAIR>(b, bias + grp * 96);
-          wait_acc(sy, 1000 + i);
-          tape_drain();
-          if (two_pass) {
-            write_e0(0);
-            signal_a(sy);
-            load_bias<PAIR>(b, bias + grp * 96);
-            wait_acc(sy, 1100 + i);
-          }
-          // whh = 192: three 32-column blocks per group
-          epilogue<ACT_RELU, true, false, DBG, 6, TRAIN, PAIR>(tmem_row, grp * 96, bias, b, X, row, nullptr,
-                                                         (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) ? dbg_row : nullptr,
-                                                         mask_slot(i));
-          signal_a(sy);
-          tape_put(0, dm.whh / 64, dm.tx_wh + i * dm.whh);
-        }
-        {
-          // last hidden layer stays in fp32: dx = tanh(fc_final h_w), ambient = fc_ambient h_h.  Group g reduces its
-          // 96 columns; the 5 partial sums per row are exchanged through the (idle) X buffer.
-          const int i = dm.w_layers - 1;
-          wait_acc(sy, 1000 + i);
-          tape_drain();
-          if (DBG) prof_event(sy.prof, 201);
-          if (i == dm.w_skip && !dm.e0_resident) { write_e0(0); signal_a(sy); wait_acc(sy, 1100 + i); }
-          uint8_t* rowp5 = X + (row >> 3) * 1024 + (row & 7) * 128;
-          const float* bias = fcw + dm.off_wbias + i * dm.whh;
-          const float* wf = fcw + dm.off_wfinal;
-          const float* bf = wf + 3 * dm.wh;          // [wf 3*wh | bf 4 | wa amb*hh | ba 4], all 16-byte aligned
-          const float* wa = bf + 4;
-          const float* ba = wa + C::AMB_DIM * dm.hh;
-          float part[3 + (C::AMB_DIM > 0 ? C::AMB_DIM : 1)] = {};
-          uint32_t hmask[3] = {0u, 0u, 0u};
-#pragma unroll
-          for (int blk = 0; blk < 3; ++blk) {
-            const int c0 = grp * 96 + 32 * blk;
-            uint32_t v[32];
-            tmem_ld32(tmem_row + c0, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bb = ldc4<PAIR>(bias + c0 + 4 * j);
-              float h[4] = {fmaxf(__uint_as_float(v[4 * j + 0]) + bb.x, 0.f), fmaxf(__uint_as_float(v[4 * j + 1]) + bb.y, 0.f),
-                            fmaxf(__uint_as_float(v[4 * j + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * j + 3]) + bb.w, 0.f)};
-              if (TRAIN) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) hmask[blk] |= (h[q] > 0.f ? 1u : 0u) << (4 * j + q);
-                // the tape needs this layer's output as an operand chunk too (X chunks 0-2 are free here)
-                const int col = c0 + 4 * j;
-                *reinterpret_cast<uint2*>(rowp5 + (col >> 6) * kChunkBytes + (((((col & 63) >> 3) ^ row) & 7) << 4) +
-                                          (col & 7) * 2) = make_uint2(pack2<true>(h[0], h[1]), pack2<true>(h[2], h[3]));
-              }
-              if (DBG && dbg_row && dbg_pass == SAHS_DBG_WARP(i)) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) dbg_row[c0 + 4 * j + q] = h[q];
-              }
-              if (c0 < dm.wh) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                  const float4 w = ldc4<PAIR>(wf + k * dm.wh + c0 + 4 * j);
-                  part[k] += h[0] * w.x + h[1] * w.y + h[2] * w.z + h[3] * w.w;
-                }
-              } else {
-#pragma unroll
-                for (int k = 0; k < C::AMB_DIM; ++k) {
-                  const float4 w = ldc4<PAIR>(wa + k * dm.hh + (c0 + 4 * j - dm.wh));
-                  part[3 + k] += h[0] * w.x + h[1] * w.y + h[2] * w.z + h[3] * w.w;
-                }
-              }
-            }
-          }
-          if (TRAIN) {
-            uint4* ms = mask_slot(i);
-            if (ms) *ms = make_uint4(hmask[0], hmask[1], hmask[2], 0u);
-          }
-          if (DBG) prof_event(sy.prof, 202);   // fp32 last deformation layer done
-          if (TRAIN) {
-            fence_proxy_async_smem();
-            tape_put(0, dm.whh / 64, dm.tx_wh + i * dm.whh);
-          }
-          // [2][128][8] floats; training keeps chunks 0-2 for the tape store above and uses the (now idle) chunk 3
-          float* scratch = reinterpret_cast<float*>(X + (TRAIN ? 3 * kChunkBytes : 0));
-#pragma unroll
-          for (int k = 0; k < 3 + C::AMB_DIM; ++k) scratch[(grp * 128 + row) * 8 + k] = part[k];
-          group_sync();
-#pragma unroll
-          for (int k = 0; k < 3; ++k)
-            mapped[k] = pt[k] + tanhf(scratch[row * 8 + k] + scratch[(128 + row) * 8 + k] + ldc1<PAIR>(bf + k));
-#pragma unroll
-          for (int k = 0; k < C::AMB_DIM; ++k)
-            amb[k] = scratch[row * 8 + 3 + k] + scratch[(128 + row) * 8 + 3 + k] + ldc1<PAIR>(ba + k);
-          group_sync();   // scratch is dead before E1 overwrites it
-          tape_drain();
-          if (DBG) prof_event(sy.prof, 203);   // tanh / ambient exchange done
-        }
-      }
-      if (TRAIN && valid && grp == 0) {
-        float* sv = tr.saves + p * 8;
-        sv[0] = mapped[0]; sv[1] = mapped[1]; sv[2] = mapped[2];
-#pragma unroll
-        for (int k = 0; k < C::AMB_DIM; ++k) sv[3 + k] = amb[k];
-      }
-      // -------- spatial embedding gather: each group keeps its 16 channels packed until layers_dir.0 --------
-      uint32_t emb_pk[8];
-      {
-        float emb[16];
-        grid_gather16(grid, grp * 16, mapped[0], mapped[1], mapped[2], emb);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) emb_pk[q] = pack2<kTrunkF16>(emb[2 * q], emb[2 * q + 1]);
-        if (DBG && dbg_row && dbg_pass == SAHS_DBG_MAPPED) {
-#pragma unroll
-          for (int q = 0; q < 16; ++q) dbg_row[8 + grp * 16 + q] = emb[q];
-          if (grp == 0) {
-            dbg_row[0] = mapped[0]; dbg_row[1] = mapped[1]; dbg_row[2] = mapped[2];
-#pragma unroll
-            for (int k = 0; k < C::AMB_DIM; ++k) dbg_row[3 + k] = amb[k];
-          }
-        }
-      }
-      if (DBG) prof_event(sy.prof, 204);   // embedding gather done
-      // -------- trunk (fp16 operands, kTrunkF16) --------
-      auto write_e1 = [&]() {
-        RowStream<kTrunkF16, C::E1_PAD / 8> st(X, 0, row, grp);
-        int col = pe_stream<C::XYZ_L, true, 3>(st, 0, mapped);
-        if (C::AMB_PE > 0) col = pe_stream<C::AMB_L, C::AMB_INC, (C::AMB_DIM > 0 ? C::AMB_DIM : 1)>(st, col, amb);
-#pragma unroll
-        for (int i = C::E1_DIM; i < C::E1_PAD; ++i) st.put(col++, 0.f);
-      };
-      write_e1();
-      if (DBG) prof_event(sy.prof, 205);   // E1 written
-      signal_a(sy);
-      tape_put(0, dm.e1_chunks, dm.tx_e1);
-      for (int i = 0; i < dm.t_layers; ++i) {
-        const float* bias = fcw + dm.off_tbias + i * dm.th;
-        float4 b[4];
-        if (i != dm.t_skip) load_bias<PAIR>(b, bias + grp * 128);
-        wait_acc(sy, 2000 + i);
-        tape_drain();
-        if (i == dm.t_skip) {
-          write_e1();
-          signal_a(sy);
-          load_bias<PAIR>(b, bias + grp * 128);
-          wait_acc(sy, 2100 + i);
-        }
-        epilogue<ACT_LEAKY, kTrunkF16, false, DBG, 8, TRAIN, PAIR>(
-            tmem_row, grp * 128, bias, b, X, row, nullptr,
-            (DBG && dbg_row && dbg_pass == SAHS_DBG_TRUNK(i)) ? dbg_row : nullptr,
-            mask_slot((C::USE_W ? dm.w_layers : 0) + i));
-        signal_a(sy);
-        tape_put(0, dm.th / 64, dm.tx_th + i * dm.th);
-      }
-      // fc_feat (no activation) + sigma = fc_alpha(feat) in fp32 (partial dot per group)
-      float4 bfe[4];
-      load_bias<PAIR>(bfe, fcw + dm.off_featb + grp * 128);
-      wait_acc(sy, 2200);
-      tape_drain();
-      float sigma = epilogue<ACT_NONE, kTrunkF16, true, DBG, 8, TRAIN, PAIR>(
-          tmem_row, grp * 128, fcw + dm.off_featb, bfe, X, row, fcw + dm.off_alpha,
-          (DBG && dbg_row && dbg_pass == SAHS_DBG_TRUNK(dm.t_layers)) ? dbg_row : nullptr,
-          nullptr);
-      if (grp == 1) xchg[row] = sigma;
-      signal_a(sy);
-      tape_put(0, dm.th / 64, dm.tx_feat);
-      // -------- heads: layers_dir.0 = [feat | PE(dir) | emb], layers_seg.0 = feat --------
-      wait_acc(sy, 3000);
-      tape_drain();
-      {
-        // extra K-chunk: cols [0,27) PE(dir), [27,59) embedding, zero padding up to 64
-        RowStream<kTrunkF16, 8, false> st(X, 0, row, 0);
-        if (grp == 0) {
-          int col = pe_stream<C::DIR_L, true, 3>(st, 0, dir);
-#pragma unroll
-          for (int i = C::DIR_DIM; i < 64; ++i) st.put(col++, 0.f);
-        }
-        group_sync();     // group 0's zero fill precedes the scalar embedding stores of both groups
-        uint8_t* rowp = X + (row >> 3) * 1024 + (row & 7) * 128;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int col = C::DIR_DIM + grp * 16 + q;
-          const uint32_t pair = emb_pk[q >> 1];
-          const uint16_t hv = (q & 1) ? (uint16_t)(pair >> 16) : (uint16_t)(pair & 0xffffu);
-          *reinterpret_cast<uint16_t*>(rowp + ((((col >> 3) ^ row) & 7) << 4) + (col & 7) * 2) = hv;
-        }
-      }
-      signal_a(sy);
-      tape_put(0, 1, dm.tx_xtra);
-      for (int i = 0; i < 4; ++i) {
-        const float* bias = fcw + dm.off_hbias + i * 2 * dm.hd;
-        float4 b[4];
-        load_bias<PAIR>(b, bias + grp * 128);
-        wait_acc(sy, 3100 + i);
-        tape_drain();
-        epilogue<ACT_LEAKY, kTrunkF16, false, DBG, 8, TRAIN, PAIR>(
-            tmem_row, grp * 128, bias, b, X, row, nullptr,
-            (DBG && dbg_row && dbg_pass == SAHS_DBG_HEAD(i)) ? dbg_row : nullptr,
-            mask_slot((C::USE_W ? dm.w_layers : 0) + dm.t_layers + i));
-        signal_a(sy);
-        tape_put(0, 2 * dm.hd / 64, dm.tx_hh + i * 2 * dm.hd);
-      }
-      // -------- output layer: cols 0-2 rgb, 3-14 seg (+ sigma) --------
-      wait_acc(sy, 3200);
-      if (grp == 0) {
-        uint32_t v[16];
-        tmem_ld16(tmem_row, v);
-        tmem_ld_wait();
-        float o[16];
-#pragma unroll
-        for (int k = 0; k < 15; ++k) o[k] = __uint_as_float(v[k]) + ldc1<PAIR>(fcw + dm.off_outb + k);
-        o[15] = sigma + xchg[row] + ldc1<PAIR>(fcw + dm.off_alpha + dm.th);
-        if (valid) {
-          float4* dst = reinterpret_cast<float4*>(raw_out + p * SAHS_RAW_CH);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-        }
-      }
-      tc_fence_before();
-      group_sync();   // xchg[] consumed before the next tile's fc_feat epilogue rewrites it
-      if (DBG || kProfProd) prof_event(sy.prof, 3);   // tile end
+      field_tile_program<C, DBG, TRAIN, PAIR>(dm, sy, X, fcw, xchg, grid, ro, rd, zv, S, P, ntiles, raw_out, dbg, dbg_pass,
+                                              tr, tile, (int)threadIdx.x, 1, tmem_row, prof_buf, iter);
     }
     if (TRAIN && threadIdx.x == 0) tma_store_wait_all();   // tape stores complete before the CTA exits
   }
@@ -489,6 +504,124 @@ field_fwd_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__
     if (PAIR) tmem_dealloc_pair(tmem_base, kTmemCols);
     else tmem_dealloc(tmem_base, kTmemCols);
   }
+}
+
+
+// ---- two-tile ("duo") render kernel: one cluster per SM pair, two tile pairs in flight, one in-order issuer --------
+// (field_dev.cuh "duo variants").  Render path only: no tapes, no debug outputs.
+template <class C, bool PROF>
+__global__ void __launch_bounds__(kDuoThreads, 1)
+field_fwd_duo_kernel(const __grid_constant__ FieldPlan plan, const __grid_constant__ NetDims dm,
+                     const uint8_t* __restrict__ packed, const float* __restrict__ fc, const float* __restrict__ grid,
+                     const float* __restrict__ ro, const float* __restrict__ rd, const float* __restrict__ zv,
+                     int S, long long P, float* __restrict__ raw_out, int* __restrict__ status, long long* prof, int one_set) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  float* fc_s = reinterpret_cast<float*>(smem + kDuoOffFc);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDuoOffBars);      // [set][full NS | empty NS | a_ready | acc_ready]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kDuoBarsPerSet);
+  uint32_t* peer_tmem = tmem_ptr + 1;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const long long ntiles = (P + kTileRows - 1) / kTileRows;
+  const long long npairs = (ntiles + 1) / 2;
+  const uint32_t rank = cluster_ctarank();
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) {
+      status[0] = 2;
+      __trap();
+    }
+    for (int k = 0; k < 2; ++k) {
+      uint64_t* b = bars + k * kDuoBarsPerSet;
+      for (int i = 0; i < kDuoSlots; ++i) { mbar_init(&b[i], rank == 0 ? 2 : 1); mbar_init(&b[kDuoSlots + i], 1); }
+      mbar_init(&b[2 * kDuoSlots], 2 * (kWorkerThreads / 32));   // a_ready: one arrival per worker warp of both CTAs
+      mbar_init(&b[2 * kDuoSlots + 1], 1);                        // acc_ready
+    }
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < dm.fc_total; i += kDuoThreads) fc_s[i] = __ldg(fc + i);
+  if (warp == kDuoMmaWarp) tmem_alloc_pair(tmem_ptr, kDuoTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (rank == 1 && threadIdx.x == 0) st_cluster_u32(mapa_u32(peer_tmem, 0), tmem_base);
+  cluster_sync_all();
+  // one_set (measurement switch SAHS_DUO_ONE_SET=1): set 1 gets no tiles, set 0 all of them -- a pass then runs without a
+  // concurrent epilogue of the other set
+  const long long cid = cluster_id_x(), ncl = cluster_num_x();
+  const long long step = one_set ? ncl : 2 * ncl;
+  const long long first[2] = {cid, one_set ? npairs : cid + ncl};
+  if (warp < 16) {
+    // ================================ workers of set `k` ======================================
+    const int k = warp >> 3;
+    uint64_t* b = bars + k * kDuoBarsPerSet;
+    uint64_t* a_ready = &b[2 * kDuoSlots];
+    SyncT<true> sy{a_ready, &b[2 * kDuoSlots + 1], 0u, status, mapa_u32(a_ready, 0)};
+    uint8_t* X = smem + k * kSmemX;
+    float* xchg = reinterpret_cast<float*>(smem + kDuoOffXchg + k * 512);
+    const int tid = (int)threadIdx.x & 255;
+    const uint32_t tmem_row = tmem_base + (uint32_t)(k * 256) + ((uint32_t)((warp & 3) * 32) << 16);
+    int iter = 0;
+    for (long long it = first[k]; it < npairs; it += step, ++iter) {
+      const long long tile = 2 * it + rank;   // possibly one past the end: all rows masked
+      // SAHS_DBG_PROF_DUO: thread 0 of each set of cluster 0's leader records its 4th tile (signal / accumulator events)
+      if (PROF) {
+        sy.prof = (prof && cid == 0 && rank == 0 && tid == 0 && iter == 3) ? prof + k * 4096 : nullptr;
+        prof_event(sy.prof, 2);
+      }
+      field_tile_program<C, false, false, true>(dm, sy, X, fc_s, xchg, grid, ro, rd, zv, S, P, ntiles, raw_out, nullptr, -1,
+                                                TrainOut{nullptr, nullptr, nullptr}, tile, tid, 1 + k, tmem_row, nullptr,
+                                                iter);
+      if (PROF) prof_event(sy.prof, 3);
+    }
+  } else if (warp < kDuoMmaWarp) {
+    const int k = warp - kDuoTmaWarp0;
+    uint64_t* b = bars + k * kDuoBarsPerSet;
+    tma_warp_loop_duo(plan, packed, smem + kDuoOffSlots + k * kDuoRingBytes, b, b + kDuoSlots, first[k], npairs, step, rank,
+                      status, lane);
+  } else if (warp == kDuoMmaWarp) {
+    if (rank == 0) {
+      // the pair's accumulators must sit at the same TMEM columns in both SMs.  Checked here by the whole (converged)
+      // issuer warp on a shuffled value: a single-thread check ahead of the role dispatch makes the compiler treat the
+      // issue loop as possibly divergent (BRA.DIV + per-instruction election + R2UR: ~4x slower issue).
+      const uint32_t peer_base = __shfl_sync(0xffffffffu, *peer_tmem, 0);
+      if (peer_base != tmem_base) {
+        status[0] = 3;
+        status[1] = (int)tmem_base;
+        status[2] = (int)peer_base;
+        __threadfence_system();
+        __trap();
+      }
+      mma_warp_loop_duo<PROF>(plan, smem, smem + kSmemX, smem + kDuoOffSlots, smem + kDuoOffSlots + kDuoRingBytes, bars,
+                        bars + kDuoBarsPerSet, tmem_base, first[0], first[1], step, npairs, status,
+                        (PROF && prof && cid == 0 && lane == 0)
+                            ? reinterpret_cast<long long*>(reinterpret_cast<uintptr_t>(prof + 2 * 4096) | (uintptr_t)(P & 1))
+                            : nullptr);   // (odd point count: per-stage issuer events as well)
+    } else {
+      relay_warp_loop_duo(plan, bars, first[0], npairs, step, status, lane);
+    }
+  } else if (rank == 1) {
+    relay_warp_loop_duo(plan, bars + kDuoBarsPerSet, first[1], npairs, step, status, lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's smem / TMEM / barriers stay alive until both CTAs are done
+  if (warp == kDuoMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, kDuoTmemCols);
+  }
+}
+
+// The two-tile kernel is opt-in (SAHS_FIELD_DUO=1).  Measured on one box, same frame, fine-level launch (profiles/
+// r2_field_variants_ab.txt): two CTA pairs per SM pair 63.9 ms, two-tile kernel 65.1 ms.  Serving the passes first come
+// first served does remove the lock step, but the kernel is not bound by the issue order: with the mbarrier-wait
+// latency hidden (early peek) a pass still runs at ~92 cycles per N = 128 MMA instead of 70, because shared-memory
+// bandwidth is saturated -- MMA operand reads (~41 % of the data pipe at 45 % tensor-pipe activity) plus the epilogues'
+// loads and stores (40 %, ncu l1tex__data_pipe_lsu_wavefronts_mem_shared) -- and the GPU sits at its power cap
+// (DESIGN.md section 5, round 2).
+static bool field_duo_enabled() {
+  const char* e = getenv("SAHS_FIELD_DUO");
+  return e && e[0] == '1';
 }
 
 // The CTA-pair (cta_group::2) kernel is the default render path; SAHS_FIELD_PAIR=0 selects the single-CTA kernel
@@ -509,6 +642,33 @@ int launch_field(const HostPlan& hp, const void* packed, const float* fc, const 
   const uint8_t* pk = (const uint8_t*)packed;
   const bool prof_prod = dbg != nullptr && dbg_pass == SAHS_DBG_PROF_PROD;   // production kernel + per-pass events
   const bool prof = dbg != nullptr && (dbg_pass == SAHS_DBG_PROF || dbg_pass == SAHS_DBG_PROF_LIGHT);
+  const bool prof_duo = dbg != nullptr && dbg_pass == SAHS_DBG_PROF_DUO;
+  if ((!dbg || prof_duo) && !tr.tape_x && field_pair_enabled() && field_duo_enabled() && hp.dims.fc_total <= kPairFcFloats) {
+    // render path: one cluster per SM pair, two tile pairs in flight per cluster
+    auto kfn = prof_duo ? field_fwd_duo_kernel<C, true> : field_fwd_duo_kernel<C, false>;
+    SAHS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, kDuoSmemTotal));
+    const long long npairs = (ntiles + 1) / 2;
+    long long nclusters = sahs_num_sms() / 2;
+    if (nclusters > (npairs + 1) / 2) nclusters = (npairs + 1) / 2;
+    if (nclusters < 1) nclusters = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * nclusters));
+    cfg.blockDim = dim3(kDuoThreads);
+    cfg.dynamicSmemBytes = kDuoSmemTotal;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    long long* prof_ptr = prof_duo ? reinterpret_cast<long long*>(dbg) : nullptr;
+    static const int one_set = [] { const char* e = getenv("SAHS_DUO_ONE_SET"); return (e && e[0] == '1') ? 1 : 0; }();
+    SAHS_CUDA(cudaLaunchKernelEx(&cfg, kfn, hp.plan, hp.dims, pk, fc, grid, ro, rd, z, S, P, raw, status, prof_ptr, one_set));
+    SAHS_LAUNCH_CHECK();
+    return SAHS_OK;
+  }
   if ((!dbg || prof || prof_prod) && field_pair_enabled() && hp.dims.fc_total <= kPairFcFloats) {
     // CTA pairs: clusters of 2, two clusters resident per SM pair
     auto kfn = tr.tape_x ? field_fwd_kernel<C, false, true, true>

@@ -1,5 +1,6 @@
 // Host side of the fused field path: plan construction, weight packing (fp32 state_dict -> 16-bit (fp16; bf16 when a stage is not flagged f16) swizzled stage
 // images), per-frame constant folding.  See field_plan.cuh for the layout.
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include <cuda_fp16.h>
@@ -50,6 +51,7 @@ struct Builder {
   bool f16 = false;   // operand format of the stages being emitted
   bool lo = false;    // emit the residual image fp16(w - fp16(w))
   int a_chunk2 = 0xFF;
+  bool wide = false;  // emit ST_WIDE stages where a layer is 256 outputs wide (render plans; see field_plan.cuh)
 
   // one stage: rows [row0,row0+n) x cols [col0, col0+kvalid) of weight `pidx` (ld = in_features)
   void stage(int pidx, int ld, int row0, int n, int col0, int kvalid, int a_chunk, int d_col, bool fresh) {
@@ -61,7 +63,8 @@ struct Builder {
     r.a_chunk = (uint8_t)a_chunk;
     r.d_col8 = (uint8_t)(d_col / 8);
     r.a_chunk2 = (uint8_t)a_chunk2;
-    r.pad[0] = r.pad[1] = r.pad[2] = 0;
+    r.a_k16 = 0;
+    r.pad[0] = r.pad[1] = 0;
     PackStage& ps = hp.pack[ns];
     memset(&ps, 0, sizeof(ps));
     ps.dst_off = off;
@@ -75,6 +78,39 @@ struct Builder {
     off += (uint32_t)n * 128u;
     pass_open = true;
     ++ns;
+  }
+  // ST_WIDE stage: all 256 outputs x inputs [col0, col0 + kvalid) of weight `pidx`, kvalid <= 32; the A operand is the
+  // half `khalf` of chunk a_chunk
+  void wstage(int pidx, int ld, int col0, int kvalid, int a_chunk, int khalf, bool fresh) {
+    const uint32_t off0 = off;
+    stage(pidx, ld, 0, 256, col0, kvalid, a_chunk, 0, fresh);
+    StageRec& r = hp.plan.st[ns - 1];
+    r.kflags |= (uint8_t)(ST_WIDE << 3);
+    r.a_k16 = (uint8_t)(2 * khalf);
+    hp.pack[ns - 1].wide = 1;
+    off = off0 + 256u * 64u;
+  }
+  // a 256-output layer block over inputs [col0, col0 + kdim) read from X chunks a_chunk0..: wide stages when enabled,
+  // else the two 128-row halves one after the other (same K order per output either way: bit-identical results)
+  void block256(int pidx, int ld, int col0, int kdim, int a_chunk0, bool fresh_first) {
+    const int nch = (kdim + 63) / 64;
+    if (wide) {
+      bool fresh = fresh_first;
+      for (int kc = 0; kc < nch; ++kc)
+        for (int h = 0; h < 2; ++h) {
+          int kv = kdim - 64 * kc - 32 * h;
+          if (kv <= 0) continue;
+          if (kv > 32) kv = 32;
+          wstage(pidx, ld, col0 + 64 * kc + 32 * h, kv, a_chunk0 + kc, h, fresh);
+          fresh = false;
+        }
+      return;
+    }
+    for (int half = 0; half < 2; ++half)
+      for (int kc = 0; kc < nch; ++kc) {
+        int kv = kdim - 64 * kc; if (kv > 64) kv = 64;
+        stage(pidx, ld, 128 * half, 128, col0 + 64 * kc, kv, a_chunk0 + kc, 128 * half, fresh_first && kc == 0);
+      }
   }
   // dgrad stage: image rows = input features [in_col0, in_col0 + n_valid) (zero padded to n), image columns
   // [dst_col0, dst_col0 + k_valid) = output features [out_row0, out_row0 + k_valid); the A operand is the 64-wide chunk
@@ -100,7 +136,7 @@ void finalize_plan(FieldPlan& plan) {
     StageRec& r = plan.st[i];
     const uint32_t flags = r.kflags >> 3;
     r.idesc = sahs_idesc_m128((uint32_t)r.n8 * 8u, (flags & ST_F16) != 0);
-    r.a_off = (uint16_t)(r.a_chunk * (kChunkBytes >> 4));
+    r.a_off = (uint16_t)(r.a_chunk * (kChunkBytes >> 4) + r.a_k16 * 2);   // 16-byte units; a K = 16 step is 32 bytes
     r.a2_off = (uint16_t)((r.a_chunk2 == 0xFF ? 0 : r.a_chunk2) * (kChunkBytes >> 4));
   }
 }
@@ -124,6 +160,9 @@ int sahs_build_host_plan(const sahs_model_spec& s, const float* const* params, H
   if (!index_params(s, pi)) return SAHS_EINVAL;
   Builder b{hp, params};
   b.f16 = true;   // all operands fp16 (see field_fwd.cu "Precision")
+  // (training keeps the narrow stages; SAHS_FIELD_WIDE=0, read once per process: A/B measurements)
+  static const bool wide_on = [] { const char* e = getenv("SAHS_FIELD_WIDE"); return !(e && e[0] == '0'); }();
+  b.wide = wide_on && !train && d.th == 256;
   hp.num_fold = 0;
   hp.num_copy = 0;
   auto P = [&](int i) -> const float* { return params ? params[i] : nullptr; };
@@ -217,28 +256,18 @@ int sahs_build_host_plan(const sahs_model_spec& s, const float* const* params, H
     for (int i = 0; i < d.t_layers; ++i) {
       const bool first = i == 0, skip = i == d.t_skip;
       const int ld = first ? tin : (skip ? d.th + tin : d.th);
-      if (!first) {
-        for (int half = 0; half < d.th / 128; ++half)
-          for (int kc = 0; kc < d.th / 64; ++kc)
-            b.stage(pi.trunk_w[i], ld, 128 * half, 128, 64 * kc, 64, kc, 128 * half, kc == 0);
-      }
+      if (!first) b.block256(pi.trunk_w[i], ld, 0, d.th, 0, true);
       if (first || skip) {
         if (skip) b.end_pass();
         const int c0 = first ? 0 : d.th;
-        for (int half = 0; half < d.th / 128; ++half)
-          for (int kc = 0; kc < d.e1_chunks; ++kc) {
-            int kv = d.e1_dim - 64 * kc; if (kv > 64) kv = 64;
-            b.stage(pi.trunk_w[i], ld, 128 * half, 128, c0 + 64 * kc, kv, kc, 128 * half, first && kc == 0);
-          }
+        b.block256(pi.trunk_w[i], ld, c0, d.e1_dim, 0, first);
         fold(pi.trunk_b[i], pi.trunk_w[i], ld, c0 + d.e1_dim, d.ct_len, d.ct_off, d.th, d.off_tbias + i * d.th);
       } else {
         fold(pi.trunk_b[i], -1, 0, 0, 0, 0, d.th, d.off_tbias + i * d.th);
       }
       b.end_pass();
     }
-    for (int half = 0; half < d.th / 128; ++half)
-      for (int kc = 0; kc < d.th / 64; ++kc)
-        b.stage(pi.feat_w, d.th, 128 * half, 128, 64 * kc, 64, kc, 128 * half, kc == 0);
+    b.block256(pi.feat_w, d.th, 0, d.th, 0, true);
     b.end_pass();
     fold(pi.feat_b, -1, 0, 0, 0, 0, d.th, d.off_featb);
     hp.copy[hp.num_copy++] = CopySection{P(pi.alpha_w), d.th, d.off_alpha};
@@ -356,9 +385,10 @@ struct PackBatch {
 
 __global__ void pack_stage_kernel(const __grid_constant__ PackBatch batch, uint8_t* __restrict__ out) {
   const PackStage& ps = batch.st[blockIdx.x];
-  const int total = ps.n * 64;
+  const int kshift = ps.wide ? 5 : 6;            // image columns: 32 (ST_WIDE) or 64
+  const int total = ps.n << kshift;
   for (int e = blockIdx.y * blockDim.x + threadIdx.x; e < total; e += blockDim.x * gridDim.y) {
-    int row = e >> 6, col = e & 63;
+    int row = e >> kshift, col = e & ((1 << kshift) - 1);
     float v = 0.f;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -370,10 +400,11 @@ __global__ void pack_stage_kernel(const __grid_constant__ PackBatch batch, uint8
     if (ps.f16) {
       __half h = __float2half_rn(v);
       if (ps.lo) h = __float2half_rn(v - __half2float(h));
-      *reinterpret_cast<__half*>(out + ps.dst_off + sw128_offset(row, col)) = h;
+      *reinterpret_cast<__half*>(out + ps.dst_off + (ps.wide ? sw64_offset(row, col) : sw128_offset(row, col))) = h;
     }
     else
-      *reinterpret_cast<__nv_bfloat16*>(out + ps.dst_off + sw128_offset(row, col)) = __float2bfloat16_rn(v);
+      *reinterpret_cast<__nv_bfloat16*>(out + ps.dst_off + (ps.wide ? sw64_offset(row, col) : sw128_offset(row, col))) =
+          __float2bfloat16_rn(v);
   }
 }
 
@@ -492,7 +523,7 @@ extern "C" int sahs_debug_plan(const sahs_model_spec* spec, int param_count, int
     const StageRec& r = hp.plan.st[i];
     const PackStage& ps = hp.pack[i];
     int32_t* o = stages + 14 * i;
-    o[0] = r.n8 * 8; o[1] = r.kflags & 7; o[2] = r.kflags >> 3; o[3] = r.a_chunk; o[4] = r.d_col8 * 8;
+    o[0] = r.n8 * 8; o[1] = r.kflags & 7; o[2] = r.kflags >> 3; o[3] = r.a_chunk | (r.a_k16 << 8); o[4] = r.d_col8 * 8;
     o[5] = (int32_t)ps.dst_off; o[6] = id_of(ps.src[0].w); o[7] = ps.src[0].src_row0; o[8] = ps.src[0].src_col0;
     o[9] = ps.src[0].dst_row0; o[10] = ps.src[0].nrows; o[11] = ps.src[0].ncols; o[12] = r.a_chunk2; o[13] = ps.lo;
   }

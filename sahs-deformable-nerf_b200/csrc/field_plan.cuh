@@ -18,7 +18,12 @@ constexpr int kChunkBytes = kTileRows * kChunkCols * 2;  // 16 KB
 constexpr int kMaxStages = 160;
 constexpr int kStageSlotBytes = 16384;
 
-enum : uint8_t { ST_WAIT_A = 1, ST_COMMIT = 2, ST_FRESH = 4, ST_F16 = 8 };  // F16: fp16 operands (else bf16)
+enum : uint8_t { ST_WAIT_A = 1, ST_COMMIT = 2, ST_FRESH = 4, ST_F16 = 8, ST_WIDE = 16 };  // F16: fp16 operands (else bf16)
+// ST_WIDE: the B block is [256 outputs x 32 inputs] (K-major rows of 64 bytes, SWIZZLE_64B, 16 KB) instead of
+// [n <= 128 outputs x 64 inputs] (128-byte rows, SWIZZLE_128B): one N = 256 MMA per K = 16 step.  An N = 128 MMA reads
+// 4 KB of A + 4 KB of B per 64 tensor cycles -- with the half of B it serves to the peer CTA that is 117 B/cycle of the
+// SM's 128 B/cycle of shared-memory bandwidth, so every TMA write and epilogue store slows the MMAs (measured 92 cycles
+// per MMA in the kernel against 70 alone); N = 256 reads A once for twice the work: 96 B/cycle.
 
 struct StageRec {   // 16 bytes, lives in kernel parameter space
   uint8_t n8;       // N / 8
@@ -26,7 +31,8 @@ struct StageRec {   // 16 bytes, lives in kernel parameter space
   uint8_t a_chunk;  // which X chunk is the A operand
   uint8_t d_col8;   // accumulator column offset / 8
   uint8_t a_chunk2; // second A chunk multiplied by the same stage (split precision: the lo part), 0xFF = none
-  uint8_t pad[3];
+  uint8_t a_k16;    // first K = 16 step of the A chunk this stage multiplies (ST_WIDE stages cover half a chunk: 0 or 2)
+  uint8_t pad[2];
   // derived on the host (sahs_finalize_plan) so that the MMA issue loop decodes a stage with one 16-byte load:
   uint32_t idesc;   // tcgen05 instruction descriptor for M = 128 (the pair kernel ORs in M = 256)
   uint16_t a_off;   // a_chunk  * kChunkBytes / 16: offset of the A descriptor's address field
@@ -39,7 +45,7 @@ inline uint32_t sahs_idesc_m128(uint32_t n, bool f16) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
-struct FieldPlan {
+struct alignas(8) FieldPlan {   // (8: the issue loops read a StageRec as two 8-byte constant loads)
   int32_t num_stages;
   int32_t total_bytes;  // packed image bytes of one level
   StageRec st[kMaxStages];
@@ -59,6 +65,7 @@ struct PackStage {
   int32_t n;          // rows of the image (zero padded)
   int32_t f16;        // store fp16 instead of bf16
   int32_t lo;         // store the residual fp16(w - fp16(w)) (split-precision deformation phase)
+  int32_t wide;       // ST_WIDE image: rows of 32 inputs (64 bytes), SWIZZLE_64B
 };
 
 // fp32 per-frame constant block: offsets in floats
@@ -97,6 +104,14 @@ struct NetDims {
   int td_wh, td_final, td_th, td_feat, td_hh, td_out, td_total;
   int n_mask_layers;
 };
+
+// bytes of a stage's B image (both CTAs' halves together)
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline uint32_t sahs_stage_bytes(const StageRec& r) {
+  return (uint32_t)r.n8 * (((r.kflags >> 3) & ST_WIDE) ? 512u : 1024u);
+}
 
 inline int sahs_round_up(int v, int m) { return (v + m - 1) / m * m; }
 

@@ -217,6 +217,20 @@ __host__ __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t
   return (row >> 3) * 1024u + (row & 7u) * 128u + ((((col >> 3) ^ row) & 7u) << 4) + (col & 7u) * 2u;
 }
 
+// K-major SWIZZLE_64B operand tile (rows of 32 16-bit elements = 64 B, 8-row groups of 512 B, 16-byte units XOR-swizzled
+// by (row >> 1) & 3): the B operand of ST_WIDE stages.  Layout type 4, SBO = 512 B.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
+__host__ __device__ __forceinline__ uint32_t sw64_offset(uint32_t row, uint32_t col) {
+  return (row >> 3) * 512u + (row & 7u) * 64u + ((((col >> 3) ^ (row >> 1)) & 3u) << 4) + (col & 7u) * 2u;
+}
+
 // ---- warp-converged issue -------------------------------------------------------------------------------
 // tcgen05.mma / tcgen05.commit take uniform-register operands.  Issued from a divergent `if (lane == 0)` region, ptxas
 // wraps each of them in a per-thread election loop whose back-branch waits until the instruction has consumed its

@@ -83,12 +83,12 @@ def _train_worker(rank, world, port):
         bg = fr["background"].view(-1, 15).to(dev)
         drv = fr["driving"].to(dev)
         R = ro.shape[0]
-        target = torch.rand(R, 3, generator=torch.Generator().manual_seed(9)).to(dev)
+        target = torch.rand(R, 15, generator=torch.Generator().manual_seed(9)).to(dev)   # colour + semantic channels
 
         def loss_of(sl):
             out = sahs.run_one_iter_of_nerf(H, W, 1.0, model, ro[sl], rd[sl], cfg, mode="train", driving=drv, pose=pose,
                                             background_prior=bg[sl])
-            return ((out[3][:, :3] - target[sl]) ** 2).mean() + ((out[0][:, :3] - target[sl]) ** 2).mean()
+            return ((out[3] - target[sl]) ** 2).mean() + ((out[0] - target[sl]) ** 2).mean()
 
         # reference: the whole batch on this rank
         model.zero_grad(set_to_none=True)

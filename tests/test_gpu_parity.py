@@ -363,23 +363,28 @@ def test_field_empty_and_ragged(sahs):
 
 @pytest.mark.parametrize("cfg_name", ["audio/person_2_auto", "expression/person_2", "expression/person_1"])
 def test_field_pair_kernel_matches_single_cta_kernel(sahs, cfg_name, monkeypatch):
-    """The CTA-pair (cta_group::2) render kernel and the single-CTA kernel run the same arithmetic on every row:
-    bit-identical outputs for odd tile counts, a masked peer tile (one tile), ragged tails and many tiles."""
+    """The three render kernels run the same arithmetic on every row -- the CTA-pair kernel (default), the two-tile
+    "duo" kernel (SAHS_FIELD_DUO=1: one cluster per SM pair, two tile pairs in flight, one in-order issuer) and the
+    single-CTA kernel (SAHS_FIELD_PAIR=0): bit-identical outputs for odd tile counts, masked peer tiles (one tile),
+    a set without work (two tiles), ragged tails and many tiles per cluster."""
     cfg, spec, sd, model = _model(sahs, cfg_name)
     fr = FX.make_frame_inputs(spec, 8, 8, seed=1)
     drv, pose = fr["driving"].to(DEV), fr["pose"].to(DEV)
     gen = torch.Generator().manual_seed(11)
-    for n in (1, 129, 5 * 128 + 7, 1200 * 128):
+    for n in (1, 129, 257, 3 * 128 + 1, 5 * 128 + 7, 300 * 128 + 5, 1200 * 128):
         xyz = (torch.rand(n, 3, generator=gen) * 2 - 1) * 0.35
         dirs = torch.randn(n, 3, generator=gen) * 0.3 + torch.tensor([0, 0, -1.0])
         x = torch.cat((xyz, dirs), -1).to(DEV)
         outs = []
-        for pair in ("0", "1"):
+        for pair, duo in (("0", "0"), ("1", "0"), ("1", "1")):
             monkeypatch.setenv("SAHS_FIELD_PAIR", pair)
+            monkeypatch.setenv("SAHS_FIELD_DUO", duo)
             with torch.no_grad():
                 outs.append(model("fine", x, drv, pose, None))
             torch.cuda.synchronize()
-        assert torch.equal(outs[0], outs[1]), (cfg_name, n)
+            assert sahs.ops.field_status()[0] == 0, (cfg_name, n, pair, duo, sahs.ops.field_status())
+        assert torch.equal(outs[0], outs[1]), (cfg_name, n, "pair vs single")
+        assert torch.equal(outs[0], outs[2]), (cfg_name, n, "duo vs single")
     assert sahs.ops.field_status()[0] == 0
 
 

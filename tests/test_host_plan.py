@@ -11,7 +11,7 @@ import torch
 import sahs_fixtures as FX
 from oracle import sahs_oracle as O
 
-ST_WAIT_A, ST_COMMIT, ST_FRESH, ST_F16 = 1, 2, 4, 8
+ST_WAIT_A, ST_COMMIT, ST_FRESH, ST_F16, ST_WIDE = 1, 2, 4, 8, 16
 
 
 def _ordered_param_names(spec, level):
@@ -98,9 +98,11 @@ def _emulate(spec_model, ospec, sd, level, xyz, dirs, driving_vec, pose):
                 hi = img.astype(np.float16).astype(np.float32)
                 img = (img - hi).astype(np.float16).astype(np.float32) if lo else hi
             k = 16 * ks
-            contrib = X[:, a_chunk * 64:a_chunk * 64 + k] @ img[:, :k].T
+            k0 = 16 * (a_chunk >> 8)                 # ST_WIDE stages multiply half a chunk (a_k16 rides in bits 8..)
+            a_chunk &= 0xFF
+            contrib = X[:, a_chunk * 64 + k0:a_chunk * 64 + k0 + k] @ img[:, :k].T
             if a_chunk2 != 255:
-                contrib = contrib + X[:, a_chunk2 * 64:a_chunk2 * 64 + k] @ img[:, :k].T
+                contrib = contrib + X[:, a_chunk2 * 64 + k0:a_chunk2 * 64 + k0 + k] @ img[:, :k].T
             if flags & ST_FRESH:
                 D[:, d_col:d_col + n] = contrib
             else:
@@ -222,9 +224,13 @@ def test_plan_interpreter_matches_oracle(cfg_name):
         assert np.abs(got[:, 15] - ref[:, 15]).max() < (2e-4 if ospec.xyz_L <= 10 else 1e-3) * scale, (cfg_name, level)
         # stage images are laid out back to back in consumption order
         offs = stages[:, 5]
-        assert offs[0] == 0 and np.all(np.diff(offs) == stages[:-1, 0] * 128)
-        assert dm["total_bytes"] == offs[-1] + stages[-1, 0] * 128
-        assert np.all(stages[:, 0] % 16 == 0) and np.all(stages[:, 0] <= 128)      # UMMA M=128 needs N%16==0
+        wide = (stages[:, 2] & ST_WIDE) != 0                          # ST_WIDE: [256 x 32] images, 64-byte rows
+        nbytes = stages[:, 0] * np.where(wide, 64, 128)
+        assert offs[0] == 0 and np.all(np.diff(offs) == nbytes[:-1])
+        assert dm["total_bytes"] == offs[-1] + nbytes[-1]
+        assert np.all(stages[:, 0] % 16 == 0) and np.all(stages[~wide, 0] <= 128)      # UMMA M=128 needs N%16==0
+        assert np.any(wide) and np.all(stages[wide, 0] == 256) and np.all(stages[wide, 1] <= 2)
+        assert np.all(nbytes <= 16384)                                  # a stage fits one ring slot
         assert np.all((stages[:, 1] >= 1) & (stages[:, 1] <= 4))
 
 
