@@ -462,31 +462,44 @@ def main():
         sample_prob = torch.ones(12, device=dev)
         mask_i32 = f0["mask"].view(-1, 12).to(torch.int32).contiguous()
         step_no = [0]
+        from sahs_b200 import ops as OPS
+        from sahs_b200.train import GraphedStep
+        seed_ctr = torch.zeros((), dtype=torch.int64, device=dev)
 
-        def train_step(n=nrays):
-            nonlocal sample_prob
-            # semantic-weighted ray batch on the device (train script :390-420; sahs_weighted_sample)
-            step_no[0] += 1
-            sel = sahs_b200.weighted_sample(mask_i32, sample_prob, n, seed=(42 + rank) * 1000003 + step_no[0])
-            out = sahs_b200.run_one_iter_of_nerf(H, W, 1200.0, tmodel, ro_all[sel], rd_all[sel], cfg_t, mode="train",
-                                                 driving=f0["driving"], pose=f0["pose"], background_prior=bg_dev[sel],
-                                                 inHead=f0["mask"].view(-1, 12)[sel])
-            loss, sample_prob = sahs_b200.stage1_loss(out[0], out[3], target_all[sel], maskf[sel])
-            opt.zero_grad(set_to_none=True)
-            loss.backward()
-            opt.step()                                           # includes the data-parallel gradient average
-            opt.param_groups[0]["lr"] = sahs_b200.exp_lr(lr0, decay, decay_steps, step_no[0])   # train script :503-509
-            return loss
+        def make_step(n, model_t, opt_t, graphed):
+            state = {"prob": torch.ones(12, device=dev)}
 
-        def time_train(n):
+            def train_step():
+                # semantic-weighted ray batch on the device (train script :390-420; sahs_weighted_sample)
+                if graphed:
+                    sel = OPS.weighted_sample(mask_i32, state["prob"], n, seed=(42 + rank) * 1000003, seed_counter=seed_ctr)
+                else:
+                    step_no[0] += 1
+                    sel = sahs_b200.weighted_sample(mask_i32, state["prob"], n, seed=(42 + rank) * 1000003 + step_no[0])
+                out = sahs_b200.run_one_iter_of_nerf(H, W, 1200.0, model_t, ro_all[sel], rd_all[sel], cfg_t, mode="train",
+                                                     driving=f0["driving"], pose=f0["pose"], background_prior=bg_dev[sel],
+                                                     inHead=f0["mask"].view(-1, 12)[sel])
+                loss, prob = sahs_b200.stage1_loss(out[0], out[3], target_all[sel], maskf[sel])
+                state["prob"].copy_(prob)                            # dynamic sample_prob (train script :466-468)
+                opt_t.zero_grad(set_to_none=True)
+                loss.backward()
+                opt_t.step()                                         # includes the data-parallel gradient average
+                if graphed:
+                    OPS.counter_add(seed_ctr, 1)
+                else:                                                # train script :503-509
+                    opt_t.param_groups[0]["lr"] = sahs_b200.exp_lr(lr0, decay, decay_steps, step_no[0])
+                return loss.detach()
+            return train_step
+
+        def time_train(step, graphed=False):
             for _ in range(3):
-                train_step(n)
+                step()
             barrier()
             l0 = lib.sahs_launch_count()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
             for _ in range(args.steps):
-                last = train_step(n)
+                last = step()
             a1.record()
             barrier()
             tms = torch.tensor([a0.elapsed_time(a1)], device=dev)
@@ -494,7 +507,15 @@ def main():
                 dist.all_reduce(tms, op=dist.ReduceOp.MAX)
             return float(tms) / args.steps, last, int((lib.sahs_launch_count() - l0) / args.steps)
 
-        tms_step, last, nl = time_train(nrays)
+        eager_ms, last, nl = time_train(make_step(nrays, tmodel, opt, False))
+        # the same step recorded as one CUDA graph (capturable optimizer: step count + lr schedule on the device)
+        gmodel = getattr(sahs_b200.models, cfg_t.models.mask.type)(cfg_t)
+        gmodel.load_state_dict(sd)
+        gmodel = gmodel.to(dev)
+        gopt = sahs_b200.FlatAdam(gmodel.parameters(), lr=lr0, capturable=True, schedule=(decay, decay_steps))
+        gstep = GraphedStep(make_step(nrays, gmodel, gopt, True), warmup=3)
+        tms_step, last, _ = time_train(gstep, True)
+        tmodel = gmodel                                              # (tape layout below)
         pts_step = nrays * (2 * nc + nf)
         tflop_step = 3.0 * pts_step * flops_per_point / 1e12       # forward + dgrad + wgrad
         tl = tmodel._train_states["fine"].lay
@@ -504,7 +525,9 @@ def main():
             tape_bytes += 2 * rows * 2 * (tl["tx_total"] + tl["td_total"])
         train = {"metric": "train_rays_per_s", "value": world * nrays / (tms_step / 1e3), "unit": "rays/s",
                  "ms_per_step": tms_step, "rays_per_step_per_gpu": nrays, "loss": float(last.detach()),
-                 "our_kernel_launches_per_step": nl,
+                 "our_kernel_launches_per_step": nl, "eager_ms_per_step": eager_ms,
+                 "launch": "one CUDA graph per step (sahs_b200.train.GraphedStep); eager_ms_per_step is the same step "
+                           "issued launch by launch",
                  "roofline": {"bound": "tensor", "achieved": tflop_step / (tms_step / 1e3), "peak": peak_tf,
                               "unit": "TFLOP/s", "frac": tflop_step / (tms_step / 1e3) / peak_tf,
                               "algorithmic_tflop_per_step": tflop_step,
@@ -518,7 +541,12 @@ def main():
         if world > 1:
             # strong scaling of the training step: a fixed GLOBAL batch of 16,384 rays
             gl = 16384
-            sms, _, _ = time_train(gl // world)
+            smodel = getattr(sahs_b200.models, cfg_t.models.mask.type)(cfg_t)
+            smodel.load_state_dict(sd)
+            smodel = smodel.to(dev)
+            sopt = sahs_b200.FlatAdam(smodel.parameters(), lr=lr0, capturable=True, schedule=(decay, decay_steps))
+            sms, _, _ = time_train(GraphedStep(make_step(gl // world, smodel, sopt, True), warmup=3), True)
+            del smodel, sopt
             train["strong"] = {"global_rays_per_step": gl, "rays_per_gpu": gl // world, "ms_per_step": sms,
                                "value": gl / (sms / 1e3), "unit": "rays/s",
                                "collective": "one NCCL all-reduce of the flat fp32 gradient buffer per step"}

@@ -189,6 +189,10 @@ int sahs_frame_postprocess(const float* map15, int64_t num_rays, uint8_t* rgb_u8
 int sahs_weighted_sample(const int32_t* mask, const float* class_prob, int64_t num_pixels, int num_classes,
                          int num_select, uint64_t seed, int64_t* out_indices, void* workspace, size_t workspace_bytes,
                          void* stream);
+/* Same draw with seed + *seed_counter_dev as the seed (read on the device: capturable in a CUDA graph). */
+int sahs_weighted_sample_dev(const int32_t* mask, const float* class_prob, int64_t num_pixels, int num_classes,
+                             int num_select, uint64_t seed, const unsigned long long* seed_counter_dev,
+                             int64_t* out_indices, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Stage-I training loss and its gradient in two small launches (replaces ~75 elementwise/reduction launches per step).
  * ref: nerf/nerf_helpers.py:14-62 (MaskCrossEntropyLoss, MaskMSELoss), assembled as in train_stage_rays_auto.py:455-468:
@@ -211,6 +215,17 @@ int sahs_stage1_loss(const float* map_coarse, const float* map_fine, const float
  * (hyper-parameters are doubles because 1 - beta2 must be formed in double, as Python does). */
 int sahs_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
                    double beta1, double beta2, double eps, int step, float grad_scale, void* stream);
+
+/* The same step with the step count and the exponential learning-rate schedule (ref: train_stage_rays_auto.py:503-509)
+ * in DEVICE memory, so that a whole training step can be recorded in a CUDA graph and replayed without host code:
+ * hyper_dev (8 doubles): [0] lr0, [1] decay factor, [2] decay steps (cfg.scheduler.lr_decay * 1000), [3] beta1,
+ * [4] beta2, [5] eps, [6] t = the step being applied (>= 1), [7] i = schedule position, lr = lr0 * factor^(i / steps).
+ * sahs_adam_advance adds 1 to [6] and [7] (one launch, after the step); sahs_counter_add adds `inc` to a device
+ * counter (the per-step part of the ray sampler's seed, see sahs_weighted_sample_dev). */
+int sahs_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                       const double* hyper_dev, float grad_scale, void* stream);
+int sahs_adam_advance(double* hyper_dev, void* stream);
+int sahs_counter_add(unsigned long long* counter_dev, unsigned long long inc, void* stream);
 
 /* Diagnostic word written by the field kernel when a bounded mbarrier wait times out (0 = healthy):
  * out4_host[0] code (+100 dgrad kernel, +200 wgrad kernel), [1] tag, [2] block, [3] thread.  The words live in mapped

@@ -9,6 +9,28 @@ namespace {
 constexpr int kWarpsPerBlock = 8;
 constexpr int kMaxChunks = 8;  // S <= 256
 
+// exp / reciprocal of the forward kernel: ex2.approx + rcp.approx (<= 2 ulp each; composited maps move by ~1e-7, far
+// inside the 2e-5 parity bar) -- the accurate expf / IEEE division were a third of the kernel's instructions, and the
+// kernel is issue-bound, not HBM-bound (ncu r1: issue active 65 %, DRAM 43 %).
+__device__ __forceinline__ float fast_exp(float x) { return __expf(x); }
+__device__ __forceinline__ float fast_rcp(float x) { return __fdividef(1.0f, x); }
+
+// Sums of 16 per-lane values over the warp by recursive halving: 8 + 4 + 2 + 1 + 1 = 16 shuffles instead of 16 x 5.
+// On return lane L holds the warp total of v[L >> 1] (in v[0]).
+__device__ __forceinline__ void warp_sum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? v[i] : v[i + half];
+      const float keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -20,7 +42,10 @@ struct SampleColor {
 };
 
 // activation of the 15 colour/semantic channels of one sample (last_raw: pass-through of raw values)
+template <bool FAST = false>
 __device__ __forceinline__ void activate(const float (&raw)[16], bool passthrough, bool seg_softmax, SampleColor& out) {
+  auto ex = [](float x) { return FAST ? fast_exp(x) : expf(x); };
+  auto rc = [](float x) { return FAST ? fast_rcp(x) : 1.0f / x; };
   if (passthrough) {
 #pragma unroll
     for (int k = 0; k < SAHS_MAP_CH; ++k) out.c[k] = raw[k];
@@ -28,22 +53,22 @@ __device__ __forceinline__ void activate(const float (&raw)[16], bool passthroug
   }
   if (seg_softmax) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) out.c[k] = 1.0f / (1.0f + expf(-raw[k]));
+    for (int k = 0; k < 3; ++k) out.c[k] = rc(1.0f + ex(-raw[k]));
     float m = raw[3];
 #pragma unroll
     for (int k = 4; k < SAHS_MAP_CH; ++k) m = fmaxf(m, raw[k]);
     float den = 0.f;
 #pragma unroll
     for (int k = 3; k < SAHS_MAP_CH; ++k) {
-      out.c[k] = expf(raw[k] - m);
+      out.c[k] = ex(raw[k] - m);
       den += out.c[k];
     }
-    float inv = 1.0f / den;
+    float inv = rc(den);
 #pragma unroll
     for (int k = 3; k < SAHS_MAP_CH; ++k) out.c[k] *= inv;
   } else {
 #pragma unroll
-    for (int k = 0; k < SAHS_MAP_CH; ++k) out.c[k] = 1.0f / (1.0f + expf(-raw[k]));
+    for (int k = 0; k < SAHS_MAP_CH; ++k) out.c[k] = rc(1.0f + ex(-raw[k]));
   }
 }
 
@@ -62,6 +87,7 @@ struct Density {
   bool on;                       // relu active
 };
 
+template <bool FAST = false>
 __device__ __forceinline__ Density density(float raw_sigma, float noise, float z, float z_next, bool last, float rd_norm) {
   Density d;
   float pre = raw_sigma + noise;
@@ -69,13 +95,13 @@ __device__ __forceinline__ Density density(float raw_sigma, float noise, float z
   d.sigma = d.on ? pre : 0.f;
   if (last) d.sigma += 1e-6f;
   d.delta = (last ? 1e10f : (z_next - z)) * rd_norm;
-  d.alpha = 1.0f - expf(-d.sigma * d.delta);
+  d.alpha = 1.0f - (FAST ? fast_exp(-d.sigma * d.delta) : expf(-d.sigma * d.delta));
   d.t = 1.0f - d.alpha + 1e-10f;
   return d;
 }
 
 template <int CHUNKS>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rd,
                      const float* __restrict__ noise, const float* __restrict__ bg, int apply_bg, int R, int S,
                      int white, float* __restrict__ rgb_map, float* __restrict__ disp, float* __restrict__ acc,
@@ -86,6 +112,10 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
     const float dx = rd[(size_t)r * 3], dy = rd[(size_t)r * 3 + 1], dz = rd[(size_t)r * 3 + 2];
     const float rd_norm = sqrtf(dx * dx + dy * dy + dz * dz);
     const float* zr = z + (size_t)r * S;
+    // background of the last sample: fetched by 15 lanes at the start of the ray (one coalesced request) and handed to
+    // the last lane by shuffles -- as 15 dependent-latency loads by the last lane alone it stalled the warp once per ray
+    const float bgv = (bg && apply_bg && lane < SAHS_MAP_CH) ? __ldg(bg + (size_t)r * SAHS_MAP_CH + lane) : 0.f;
+    const int last_chunk = (S - 1) >> 5;
     float carry = 1.0f;  // transmittance entering this 32-sample chunk
     float accum[SAHS_MAP_CH + 2];
 #pragma unroll
@@ -102,16 +132,19 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
         float rw[16];
         load_raw(raw + ((size_t)r * S + s) * SAHS_RAW_CH, rw);
         const float raw_sigma = rw[15];
-        if (last && bg && apply_bg) {
-#pragma unroll
-          for (int k = 0; k < SAHS_MAP_CH; ++k) rw[k] = bg[(size_t)r * SAHS_MAP_CH + k];
-        }
-        activate(rw, bg != nullptr && last, bg != nullptr, col);
+        activate<true>(rw, bg != nullptr && last, bg != nullptr, col);
         zs = zr[s];
         float zn = last ? 0.f : zr[s + 1];
-        Density d = density(raw_sigma, noise ? noise[(size_t)r * S + s] : 0.f, zs, zn, last, rd_norm);
+        Density d = density<true>(raw_sigma, noise ? noise[(size_t)r * S + s] : 0.f, zs, zn, last, rd_norm);
         t = d.t;
         alpha = d.alpha;
+      }
+      if (m == last_chunk && bg && apply_bg) {   // warp-uniform: the chunk that holds the ray's last sample
+#pragma unroll
+        for (int k = 0; k < SAHS_MAP_CH; ++k) {
+          const float b = __shfl_sync(0xffffffffu, bgv, k);
+          if (last) col.c[k] = b;                 // background overwrite of the last sample (passed through raw)
+        }
       }
       // inclusive product scan of t over the warp, then shift to exclusive
       float incl = t;
@@ -133,21 +166,22 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
         accum[SAHS_MAP_CH + 1] += w;
       }
     }
+    // 15 channel sums + the depth sum by recursive halving (lane L ends up with the total of value L >> 1), acc apart
+    const float a = warp_sum(accum[SAHS_MAP_CH + 1]);
+    float v16[16];
 #pragma unroll
-    for (int k = 0; k < SAHS_MAP_CH + 2; ++k) accum[k] = warp_sum(accum[k]);
-    const float dep = accum[SAHS_MAP_CH], a = accum[SAHS_MAP_CH + 1];
-    if (lane < SAHS_MAP_CH) {
-      float v = 0.f;
-#pragma unroll
-      for (int k = 0; k < SAHS_MAP_CH; ++k)
-        if (lane == k) v = accum[k];
-      if (white) v += 1.0f - a;
-      rgb_map[(size_t)r * SAHS_MAP_CH + lane] = v;
-    }
-    if (lane == 0) {
-      depth[r] = dep;
-      acc[r] = a;
-      disp[r] = 1.0f / fmaxf(1e-10f, dep / a);
+    for (int k = 0; k < 16; ++k) v16[k] = accum[k];          // [0,15) channels, [15] = sum w z
+    warp_sum16(v16, lane);
+    const float tot = v16[0];
+    const int ch = lane >> 1;
+    if (!(lane & 1)) {
+      if (ch < SAHS_MAP_CH) {
+        rgb_map[(size_t)r * SAHS_MAP_CH + ch] = white ? tot + (1.0f - a) : tot;
+      } else {
+        depth[r] = tot;
+        acc[r] = a;
+        disp[r] = 1.0f / fmaxf(1e-10f, tot / a);
+      }
     }
   }
 }

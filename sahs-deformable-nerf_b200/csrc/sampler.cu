@@ -46,7 +46,9 @@ __device__ __forceinline__ uint32_t philox_u32(uint64_t i, uint64_t seed) {
 }
 
 __global__ void sample_key_kernel(const int32_t* __restrict__ mask, const float* __restrict__ class_prob, int64_t n,
-                                  int C, int n_select, uint64_t seed, uint32_t* __restrict__ keys, SelState* st) {
+                                  int C, int n_select, uint64_t seed, const unsigned long long* __restrict__ seed_dev,
+                                  uint32_t* __restrict__ keys, SelState* st) {
+  if (seed_dev) seed += *seed_dev;   // capturable form: the per-step part of the seed lives in device memory
   __shared__ float prob[32];
   __shared__ uint32_t pos;
   if (threadIdx.x < 32) prob[threadIdx.x] = threadIdx.x < C ? class_prob[threadIdx.x] : 0.f;
@@ -118,9 +120,9 @@ __global__ void sample_compact_kernel(const uint32_t* __restrict__ keys, int64_t
 
 }  // namespace
 
-extern "C" int sahs_weighted_sample(const int32_t* mask, const float* class_prob, int64_t num_pixels, int num_classes,
-                                    int num_select, uint64_t seed, int64_t* out_indices, void* workspace,
-                                    size_t workspace_bytes, void* stream) {
+static int weighted_sample_impl(const int32_t* mask, const float* class_prob, int64_t num_pixels, int num_classes,
+                                int num_select, uint64_t seed, const unsigned long long* seed_dev, int64_t* out_indices,
+                                void* workspace, size_t workspace_bytes, void* stream) {
   SAHS_CHECK_ARG(num_pixels >= 0 && num_select >= 0 && num_select <= num_pixels, "bad extents");
   SAHS_CHECK_ARG(num_classes >= 1 && num_classes <= 32, "1..32 classes");
   if (num_select == 0) return SAHS_OK;
@@ -134,7 +136,8 @@ extern "C" int sahs_weighted_sample(const int32_t* mask, const float* class_prob
   uint32_t* keys = (uint32_t*)((uint8_t*)workspace + kHeader);
   SAHS_CUDA(cudaMemsetAsync(state, 0, sizeof(SelState), st));
   const unsigned blocks = (unsigned)((num_pixels + 255) / 256);
-  sample_key_kernel<<<blocks, 256, 0, st>>>(mask, class_prob, num_pixels, num_classes, num_select, seed, keys, state);
+  sample_key_kernel<<<blocks, 256, 0, st>>>(mask, class_prob, num_pixels, num_classes, num_select, seed, seed_dev, keys,
+                                            state);
   SAHS_LAUNCH_CHECK();
   const unsigned hb = blocks < 592u ? blocks : 592u;
   for (int shift = 24; shift >= 0; shift -= 8) {
@@ -146,4 +149,19 @@ extern "C" int sahs_weighted_sample(const int32_t* mask, const float* class_prob
   sample_compact_kernel<<<hb, 256, 0, st>>>(keys, num_pixels, num_select, state, out_indices);
   SAHS_LAUNCH_CHECK();
   return SAHS_OK;
+}
+
+extern "C" int sahs_weighted_sample(const int32_t* mask, const float* class_prob, int64_t num_pixels, int num_classes,
+                                    int num_select, uint64_t seed, int64_t* out_indices, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  return weighted_sample_impl(mask, class_prob, num_pixels, num_classes, num_select, seed, nullptr, out_indices, workspace,
+                              workspace_bytes, stream);
+}
+
+extern "C" int sahs_weighted_sample_dev(const int32_t* mask, const float* class_prob, int64_t num_pixels, int num_classes,
+                                        int num_select, uint64_t seed, const unsigned long long* seed_counter_dev,
+                                        int64_t* out_indices, void* workspace, size_t workspace_bytes, void* stream) {
+  SAHS_CHECK_ARG(seed_counter_dev, "null seed counter");
+  return weighted_sample_impl(mask, class_prob, num_pixels, num_classes, num_select, seed, seed_counter_dev, out_indices,
+                              workspace, workspace_bytes, stream);
 }

@@ -214,14 +214,16 @@ _SEL_POSITIVE_OFFSET = 4 * (256 + 6)      # byte offset of SelState::positive (c
 
 
 def weighted_sample(mask: torch.Tensor, class_prob: torch.Tensor, num_select: int, seed: int,
-                    validate: bool = False) -> torch.Tensor:
+                    validate: bool = False, seed_counter: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Semantic-weighted ray batch: `num_select` distinct pixel indices, drawn without replacement with probability
     proportional to sum_c class_prob[c] * mask[i, c] -- the device-side replacement of
     np.random.choice(H*W, n, replace=False, p=probs) (ref: train_stage_rays_auto.py:390-420).
     mask: int32 [..., C] (one-hot in the reference); returns int64 [num_select] (a set: order unspecified).
     With fewer positive-weight pixels than `num_select`, np.random.choice raises ("Fewer non-zero entries in p than
     size"); the kernel instead fills the remainder with zero-weight pixels.  `validate=True` reads the kernel's count of
-    positive-weight pixels back (one device sync) and raises ValueError like numpy; the training loop leaves it off."""
+    positive-weight pixels back (one device sync) and raises ValueError like numpy; the training loop leaves it off.
+    `seed_counter` (int64 device scalar): the kernel uses seed + counter, read on the device -- the form a CUDA graph can
+    replay (advance the counter with `counter_add` once per step)."""
     lib = L.load()
     if not mask.is_cuda:
         raise RuntimeError("weighted_sample needs CUDA tensors (there is no CPU fallback)")
@@ -237,8 +239,15 @@ def weighted_sample(mask: torch.Tensor, class_prob: torch.Tensor, num_select: in
         ws = torch.empty(2048 + 4 * n, dtype=torch.uint8, device=m.device)
         _SAMPLER_WS[key] = ws
     out = torch.empty(num_select, dtype=torch.int64, device=m.device)
-    L.check(lib.sahs_weighted_sample(L.ptr(m), L.ptr(prob), n, C_, int(num_select), int(seed) & 0xFFFFFFFFFFFFFFFF,
-                                     L.ptr(out), L.ptr(ws), ws.numel(), L.stream_ptr(m.device)), "weighted_sample")
+    if seed_counter is not None:
+        if seed_counter.dtype != torch.int64 or not seed_counter.is_cuda or seed_counter.numel() != 1:
+            raise RuntimeError("seed_counter must be a CUDA int64 scalar tensor")
+        L.check(lib.sahs_weighted_sample_dev(L.ptr(m), L.ptr(prob), n, C_, int(num_select), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                             L.ptr(seed_counter), L.ptr(out), L.ptr(ws), ws.numel(),
+                                             L.stream_ptr(m.device)), "weighted_sample_dev")
+    else:
+        L.check(lib.sahs_weighted_sample(L.ptr(m), L.ptr(prob), n, C_, int(num_select), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                         L.ptr(out), L.ptr(ws), ws.numel(), L.stream_ptr(m.device)), "weighted_sample")
     if validate:
         positive = int(ws[_SEL_POSITIVE_OFFSET:_SEL_POSITIVE_OFFSET + 4].view(torch.int32).item())
         if positive < num_select:
@@ -251,3 +260,9 @@ def field_status():
     out = (C.c_int * 4)()
     L.check(lib.sahs_field_status(out), "field_status")
     return list(out)
+
+
+def counter_add(counter: torch.Tensor, inc: int = 1) -> None:
+    """counter (CUDA int64 scalar) += inc, as one tiny launch on the current stream (capturable)."""
+    lib = L.load()
+    L.check(lib.sahs_counter_add(L.ptr(counter), int(inc), L.stream_ptr(counter.device)), "counter_add")

@@ -27,7 +27,14 @@ def exp_lr(lr0: float, decay_factor: float, decay_steps: float, iteration: int) 
 
 
 class FlatAdam(torch.optim.Optimizer):
-    def __init__(self, params: Iterable, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, group=None):
+    """`capturable=True`: the step count and the exponential learning-rate schedule (`schedule=(decay_factor,
+    decay_steps)`, ref: train_stage_rays_auto.py:503-509; None = constant lr) live in device memory, `step()` is
+    `sahs_adam_step_dev` + `sahs_adam_advance` with no host-side state, so a whole training step -- sampler, forward,
+    loss, backward, all-reduce, this step -- can be recorded in a CUDA graph (sahs_b200.train.GraphedStep).  In this mode
+    `param_groups[..]["lr"]` is the INITIAL rate; the running one is `current_lr()` (reads the device)."""
+
+    def __init__(self, params: Iterable, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, group=None,
+                 capturable: bool = False, schedule=None):
         if lr < 0 or eps < 0 or not (0 <= betas[0] < 1) or not (0 <= betas[1] < 1):
             raise ValueError("bad Adam hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps))
@@ -53,6 +60,14 @@ class FlatAdam(torch.optim.Optimizer):
         self.flat_exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         self._steps = 0
         self._step_t = torch.tensor(0.0)                     # one counter object shared by every parameter's state
+        self._capturable = bool(capturable)
+        self._hyper = None
+        if capturable:
+            if len(self.param_groups) != 1:
+                raise ValueError("capturable FlatAdam supports one parameter group")
+            factor, steps = schedule if schedule is not None else (1.0, 1.0)
+            self._hyper = torch.tensor([lr, float(factor), float(steps), betas[0], betas[1], eps, 1.0, 0.0],
+                                       dtype=torch.float64, device=dev)
         self._grad_views = []
         with torch.no_grad():
             for p, off in zip(plist, offs):
@@ -121,8 +136,16 @@ class FlatAdam(torch.optim.Optimizer):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self._group) > 1:
             dist.all_reduce(self.flat_grad, group=self._group)
             scale = 1.0 / dist.get_world_size(self._group)
-        self._steps += 1
         stream = L.stream_ptr(self.flat_param.device)
+        if self._capturable:
+            if partial:
+                raise RuntimeError("capturable FlatAdam needs a gradient for every parameter")
+            L.check(lib.sahs_adam_step_dev(self.flat_param.data_ptr(), self.flat_grad.data_ptr(),
+                                           self.flat_exp_avg.data_ptr(), self.flat_exp_avg_sq.data_ptr(), self._n,
+                                           self._hyper.data_ptr(), scale, stream), "adam_step_dev")
+            L.check(lib.sahs_adam_advance(self._hyper.data_ptr(), stream), "adam_advance")
+            return loss
+        self._steps += 1
         for gi, b, e in (self._live_runs() if partial else self._segments):
             g = self.param_groups[gi]
             if e <= b:
@@ -151,6 +174,16 @@ class FlatAdam(torch.optim.Optimizer):
             if cur is not None:
                 runs.append(tuple(cur))
         return runs
+
+    def current_lr(self) -> float:
+        """Learning rate of the next step (capturable mode: computed from the device-side schedule; one sync)."""
+        if not self._capturable:
+            return float(self.param_groups[0]["lr"])
+        h = self._hyper.cpu().tolist()
+        return h[0] * (h[1] ** (h[7] / h[2]))
+
+    def steps_done(self) -> int:
+        return int(self._hyper[6].item()) - 1 if self._capturable else self._steps
 
     def averaged_gradients(self) -> Optional[torch.Tensor]:
         """The flat gradient buffer of the last step (summed over ranks; multiply by 1 / world size for the mean)."""

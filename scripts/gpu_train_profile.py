@@ -10,7 +10,7 @@ import sahs_b200
 DEV = "cuda:0"
 cfg = FX.load_cfg("audio/person_2_auto")
 spec = O.spec_from_cfg(cfg)
-sd = FX.make_state_dict(spec, seed=42, dense=True)
+sd = FX.make_state_dict(spec, seed=42, dense=True, trained_like=os.environ.get("SAHS_FIXTURE", "trained") != "dense")
 H = W = 512
 fr = FX.make_frame_inputs(spec, H, W, seed=0)
 model = sahs_b200.AudioFaceModel(cfg); model.load_state_dict(sd); model = model.to(DEV)

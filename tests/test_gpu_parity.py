@@ -226,6 +226,33 @@ def test_composite_backward_vs_oracle_autograd(sahs, name):
     assert maxabs(raw_g.grad, ref) <= 2e-4 * float(ref.abs().max())
 
 
+@pytest.mark.parametrize("S", [1, 7, 40, 96, 200])
+def test_composite_odd_sample_counts_vs_oracle(sahs, S):
+    """Sample counts that are not a power-of-two number of 32-lane chunks (the kernel rounds the chunk count up to
+    1 / 2 / 4 / 8: the last sample -- the background one -- then sits in an inner chunk), forward and backward."""
+    from sahs_b200 import ops
+    gen = torch.Generator().manual_seed(100 + S)
+    R = 37
+    raw = torch.randn(R, S, 16, generator=gen) * 2.0
+    raw[..., -1] = torch.randn(R, S, generator=gen) * 20.0
+    z, _ = torch.sort(torch.rand(R, S, generator=gen) * 0.6 + 0.48, dim=-1)
+    rd = torch.randn(R, 3, generator=gen) * 0.2 + torch.tensor([0, 0, -1.0])
+    bg = torch.cat((torch.rand(R, 3, generator=gen), torch.ones(R, 1), torch.zeros(R, 11)), -1)
+    rin = raw.clone().requires_grad_(True)
+    rr = torch.cat((rin[:, :-1], torch.cat((bg, rin[:, -1, -1:]), -1)[:, None]), 1)
+    ref = O.composite(rr, z, rd, None, False, bg)
+    out = ops.composite_fwd(raw.to(DEV), z.to(DEV), rd.to(DEV), None, bg.to(DEV), True, False)
+    for n, o, r_ in zip(["rgb", "disp", "acc", "weights", "depth"], out, ref):
+        if n == "disp":
+            assert float(((o.cpu() - r_.detach()).abs() / r_.detach().abs()).max()) <= 1e-4
+        else:
+            assert maxabs(o, r_) <= 2e-5, (S, n, maxabs(o, r_))
+    gs = [torch.randn(t.shape, generator=gen) for t in ref]
+    sum((a * b).sum() for a, b in zip(ref, gs)).backward()
+    d_raw = ops.composite_bwd(raw.to(DEV), z.to(DEV), rd.to(DEV), None, bg.to(DEV), True, False, *[t.to(DEV) for t in gs])
+    assert maxabs(d_raw, rin.grad) <= 2e-4 * float(rin.grad.abs().max())
+
+
 def test_composite_linearity_full_frame(sahs):
     """262,144 rays x 128 samples: acc == 1 with a background prior (last alpha is 1), rgb_map is linear in the
     background colour, weights are non-negative and sum to acc."""
