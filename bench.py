@@ -323,6 +323,7 @@ def main():
         dev_frames.append(dict(pose=pose, driving=fr["driving"].to(dev), ro=ro, rd=rd, mask=fr["mask"].to(dev)))
 
     stage_events = []
+    graphed_steps = []                            # GraphedStep objects (reset before teardown, see the end of main)
 
     def stage_hook(name, fn):                     # CUDA events on the launching (current) stream around every stage
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -514,6 +515,7 @@ def main():
         gmodel = gmodel.to(dev)
         gopt = sahs_b200.FlatAdam(gmodel.parameters(), lr=lr0, capturable=True, schedule=(decay, decay_steps))
         gstep = GraphedStep(make_step(nrays, gmodel, gopt, True), warmup=3)
+        graphed_steps.append(gstep)
         tms_step, last, _ = time_train(gstep, True)
         tmodel = gmodel                                              # (tape layout below)
         pts_step = nrays * (2 * nc + nf)
@@ -545,7 +547,9 @@ def main():
             smodel.load_state_dict(sd)
             smodel = smodel.to(dev)
             sopt = sahs_b200.FlatAdam(smodel.parameters(), lr=lr0, capturable=True, schedule=(decay, decay_steps))
-            sms, _, _ = time_train(GraphedStep(make_step(gl // world, smodel, sopt, True), warmup=3), True)
+            sstep = GraphedStep(make_step(gl // world, smodel, sopt, True), warmup=3)
+            graphed_steps.append(sstep)
+            sms, _, _ = time_train(sstep, True)
             del smodel, sopt
             train["strong"] = {"global_rays_per_step": gl, "rays_per_gpu": gl // world, "ms_per_step": sms,
                                "value": gl / (sms / 1e3), "unit": "rays/s",
@@ -711,8 +715,21 @@ def main():
             "clocks": clocks, "train": train, "strong": strong, "clip": clip, "config4": config4,
         }
         _emit(json.dumps(line))
+    # Teardown.  The training legs recorded CUDA graphs that contain NCCL all-reduces; destroying the process group (or
+    # letting the interpreter tear CUDA down) while such graphs are alive can block forever (seen at N = 8: the JSON line
+    # was out, then the job sat in teardown until the box's time limit).  So: drop the graphs, drain the device, meet
+    # the other ranks once more, and leave without running NCCL's / CUDA's destructors.
+    threading.Timer(60.0, lambda: os._exit(0)).start()          # the JSON line is out: never sit in teardown
+    for g in graphed_steps:
+        g.graph.reset()
+    graphed_steps.clear()
+    torch.cuda.synchronize()
     if world > 1:
-        dist.destroy_process_group()
+        dist.barrier()
+        torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":
