@@ -180,6 +180,13 @@ int sahs_sample_pdf(const float* bins, const float* weights, const float* u, int
 int sahs_frame_postprocess(const float* map15, int64_t num_rays, uint8_t* rgb_u8, uint8_t* label_u8,
                            uint8_t* seg_color_u8, void* stream);
 
+/* Depth map -> normal map, `torch_normal_map` of the eval script (ref: eval_stage_rays.py:116-151).  depth [size, size]
+ * (the reference only broadcasts for square maps), intrinsics [fx, fy, cx, cy] with cx, cy relative; weights [size, size]
+ * = the fine pass's background weight for the clean-up step (NULL: `clean=False` / no weights); central_difference
+ * != 0 uses a stride of 2.  normals_out: [size - k, size - k, 3] fp32 in [0, 255], k = 1 or 2. */
+int sahs_normal_map(const float* depth, int size, float fx, float fy, float cx_rel, float cy_rel, const float* weights,
+                    int central_difference, float* normals_out, void* stream);
+
 /* Semantic-weighted ray batch on the device (replaces the host-side np.random.choice(H*W, n, replace=False, p=probs)
  * of train_stage_rays_auto.py:390-420): weight_i = sum_c class_prob[c] * mask[i, c] (mask: int32 [num_pixels,
  * num_classes], one-hot in the reference), num_select distinct pixel indices drawn without replacement with

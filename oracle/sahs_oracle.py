@@ -499,6 +499,27 @@ def frame_postprocess(rgb_map: torch.Tensor):
     return rgb, label.to(torch.uint8), pal[label]
 
 
+def torch_normal_map(depthmap: torch.Tensor, focal, weights: Optional[torch.Tensor] = None, clean: bool = True,
+                     central_difference: bool = False) -> torch.Tensor:
+    """Depth map -> normal map, ref: eval_stage_rays.py:116-151 (square maps, as the reference's broadcasting requires)."""
+    n = depthmap.shape[0]
+    cx, cy, fx, fy = focal[2] * n, focal[3] * n, focal[0], focal[1]
+    cols = torch.arange(n).view(1, n).expand(n, n)
+    rows = torch.arange(n).view(n, 1).expand(n, n)
+    points = torch.stack((((cols - cx) * depthmap) / fx, -((rows - cy) * depthmap) / fy, depthmap), dim=-1)
+    k = 2 if central_difference else 1
+    dx = points[k:, :, :] - points[:-k, :, :]
+    dy = points[:, k:, :] - points[:, :-k, :]
+    normals = torch.cross(dy[:-k, :, :], dx[:, :-k, :], dim=2)
+    normals = normals / torch.sqrt(torch.sum(normals * normals, 2, keepdim=True))
+    normals = normals * 0.5 + 0.5
+    if clean and weights is not None:
+        mask = weights[:-k, :-k, None].expand(-1, -1, 3)
+        normals = torch.where(mask > 0.22, torch.ones_like(normals), normals)
+        normals = (1 - mask) * normals + mask * torch.ones_like(normals)
+    return normals * 255
+
+
 def weighted_sample_probs(mask: torch.Tensor, class_prob: torch.Tensor) -> np.ndarray:
     """probs of the semantic-weighted ray sampler (ref: train_stage_rays_auto.py:390-394):
     sum_c sample_prob[c] * mask[..., c], normalised."""

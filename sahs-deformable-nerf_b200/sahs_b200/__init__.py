@@ -29,3 +29,12 @@ def weighted_sample(mask, class_prob, num_select, seed):
     import torch
     return torch.ops.sahs_b200.weighted_sample(mask, class_prob, int(num_select), int(seed) & 0x7FFFFFFFFFFFFFFF)
 from .optim import FlatAdam, exp_lr  # noqa: F401,E402
+
+
+
+def torch_normal_map(depthmap, focal, weights=None, clean=True, central_difference=False):
+    """ref: eval_stage_rays.py:116-151 (same signature and result: [N-k, N-k, 3] fp32 in [0, 255])."""
+    import torch
+    fx, fy, cx, cy = [float(v) for v in focal]
+    w = weights if (clean and weights is not None) else None
+    return torch.ops.sahs_b200.normal_map(depthmap, fx, fy, cx, cy, w, bool(central_difference))

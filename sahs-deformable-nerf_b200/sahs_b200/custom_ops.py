@@ -11,7 +11,7 @@ NotImplementedError from the dispatcher -- the product path has no fallback.
   stage (2)  sahs_b200::field_fwd, ::field_fwd_train, ::field_bwd
   stage (3)  sahs_b200::composite_fwd, ::composite_bwd
   stage (4)  sahs_b200::sample_pdf, ::sample_pdf_merge
-  next rows  sahs_b200::frame_postprocess, ::weighted_sample
+  next rows  sahs_b200::frame_postprocess, ::normal_map, ::weighted_sample
 
 The reference-named Python functions (train_utils / nerf_helpers / volume_rendering_utils / models) call these ops;
 autograd is wired by torch.autograd.Function classes on top (volume_rendering_utils._CompositeFn, train.FieldTrainFn).
@@ -149,5 +149,10 @@ _define("weighted_sample(Tensor mask, Tensor class_prob, int num_select, int see
         lambda mask, prob, n, seed: ops.weighted_sample(mask, prob, n, seed),
         lambda mask, prob, n, seed: _e((n,), mask, torch.int64))
 
+_define("normal_map(Tensor depthmap, float fx, float fy, float cx, float cy, Tensor? weights, bool central_difference) -> Tensor",
+        lambda d, fx, fy, cx, cy, w, central: ops.normal_map(d, (fx, fy, cx, cy), w, central),
+        lambda d, fx, fy, cx, cy, w, central: _e((d.shape[0] - (2 if central else 1), d.shape[1] - (2 if central else 1), 3), d))
+
 OP_NAMES = ("get_ray_bundle", "coarse_z", "positional_encoding", "field_fwd", "field_fwd_train", "field_bwd",
-            "composite_fwd", "composite_bwd", "sample_pdf_merge", "sample_pdf", "frame_postprocess", "weighted_sample")
+            "composite_fwd", "composite_bwd", "sample_pdf_merge", "sample_pdf", "frame_postprocess", "weighted_sample",
+            "normal_map")

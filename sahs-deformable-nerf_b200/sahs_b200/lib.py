@@ -32,7 +32,7 @@ EXPORTS = (
     "sahs_field_fwd", "sahs_composite_fwd", "sahs_composite_bwd", "sahs_sample_pdf_merge", "sahs_sample_pdf",
     "sahs_field_status", "sahs_debug_plan", "sahs_train_layout", "sahs_pack_params_train", "sahs_pack_params_bwd",
     "sahs_field_fwd_train", "sahs_field_bwd", "sahs_field_wgrad", "sahs_frame_postprocess", "sahs_weighted_sample", "sahs_stage1_loss",
-    "sahs_adam_step", "sahs_adam_step_dev", "sahs_adam_advance", "sahs_counter_add", "sahs_weighted_sample_dev",
+    "sahs_adam_step", "sahs_adam_step_dev", "sahs_adam_advance", "sahs_counter_add", "sahs_weighted_sample_dev", "sahs_normal_map",
 )
 
 
@@ -79,6 +79,7 @@ def load() -> C.CDLL:
         "sahs_adam_advance": (C.c_int, [vp, vp]),
         "sahs_counter_add": (C.c_int, [vp, C.c_uint64, vp]),
         "sahs_weighted_sample_dev": (C.c_int, [vp, vp, i64, i32, i32, C.c_uint64, vp, vp, vp, C.c_size_t, vp]),
+        "sahs_normal_map": (C.c_int, [vp, i32, f32, f32, f32, f32, vp, i32, vp, vp]),
         "sahs_stage1_loss": (C.c_int, [vp, vp, vp, vp, i32, i32, C.c_float, C.c_float, i32, i32, vp, vp, vp, vp, vp, vp]),
         "sahs_field_status": (C.c_int, [C.POINTER(C.c_int)]),
     }

@@ -266,3 +266,22 @@ def counter_add(counter: torch.Tensor, inc: int = 1) -> None:
     """counter (CUDA int64 scalar) += inc, as one tiny launch on the current stream (capturable)."""
     lib = L.load()
     L.check(lib.sahs_counter_add(L.ptr(counter), int(inc), L.stream_ptr(counter.device)), "counter_add")
+
+
+def normal_map(depthmap: torch.Tensor, focal, weights: Optional[torch.Tensor] = None, central_difference: bool = False):
+    """`torch_normal_map` of the eval script (ref: eval_stage_rays.py:116-151): [N,N] depth -> [N-k,N-k,3] fp32 normals
+    in [0,255] (k = 2 with central differences, else 1); `weights` = the fine pass's background weight for the clean-up."""
+    lib = L.load()
+    d = L.f32c(depthmap)
+    if d.dim() != 2 or d.shape[0] != d.shape[1]:
+        raise RuntimeError("torch_normal_map needs a square [N, N] depth map (the reference's meshgrid only broadcasts then)")
+    n = d.shape[0]
+    k = 2 if central_difference else 1
+    w = L.f32c(weights) if weights is not None else None
+    if w is not None and w.shape != d.shape:
+        raise RuntimeError("weights must have the depth map's shape")
+    fx, fy, cx, cy = [float(v) for v in focal]
+    out = torch.empty(n - k, n - k, 3, dtype=torch.float32, device=d.device)
+    L.check(lib.sahs_normal_map(L.ptr(d), n, fx, fy, cx, cy, L.ptr(w), int(bool(central_difference)), L.ptr(out),
+                                L.stream_ptr(d.device)), "normal_map")
+    return out

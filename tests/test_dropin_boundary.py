@@ -119,3 +119,32 @@ def test_oracle_ray_bundle_by_mask_matches_reference():
     ro, rd = nerf.get_ray_bundle_by_mask(16, 16, intr, pose, mask)
     ro_o, rd_o = O.get_ray_bundle_by_mask(16, 16, list(intr), pose, mask)
     assert torch.equal(ro, ro_o) and torch.equal(rd, rd_o)
+
+
+def _reference_script_function(script, name):
+    """A function of one of the reference's CLI scripts, which cannot be imported here (matplotlib / imageio at module
+    level): its source segment is compiled on its own, with the names it needs taken from the reference's `nerf` package."""
+    import ast
+    nerf = _ref()
+    path = os.path.join(RH.REF_ROOT, script)
+    src = open(path).read()
+    tree = ast.parse(src)
+    node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {"torch": torch, "np": np, "meshgrid_xy": nerf.meshgrid_xy}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return ns[name]
+
+
+def test_oracle_normal_map_matches_reference():
+    ref_fn = _reference_script_function("eval_stage_rays.py", "torch_normal_map")
+    gen = torch.Generator().manual_seed(6)
+    n = 24
+    depth = 0.5 + 0.2 * torch.rand(n, n, generator=gen)
+    weights = torch.rand(n, n, generator=gen) * 0.5
+    focal = np.array([1200.0 * n / 512, 1150.0 * n / 512, 0.5, 0.48])
+    for central in (False, True):
+        for w in (None, weights):
+            want = ref_fn(depth.clone(), focal, weights=None if w is None else w.clone(), clean=True, central_difference=central)
+            got = O.torch_normal_map(depth, list(focal), w, True, central)
+            assert got.shape == want.shape
+            assert float((got - want).abs().max()) <= 2e-3, (central, w is None)      # values in [0, 255]

@@ -637,6 +637,25 @@ def test_trainable_background_gets_its_gradient(sahs):
     assert maxabs(bg_h.grad, o3[3][:, -1:].expand(-1, 15)) == 0.0
 
 
+@pytest.mark.parametrize("central", [False, True])
+def test_normal_map_vs_oracle(sahs, central):
+    """torch_normal_map (ref: eval_stage_rays.py:116-151) on a rendered-looking depth map with and without the
+    background-weight clean-up; the oracle is pinned against the reference's function on CPU."""
+    gen = torch.Generator().manual_seed(8)
+    n = 512
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, n), torch.linspace(-1, 1, n), indexing="ij")
+    depth = 0.6 + 0.1 * torch.sin(3 * xx) * torch.cos(2 * yy) + 0.002 * torch.rand(n, n, generator=gen)
+    weights = torch.rand(n, n, generator=gen) * 0.5
+    focal = [1200.0, 1200.0, 0.5, 0.5]
+    for w in (None, weights):
+        want = O.torch_normal_map(depth, focal, w, True, central)
+        got = sahs.torch_normal_map(depth.to(DEV), np.array(focal), None if w is None else w.to(DEV), clean=True,
+                                    central_difference=central)
+        assert got.shape == want.shape and got.dtype == torch.float32
+        assert maxabs(got, want) <= 0.05, maxabs(got, want)          # values in [0, 255]; fp32 rounding of the normalisation
+    assert sahs.torch_normal_map(depth.to(DEV), focal, weights.to(DEV), clean=False).shape == (n - 1, n - 1, 3)
+
+
 def test_weighted_sampler_validate_raises_like_numpy(sahs):
     from sahs_b200 import ops
     mask = torch.eye(20, dtype=torch.int32, device=DEV)
