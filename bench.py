@@ -514,6 +514,7 @@ def main():
         gmodel.load_state_dict(sd)
         gmodel = gmodel.to(dev)
         gopt = sahs_b200.FlatAdam(gmodel.parameters(), lr=lr0, capturable=True, schedule=(decay, decay_steps))
+        TU.RNG_COUNTER = seed_ctr                                   # in-kernel draws: fresh on every replay
         gstep = GraphedStep(make_step(nrays, gmodel, gopt, True), warmup=3)
         graphed_steps.append(gstep)
         tms_step, last, _ = time_train(gstep, True)

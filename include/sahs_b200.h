@@ -142,6 +142,25 @@ int sahs_field_wgrad(const sahs_model_spec* spec, int level, float* const* grads
                      const void* tape_d, int num_points, void* units_workspace, size_t workspace_bytes,
                      unsigned long long* upload_token, void* stream);
 
+/* ---- in-kernel random draws (stochastic mode: perturb, radiance_field_noise_std, random u) ------------------------- */
+/* Philox-4x32-10 keyed by `seed` (+ *counter_dev when given: read on the device, so a CUDA graph replays fresh draws),
+ * counter = (element index, stream): element (ray, sample) of draw `stream` always gets the same value, whichever kernel
+ * asks -- the compositing forward and backward regenerate identical noise instead of storing it.  Streams used by
+ * predict_and_render_radiance: 0 t_rand (ref: nerf/train_utils.py:112), 1 coarse noise, 2 u (nerf_helpers.py:473),
+ * 3 fine noise (volume_rendering_utils.py:47).  Uniforms are k * 2^-24, k in [0, 2^24) like torch.rand; normals are
+ * Box-Muller over two 24-bit uniforms.  The reference draws from torch's generator, so parity in this mode is in
+ * distribution; sahs_rng_fill materialises the same values for tests. */
+typedef struct sahs_rng {
+  unsigned long long seed;
+  const unsigned long long* counter_dev; /* may be NULL */
+  unsigned int stream;
+  unsigned int reserved;
+} sahs_rng;
+int sahs_rng_fill(float* out, int64_t n, const sahs_rng* rng, int normal, float scale, void* stream);
+/* sahs_coarse_z with t_rand drawn in the kernel (rng != NULL: perturbed depths). */
+int sahs_coarse_z_rng(int num_rays, int num_samples, float near_, float far_, int lindisp, const float* t_vals,
+                      const sahs_rng* rng, float* z_out, void* stream);
+
 /* ---- (3) alpha compositing ---------------------------------------------------------------------- */
 /* volume_render_radiance_field, ref: nerf/volume_rendering_utils.py:7-78 (+ cumprod_exclusive,
  * nerf/nerf_helpers.py:99-120) fused with the background overwrite raw[:, -1, :-1] = background_prior
@@ -157,6 +176,16 @@ int sahs_composite_bwd(const float* raw, const float* z, const float* rd, const 
                        int bg_ch, int apply_bg_overwrite, int num_rays, int num_samples, int white_background,
                        const float* d_rgb_map, const float* d_disp, const float* d_acc, const float* d_weights,
                        const float* d_depth, float* d_raw, void* stream);
+/* The same two kernels with the density noise drawn in the kernel: noise = noise_std * N(0,1) from `rng` (identical in
+ * forward and backward); no [R,S] noise tensor exists. */
+int sahs_composite_fwd_rng(const float* raw, const float* z, const float* rd, float noise_std, const sahs_rng* rng,
+                           const float* bg, int bg_ch, int apply_bg_overwrite, int num_rays, int num_samples,
+                           int white_background, float* rgb_map, float* disp, float* acc, float* weights, float* depth,
+                           void* stream);
+int sahs_composite_bwd_rng(const float* raw, const float* z, const float* rd, float noise_std, const sahs_rng* rng,
+                           const float* bg, int bg_ch, int apply_bg_overwrite, int num_rays, int num_samples,
+                           int white_background, const float* d_rgb_map, const float* d_disp, const float* d_acc,
+                           const float* d_weights, const float* d_depth, float* d_raw, void* stream);
 
 /* ---- (4) hierarchical importance resampling + merge ---------------------------------------------- */
 /* sample_pdf_2 on bins = mid(z), weights[...,1:-1] (ref: nerf/nerf_helpers.py:454-497, call site
@@ -167,6 +196,9 @@ int sahs_composite_bwd(const float* raw, const float* z, const float* rd, const 
 int sahs_sample_pdf_merge(const float* z, const float* weights, const float* u, int u_per_ray, int num_rays,
                           int num_samples, int num_fine, float* z_samples, float* z_merged, int64_t* inds,
                           void* stream);
+/* sahs_sample_pdf_merge with u ~ U[0,1) drawn in the kernel (det = False, ref: nerf/nerf_helpers.py:473). */
+int sahs_sample_pdf_merge_rng(const float* z, const float* weights, const sahs_rng* rng, int num_rays, int num_samples,
+                              int num_fine, float* z_samples, float* z_merged, int64_t* inds, void* stream);
 
 /* sample_pdf_2(bins [R,nb], weights [R,nb-1], num_fine) alone, the reference's public helper signature
  * (ref: nerf/nerf_helpers.py:454-497); same arithmetic as above without the merge. */

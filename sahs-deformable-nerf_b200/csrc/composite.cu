@@ -81,6 +81,12 @@ __device__ __forceinline__ void load_raw(const float* __restrict__ p, float (&ra
   }
 }
 
+// density noise of sample `idx`: the caller's tensor, or noise_std * N(0,1) drawn here (same value in fwd and bwd)
+__device__ __forceinline__ float sample_noise(const float* __restrict__ noise, float noise_std, const RngArg& rng, size_t idx) {
+  if (noise) return noise[idx];
+  return rng.on ? noise_std * rng_normal(rng, (uint64_t)idx) : 0.f;
+}
+
 // per-sample density terms shared by forward and backward
 struct Density {
   float sigma, delta, alpha, t;  // t = 1 - alpha + 1e-10
@@ -103,7 +109,8 @@ __device__ __forceinline__ Density density(float raw_sigma, float noise, float z
 template <int CHUNKS>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4)
 composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rd,
-                     const float* __restrict__ noise, const float* __restrict__ bg, int apply_bg, int R, int S,
+                     const float* __restrict__ noise, float noise_std, RngArg rng, const float* __restrict__ bg,
+                     int apply_bg, int R, int S,
                      int white, float* __restrict__ rgb_map, float* __restrict__ disp, float* __restrict__ acc,
                      float* __restrict__ weights, float* __restrict__ depth) {
   const int lane = threadIdx.x & 31;
@@ -135,7 +142,7 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
         activate<true>(rw, bg != nullptr && last, bg != nullptr, col);
         zs = zr[s];
         float zn = last ? 0.f : zr[s + 1];
-        Density d = density<true>(raw_sigma, noise ? noise[(size_t)r * S + s] : 0.f, zs, zn, last, rd_norm);
+        Density d = density<true>(raw_sigma, sample_noise(noise, noise_std, rng, (size_t)r * S + s), zs, zn, last, rd_norm);
         t = d.t;
         alpha = d.alpha;
       }
@@ -193,7 +200,8 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
 template <int CHUNKS>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rd,
-                     const float* __restrict__ noise, const float* __restrict__ bg, int apply_bg, int R, int S,
+                     const float* __restrict__ noise, float noise_std, RngArg rng, const float* __restrict__ bg,
+                     int apply_bg, int R, int S,
                      int white, const float* __restrict__ d_rgb_map, const float* __restrict__ d_disp,
                      const float* __restrict__ d_acc, const float* __restrict__ d_weights,
                      const float* __restrict__ d_depth, float* __restrict__ d_raw) {
@@ -233,7 +241,7 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
         for (int k = 0; k < SAHS_MAP_CH; ++k) gcol_[m] += g_rgb[k] * col.c[k];
         zs_[m] = zr[s];
         float zn = last ? 0.f : zr[s + 1];
-        Density d = density(raw_sigma, noise ? noise[(size_t)r * S + s] : 0.f, zs_[m], zn, last, rd_norm);
+        Density d = density(raw_sigma, sample_noise(noise, noise_std, rng, (size_t)r * S + s), zs_[m], zn, last, rd_norm);
         t = d.t; alpha = d.alpha;
         dadsig_[m] = d.on ? d.delta * expf(-d.sigma * d.delta) : 0.f;
       }
@@ -334,10 +342,10 @@ int pick_grid(int R) {
     else { constexpr int C = 8; BODY; }                    \
   } while (0)
 
-extern "C" int sahs_composite_fwd(const float* raw, const float* z, const float* rd, const float* noise,
-                                  const float* bg, int bg_ch, int apply_bg_overwrite, int num_rays, int num_samples,
-                                  int white_background, float* rgb_map, float* disp, float* acc, float* weights,
-                                  float* depth, void* stream) {
+static int composite_fwd_impl(const float* raw, const float* z, const float* rd, const float* noise, float noise_std,
+                              const sahs_rng* rng, const float* bg, int bg_ch, int apply_bg_overwrite, int num_rays,
+                              int num_samples, int white_background, float* rgb_map, float* disp, float* acc,
+                              float* weights, float* depth, void* stream) {
   if (num_rays == 0) return SAHS_OK;
   SAHS_CHECK_ARG(raw && z && rd && rgb_map && disp && acc && weights && depth, "null pointer");
   SAHS_CHECK_ARG(num_samples >= 1 && num_samples <= 32 * kMaxChunks, "num_samples must be in [1,256]");
@@ -345,8 +353,41 @@ extern "C" int sahs_composite_fwd(const float* raw, const float* z, const float*
   if (num_rays == 0) return SAHS_OK;
   int grid = pick_grid(num_rays);
   DISPATCH_CHUNKS(num_samples, (composite_fwd_kernel<C><<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-                                   raw, z, rd, noise, bg, apply_bg_overwrite, num_rays, num_samples, white_background,
-                                   rgb_map, disp, acc, weights, depth)));
+                                   raw, z, rd, noise, noise_std, rng_arg(rng), bg, apply_bg_overwrite, num_rays, num_samples,
+                                   white_background, rgb_map, disp, acc, weights, depth)));
+  SAHS_LAUNCH_CHECK();
+  return SAHS_OK;
+}
+
+extern "C" int sahs_composite_fwd(const float* raw, const float* z, const float* rd, const float* noise,
+                                  const float* bg, int bg_ch, int apply_bg_overwrite, int num_rays, int num_samples,
+                                  int white_background, float* rgb_map, float* disp, float* acc, float* weights,
+                                  float* depth, void* stream) {
+  return composite_fwd_impl(raw, z, rd, noise, 0.f, nullptr, bg, bg_ch, apply_bg_overwrite, num_rays, num_samples,
+                            white_background, rgb_map, disp, acc, weights, depth, stream);
+}
+
+extern "C" int sahs_composite_fwd_rng(const float* raw, const float* z, const float* rd, float noise_std,
+                                      const sahs_rng* rng, const float* bg, int bg_ch, int apply_bg_overwrite,
+                                      int num_rays, int num_samples, int white_background, float* rgb_map, float* disp,
+                                      float* acc, float* weights, float* depth, void* stream) {
+  return composite_fwd_impl(raw, z, rd, nullptr, noise_std, noise_std > 0.f ? rng : nullptr, bg, bg_ch, apply_bg_overwrite,
+                            num_rays, num_samples, white_background, rgb_map, disp, acc, weights, depth, stream);
+}
+
+static int composite_bwd_impl(const float* raw, const float* z, const float* rd, const float* noise, float noise_std,
+                              const sahs_rng* rng, const float* bg, int bg_ch, int apply_bg_overwrite, int num_rays,
+                              int num_samples, int white_background, const float* d_rgb_map, const float* d_disp,
+                              const float* d_acc, const float* d_weights, const float* d_depth, float* d_raw,
+                              void* stream) {
+  if (num_rays == 0) return SAHS_OK;
+  SAHS_CHECK_ARG(raw && z && rd && d_raw, "null pointer");
+  SAHS_CHECK_ARG(num_samples >= 1 && num_samples <= 32 * kMaxChunks, "num_samples must be in [1,256]");
+  SAHS_CHECK_ARG(bg == nullptr || bg_ch == SAHS_MAP_CH, "background_prior must have 15 channels");
+  int grid = pick_grid(num_rays);
+  DISPATCH_CHUNKS(num_samples, (composite_bwd_kernel<C><<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+                                   raw, z, rd, noise, noise_std, rng_arg(rng), bg, apply_bg_overwrite, num_rays, num_samples,
+                                   white_background, d_rgb_map, d_disp, d_acc, d_weights, d_depth, d_raw)));
   SAHS_LAUNCH_CHECK();
   return SAHS_OK;
 }
@@ -356,15 +397,16 @@ extern "C" int sahs_composite_bwd(const float* raw, const float* z, const float*
                                   int white_background, const float* d_rgb_map, const float* d_disp,
                                   const float* d_acc, const float* d_weights, const float* d_depth, float* d_raw,
                                   void* stream) {
-  if (num_rays == 0) return SAHS_OK;
-  SAHS_CHECK_ARG(raw && z && rd && d_raw, "null pointer");
-  SAHS_CHECK_ARG(num_samples >= 1 && num_samples <= 32 * kMaxChunks, "num_samples must be in [1,256]");
-  SAHS_CHECK_ARG(bg == nullptr || bg_ch == SAHS_MAP_CH, "background_prior must have 15 channels");
-  if (num_rays == 0) return SAHS_OK;
-  int grid = pick_grid(num_rays);
-  DISPATCH_CHUNKS(num_samples, (composite_bwd_kernel<C><<<grid, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-                                   raw, z, rd, noise, bg, apply_bg_overwrite, num_rays, num_samples, white_background,
-                                   d_rgb_map, d_disp, d_acc, d_weights, d_depth, d_raw)));
-  SAHS_LAUNCH_CHECK();
-  return SAHS_OK;
+  return composite_bwd_impl(raw, z, rd, noise, 0.f, nullptr, bg, bg_ch, apply_bg_overwrite, num_rays, num_samples,
+                            white_background, d_rgb_map, d_disp, d_acc, d_weights, d_depth, d_raw, stream);
+}
+
+extern "C" int sahs_composite_bwd_rng(const float* raw, const float* z, const float* rd, float noise_std,
+                                      const sahs_rng* rng, const float* bg, int bg_ch, int apply_bg_overwrite,
+                                      int num_rays, int num_samples, int white_background, const float* d_rgb_map,
+                                      const float* d_disp, const float* d_acc, const float* d_weights,
+                                      const float* d_depth, float* d_raw, void* stream) {
+  return composite_bwd_impl(raw, z, rd, nullptr, noise_std, noise_std > 0.f ? rng : nullptr, bg, bg_ch, apply_bg_overwrite,
+                            num_rays, num_samples, white_background, d_rgb_map, d_disp, d_acc, d_weights, d_depth, d_raw,
+                            stream);
 }

@@ -130,8 +130,14 @@ __device__ __forceinline__ void grid_backward(const float* __restrict__ g, float
               iz = __fmul_rn(__fadd_rn(z, 1.f), sc);   // same roundings as grid_gather16
   const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
   float gx = 0.f, gy = 0.f, gz = 0.f;
+  // Corner order rotated by lane: the lanes of a warp are consecutive samples of a ray, and where the fine samples
+  // cluster at a surface (any trained field) most of them fall into the same voxel -- all issuing the same corner's
+  // reduction at the same time serialises 32 atomics on one L2 address (measured: dgrad 0.74 ms per level on white-noise
+  // weights, 1.00 ms on the trained-like fixture).  Rotated, a warp instruction touches all 8 corners at once.
+  const int rot = (int)(threadIdx.x & 7);
 #pragma unroll 1
-  for (int corner = 0; corner < 8; ++corner) {
+  for (int ci = 0; ci < 8; ++ci) {
+    const int corner = (ci + rot) & 7;
     const int bx = corner & 1, by = (corner >> 1) & 1, bz = corner >> 2;
     const float xi = fx + bx, yi = fy + by, zi = fz + bz;
     const float wx = 1.f - fabsf(ix - xi), wy = 1.f - fabsf(iy - yi), wz = 1.f - fabsf(iz - zi);

@@ -149,7 +149,27 @@ extern "C" int sahs_param_count(const sahs_model_spec* spec) {
   return pi.count;
 }
 
+static int build_host_plan_uncached(const sahs_model_spec& s, const float* const* params, HostPlan& hp, bool train);
+
+// The launch paths call this once per kernel launch with params == NULL (they need the stage table and the dimensions,
+// not the pack sources): that result depends on the spec alone, so it is built once per (thread, spec, train) and copied.
 int sahs_build_host_plan(const sahs_model_spec& s, const float* const* params, HostPlan& hp, bool train) {
+  if (params) return build_host_plan_uncached(s, params, hp, train);
+  struct Cached { bool valid = false; sahs_model_spec spec; HostPlan hp; };
+  static thread_local Cached cache[2];
+  Cached& c = cache[train ? 1 : 0];
+  if (!c.valid || memcmp(&c.spec, &s, sizeof(s)) != 0) {
+    c.valid = false;
+    int rc = build_host_plan_uncached(s, nullptr, c.hp, train);
+    if (rc) return rc;
+    c.spec = s;
+    c.valid = true;
+  }
+  if (&hp != &c.hp) hp = c.hp;
+  return SAHS_OK;
+}
+
+static int build_host_plan_uncached(const sahs_model_spec& s, const float* const* params, HostPlan& hp, bool train) {
   NetDims& d = hp.dims;
   int rc = sahs_make_dims(s, d, train);
   if (rc) {

@@ -36,7 +36,7 @@ extern "C" int sahs_get_ray_bundle(int height, int width, float fx, float fy, do
 
 // ref: nerf/train_utils.py:93-113
 __global__ void coarse_z_kernel(int R, int S, float near_, float far_, int lindisp, const float* __restrict__ t_vals,
-                                const float* __restrict__ t_rand, float* __restrict__ z_out) {
+                                const float* __restrict__ t_rand, RngArg rng, float* __restrict__ z_out) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)R * S) return;
   int s = (int)(idx % S);
@@ -49,10 +49,11 @@ __global__ void coarse_z_kernel(int R, int S, float near_, float far_, int lindi
     return __fdiv_rn(1.0f, __fadd_rn(a, b));
   };
   float z = zat(s);
-  if (t_rand) {
+  if (t_rand || rng.on) {
     float lower = (s == 0) ? z : __fmul_rn(0.5f, __fadd_rn(z, zat(s - 1)));
     float upper = (s == S - 1) ? z : __fmul_rn(0.5f, __fadd_rn(zat(s + 1), z));
-    z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t_rand[idx]));
+    const float tr = t_rand ? t_rand[idx] : rng_uniform(rng, (uint64_t)idx);
+    z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), tr));
   }
   z_out[idx] = z;
 }
@@ -64,7 +65,36 @@ extern "C" int sahs_coarse_z(int num_rays, int num_samples, float near_, float f
   if (n == 0) return SAHS_OK;
   SAHS_CHECK_ARG(t_vals && z_out, "null pointer");
   coarse_z_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(num_rays, num_samples, near_, far_,
-                                                                               lindisp, t_vals, t_rand, z_out);
+                                                                               lindisp, t_vals, t_rand, rng_arg(nullptr),
+                                                                               z_out);
+  SAHS_LAUNCH_CHECK();
+  return SAHS_OK;
+}
+
+extern "C" int sahs_coarse_z_rng(int num_rays, int num_samples, float near_, float far_, int lindisp,
+                                 const float* t_vals, const sahs_rng* rng, float* z_out, void* stream) {
+  SAHS_CHECK_ARG(num_rays >= 0 && num_samples > 0, "bad arguments");
+  int64_t n = (int64_t)num_rays * num_samples;
+  if (n == 0) return SAHS_OK;
+  SAHS_CHECK_ARG(t_vals && z_out, "null pointer");
+  coarse_z_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(num_rays, num_samples, near_, far_,
+                                                                               lindisp, t_vals, nullptr, rng_arg(rng),
+                                                                               z_out);
+  SAHS_LAUNCH_CHECK();
+  return SAHS_OK;
+}
+
+__global__ void rng_fill_kernel(float* __restrict__ out, int64_t n, RngArg rng, int normal, float scale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = scale * (normal ? rng_normal(rng, (uint64_t)i) : rng_uniform(rng, (uint64_t)i));
+}
+
+extern "C" int sahs_rng_fill(float* out, int64_t n, const sahs_rng* rng, int normal, float scale, void* stream) {
+  SAHS_CHECK_ARG(n >= 0 && rng, "bad arguments");
+  if (n == 0) return SAHS_OK;
+  SAHS_CHECK_ARG(out, "null pointer");
+  rng_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, rng_arg(rng), normal, scale);
   SAHS_LAUNCH_CHECK();
   return SAHS_OK;
 }

@@ -53,6 +53,46 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// ---- Philox-4x32-10 (Salmon et al. 2011): the library's one random source -------------------------------------
+struct RngArg {   // device-side copy of sahs_rng (on == 0: no in-kernel draws)
+  unsigned long long seed;
+  const unsigned long long* counter;
+  uint32_t stream;
+  uint32_t on;
+};
+inline RngArg rng_arg(const sahs_rng* r) {
+  RngArg a{0ull, nullptr, 0u, 0u};
+  if (r) { a.seed = r->seed; a.counter = r->counter_dev; a.stream = r->stream; a.on = 1u; }
+  return a;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint64_t ctr, uint32_t stream, uint64_t key) {
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = stream, c3 = 0u;
+  uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ uint64_t rng_key(const RngArg& r) { return r.seed + (r.counter ? *r.counter : 0ull); }
+// U[0,1) on the 2^-24 grid (what torch.rand returns for fp32)
+__device__ __forceinline__ float rng_uniform(const RngArg& r, uint64_t idx) {
+  return (float)(philox4x32_10(idx, r.stream, rng_key(r)).x >> 8) * (1.0f / 16777216.0f);
+}
+// N(0,1): Box-Muller, u1 in (0,1]
+__device__ __forceinline__ float rng_normal(const RngArg& r, uint64_t idx) {
+  const uint4 q = philox4x32_10(idx, r.stream, rng_key(r));
+  const float u1 = ((float)(q.x >> 8) + 1.0f) * (1.0f / 16777216.0f);
+  const float u2 = (float)(q.y >> 8) * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
 // ---- mbarrier ----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

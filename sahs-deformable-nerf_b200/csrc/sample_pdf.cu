@@ -44,8 +44,8 @@ __device__ __forceinline__ double shfl_up_double(double v, int o) {
 
 __global__ void __launch_bounds__(kWarps * 32, kBlocksPerSm)
 sample_pdf_merge_kernel(const float* __restrict__ z, const float* __restrict__ bins_in,
-                        const float* __restrict__ weights, const float* __restrict__ u, int u_per_ray, int R, int S,
-                        int NF, float* __restrict__ z_samples, float* __restrict__ z_merged,
+                        const float* __restrict__ weights, const float* __restrict__ u, int u_per_ray, RngArg rng,
+                        int R, int S, int NF, float* __restrict__ z_samples, float* __restrict__ z_merged,
                         int64_t* __restrict__ inds_out) {
   extern __shared__ float scratch_all[];
   WarpScratch sm;
@@ -116,7 +116,7 @@ sample_pdf_merge_kernel(const float* __restrict__ z, const float* __restrict__ b
     __syncwarp();
     // ---- invert the cdf --------------------------------------------------------------------------
     for (int i = lane; i < NF; i += 32) {
-      const float uu = u_per_ray ? u[(size_t)r * NF + i] : u[i];
+      const float uu = rng.on ? rng_uniform(rng, (uint64_t)r * NF + i) : (u_per_ray ? u[(size_t)r * NF + i] : u[i]);
       // searchsorted(right=True): first index with cdf[idx] > u  == number of entries <= u
       int lo = 0, hi = nb;
       while (lo < hi) {
@@ -249,9 +249,27 @@ extern "C" int sahs_sample_pdf_merge(const float* z, const float* weights, const
   int cap = sahs_num_sms() * kBlocksPerSm;
   if (blocks > cap) blocks = cap;
   const size_t smem = scratch_bytes(num_samples, num_fine);
-  sample_pdf_merge_kernel<<<blocks, kWarps * 32, smem, (cudaStream_t)stream>>>(z, nullptr, weights, u, u_per_ray, num_rays,
-                                                                          num_samples, num_fine, z_samples, z_merged,
-                                                                          inds);
+  sample_pdf_merge_kernel<<<blocks, kWarps * 32, smem, (cudaStream_t)stream>>>(z, nullptr, weights, u, u_per_ray,
+                                                                          rng_arg(nullptr), num_rays, num_samples,
+                                                                          num_fine, z_samples, z_merged, inds);
+  SAHS_LAUNCH_CHECK();
+  return SAHS_OK;
+}
+
+extern "C" int sahs_sample_pdf_merge_rng(const float* z, const float* weights, const sahs_rng* rng, int num_rays,
+                                         int num_samples, int num_fine, float* z_samples, float* z_merged,
+                                         int64_t* inds, void* stream) {
+  if (num_rays == 0) return SAHS_OK;
+  SAHS_CHECK_ARG(z && weights && rng && z_samples && z_merged, "null pointer");
+  SAHS_CHECK_ARG(num_samples >= 3 && num_samples <= kMaxS, "num_samples must be in [3,256]");
+  SAHS_CHECK_ARG(num_fine >= 1 && num_samples + num_fine <= kMaxMerged, "num_samples + num_fine must be <= 512");
+  int blocks = (num_rays + kWarps - 1) / kWarps;
+  int cap = sahs_num_sms() * kBlocksPerSm;
+  if (blocks > cap) blocks = cap;
+  const size_t smem = scratch_bytes(num_samples, num_fine);
+  sample_pdf_merge_kernel<<<blocks, kWarps * 32, smem, (cudaStream_t)stream>>>(z, nullptr, weights, nullptr, 1, rng_arg(rng),
+                                                                          num_rays, num_samples, num_fine, z_samples,
+                                                                          z_merged, inds);
   SAHS_LAUNCH_CHECK();
   return SAHS_OK;
 }
@@ -268,8 +286,8 @@ extern "C" int sahs_sample_pdf(const float* bins, const float* weights, const fl
   if (blocks > cap) blocks = cap;
   const size_t smem = scratch_bytes(num_bins + 1, num_fine);
   sample_pdf_merge_kernel<<<blocks, kWarps * 32, smem, (cudaStream_t)stream>>>(nullptr, bins, weights, u, u_per_ray,
-                                                                          num_rays, num_bins + 1, num_fine, samples,
-                                                                          nullptr, inds);
+                                                                          rng_arg(nullptr), num_rays, num_bins + 1,
+                                                                          num_fine, samples, nullptr, inds);
   SAHS_LAUNCH_CHECK();
   return SAHS_OK;
 }

@@ -72,6 +72,13 @@ _define("positional_encoding(Tensor x, int num_freqs, bool include_input) -> Ten
         lambda x, n, inc: _e(tuple(x.shape[:-1]) + (x.shape[-1] * ((1 if inc else 0) + 2 * n),), x))
 
 
+_define("coarse_z_rng(int num_rays, int num_samples, float near, float far, bool lindisp, Tensor t_vals, int seed, "
+        "Tensor? counter, int stream) -> Tensor",
+        lambda r, s, near, far, lindisp, t_vals, seed, ctr, st:
+            ops.coarse_z(r, s, near, far, lindisp, t_vals.device, None, t_vals, rng=(seed, ctr, st)),
+        lambda r, s, near, far, lindisp, t_vals, seed, ctr, st: _e((r, s), t_vals))
+
+
 # ---- stage (2) ------------------------------------------------------------------------------------------------------
 def _field_fwd_cuda(spec, level, packed, fc, grid, ro, rd, z):
     return ops.field_fwd(_cspec(spec), level, packed, fc, grid, ro, rd, z)
@@ -129,10 +136,29 @@ _define("composite_bwd(Tensor raw, Tensor z, Tensor rd, Tensor? noise, Tensor? b
         lambda raw, *a: torch.empty_like(raw))
 
 
+_define("composite_fwd_rng(Tensor raw, Tensor z, Tensor rd, float noise_std, int seed, Tensor? counter, int stream, Tensor? bg, "
+        "bool apply_bg_overwrite, bool white_background) -> (Tensor, Tensor, Tensor, Tensor, Tensor)",
+        lambda raw, z, rd, std, seed, ctr, st, bg, apply_bg, white:
+            ops.composite_fwd(raw, z, rd, None, bg, apply_bg, white, noise_std=std, rng=(seed, ctr, st)),
+        lambda raw, z, rd, std, seed, ctr, st, bg, apply_bg, white: _composite_meta(raw, z, rd, None, bg, apply_bg, white))
+
+_define("composite_bwd_rng(Tensor raw, Tensor z, Tensor rd, float noise_std, int seed, Tensor? counter, int stream, Tensor? bg, "
+        "bool apply_bg_overwrite, bool white_background, Tensor? d_rgb, Tensor? d_disp, Tensor? d_acc, Tensor? d_w, "
+        "Tensor? d_depth) -> Tensor",
+        lambda raw, z, rd, std, seed, ctr, st, bg, apply_bg, white, d_rgb, d_disp, d_acc, d_w, d_depth:
+            ops.composite_bwd(raw, z, rd, None, bg, apply_bg, white, d_rgb, d_disp, d_acc, d_w, d_depth, noise_std=std,
+                              rng=(seed, ctr, st)),
+        lambda raw, *a: torch.empty_like(raw))
+
+
 # ---- stage (4) ------------------------------------------------------------------------------------------------------
 _define("sample_pdf_merge(Tensor z, Tensor weights, int num_fine, Tensor? u) -> (Tensor, Tensor)",
         lambda z, w, nf, u: ops.sample_pdf_merge(z, w, nf, u),
         lambda z, w, nf, u: (_e((z.shape[0], nf), z), _e((z.shape[0], z.shape[1] + nf), z)))
+
+_define("sample_pdf_merge_rng(Tensor z, Tensor weights, int num_fine, int seed, Tensor? counter, int stream) -> (Tensor, Tensor)",
+        lambda z, w, nf, seed, ctr, st: ops.sample_pdf_merge(z, w, nf, None, rng=(seed, ctr, st)),
+        lambda z, w, nf, seed, ctr, st: (_e((z.shape[0], nf), z), _e((z.shape[0], z.shape[1] + nf), z)))
 
 _define("sample_pdf(Tensor bins, Tensor weights, int num_samples, Tensor? u) -> Tensor",
         lambda bins, w, n, u: ops.sample_pdf_bins(bins, w, n, u),
@@ -153,6 +179,7 @@ _define("normal_map(Tensor depthmap, float fx, float fy, float cx, float cy, Ten
         lambda d, fx, fy, cx, cy, w, central: ops.normal_map(d, (fx, fy, cx, cy), w, central),
         lambda d, fx, fy, cx, cy, w, central: _e((d.shape[0] - (2 if central else 1), d.shape[1] - (2 if central else 1), 3), d))
 
-OP_NAMES = ("get_ray_bundle", "coarse_z", "positional_encoding", "field_fwd", "field_fwd_train", "field_bwd",
-            "composite_fwd", "composite_bwd", "sample_pdf_merge", "sample_pdf", "frame_postprocess", "weighted_sample",
+OP_NAMES = ("get_ray_bundle", "coarse_z", "coarse_z_rng", "positional_encoding", "field_fwd", "field_fwd_train", "field_bwd",
+            "composite_fwd", "composite_bwd", "composite_fwd_rng", "composite_bwd_rng", "sample_pdf_merge",
+            "sample_pdf_merge_rng", "sample_pdf", "frame_postprocess", "weighted_sample",
             "normal_map")

@@ -26,6 +26,11 @@ class ModelSpecC(C.Structure):
         "trunk_layers", "trunk_hidden", "trunk_skip", "trunk_driving", "trunk_pose", "use_grid")]
 
 
+class RngC(C.Structure):
+    """struct sahs_rng"""
+    _fields_ = [("seed", C.c_uint64), ("counter_dev", C.c_void_p), ("stream", C.c_uint32), ("reserved", C.c_uint32)]
+
+
 EXPORTS = (
     "sahs_abi_version", "sahs_last_error", "sahs_launch_count", "sahs_param_count", "sahs_get_ray_bundle",
     "sahs_coarse_z", "sahs_positional_encoding", "sahs_field_sizes", "sahs_pack_params", "sahs_fold_frame",
@@ -33,6 +38,7 @@ EXPORTS = (
     "sahs_field_status", "sahs_debug_plan", "sahs_train_layout", "sahs_pack_params_train", "sahs_pack_params_bwd",
     "sahs_field_fwd_train", "sahs_field_bwd", "sahs_field_wgrad", "sahs_frame_postprocess", "sahs_weighted_sample", "sahs_stage1_loss",
     "sahs_adam_step", "sahs_adam_step_dev", "sahs_adam_advance", "sahs_counter_add", "sahs_weighted_sample_dev", "sahs_normal_map",
+    "sahs_rng_fill", "sahs_coarse_z_rng", "sahs_composite_fwd_rng", "sahs_composite_bwd_rng", "sahs_sample_pdf_merge_rng",
 )
 
 
@@ -80,6 +86,13 @@ def load() -> C.CDLL:
         "sahs_counter_add": (C.c_int, [vp, C.c_uint64, vp]),
         "sahs_weighted_sample_dev": (C.c_int, [vp, vp, i64, i32, i32, C.c_uint64, vp, vp, vp, C.c_size_t, vp]),
         "sahs_normal_map": (C.c_int, [vp, i32, f32, f32, f32, f32, vp, i32, vp, vp]),
+        "sahs_rng_fill": (C.c_int, [vp, i64, C.POINTER(RngC), i32, f32, vp]),
+        "sahs_coarse_z_rng": (C.c_int, [i32, i32, f32, f32, i32, vp, C.POINTER(RngC), vp, vp]),
+        "sahs_composite_fwd_rng": (C.c_int, [vp, vp, vp, f32, C.POINTER(RngC), vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp,
+                                             vp]),
+        "sahs_composite_bwd_rng": (C.c_int, [vp, vp, vp, f32, C.POINTER(RngC), vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp,
+                                             vp, vp]),
+        "sahs_sample_pdf_merge_rng": (C.c_int, [vp, vp, C.POINTER(RngC), i32, i32, i32, vp, vp, vp, vp]),
         "sahs_stage1_loss": (C.c_int, [vp, vp, vp, vp, i32, i32, C.c_float, C.c_float, i32, i32, vp, vp, vp, vp, vp, vp]),
         "sahs_field_status": (C.c_int, [C.POINTER(C.c_int)]),
     }

@@ -29,6 +29,23 @@ def linspace_dev(steps: int, device) -> torch.Tensor:
 _linspace_dev = linspace_dev
 
 
+def make_rng(seed: int, counter: Optional[torch.Tensor], stream: int) -> L.RngC:
+    """struct sahs_rng: Philox key = seed (+ the device counter when given), `stream` selects the draw."""
+    if counter is not None and (counter.dtype != torch.int64 or not counter.is_cuda or counter.numel() != 1):
+        raise RuntimeError("rng counter must be a CUDA int64 scalar tensor")
+    return L.RngC(int(seed) & 0xFFFFFFFFFFFFFFFF, L.ptr(counter) if counter is not None else None, int(stream), 0)
+
+
+def rng_fill(n: int, seed: int, counter: Optional[torch.Tensor], stream: int, normal: bool, scale: float, device):
+    """The values the kernels draw for (seed, counter, stream), materialised (tests / diagnostics)."""
+    lib = L.load()
+    out = torch.empty(int(n), dtype=torch.float32, device=device)
+    r = make_rng(seed, counter, stream)
+    L.check(lib.sahs_rng_fill(L.ptr(out), int(n), C.byref(r), int(bool(normal)), float(scale), L.stream_ptr(device)),
+            "rng_fill")
+    return out
+
+
 def get_ray_bundle(height: int, width: int, intrinsics, c2w: torch.Tensor):
     """ref: nerf/nerf_helpers.py:178-233.  Returns (ro, rd) of shape (H, W, 3)."""
     lib = L.load()
@@ -42,12 +59,17 @@ def get_ray_bundle(height: int, width: int, intrinsics, c2w: torch.Tensor):
 
 
 def coarse_z(num_rays: int, num_samples: int, near: float, far: float, lindisp: bool, device,
-             t_rand: Optional[torch.Tensor] = None, t_vals: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """ref: nerf/train_utils.py:93-113."""
+             t_rand: Optional[torch.Tensor] = None, t_vals: Optional[torch.Tensor] = None, rng=None) -> torch.Tensor:
+    """ref: nerf/train_utils.py:93-113.  rng = (seed, counter, stream): perturbed depths with t_rand drawn in the kernel."""
     lib = L.load()
     if t_vals is None:
         t_vals = _linspace_dev(num_samples, device)
     z = torch.empty(num_rays, num_samples, dtype=torch.float32, device=device)
+    if rng is not None and t_rand is None:
+        r = make_rng(*rng)
+        L.check(lib.sahs_coarse_z_rng(num_rays, num_samples, float(near), float(far), int(bool(lindisp)), L.ptr(t_vals),
+                                      C.byref(r), L.ptr(z), L.stream_ptr(device)), "coarse_z_rng")
+        return z
     tr = L.f32c(t_rand) if t_rand is not None else None
     L.check(lib.sahs_coarse_z(num_rays, num_samples, float(near), float(far), int(bool(lindisp)), L.ptr(t_vals),
                               L.ptr(tr), L.ptr(z), L.stream_ptr(device)), "coarse_z")
@@ -117,8 +139,10 @@ def field_bwd(cspec, level: int, packed_t, frame_const, grid, ro, rd, z, d_raw, 
     return tape_d, grid_grad
 
 
-def composite_fwd(raw, z, rd, noise=None, bg=None, apply_bg_overwrite=False, white_background=False):
-    """ref: nerf/volume_rendering_utils.py:7-78.  Returns (rgb_map, disp, acc, weights, depth)."""
+def composite_fwd(raw, z, rd, noise=None, bg=None, apply_bg_overwrite=False, white_background=False, noise_std=0.0,
+                  rng=None):
+    """ref: nerf/volume_rendering_utils.py:7-78.  Returns (rgb_map, disp, acc, weights, depth).  Density noise: the
+    `noise` tensor, or (noise_std, rng = (seed, counter, stream)) drawn in the kernel."""
     lib = L.load()
     raw, z, rd = L.f32c(raw), L.f32c(z), L.f32c(rd)
     R, S = z.shape
@@ -134,19 +158,33 @@ def composite_fwd(raw, z, rd, noise=None, bg=None, apply_bg_overwrite=False, whi
     acc = torch.empty_like(disp)
     depth = torch.empty_like(disp)
     w = torch.empty(R, S, dtype=torch.float32, device=dev)
+    if noise is None and rng is not None and noise_std > 0.0:
+        r = make_rng(*rng)
+        L.check(lib.sahs_composite_fwd_rng(L.ptr(raw), L.ptr(z), L.ptr(rd), float(noise_std), C.byref(r), L.ptr(bg), MAP_CH,
+                                           int(apply_bg_overwrite), R, S, int(white_background), L.ptr(rgb), L.ptr(disp),
+                                           L.ptr(acc), L.ptr(w), L.ptr(depth), L.stream_ptr(dev)), "composite_fwd_rng")
+        return rgb, disp, acc, w, depth
     L.check(lib.sahs_composite_fwd(L.ptr(raw), L.ptr(z), L.ptr(rd), L.ptr(noise), L.ptr(bg), MAP_CH,
                                    int(apply_bg_overwrite), R, S, int(white_background), L.ptr(rgb), L.ptr(disp),
                                    L.ptr(acc), L.ptr(w), L.ptr(depth), L.stream_ptr(dev)), "composite_fwd")
     return rgb, disp, acc, w, depth
 
 
-def composite_bwd(raw, z, rd, noise, bg, apply_bg_overwrite, white_background, d_rgb, d_disp, d_acc, d_w, d_depth):
+def composite_bwd(raw, z, rd, noise, bg, apply_bg_overwrite, white_background, d_rgb, d_disp, d_acc, d_w, d_depth,
+                  noise_std=0.0, rng=None):
     lib = L.load()
     raw, z, rd = L.f32c(raw), L.f32c(z), L.f32c(rd)
     R, S = z.shape
     c = lambda t: L.f32c(t) if t is not None else None
     noise, bg, d_rgb, d_disp, d_acc, d_w, d_depth = map(c, (noise, bg, d_rgb, d_disp, d_acc, d_w, d_depth))
     d_raw = torch.empty_like(raw)
+    if noise is None and rng is not None and noise_std > 0.0:
+        r = make_rng(*rng)
+        L.check(lib.sahs_composite_bwd_rng(L.ptr(raw), L.ptr(z), L.ptr(rd), float(noise_std), C.byref(r), L.ptr(bg), MAP_CH,
+                                           int(apply_bg_overwrite), R, S, int(white_background), L.ptr(d_rgb),
+                                           L.ptr(d_disp), L.ptr(d_acc), L.ptr(d_w), L.ptr(d_depth), L.ptr(d_raw),
+                                           L.stream_ptr(raw.device)), "composite_bwd_rng")
+        return d_raw
     L.check(lib.sahs_composite_bwd(L.ptr(raw), L.ptr(z), L.ptr(rd), L.ptr(noise), L.ptr(bg), MAP_CH,
                                    int(apply_bg_overwrite), R, S, int(white_background), L.ptr(d_rgb), L.ptr(d_disp),
                                    L.ptr(d_acc), L.ptr(d_w), L.ptr(d_depth), L.ptr(d_raw), L.stream_ptr(raw.device)),
@@ -154,13 +192,22 @@ def composite_bwd(raw, z, rd, noise, bg, apply_bg_overwrite, white_background, d
     return d_raw
 
 
-def sample_pdf_merge(z, weights, num_fine: int, u: Optional[torch.Tensor] = None, return_inds: bool = False):
+def sample_pdf_merge(z, weights, num_fine: int, u: Optional[torch.Tensor] = None, return_inds: bool = False, rng=None):
     """sample_pdf_2(mid(z), weights[...,1:-1], num_fine) + sort(cat(z, samples)).
-    ref: nerf/nerf_helpers.py:454-497, nerf/train_utils.py:157-166.  u=None -> deterministic linspace."""
+    ref: nerf/nerf_helpers.py:454-497, nerf/train_utils.py:157-166.  u=None -> deterministic linspace, unless
+    rng = (seed, counter, stream): u ~ U[0,1) drawn in the kernel."""
     lib = L.load()
     z, weights = L.f32c(z), L.f32c(weights)
     R, S = z.shape
     dev = z.device
+    if u is None and rng is not None:
+        zs = torch.empty(R, num_fine, dtype=torch.float32, device=dev)
+        zm = torch.empty(R, S + num_fine, dtype=torch.float32, device=dev)
+        inds = torch.empty(R, num_fine, dtype=torch.int64, device=dev) if return_inds else None
+        r = make_rng(*rng)
+        L.check(lib.sahs_sample_pdf_merge_rng(L.ptr(z), L.ptr(weights), C.byref(r), R, S, num_fine, L.ptr(zs), L.ptr(zm),
+                                              L.ptr(inds), L.stream_ptr(dev)), "sample_pdf_merge_rng")
+        return (zs, zm, inds) if return_inds else (zs, zm)
     if u is None:
         uu, per_ray = _linspace_dev(num_fine, dev), 0
     else:

@@ -22,6 +22,21 @@ MAX_RAYS_PER_CHUNK = 1 << 19
 STAGE_HOOK = None
 
 
+# In-kernel random draws (stochastic mode).  Every ray chunk takes a fresh Philox key derived from torch's seed and a
+# host-side call counter, so `torch.manual_seed` makes runs reproducible.  RNG_COUNTER (optional CUDA int64 scalar) is
+# added to the key ON THE DEVICE: a training step recorded in a CUDA graph (sahs_b200.train.GraphedStep) has its host-side
+# key frozen, and advancing this counter once per step (ops.counter_add) is what gives every replay fresh draws.
+RNG_COUNTER = None
+_RNG_CALLS = [0]
+
+
+def next_rng():
+    """(seed, device counter or None) for the draws of one ray chunk."""
+    _RNG_CALLS[0] += 1
+    seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _RNG_CALLS[0] * 0xD1B54A32D192ED03) & 0x7FFFFFFFFFFFFFFF
+    return seed, RNG_COUNTER
+
+
 def _stage(name, fn):
     return fn() if STAGE_HOOK is None else STAGE_HOOK(name, fn)
 
@@ -43,39 +58,38 @@ def _render_chunk(model, nerf_opts, ro, rd, near, far, driving_vec, pose_code, b
     noise_std = float(nerf_opts.radiance_field_noise_std)
     white = bool(nerf_opts.white_background)
     draws = draws or {}
-    t_rand = None
-    if perturb:
-        t_rand = draws.get("t_rand")
-        if t_rand is None:
-            t_rand = torch.rand(R, nc, dtype=torch.float32, device=dev)
-
-    def noise_for(key, S):
-        if noise_std <= 0.0:
-            return None
-        n = draws.get(key)
-        return n if n is not None else torch.randn(R, S, dtype=torch.float32, device=dev) * noise_std
-
+    # Stochastic mode: the reference draws t_rand (train_utils.py:112), the density noise (volume_rendering_utils.py:47)
+    # and u (nerf_helpers.py:473) from torch's generator.  Here they are drawn inside the kernels (Philox streams 0-3
+    # of one key per chunk): no [R,S] tensor is materialised.  Tests inject the reference's own draws through `draws`.
+    rng = next_rng() if (perturb or noise_std > 0.0) else None
     if not ro.is_cuda:
         raise RuntimeError("sahs_b200 ops need CUDA tensors (there is no CPU path)")
     T = torch.ops.sahs_b200
-    z_c = T.coarse_z(R, nc, near, far, bool(nerf_opts.lindisp), ops.linspace_dev(nc, dev), t_rand)
+    t_vals = ops.linspace_dev(nc, dev)
+    t_rand = draws.get("t_rand") if perturb else None
+    if perturb and t_rand is None:
+        z_c = T.coarse_z_rng(R, nc, near, far, bool(nerf_opts.lindisp), t_vals, rng[0], rng[1], 0)
+    else:
+        z_c = T.coarse_z(R, nc, near, far, bool(nerf_opts.lindisp), t_vals, t_rand)
+
+    def comp(name, raw, z, key, stream):
+        n = draws.get(key) if noise_std > 0.0 else None
+        r = (rng[0], rng[1], stream) if (noise_std > 0.0 and n is None) else None
+        return _stage(name, lambda: composite(raw, z, rd, n, bg, bg is not None, white, noise_std, r))
+
     raw_c = _stage("field_coarse", lambda: model.field("coarse", ro, rd, z_c, driving_vec, pose_code))
-    n_c = noise_for("noise_c", nc)
-    rgb_c, disp_c, acc_c, w_c, depth_c = _stage("composite_coarse",
-                                                lambda: composite(raw_c, z_c, rd, n_c, bg, bg is not None, white))
+    rgb_c, disp_c, acc_c, w_c, depth_c = comp("composite_coarse", raw_c, z_c, "noise_c", 1)
     if nf <= 0:
         raise RuntimeError("num_fine == 0 is a dead branch in the reference (depth_fine undefined, "
                            "ref: nerf/train_utils.py:205-206); not supported")
-    u = None
-    if perturb:                                   # det = (perturb == 0.0), ref: nerf/train_utils.py:162
-        u = draws.get("u")
-        if u is None:
-            u = torch.rand(R, nf, dtype=torch.float32, device=dev)
-    z_s, z_f = _stage("sample_pdf_merge", lambda: T.sample_pdf_merge(z_c, w_c.detach(), nf, u))   # .detach(), ref: :164
+    u = draws.get("u") if perturb else None                     # det = (perturb == 0.0), ref: nerf/train_utils.py:162
+    if perturb and u is None:
+        z_s, z_f = _stage("sample_pdf_merge",
+                          lambda: T.sample_pdf_merge_rng(z_c, w_c.detach(), nf, rng[0], rng[1], 2))   # .detach(), ref: :164
+    else:
+        z_s, z_f = _stage("sample_pdf_merge", lambda: T.sample_pdf_merge(z_c, w_c.detach(), nf, u))
     raw_f = _stage("field_fine", lambda: model.field("fine", ro, rd, z_f, driving_vec, pose_code))
-    n_f = noise_for("noise_f", nc + nf)
-    rgb_f, disp_f, acc_f, w_f, depth_f = _stage("composite_fine",
-                                                lambda: composite(raw_f, z_f, rd, n_f, bg, bg is not None, white))
+    rgb_f, disp_f, acc_f, w_f, depth_f = comp("composite_fine", raw_f, z_f, "noise_f", 3)
     return rgb_c, disp_c, acc_c, rgb_f, disp_f, acc_f, w_f[:, -1], depth_f
 
 

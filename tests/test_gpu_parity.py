@@ -656,6 +656,80 @@ def test_normal_map_vs_oracle(sahs, central):
     assert sahs.torch_normal_map(depth.to(DEV), focal, weights.to(DEV), clean=False).shape == (n - 1, n - 1, 3)
 
 
+def test_in_kernel_random_draws(sahs):
+    """Stochastic mode without materialised random tensors: t_rand, the density noise and u are drawn inside the kernels
+    (Philox-4x32-10, include/sahs_b200.h `sahs_rng`).  (1) the generator: range, moments, reproducibility, independent
+    streams, the device counter; (2) every kernel that draws equals, BIT FOR BIT, the same kernel fed the materialised
+    values (`sahs_rng_fill`) -- forward and backward of the compositing regenerate identical noise; (3) the pipeline."""
+    from sahs_b200 import ops
+    seed, n = 123456789, 1 << 20
+    u = ops.rng_fill(n, seed, None, 0, False, 1.0, DEV)
+    g = ops.rng_fill(n, seed, None, 1, True, 1.0, DEV)
+    assert float(u.min()) >= 0.0 and float(u.max()) < 1.0
+    assert abs(float(u.mean()) - 0.5) < 2e-3 and abs(float(u.var()) - 1.0 / 12) < 1e-3
+    assert abs(float(g.mean())) < 4e-3 and abs(float(g.var()) - 1.0) < 6e-3 and abs(float((g ** 4).mean()) - 3.0) < 0.05
+    assert torch.equal(u, ops.rng_fill(n, seed, None, 0, False, 1.0, DEV))
+    assert not torch.equal(u, ops.rng_fill(n, seed, None, 2, False, 1.0, DEV))          # another stream
+    ctr = torch.full((), 5, dtype=torch.int64, device=DEV)
+    assert torch.equal(ops.rng_fill(n, seed, ctr, 0, False, 1.0, DEV), ops.rng_fill(n, seed + 5, None, 0, False, 1.0, DEV))
+    assert abs(float(torch.corrcoef(torch.stack((u[:-1], u[1:])))[0, 1])) < 4e-3         # neighbours uncorrelated
+    # (2) kernels
+    R, S, NF = 300, 64, 64
+    opts = O.RenderOpts(num_coarse=S, near=0.4838, far=1.0838, perturb=True)
+    z_rng = ops.coarse_z(R, S, opts.near, opts.far, False, DEV, rng=(seed, ctr, 0))
+    t_rand = ops.rng_fill(R * S, seed, ctr, 0, False, 1.0, DEV).view(R, S)
+    assert torch.equal(z_rng, ops.coarse_z(R, S, opts.near, opts.far, False, DEV, t_rand))
+    assert torch.equal(z_rng.cpu(), O.coarse_z(opts, R, t_rand.cpu()))
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    raw = torch.randn(R, S, 16, device=DEV, generator=gen)
+    raw[..., -1] = torch.randn(R, S, device=DEV, generator=gen) * 10
+    rd = torch.randn(R, 3, device=DEV, generator=gen) * 0.1
+    rd[:, 2] = -1
+    bg = torch.rand(R, 15, device=DEV, generator=gen)
+    std = 0.1
+    noise = ops.rng_fill(R * S, seed, ctr, 1, True, std, DEV).view(R, S)
+    a = ops.composite_fwd(raw, z_rng, rd, None, bg, True, False, noise_std=std, rng=(seed, ctr, 1))
+    b = ops.composite_fwd(raw, z_rng, rd, noise, bg, True, False)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    assert not torch.equal(a[3], ops.composite_fwd(raw, z_rng, rd, None, bg, True, False)[3])   # the noise matters
+    gs = [torch.randn(t.shape, device=DEV, generator=gen) for t in a]
+    da = ops.composite_bwd(raw, z_rng, rd, None, bg, True, False, *gs, noise_std=std, rng=(seed, ctr, 1))
+    db = ops.composite_bwd(raw, z_rng, rd, noise, bg, True, False, *gs)
+    assert torch.equal(da, db)
+    w = a[3]
+    zs, zm = ops.sample_pdf_merge(z_rng, w, NF, None, rng=(seed, ctr, 2))
+    uu = ops.rng_fill(R * NF, seed, ctr, 2, False, 1.0, DEV).view(R, NF)
+    zs2, zm2 = ops.sample_pdf_merge(z_rng, w, NF, uu)
+    assert torch.equal(zs, zs2) and torch.equal(zm, zm2)
+    # (3) pipeline in the shipped stochastic training settings: finite, reproducible under torch.manual_seed, fresh
+    # draws from call to call, and the autograd path runs
+    from sahs_b200 import train_utils as TU
+    cfg, spec, sd, model = _model(sahs, "audio/person_2_auto", trained_like=True)
+    cfg.nerf.train.perturb, cfg.nerf.train.radiance_field_noise_std = True, 0.1
+    fr = FX.make_frame_inputs(spec, 8, 8, seed=2)
+    pose = fr["pose"].to(DEV)
+    with torch.no_grad():
+        ro, rdd = sahs.get_ray_bundle(8, 8, fr["intrinsics"], pose)
+    kw = dict(mode="train", driving=fr["driving"].to(DEV), pose=pose, background_prior=fr["background"].view(-1, 15).to(DEV))
+
+    def run():
+        with torch.no_grad():
+            return sahs.run_one_iter_of_nerf(8, 8, 1.0, model, ro, rdd, cfg, **kw)
+
+    torch.manual_seed(11)
+    TU._RNG_CALLS[0] = 0
+    o1, o2 = run(), run()
+    torch.manual_seed(11)
+    TU._RNG_CALLS[0] = 0
+    o3 = run()
+    assert all(bool(torch.isfinite(t).all()) for t in o1)
+    assert torch.equal(o1[3], o3[3]) and not torch.equal(o1[3], o2[3])
+    out = sahs.run_one_iter_of_nerf(8, 8, 1.0, model, ro, rdd, cfg, **kw)
+    (out[3].sum() + out[0].sum()).backward()
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in model.parameters())
+
+
 def test_weighted_sampler_validate_raises_like_numpy(sahs):
     from sahs_b200 import ops
     mask = torch.eye(20, dtype=torch.int32, device=DEV)
