@@ -38,6 +38,9 @@ extern "C" {
 #define SAHS_GRID_RES 32
 
 int sahs_abi_version(void);
+/* 16-bit operand format of trunk and heads on the render path: 0 = fp16 (default build: 11-bit significand, conversions
+ * saturate at +-65504), 1 = bf16 (`make BF16=1` -> lib/libsahs_b200_bf16.so).  Deformation phase and training: fp16. */
+int sahs_operand_format(void);
 const char* sahs_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches evidence) */
 uint64_t sahs_launch_count(void);

@@ -12,7 +12,6 @@ constexpr int kThreads = 320;
 constexpr int kTmaWarp = 8, kMmaWarp = 9;
 constexpr int kSlots = 3;
 constexpr int kTmemCols = 256;
-constexpr bool kTrunkF16 = true;   // operand format of trunk and heads (fp16: 8x finer than bf16 at the same MMA rate)
 constexpr int kSmemX = 4 * kChunkBytes;                       // 64 KB
 constexpr int kSmemSlots = kSlots * kStageSlotBytes;          // 48 KB
 constexpr int kSmemBar = kSmemX + kSmemSlots;                 // barriers after the tiles

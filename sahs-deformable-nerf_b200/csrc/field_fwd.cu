@@ -52,6 +52,7 @@ __device__ __forceinline__ void field_tile_program(const NetDims& dm, SyncT<PAIR
                                                    float* __restrict__ raw_out, float* __restrict__ dbg, int dbg_pass,
                                                    TrainOut tr, long long tile, int tid, int bar_id, uint32_t tmem_row,
                                                    long long* prof_buf, int iter) {
+  constexpr bool kTrunkF16 = TRAIN || kRenderTrunkF16;   // trunk / head operand format (field_plan.cuh)
   const int row = tid & (kTileRows - 1);
   const int grp = tid >> 7;
     if (DBG || (kProfProd && prof_buf)) {
@@ -287,7 +288,7 @@ __device__ __forceinline__ void field_tile_program(const NetDims& dm, SyncT<PAIR
       }
     }
     if (DBG) prof_event(sy.prof, 204);   // embedding gather done
-    // -------- trunk (fp16 operands, kTrunkF16) --------
+    // -------- trunk (fp16 operands; bf16 in a -DSAHS_RENDER_BF16 build: kTrunkF16) --------
     auto write_e1 = [&]() {
       RowStream<kTrunkF16, C::E1_PAD / 8> st(X, 0, row, grp);
       int col = pe_stream<C::XYZ_L, true, 3>(st, 0, mapped);

@@ -271,6 +271,7 @@ static int build_host_plan_uncached(const sahs_model_spec& s, const float* const
     hp.copy[hp.num_copy++] = CopySection{P(pi.hyp_fb), s.amb_dim, o};
   }
   // ---------------- trunk ---------------------------------------------------------------------------
+  b.f16 = train || kRenderTrunkF16;   // trunk and heads: fp16, or bf16 on the render path of a -DSAHS_RENDER_BF16 build
   {
     const int tin = d.e1_dim + d.ct_len;
     for (int i = 0; i < d.t_layers; ++i) {

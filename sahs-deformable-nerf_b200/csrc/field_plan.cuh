@@ -18,6 +18,15 @@ constexpr int kChunkBytes = kTileRows * kChunkCols * 2;  // 16 KB
 constexpr int kMaxStages = 160;
 constexpr int kStageSlotBytes = 16384;
 
+// Operand format of trunk and heads on the RENDER path: fp16 by default (11-bit significand, 8x finer than bf16 at the
+// same MMA rate; conversions saturate at +-65504), bf16 when the library is built with -DSAHS_RENDER_BF16 (`make BF16=1`:
+// the format the task statement names; range like fp32, 8-bit significand).  The deformation phase stays fp16 (its output
+// feeds a 2^(L-1)-amplifying encoding) and so does training (tapes, dgrad, wgrad), which scales its gradients into range.
+#ifdef SAHS_RENDER_BF16
+constexpr bool kRenderTrunkF16 = false;
+#else
+constexpr bool kRenderTrunkF16 = true;
+#endif
 enum : uint8_t { ST_WAIT_A = 1, ST_COMMIT = 2, ST_FRESH = 4, ST_F16 = 8, ST_WIDE = 16 };  // F16: fp16 operands (else bf16)
 // ST_WIDE: the B block is [256 outputs x 32 inputs] (K-major rows of 64 bytes, SWIZZLE_64B, 16 KB) instead of
 // [n <= 128 outputs x 64 inputs] (128-byte rows, SWIZZLE_128B): one N = 256 MMA per K = 16 step.  An N = 128 MMA reads

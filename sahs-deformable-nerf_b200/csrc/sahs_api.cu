@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include "sahs_common.cuh"
+#include "field_plan.cuh"
 
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_sahs_launches{0};
@@ -57,5 +58,6 @@ extern "C" int sahs_field_status(int* out4_host) {
 }
 
 extern "C" int sahs_abi_version(void) { return 2; }   // 2: sahs_field_wgrad takes an upload token
+extern "C" int sahs_operand_format(void) { return kRenderTrunkF16 ? 0 : 1; }
 extern "C" const char* sahs_last_error(void) { return g_err; }
 extern "C" uint64_t sahs_launch_count(void) { return g_sahs_launches.load(std::memory_order_relaxed); }

@@ -29,6 +29,7 @@ def weighted_sample(mask, class_prob, num_select, seed):
     import torch
     return torch.ops.sahs_b200.weighted_sample(mask, class_prob, int(num_select), int(seed) & 0x7FFFFFFFFFFFFFFF)
 from .optim import FlatAdam, exp_lr  # noqa: F401,E402
+from .train import audit_fp16_range  # noqa: F401,E402
 
 
 

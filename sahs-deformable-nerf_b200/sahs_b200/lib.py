@@ -38,7 +38,7 @@ EXPORTS = (
     "sahs_field_status", "sahs_debug_plan", "sahs_train_layout", "sahs_pack_params_train", "sahs_pack_params_bwd",
     "sahs_field_fwd_train", "sahs_field_bwd", "sahs_field_wgrad", "sahs_frame_postprocess", "sahs_weighted_sample", "sahs_stage1_loss",
     "sahs_adam_step", "sahs_adam_step_dev", "sahs_adam_advance", "sahs_counter_add", "sahs_weighted_sample_dev", "sahs_normal_map",
-    "sahs_rng_fill", "sahs_coarse_z_rng", "sahs_composite_fwd_rng", "sahs_composite_bwd_rng", "sahs_sample_pdf_merge_rng",
+    "sahs_operand_format", "sahs_rng_fill", "sahs_coarse_z_rng", "sahs_composite_fwd_rng", "sahs_composite_bwd_rng", "sahs_sample_pdf_merge_rng",
 )
 
 
@@ -55,6 +55,7 @@ def load() -> C.CDLL:
     spec_p = C.POINTER(ModelSpecC)
     sigs = {
         "sahs_abi_version": (C.c_int, []),
+        "sahs_operand_format": (C.c_int, []),
         "sahs_last_error": (C.c_char_p, []),
         "sahs_launch_count": (C.c_uint64, []),
         "sahs_param_count": (C.c_int, [spec_p]),

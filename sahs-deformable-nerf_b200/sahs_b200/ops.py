@@ -29,6 +29,12 @@ def linspace_dev(steps: int, device) -> torch.Tensor:
 _linspace_dev = linspace_dev
 
 
+def operand_format() -> str:
+    """16-bit operand format of trunk and heads on the render path of the loaded library: "f16" (default build) or
+    "bf16" (`make BF16=1`, selected with SAHS_B200_LIB=.../libsahs_b200_bf16.so)."""
+    return "bf16" if L.load().sahs_operand_format() == 1 else "f16"
+
+
 def make_rng(seed: int, counter: Optional[torch.Tensor], stream: int) -> L.RngC:
     """struct sahs_rng: Philox key = seed (+ the device counter when given), `stream` selects the draw."""
     if counter is not None and (counter.dtype != torch.int64 or not counter.is_cuda or counter.numel() != 1):

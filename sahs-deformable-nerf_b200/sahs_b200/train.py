@@ -107,6 +107,43 @@ def decode_tape(tape: torch.Tensor, num_points: int) -> torch.Tensor:
     return t.reshape(tiles, slots, 128, 64).permute(0, 2, 1, 3).reshape(tiles * 128, cols)[:num_points]
 
 
+F16_MAX = 65504.0
+
+
+def audit_fp16_range(model, level, ro, rd, z, driving_vec, pose_code) -> dict:
+    """Range audit of the fp16 operands for a checkpoint.  The kernels convert every layer's activated output to fp16 with
+    `cvt.rn.satfinite`: a value beyond +-65504 is clamped, not turned into inf, so a trained model whose hidden
+    activations outgrow fp16 would render clipped values without any error.  This runs the tape-writing forward -- it
+    stores exactly the 16-bit operands the tensor cores consume, layer by layer -- on the given rays and counts, per
+    layer, the entries sitting at +-65504 and the largest magnitude.  `saturated == 0` and a comfortable `headroom`
+    (65504 / max_abs) on a few representative frames is what qualifies a checkpoint for the fp16 build; otherwise use the
+    bf16 build (`make BF16=1`, ops.operand_format() == 1).  Diagnostic: torch ops on the decoded tape, not a hot path."""
+    with torch.no_grad():
+        raw, saved = field_forward_tapes(model, level, ro, rd, z, driving_vec, pose_code)
+        lay = saved["ts"].lay
+        X = decode_tape(saved["tape_x"], z.numel()).abs()
+        items = []
+        if lay["use_w"]:
+            for i in range(lay["w_layers"]):
+                c = lay["tx_wh"] + i * lay["whh"]
+                items.append((f"deform{i}", c, lay["wh"] + lay["hh"]))
+        for i in range(lay["t_layers"]):
+            items.append((f"trunk{i}", lay["tx_th"] + i * lay["th"], lay["th"]))
+        items.append(("feat", lay["tx_feat"], lay["th"]))
+        for i in range(4):
+            items.append((f"head{i}", lay["tx_hh"] + i * 2 * lay["hd"], 2 * lay["hd"]))
+        layers, total, worst = {}, 0, 0.0
+        for name, c, n in items:
+            blk = X[:, c:c + n]
+            sat = int((blk >= F16_MAX).sum())                 # satfinite: the clamp value itself (never inf / nan)
+            mx = float(blk.max()) if blk.numel() else 0.0
+            layers[name] = {"max_abs": mx, "saturated": sat}
+            total += sat
+            worst = max(worst, mx)
+    return {"saturated": total, "max_abs": worst, "headroom": F16_MAX / max(worst, 1e-30), "points": int(z.numel()),
+            "raw_finite": bool(torch.isfinite(raw).all()), "layers": layers}
+
+
 class FieldTrainFn(torch.autograd.Function):
     """raw = field(level, ro + rd z, rd; driving_vec, params).  Gradients: params of that level (incl. the shared
     deformation nets and the embedding grid) and driving_vec."""

@@ -14,7 +14,10 @@ R = 262144
 z = ops.coarse_z(R, 64, 0.4838, 1.0838, False, dev)
 w = torch.rand(R, 64, device=dev) ** 8
 u = torch.rand(R, 64, device=dev)
-for name, uu in (("det", None), ("stochastic", u)):
+for name, uu in (("det", None), ("stochastic", u), ("det, general kernel", None), ("stochastic, general kernel", u)):
+    os.environ.pop("SAHS_SAMPLE_PDF_GENERIC", None)
+    if "general" in name:
+        os.environ["SAHS_SAMPLE_PDF_GENERIC"] = "1"
     for _ in range(3):
         ops.sample_pdf_merge(z, w, 64, uu)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

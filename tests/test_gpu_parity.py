@@ -174,6 +174,47 @@ def test_sample_pdf_merge_paths(sahs, S, NF, shuffle):
     assert torch.equal(zm.cpu(), want)
 
 
+@pytest.mark.parametrize("mode", ["det", "stochastic", "unsorted_coarse", "ties", "flat"])
+def test_sample_pdf_64x64_kernel_equals_general_kernel(sahs, mode, monkeypatch):
+    """The renderer's shape (64 coarse + 64 new samples) has its own kernel (search-free merge).  It must return the
+    general kernel's bits -- samples, indices, merged depths -- for deterministic and stochastic u, for coarse depths
+    that are not ascending (fallback sort), for repeated depths / samples, and for flat weights; plus the oracle."""
+    from sahs_b200 import ops
+    R = 4097
+    gen = torch.Generator().manual_seed(11)
+    z, _ = torch.sort(0.48 + 0.6 * torch.rand(R, 64, generator=gen), -1)
+    w = torch.rand(R, 64, generator=gen) ** 8
+    u = None
+    if mode == "stochastic":
+        u = torch.rand(R, 64, generator=gen).to(DEV)
+    elif mode == "unsorted_coarse":
+        z = z[:, torch.randperm(64, generator=gen)].contiguous()
+    elif mode == "ties":
+        z = (z * 16).round() / 16                      # many equal depths
+        w = (w > 0.5).float()                          # zero-probability bins: runs of identical samples
+    elif mode == "flat":
+        w = torch.zeros(R, 64)
+    z, w = z.to(DEV), w.to(DEV)
+    fast = ops.sample_pdf_merge(z, w, 64, u, return_inds=True)
+    monkeypatch.setenv("SAHS_SAMPLE_PDF_GENERIC", "1")
+    general = ops.sample_pdf_merge(z, w, 64, u, return_inds=True)
+    monkeypatch.delenv("SAHS_SAMPLE_PDF_GENERIC")
+    for a, b in zip(fast, general):
+        assert torch.equal(a, b)
+    want, _ = torch.sort(torch.cat((z, fast[0]), -1), -1)
+    assert torch.equal(fast[1], want)
+    if mode in ("det", "stochastic", "flat"):
+        mids = 0.5 * (z[:, 1:] + z[:, :-1]).cpu()
+        s_o, i_o = O.sample_pdf(mids, w[:, 1:-1].cpu(), 64, det=u is None, u=None if u is None else u.cpu(), return_inds=True)
+        assert torch.equal(fast[2].cpu(), i_o) and torch.equal(fast[0].cpu(), s_o)
+    # a view that is only 4-byte aligned takes the general kernel (the fast one loads float2): same bits
+    buf = torch.zeros(R * 64 + 1, device=DEV)
+    buf[1:] = z.reshape(-1)
+    odd = ops.sample_pdf_merge(buf[1:].view(R, 64), w, 64, u, return_inds=True)
+    for a, b in zip(fast, odd):
+        assert torch.equal(a, b)
+
+
 # ------------------------------------------------------------------------------------------------------
 # (3) compositing
 # ------------------------------------------------------------------------------------------------------

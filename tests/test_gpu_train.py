@@ -485,3 +485,33 @@ def test_graphed_training_step_matches_eager():
     pg = torch.cat([p.detach().reshape(-1) for p in m_g.parameters()])
     moved = float((pe - torch.cat([v.reshape(-1) for v in sd.values()]).to(DEV)).abs().mean())
     assert float((pe - pg).abs().mean()) <= 0.05 * moved, (float((pe - pg).abs().mean()), moved)
+
+
+def test_fp16_range_audit_counts_saturation():
+    """fp16 operands clamp at +-65504 silently (cvt.rn.satfinite).  sahs_b200.audit_fp16_range reads the operands the
+    tensor cores consumed (the training forward's activation tape) and counts clamped entries per layer: none on the
+    fixture, and exactly the units pushed out of range when a bias is."""
+    sahs, cfg, spec, sd, fr, _, _ = _setup("audio/person_2_auto", 8, 8, seed=1)
+    n = 300
+    gen = torch.Generator().manual_seed(3)
+    xyz = ((torch.rand(n, 3, generator=gen) * 2 - 1) * 0.3).to(DEV)
+    dirs = (torch.randn(n, 3, generator=gen) * 0.3 + torch.tensor([0.0, 0.0, -1.0])).to(DEV)
+    z0 = torch.zeros(n, 1, device=DEV)
+
+    def audit(state):
+        model = sahs.AudioFaceModel(cfg)
+        model.load_state_dict(state)
+        model = model.to(DEV)
+        with torch.no_grad():
+            dvec, pcode = model.driving_vector(fr["driving"].to(DEV)), model.pose_code(fr["pose"].to(DEV))
+        return sahs.audit_fp16_range(model, "fine", xyz, dirs, z0, dvec, pcode)
+
+    ok = audit(sd)
+    _report(f"[audit] fixture: saturated {ok['saturated']}, max |activation| {ok['max_abs']:.1f}, headroom {ok['headroom']:.0f}x")
+    assert ok["saturated"] == 0 and ok["raw_finite"] and ok["headroom"] > 8 and ok["points"] == n
+    assert set(ok["layers"]) >= {"deform0", "trunk0", "trunk7", "feat", "head3"}
+    bad = {k: v.clone() for k, v in sd.items()}
+    bad["nerf_mlps.fine.layers_xyz.2.bias"][:100] += 1.0e5            # 100 units of trunk layer 2 beyond fp16's range
+    res = audit(bad)
+    assert res["layers"]["trunk2"]["saturated"] == 100 * n and res["layers"]["trunk2"]["max_abs"] == 65504.0
+    assert res["layers"]["trunk1"]["saturated"] == 0 and res["saturated"] >= 100 * n and res["raw_finite"]
