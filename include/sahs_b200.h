@@ -269,6 +269,48 @@ int sahs_adam_step_dev(float* params, const float* grads, float* exp_avg, float*
 int sahs_adam_advance(double* hyper_dev, void* stream);
 int sahs_counter_add(unsigned long long* counter_dev, unsigned long long inc, void* stream);
 
+/* ---- Stage II: SPADE generator ------------------------------------------------------------ */
+/* Every 3x3 convolution of Generator / Generator_audio (ref: nerf/_init_spade.py:114-139 SPADELayer, :183-199 IdEncoder,
+ * :235-282 SPADEBlock, :286-315 RefineNetwork) as one implicit-GEMM tcgen05 kernel on NHWC fp16 activations.
+ *   mode 0: nn.Conv2d(3x3, padding 1) on the input resized (nearest) by 2^up_shift / 2^down_shift to the output's size
+ *           (F.interpolate(fid, size=x.size()) of :132 and nn.Upsample(scale_factor=2) of :254 are never materialised);
+ *   mode 1: the same with stride 2 (residual_downsample :250, ResBlock2d downsample :17-18);
+ *   mode 2: nn.ConvTranspose2d(3x3, stride 2, padding 1, output_padding 1) (residual_upsample :255);
+ *   mode 3: 3-channel input stored as [H, W, 4] fp16: all nine taps in one K chunk (layer1 of both networks).
+ * packed_w: [ntiles][9 * cin / 64 chunks (mode 3: 1)][ntile rows x 64 columns fp16, 128B-swizzled K-major], chunk order
+ * tap-major (tap = 3 ky + kx); bias: [ntiles * ntile] fp32.  Built by sahs_b200/spade.py from the state_dict (spectral
+ * norm and eval-mode BatchNorm folded in).
+ * epilogue flags: 1 ReLU, 2 + aux (residual add, same geometry as the output), 8 fp32 output; or 4 = SPADE modulation:
+ * each N tile is [gamma(64) | beta(64)] of 64 channels and the kernel writes
+ *   leaky_relu((aux - mean) * rstd * (1 + gamma) + beta, 0.2)      (ref: :128-137 followed by the block's LeakyReLU(0.2))
+ * with aux = the tensor being normalised (read at (oy >> aux_shift, ox >> aux_shift): a nearest-upsampled x1 stays at
+ * its stored resolution) and mean / rstd from sahs_instnorm_stats. */
+typedef struct sahs_conv_desc {
+  const void* in;          /* fp16 NHWC [in_h, in_w, in_cs] */
+  int in_h, in_w, in_cs, cin;
+  int out_h, out_w;
+  int mode, up_shift, down_shift;
+  const void* packed_w;
+  const float* bias;
+  int ntile, ntiles;       /* output columns per CTA pass (16, 64 or 128) and number of such tiles */
+  int epilogue;
+  const void* aux;
+  int aux_cs, aux_shift;
+  const float* mean;
+  const float* rstd;
+  void* out;               /* fp16 NHWC [out_h, out_w, out_cs] (fp32 with flag 8) */
+  int out_cs, cout;
+} sahs_conv_desc;
+int sahs_spade_conv(const sahs_conv_desc* desc, void* stream);
+/* bounded-wait diagnostic of the conv kernel (0 = healthy), as sahs_field_status */
+int sahs_spade_conv_status(int* out4_host);
+/* Per-channel mean and 1 / sqrt(biased variance + eps) over num_pixels of an NHWC fp16 tensor (nn.InstanceNorm2d,
+ * affine=False; ref: nerf/_init_spade.py:118).  sums_workspace: 2 * channels doubles. */
+int sahs_instnorm_stats(const void* x, int64_t num_pixels, int channels, int channel_stride, float eps,
+                        double* sums_workspace, float* mean, float* rstd, void* stream);
+/* nn.AvgPool2d(2, stride=2) on NHWC fp16 (ref: :240-249, :292) */
+int sahs_avgpool2(const void* x, int height, int width, int channels, void* y, void* stream);
+
 /* Diagnostic word written by the field kernel when a bounded mbarrier wait times out (0 = healthy):
  * out4_host[0] code (+100 dgrad kernel, +200 wgrad kernel), [1] tag, [2] block, [3] thread.  The words live in mapped
  * host memory, so this works (and issues no CUDA call) after a kernel trapped. */

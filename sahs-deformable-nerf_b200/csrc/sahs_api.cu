@@ -27,20 +27,28 @@ int sahs_num_sms() {
   return cached;
 }
 
-// Diagnostic words of the field kernels (forward, dgrad, wgrad: 4 ints each) live in mapped pinned host memory, so
+// Diagnostic words of the tcgen05 kernels (field forward, dgrad, wgrad, Stage-II conv: 4 ints each) live in mapped pinned host memory, so
 // they stay readable after a kernel trapped and the context is gone.  Allocated once per process.
 static int* g_status_host = nullptr;
 int* sahs_status_words(int which) {
   static int* dev = [] {
     int* h = nullptr;
     int* d = nullptr;
-    if (cudaHostAlloc((void**)&h, 12 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) return (int*)nullptr;
-    for (int i = 0; i < 12; ++i) h[i] = 0;
+    if (cudaHostAlloc((void**)&h, 16 * sizeof(int), cudaHostAllocMapped) != cudaSuccess) return (int*)nullptr;
+    for (int i = 0; i < 16; ++i) h[i] = 0;
     if (cudaHostGetDevicePointer((void**)&d, h, 0) != cudaSuccess) return (int*)nullptr;
     g_status_host = h;
     return d;
   }();
   return dev ? dev + 4 * which : nullptr;
+}
+
+extern "C" int sahs_spade_conv_status(int* out4_host) {
+  for (int i = 0; i < 4; ++i) out4_host[i] = 0;
+  if (!g_status_host) return SAHS_OK;
+  const volatile int* w = g_status_host + 12;
+  for (int i = 0; i < 4; ++i) out4_host[i] = w[i];
+  return SAHS_OK;
 }
 
 extern "C" int sahs_field_status(int* out4_host) {

@@ -42,7 +42,7 @@ extern std::atomic<uint64_t> g_sahs_launches;
   } while (0)
 
 int sahs_num_sms();
-int* sahs_status_words(int which);   // device-visible diagnostic word of kernel 0 fwd / 1 dgrad / 2 wgrad
+int* sahs_status_words(int which);   // device-visible diagnostic word of kernel 0 fwd / 1 dgrad / 2 wgrad / 3 Stage-II conv
 
 // ------------------------------------------------------------------------------------------------
 // device side

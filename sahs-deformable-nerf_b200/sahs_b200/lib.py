@@ -31,6 +31,15 @@ class RngC(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("counter_dev", C.c_void_p), ("stream", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class ConvDescC(C.Structure):
+    """struct sahs_conv_desc"""
+    _fields_ = [("in_", C.c_void_p), ("in_h", C.c_int), ("in_w", C.c_int), ("in_cs", C.c_int), ("cin", C.c_int),
+                ("out_h", C.c_int), ("out_w", C.c_int), ("mode", C.c_int), ("up_shift", C.c_int), ("down_shift", C.c_int),
+                ("packed_w", C.c_void_p), ("bias", C.c_void_p), ("ntile", C.c_int), ("ntiles", C.c_int),
+                ("epilogue", C.c_int), ("aux", C.c_void_p), ("aux_cs", C.c_int), ("aux_shift", C.c_int),
+                ("mean", C.c_void_p), ("rstd", C.c_void_p), ("out", C.c_void_p), ("out_cs", C.c_int), ("cout", C.c_int)]
+
+
 EXPORTS = (
     "sahs_abi_version", "sahs_last_error", "sahs_launch_count", "sahs_param_count", "sahs_get_ray_bundle",
     "sahs_coarse_z", "sahs_positional_encoding", "sahs_field_sizes", "sahs_pack_params", "sahs_fold_frame",
@@ -38,6 +47,7 @@ EXPORTS = (
     "sahs_field_status", "sahs_debug_plan", "sahs_train_layout", "sahs_pack_params_train", "sahs_pack_params_bwd",
     "sahs_field_fwd_train", "sahs_field_bwd", "sahs_field_wgrad", "sahs_frame_postprocess", "sahs_weighted_sample", "sahs_stage1_loss",
     "sahs_adam_step", "sahs_adam_step_dev", "sahs_adam_advance", "sahs_counter_add", "sahs_weighted_sample_dev", "sahs_normal_map",
+    "sahs_spade_conv", "sahs_spade_conv_status", "sahs_instnorm_stats", "sahs_avgpool2",
     "sahs_operand_format", "sahs_rng_fill", "sahs_coarse_z_rng", "sahs_composite_fwd_rng", "sahs_composite_bwd_rng", "sahs_sample_pdf_merge_rng",
 )
 
@@ -56,6 +66,10 @@ def load() -> C.CDLL:
     sigs = {
         "sahs_abi_version": (C.c_int, []),
         "sahs_operand_format": (C.c_int, []),
+        "sahs_spade_conv": (C.c_int, [C.POINTER(ConvDescC), vp]),
+        "sahs_spade_conv_status": (C.c_int, [C.POINTER(C.c_int)]),
+        "sahs_instnorm_stats": (C.c_int, [vp, i64, i32, i32, f32, vp, vp, vp, vp]),
+        "sahs_avgpool2": (C.c_int, [vp, i32, i32, i32, vp, vp]),
         "sahs_last_error": (C.c_char_p, []),
         "sahs_launch_count": (C.c_uint64, []),
         "sahs_param_count": (C.c_int, [spec_p]),

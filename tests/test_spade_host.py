@@ -1,0 +1,131 @@
+"""CPU tests of the Stage-II SPADE path: oracle vs the reference's golden outputs, drop-in
+state_dict compatibility, and the host-side logic of sahs_b200/spade.py (weight packing, gather rules, network wiring)
+interpreted on the CPU by tests/spade_emulator.py."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import sahs_fixtures as FX  # noqa: F401  (puts the package on sys.path)
+import spade_fixtures as SF
+from oracle import spade_oracle as SO
+
+GOLD = os.path.join(SF.REPO, "tests", "golden")
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def test_oracle_matches_reference_golden():
+    g = np.load(os.path.join(GOLD, "spade_gen.npz"))
+    sd = SF.make_state_dict("generator", seed=0)
+    for tag in ("64", "96x128"):
+        out, inter = SO.generator(sd, _t(g[f"i_src_{tag}"]), _t(g[f"i_raw_{tag}"]), return_intermediates=True)
+        ref = _t(g[f"ref_out_{tag}"])
+        assert float((out - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
+        if tag == "64":
+            for k in ("layer2", "layer4", "layer5", "layer6"):
+                r = _t(g[f"ref_{k}_{tag}"])
+                assert float((inter[k] - r).abs().max()) <= 2e-4 * float(r.abs().max())
+    ga = np.load(os.path.join(GOLD, "spade_audio.npz"))
+    sda = SF.make_state_dict("generator_audio", seed=1)
+    out = SO.generator_audio(sda, _t(ga["i_src"]), _t(ga["i_raw"]), _t(ga["audio"]))
+    assert float((out - _t(ga["ref_out"])).abs().max()) <= 2e-4 * float(np.abs(ga["ref_out"]).max())
+
+
+@pytest.mark.parametrize("kind", ["generator", "generator_audio"])
+def test_state_dict_is_the_references(kind):
+    """same keys and shapes as the reference module (tests/golden/spade_keys.json, written from the live reference), and a
+    reference checkpoint loads with strict=True"""
+    from sahs_b200 import spade as SP
+    m = SP.Generator() if kind == "generator" else SP.Generator_audio()
+    want = SF.load_keys(kind)
+    got = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert got == want
+    assert list(got) == list(want)                       # same order, too
+    m.load_state_dict(SF.make_state_dict(kind, seed=3), strict=True)
+
+
+def _packed_conv(cin, cout, transposed=False, seed=0):
+    from sahs_b200 import spade as SP
+    gen = torch.Generator().manual_seed(seed)
+    w = torch.randn((cin, cout, 3, 3) if transposed else (cout, cin, 3, 3), generator=gen) * 0.1
+    b = torch.randn(cout, generator=gen)
+    return SP._pack_conv(w, b, transposed), w.half().float(), b
+
+
+@pytest.mark.parametrize("case", ["s1", "s1_up", "s1_down", "s2", "t2", "first", "tiny_cout"])
+def test_packed_conv_and_gather_rules_vs_torch(case):
+    import spade_emulator as EM
+    from sahs_b200 import spade as SP
+    gen = torch.Generator().manual_seed(5)
+    if case == "first":
+        p, w, b = _packed_conv(3, 64)
+        img = torch.rand(1, 3, 10, 12, generator=gen)
+        x = EM.EmulatedMixin._image(img)
+        got = EM.conv(p, x, 10, 12, SP.MODE_FIRST)
+        want = F.conv2d(img, w, b, padding=1)
+    elif case == "tiny_cout":
+        p, w, b = _packed_conv(64, 3)
+        assert (p.ntile, p.ntiles) == (16, 1)
+        xin = torch.randn(1, 64, 9, 7, generator=gen)
+        got = EM.conv(p, xin[0].permute(1, 2, 0), 9, 7, SP.MODE_S1)
+        want = F.conv2d(xin, w, b, padding=1)
+    else:
+        cin, cout = 128, 256
+        xin = torch.randn(1, cin, 6, 10, generator=gen)
+        x = xin[0].permute(1, 2, 0).contiguous()
+        if case == "t2":
+            p, w, b = _packed_conv(cin, cout, transposed=True)
+            got = EM.conv(p, x, 12, 20, SP.MODE_T2)
+            want = F.conv_transpose2d(xin, w, b, stride=2, padding=1, output_padding=1)
+        else:
+            p, w, b = _packed_conv(cin, cout)
+            assert (p.ntile, p.ntiles) == (128, 2)
+            if case == "s1":
+                got, want = EM.conv(p, x, 6, 10, SP.MODE_S1), F.conv2d(xin, w, b, padding=1)
+            elif case == "s1_up":
+                got = EM.conv(p, x, 12, 20, SP.MODE_S1, up=1)
+                want = F.conv2d(F.interpolate(xin, size=(12, 20), mode="nearest"), w, b, padding=1)
+            elif case == "s1_down":
+                got = EM.conv(p, x, 3, 5, SP.MODE_S1, down=1)
+                want = F.conv2d(F.interpolate(xin, size=(3, 5), mode="nearest"), w, b, padding=1)
+            else:
+                got, want = EM.conv(p, x, 3, 5, SP.MODE_S2), F.conv2d(xin, w, b, stride=2, padding=1)
+    want = want[0].permute(1, 2, 0)
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 2e-4 * max(1.0, float(want.abs().max()))
+
+
+def test_generator_host_logic_vs_oracle():
+    """the product's orchestration (folded BatchNorm / spectral norm, [gamma|beta] tiles, resize shifts, folded upsample,
+    residual wiring) interpreted on the CPU = the oracle, up to the fp16 rounding of the packed weights"""
+    import spade_emulator as EM
+    sd = SF.make_state_dict("generator", seed=0)
+    inp = SF.make_inputs(32, 40, seed=2)
+    m = EM.EmulatedGenerator()
+    m.load_state_dict(sd, strict=True)
+    taps = {}
+    got = m(inp["i_src"], inp["i_raw"], taps)
+    want, inter = SO.generator(sd, inp["i_src"], inp["i_raw"], return_intermediates=True)
+    for k, v in inter.items():
+        if k not in taps:
+            continue
+        t = taps[k].permute(2, 0, 1).unsqueeze(0)
+        assert float((t - v).abs().max()) <= 5e-3 * float(v.abs().max()), k
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 5e-3 * float(want.abs().max())
+
+
+def test_generator_audio_host_logic_vs_oracle():
+    import spade_emulator as EM
+    sd = SF.make_state_dict("generator_audio", seed=1)
+    inp = SF.make_inputs(32, 24, seed=4)
+    m = EM.EmulatedGeneratorAudio()
+    m.load_state_dict(sd, strict=True)
+    got = m(inp["i_src"], inp["i_raw"], inp["audio"])
+    want = SO.generator_audio(sd, inp["i_src"], inp["i_raw"], inp["audio"])
+    assert float((got - want).abs().max()) <= 5e-3 * float(want.abs().max())
