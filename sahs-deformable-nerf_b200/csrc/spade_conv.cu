@@ -16,8 +16,11 @@
 //   * epilogue (same worker threads, TMEM -> registers -> NHWC): bias, optional ReLU, optional residual add; or the whole
 //     SPADE modulation: the N tile holds [gamma(64) | beta(64)] of the same 64 channels and the kernel writes
 //     leaky_relu(((x - mean) * rstd) * (1 + gamma) + beta, 0.2) -- gamma, beta and the normalised tensor never reach HBM.
-//   * warp roles: warp 0 weight producer, warp 1 MMA issuer, warps 2-9 two gather groups of 128 threads that take
-//     alternate K chunks through a 3-slot A ring.  Bounded mbarrier waits (trap + status word), as everywhere in this
+//   * warp roles: warp 0 weight producer, warp 1 MMA issuer, warps 2-5 gather (128 threads = 128 operand rows; the
+//     loads of the next chunk are issued before the current one is stored, so two chunks of global loads are in flight
+//     per CTA and the gather never waits for a free slot with nothing requested), warps 6-9 epilogue.  The accumulator is
+//     double buffered in TMEM (2 x 128 columns): the epilogue of tile t runs under the main loop of tile t+1, and the
+//     gather runs straight through tile boundaries.  Bounded mbarrier waits (trap + status word), as everywhere in this
 //     library.
 #include <cuda_fp16.h>
 #include "sahs_common.cuh"
@@ -31,7 +34,7 @@ constexpr int kCOffB = kCSlots * kCChunk;            // B ring after the A ring
 constexpr int kCOffBar = 2 * kCSlots * kCChunk;      // 96 KB
 constexpr int kCOffStage = kCOffBar + 256;           // floats: bias[128] | mean[64] | rstd[64]
 constexpr int kCSmem = kCOffStage + 256 * 4;
-constexpr int kCTmemCols = 128;
+constexpr int kCTmemCols = 256;                      // two accumulators of 128 columns
 
 enum { MODE_S1 = 0, MODE_S2 = 1, MODE_T2 = 2, MODE_FIRST = 3 };
 enum { EPI_RELU = 1, EPI_ADD = 2, EPI_SPADE = 4, EPI_F32 = 8 };
@@ -52,6 +55,7 @@ struct ConvP {
   void* out;
   int out_cs, cout;
   int* status;
+  int dbg;   // measurement switches (SAHS_CONV_DBG): 1 no gather loads, 2 no operand stores, 4 no MMAs, 8 16-byte weight copies, 16 no output stores
 };
 
 // input pixel of output pixel (oy, ox) for tap (ky, kx); false: outside (contributes zero)
@@ -80,9 +84,9 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
   uint64_t* a_empty = bars + kCSlots;          // [3] tcgen05.commit
   uint64_t* b_full = bars + 2 * kCSlots;       // [3] expect_tx
   uint64_t* b_empty = bars + 3 * kCSlots;      // [3] tcgen05.commit
-  uint64_t* acc_full = bars + 4 * kCSlots;
-  uint64_t* acc_empty = bars + 4 * kCSlots + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4 * kCSlots + 2);
+  uint64_t* acc_full = bars + 4 * kCSlots;     // [2] tcgen05.commit
+  uint64_t* acc_empty = bars + 4 * kCSlots + 2;  // [2] 128 epilogue threads
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4 * kCSlots + 4);
   float* stage = reinterpret_cast<float*>(smem + kCOffStage);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int nt = blockIdx.y;                                   // N tile of this CTA
@@ -97,8 +101,10 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
     }
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 256);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 128);
+    }
     fence_mbar_init();
   }
   if (threadIdx.x < c.ntile) stage[threadIdx.x] = c.bias[nt * c.ntile + threadIdx.x];
@@ -121,8 +127,9 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
       for (int q = 0; q < c.nchunks; ++q) {
         mbar_wait(&b_empty[slot], phase ^ 1, c.status, 100);
         if (lane == 0) {
-          mbar_arrive_expect_tx(&b_full[slot], b_bytes);
-          tma_bulk_g2s(smem + kCOffB + slot * kCChunk, wsrc + (size_t)q * b_bytes, b_bytes, &b_full[slot]);
+          const uint32_t nbytes = (c.dbg & 8) ? 16u : b_bytes;
+          mbar_arrive_expect_tx(&b_full[slot], nbytes);
+          tma_bulk_g2s(smem + kCOffB + slot * kCChunk, wsrc + (size_t)q * b_bytes, nbytes, &b_full[slot]);
         }
         __syncwarp();
         if (++slot == kCSlots) { slot = 0; phase ^= 1; }
@@ -130,94 +137,128 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
     }
   } else if (warp == 1) {
     // ================= MMA issuer (converged warp, elect.sync per instruction) =================
-    uint32_t slot = 0, phase = 0, acc_par = 0;
+    uint32_t slot = 0, phase = 0;
     const uint32_t idesc = umma_idesc_m128((uint32_t)c.ntile, true);
-    int done = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++done) {
-      if (done > 0) {                      // the previous tile's accumulator must have been read
-        mbar_wait_uniform<false>(acc_empty, acc_par, c.status, 300);
-        acc_par ^= 1;
-        tc_fence_after();
-      }
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tcount) {
+      const int buf = tcount & 1;
+      // accumulator `buf` was last used by tile tcount - 2: wait until its epilogue has read it (fresh barrier: passes)
+      mbar_wait_uniform<false>(&acc_empty[buf], (uint32_t)(((tcount >> 1) & 1) ^ 1), c.status, 300);
+      tc_fence_after();
+      const uint32_t d = tmem_base + (uint32_t)buf * 128u;
       for (int q = 0; q < c.nchunks; ++q) {
         mbar_wait_uniform<false>(&a_full[slot], phase, c.status, 400);
         mbar_wait_uniform<false>(&b_full[slot], phase, c.status, 401);
         tc_fence_after();
         const uint64_t a0 = umma_smem_desc_sw128(smem_u32(smem + slot * kCChunk));
         const uint64_t b0 = umma_smem_desc_sw128(smem_u32(smem + kCOffB + slot * kCChunk));
-        tc_mma_f16_w(tmem_base, a0, b0, idesc, q > 0 ? 1u : 0u);
-        tc_mma_f16_w(tmem_base, a0 + 2, b0 + 2, idesc, 1u);
-        tc_mma_f16_w(tmem_base, a0 + 4, b0 + 4, idesc, 1u);
-        tc_mma_f16_w(tmem_base, a0 + 6, b0 + 6, idesc, 1u);
+        if (!(c.dbg & 4)) {
+          tc_mma_f16_w(d, a0, b0, idesc, q > 0 ? 1u : 0u);
+          tc_mma_f16_w(d, a0 + 2, b0 + 2, idesc, 1u);
+          tc_mma_f16_w(d, a0 + 4, b0 + 4, idesc, 1u);
+          tc_mma_f16_w(d, a0 + 6, b0 + 6, idesc, 1u);
+        }
         tc_commit_w(&a_empty[slot]);
         tc_commit_w(&b_empty[slot]);
         if (++slot == kCSlots) { slot = 0; phase ^= 1; }
       }
-      tc_commit_w(acc_full);
+      tc_commit_w(&acc_full[buf]);
+    }
+  } else if (warp < 6) {
+    // ================= gather: the A operand, one thread per row, next chunk's loads in flight =================
+    // (a coalesced mapping -- eight lanes per pixel -- was measured too: the same time on the large layers, slower on
+    // the small ones through its eight coordinate computations per chunk)
+    const int row = (warp - 2) * 32 + lane;
+    uint8_t* a_row = smem + (row >> 3) * 1024 + (row & 7) * 128;
+    const int kcs = c.cin >> 6;                            // 64-channel chunks per tap (MODE_FIRST: unused)
+    bool live = false;
+    int oy = 0, ox = 0;
+    auto set_tile = [&](int tile) {
+      const long long p = (long long)tile * 128 + row;
+      live = p < P;
+      oy = live ? (int)(p / c.out_w) : 0;
+      ox = live ? (int)(p - (long long)oy * c.out_w) : 0;
+    };
+    auto load = [&](int q, uint4 (&v)[8]) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (c.dbg & 1) return;
+      if (c.mode == MODE_FIRST) {
+        // nine taps x 4 channels (8 bytes per pixel) in one chunk: column = tap * 4 + channel
+        uint2 t[10];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          int iy, ix;
+          t[k] = make_uint2(0u, 0u);
+          if (live && src_pixel(c, oy, ox, k / 3, k % 3, iy, ix))
+            t[k] = __ldg(reinterpret_cast<const uint2*>(c.in + ((size_t)iy * c.in_w + ix) * c.in_cs));
+        }
+        t[9] = make_uint2(0u, 0u);
+#pragma unroll
+        for (int u = 0; u < 5; ++u) v[u] = make_uint4(t[2 * u].x, t[2 * u].y, t[2 * u + 1].x, t[2 * u + 1].y);
+      } else {
+        const int tap = q / kcs, kc = q - tap * kcs;
+        int iy, ix;
+        if (live && src_pixel(c, oy, ox, tap / 3, tap % 3, iy, ix)) {
+          const uint4* src = reinterpret_cast<const uint4*>(c.in + ((size_t)iy * c.in_w + ix) * c.in_cs + kc * 64);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = __ldg(src + u);
+        }
+      }
+    };
+    uint32_t slot = 0, phase = 0;
+    int tile = blockIdx.x, q = 0;
+    uint4 vn[8];
+    if (tile < tiles) {
+      set_tile(tile);
+      load(0, vn);
+    }
+    while (tile < tiles) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = vn[u];
+      int nq = q + 1, ntile = tile;
+      if (nq == c.nchunks) {
+        nq = 0;
+        ntile = tile + (int)gridDim.x;
+        if (ntile < tiles) set_tile(ntile);
+      }
+      if (ntile < tiles) load(nq, vn);                     // requested before this chunk's slot is even free
+      mbar_wait(&a_empty[slot], phase ^ 1, c.status, 200);
+      if (!(c.dbg & 2)) {
+        uint8_t* dst = a_row + slot * kCChunk;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) *reinterpret_cast<uint4*>(dst + (((u ^ row) & 7) << 4)) = v[u];
+        fence_proxy_async_smem();
+      }
+      mbar_arrive(&a_full[slot]);
+      if (++slot == kCSlots) { slot = 0; phase ^= 1; }
+      q = nq;
+      tile = ntile;
     }
   } else {
-    // ================= gather (A operand) + epilogue =================
-    const int grp = (warp - 2) >> 2;                       // chunks with (running index & 1) == grp are mine
+    // ================= epilogue: TMEM -> registers -> NHWC, under the next tile's main loop =================
     const int quarter = warp & 3;                          // TMEM lane quarter this warp may read
     const int row = quarter * 32 + lane;                   // pixel row of the tile == TMEM lane
-    const uint32_t tmem_row = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint8_t* a_row = smem + (row >> 3) * 1024 + (row & 7) * 128;
-    uint32_t slot = 0, phase = 0, run = 0, acc_par = 0;
-    const int kcs = c.cin >> 6;                            // 64-channel chunks per tap (MODE_FIRST: unused)
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    int tcount = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++tcount) {
+      const int buf = tcount & 1;
       const long long p = (long long)tile * 128 + row;
-      const bool live = p < P;
+      const bool live = p < P && !(c.dbg & 16);
       const int oy = live ? (int)(p / c.out_w) : 0, ox = live ? (int)(p - (long long)oy * c.out_w) : 0;
-      for (int q = 0; q < c.nchunks; ++q, ++run) {
-        if ((int)(run & 1u) == grp) {
-          mbar_wait(&a_empty[slot], phase ^ 1, c.status, 200);
-          uint4 v[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) v[u] = make_uint4(0u, 0u, 0u, 0u);
-          if (c.mode == MODE_FIRST) {
-            // nine taps x 4 channels (8 bytes per pixel) in one chunk: column = tap * 4 + channel
-            uint2 t[10];
-#pragma unroll
-            for (int k = 0; k < 9; ++k) {
-              int iy, ix;
-              t[k] = make_uint2(0u, 0u);
-              if (live && src_pixel(c, oy, ox, k / 3, k % 3, iy, ix))
-                t[k] = *reinterpret_cast<const uint2*>(c.in + ((size_t)iy * c.in_w + ix) * c.in_cs);
-            }
-            t[9] = make_uint2(0u, 0u);
-#pragma unroll
-            for (int u = 0; u < 5; ++u) v[u] = make_uint4(t[2 * u].x, t[2 * u].y, t[2 * u + 1].x, t[2 * u + 1].y);
-          } else {
-            const int tap = q / kcs, kc = q - tap * kcs;
-            int iy, ix;
-            if (live && src_pixel(c, oy, ox, tap / 3, tap % 3, iy, ix)) {
-              const uint4* src = reinterpret_cast<const uint4*>(c.in + ((size_t)iy * c.in_w + ix) * c.in_cs + kc * 64);
-#pragma unroll
-              for (int u = 0; u < 8; ++u) v[u] = __ldg(src + u);
-            }
-          }
-          uint8_t* dst = a_row + slot * kCChunk;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) *reinterpret_cast<uint4*>(dst + (((u ^ row) & 7) << 4)) = v[u];
-          fence_proxy_async_smem();
-          mbar_arrive(&a_full[slot]);
-        }
-        if (++slot == kCSlots) { slot = 0; phase ^= 1; }
-      }
-      // ---- epilogue ----
-      mbar_wait(acc_full, acc_par, c.status, 500);
-      acc_par ^= 1;
+      mbar_wait(&acc_full[buf], (uint32_t)((tcount >> 1) & 1), c.status, 500);
       tc_fence_after();
+      const uint32_t tmem_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * 128u;
       if (c.epi & EPI_SPADE) {
-        // columns [0,64) gamma, [64,128) beta of channels nt*64 .. nt*64+63; this group: 32 of them
+        // columns [0,64) gamma, [64,128) beta of channels nt*64 .. nt*64+63
         const long long ap = c.aux_shift ? ((long long)(oy >> c.aux_shift) * (c.out_w >> c.aux_shift) + (ox >> c.aux_shift)) : p;
-        const __half* xrow = c.aux + (size_t)ap * c.aux_cs + nt * 64 + grp * 32;
-        __half* orow = reinterpret_cast<__half*>(c.out) + (size_t)p * c.out_cs + nt * 64 + grp * 32;
+        const __half* xrow = c.aux + (size_t)ap * c.aux_cs + nt * 64;
+        __half* orow = reinterpret_cast<__half*>(c.out) + (size_t)p * c.out_cs + nt * 64;
 #pragma unroll 1
-        for (int i = 0; i < 32; i += 16) {
+        for (int i = 0; i < 64; i += 16) {
           uint32_t gm[16], bt[16];
-          tmem_ld16(tmem_row + grp * 32 + i, gm);
-          tmem_ld16(tmem_row + 64 + grp * 32 + i, bt);
+          tmem_ld16(tmem_row + i, gm);
+          tmem_ld16(tmem_row + 64 + i, bt);
           tmem_ld_wait();
           if (live) {
             uint4 xv[2];
@@ -231,7 +272,7 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
               float r[2];
 #pragma unroll
               for (int k = 0; k < 2; ++k) {
-                const int ch = grp * 32 + i + e + k;
+                const int ch = i + e + k;
                 const float xn = (__half2float(xh[e + k]) - stage[128 + ch]) * stage[192 + ch];
                 const float g = __uint_as_float(gm[e + k]) + stage[ch];
                 const float b = __uint_as_float(bt[e + k]) + stage[64 + ch];
@@ -245,19 +286,17 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
           }
         }
       } else {
-        const int cg = c.ntile == 16 ? (grp == 0 ? 16 : 0) : c.ntile / 2;     // columns of this group
-        const int cbase = c.ntile == 16 ? 0 : grp * cg;
 #pragma unroll 1
-        for (int i = 0; i < cg; i += 16) {
+        for (int i = 0; i < c.ntile; i += 16) {
           uint32_t acc[16];
-          tmem_ld16(tmem_row + cbase + i, acc);
+          tmem_ld16(tmem_row + i, acc);
           tmem_ld_wait();
           if (live) {
-            const int ch0 = nt * c.ntile + cbase + i;
+            const int ch0 = nt * c.ntile + i;
             float r[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-              r[e] = __uint_as_float(acc[e]) + stage[cbase + i + e];
+              r[e] = __uint_as_float(acc[e]) + stage[i + e];
               if (c.epi & EPI_RELU) r[e] = fmaxf(r[e], 0.f);
             }
             if ((c.epi & EPI_ADD) && ch0 + 16 <= c.cout) {
@@ -285,7 +324,7 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
         }
       }
       tc_fence_before();
-      mbar_arrive(acc_empty);
+      mbar_arrive(&acc_empty[buf]);
     }
   }
   __syncthreads();
@@ -370,7 +409,8 @@ __global__ void __launch_bounds__(256) avgpool2_kernel(const __half* __restrict_
 
 extern "C" int sahs_spade_conv(const sahs_conv_desc* d, void* stream) {
   SAHS_CHECK_ARG(d && d->in && d->packed_w && d->bias && d->out, "null pointer");
-  SAHS_CHECK_ARG(d->out_h > 0 && d->out_w > 0 && d->in_h > 0 && d->in_w > 0, "bad geometry");
+  SAHS_CHECK_ARG(d->out_h > 0 && d->out_w > 0 && d->in_h > 0 && d->in_w > 0 && d->out_h < 32768 && d->out_w < 32768,
+                 "bad geometry");
   SAHS_CHECK_ARG(d->ntile == 16 || d->ntile == 64 || d->ntile == 128, "ntile must be 16, 64 or 128");
   SAHS_CHECK_ARG(d->ntiles >= 1 && d->ntiles <= 64, "bad N tile count");
   SAHS_CHECK_ARG(d->mode >= MODE_S1 && d->mode <= MODE_FIRST, "bad mode");
@@ -424,6 +464,7 @@ extern "C" int sahs_spade_conv(const sahs_conv_desc* d, void* stream) {
   c.mean = d->mean; c.rstd = d->rstd;
   c.out = d->out; c.out_cs = d->out_cs; c.cout = d->cout;
   c.status = sahs_status_words(3);
+  { const char* e = getenv("SAHS_CONV_DBG"); c.dbg = e ? atoi(e) : 0; }
   SAHS_CHECK_ARG(c.status, "status word allocation failed");
   const long long P = (long long)d->out_h * d->out_w;
   const int tiles = (int)((P + 127) / 128);

@@ -227,6 +227,7 @@ class Generator(nn.Module):
         self.refine_network = RefineNetwork(64, 128, 256)
         self._packed: Optional[Dict[str, _Packed]] = None
         self._ws: Dict[int, torch.Tensor] = {}
+        self.tally: Optional[Dict[str, float]] = None     # set to {} to count launches and algorithmic FLOPs of a forward
 
     # -- packing (redone after load_state_dict / device moves; call invalidate_packed() after editing parameters in place)
     def invalidate_packed(self):
@@ -311,6 +312,11 @@ class Generator(nn.Module):
         d.mean, d.rstd = (L.ptr(spade[1]), L.ptr(spade[2])) if spade is not None else (None, None)
         d.out, d.out_cs, d.cout = L.ptr(out), p.cout, p.cout
         L.check(lib.sahs_spade_conv(C.byref(d), L.stream_ptr(dev)), "spade_conv")
+        if self.tally is not None:
+            n_out = 2 * p.cout if spade is not None else p.cout
+            taps = 9.0 / 4.0 if mode == MODE_T2 else 9.0          # a stride-2 transposed conv touches 9/4 taps per output
+            self.tally["flop"] = self.tally.get("flop", 0.0) + 2.0 * out_h * out_w * n_out * taps * p.cin
+            self.tally["conv_launches"] = self.tally.get("conv_launches", 0) + 1
         return out
 
     def _stats(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -323,12 +329,16 @@ class Generator(nn.Module):
         rstd = torch.empty(c, dtype=torch.float32, device=x.device)
         L.check(lib.sahs_instnorm_stats(L.ptr(x), x.shape[0] * x.shape[1], c, x.stride(1), 1e-5, L.ptr(ws), L.ptr(mean),
                                         L.ptr(rstd), L.stream_ptr(x.device)), "instnorm_stats")
+        if self.tally is not None:
+            self.tally["other_launches"] = self.tally.get("other_launches", 0) + 2
         return mean, rstd
 
     def _avgpool(self, x: torch.Tensor) -> torch.Tensor:
         lib = L.load()
         y = torch.empty(x.shape[0] // 2, x.shape[1] // 2, x.shape[2], dtype=torch.float16, device=x.device)
         L.check(lib.sahs_avgpool2(L.ptr(x), x.shape[0], x.shape[1], x.shape[2], L.ptr(y), L.stream_ptr(x.device)), "avgpool2")
+        if self.tally is not None:
+            self.tally["other_launches"] = self.tally.get("other_launches", 0) + 1
         return y
 
     # -- network
@@ -446,3 +456,28 @@ class Generator_audio(Generator):
 
         out = self._refine(P, self._image(I_raw), fid1, fid2, fid3, taps)
         return out.permute(2, 0, 1).unsqueeze(0)
+
+
+class GraphedGenerator:
+    """One CUDA graph per frame: the ~110 launches of a forward (convs, statistics, pooling, layout conversion) are
+    recorded once for fixed input shapes and replayed; inputs are copied into the graph's static buffers.  Use for clip
+    refinement (one identity photo, many Stage-I frames)."""
+
+    def __init__(self, gen: Generator, *example_inputs: torch.Tensor, warmup: int = 2):
+        self.gen = gen
+        self.inputs = [t.detach().clone() for t in example_inputs]
+        side = torch.cuda.Stream(device=self.inputs[0].device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                gen(*self.inputs)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.output = gen(*self.inputs)
+
+    def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
+        for dst, src in zip(self.inputs, inputs):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.output
