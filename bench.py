@@ -194,6 +194,99 @@ def cpu_train_step_rays_per_s(cfg_name, n_rays, frame_seed=100):
     return n_rays / dt, dt, torch.get_num_threads()
 
 
+def bench_stage2(dev, peak_tf, steps, cpu_leg=True):
+    """Stage II: the SPADE Generator refining one 512x512 Stage-I frame.  Device-resident time as
+    one CUDA graph per frame, e2e with host buffers (H2D of the identity photo and the Stage-I frame, D2H of the refined
+    frame), algorithmic FLOPs against the tensor peak, parity against the oracle on the host, and two baselines: the
+    reference algorithm through cuDNN on this GPU and on the host cores."""
+    import spade_fixtures as SF
+    from oracle import spade_oracle as SO
+    from sahs_b200 import spade as SP
+    sd = SF.make_state_dict("generator", seed=0)
+    inp = SF.make_inputs(H, W, seed=5)
+    m = SP.Generator()
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev)
+    a_host, b_host = inp["i_src"].pin_memory(), inp["i_raw"].pin_memory()
+    a, b = a_host.to(dev), b_host.to(dev)
+    m.tally = {}
+    out = m(a, b)
+    tally, m.tally = m.tally, None
+    g = SP.GraphedGenerator(m, a, b)
+    for _ in range(3):
+        g(a, b)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        g(a, b)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out_host = torch.empty(1, 3, H, W, dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out_host.copy_(g(a_host, b_host), non_blocking=True)      # H2D into the graph's static inputs, replay, D2H
+        torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / steps
+    tf = tally["flop"] / 1e12
+    res = {"workload": f"Stage-II SPADE Generator on one {H}x{W} Stage-I frame + identity photo (nerf/_init_spade.py:318-328), "
+                       "synthetic weights (tests/spade_fixtures.py seed 0), fp16 NHWC activations",
+           "ms_per_frame": ms, "frames_per_s": 1e3 / ms, "launch": "one CUDA graph per frame (sahs_b200.spade.GraphedGenerator)",
+           "conv_launches": int(tally["conv_launches"]), "helper_launches": int(tally["other_launches"]),
+           "e2e": {"ms_per_frame": e2e_ms, "frames_per_s": 1e3 / e2e_ms, "h2d_bytes_per_step": 2 * 3 * H * W * 4,
+                   "d2h_bytes_per_step": 3 * H * W * 4},
+           "roofline": {"bound": "tensor", "kernel": "spade_conv_kernel (all 70 launches of a frame; helpers included in the time)",
+                        "algorithmic_tflop_per_frame": tf, "achieved": tf / ms * 1e3, "peak": peak_tf, "unit": "TFLOP/s",
+                        "frac": tf / ms * 1e3 / peak_tf}}
+    # the reference algorithm through cuDNN on this GPU (oracle port with its tensors on the device)
+    sdd = {k: v.to(dev) for k, v in sd.items()}
+
+    def timed(fn, n=5):
+        for _ in range(2):
+            fn()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s0.record()
+        for _ in range(n):
+            fn()
+        s1.record()
+        torch.cuda.synchronize()
+        return s0.elapsed_time(s1) / n
+
+    with torch.no_grad():
+        tf32 = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        ref_gpu = SO.generator(sdd, a, b)
+        ms_fp32 = timed(lambda: SO.generator(sdd, a, b))
+        torch.backends.cudnn.allow_tf32 = tf32
+        sdh = {k: (v.half() if v.is_floating_point() else v) for k, v in sdd.items()}
+        ah = a.half().contiguous(memory_format=torch.channels_last)
+        bh = b.half().contiguous(memory_format=torch.channels_last)
+        ms_fp16 = timed(lambda: SO.generator(sdh, ah, bh))
+    rng = float(ref_gpu.abs().max())
+    res["cudnn_gpu_baseline"] = {"kind": "port", "what": "the reference algorithm as PyTorch / cuDNN ops on this GPU (oracle port)",
+                                 "fp32_ms_per_frame": ms_fp32, "fp16_channels_last_ms_per_frame": ms_fp16,
+                                 "speedup_ours_vs_fp16": ms_fp16 / ms, "speedup_ours_vs_fp32": ms_fp32 / ms,
+                                 "maxabs_vs_ours_over_range": float((out - ref_gpu).abs().max()) / rng}
+    del sdd, sdh, ref_gpu
+    if cpu_leg:
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            ref = SO.generator(sd, inp["i_src"], inp["i_raw"])
+        dt = time.perf_counter() - t0
+        err = (out.cpu() - ref)
+        res["cpu_baseline"] = {"value": 1.0 / dt, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"one {H}x{W} frame ({dt:.1f} s), oracle port, all host threads"}
+        res["parity"] = {"against": "oracle port on the host (fp32), full frame",
+                         "maxabs_over_range": float(err.abs().max()) / float(ref.abs().max()),
+                         "psnr": _psnr(out.cpu() / float(ref.abs().max()), ref / float(ref.abs().max()))}
+    g.graph.reset()
+    return res
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -265,6 +358,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step / config-4 / clip measurements")
     ap.add_argument("--no-torch-gpu", action="store_true", help="skip the PyTorch-fp32-on-this-GPU baseline leg")
+    ap.add_argument("--no-stage2", action="store_true", help="skip the Stage-II SPADE generator leg")
     ap.add_argument("--clip-frames", type=int, default=0, help="frames of the clip (0: 1000 at 8 GPUs, else 16 per GPU)")
     args = ap.parse_args()
     _capture_stdout()
@@ -698,6 +792,10 @@ def main():
                          "rgb_maxabs_vs_ours": _maxabs(ours_f, ref_t[3]), "depth_maxabs_vs_ours": _maxabs(ours_d, ref_t[7])}
             del ref_t
             torch.cuda.empty_cache()
+    stage2 = None
+    if rank == 0 and world == 1 and not args.no_stage2:
+        torch.cuda.empty_cache()
+        stage2 = bench_stage2(dev, peak_tf, max(5, min(args.steps, 20)), cpu_leg=not args.no_cpu_baseline)
     if rank == 0:
         line = {
             "metric": "render_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
@@ -713,7 +811,7 @@ def main():
                     "ms_per_frame": 1e3 * float(e2e_s) / args.steps},
             "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels, "composite_per_frame": composite_frame,
             "stage_ms": stage_ms, "cpu_baseline": cpu_baseline, "torch_gpu_baseline": torch_gpu, "parity": parity,
-            "clocks": clocks, "train": train, "strong": strong, "clip": clip, "config4": config4,
+            "clocks": clocks, "train": train, "strong": strong, "clip": clip, "config4": config4, "stage2": stage2,
         }
         _emit(json.dumps(line))
     # Teardown.  The training legs recorded CUDA graphs that contain NCCL all-reduces; destroying the process group (or

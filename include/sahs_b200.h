@@ -278,7 +278,7 @@ int sahs_counter_add(unsigned long long* counter_dev, unsigned long long inc, vo
  *   mode 2: nn.ConvTranspose2d(3x3, stride 2, padding 1, output_padding 1) (residual_upsample :255);
  *   mode 3: 3-channel input stored as [H, W, 4] fp16: all nine taps in one K chunk (layer1 of both networks).
  * packed_w: [ntiles][9 * cin / 64 chunks (mode 3: 1)][ntile rows x 64 columns fp16, 128B-swizzled K-major], chunk order
- * tap-major (tap = 3 ky + kx); bias: [ntiles * ntile] fp32.  Built by sahs_b200/spade.py from the state_dict (spectral
+ * [ky][64-channel chunk][kx]; bias: [ntiles * ntile] fp32.  Built by sahs_b200/spade.py from the state_dict (spectral
  * norm and eval-mode BatchNorm folded in).
  * epilogue flags: 1 ReLU, 2 + aux (residual add, same geometry as the output), 8 fp32 output; or 4 = SPADE modulation:
  * each N tile is [gamma(64) | beta(64)] of 64 channels and the kernel writes

@@ -16,18 +16,22 @@
 //   * epilogue (same worker threads, TMEM -> registers -> NHWC): bias, optional ReLU, optional residual add; or the whole
 //     SPADE modulation: the N tile holds [gamma(64) | beta(64)] of the same 64 channels and the kernel writes
 //     leaky_relu(((x - mean) * rstd) * (1 + gamma) + beta, 0.2) -- gamma, beta and the normalised tensor never reach HBM.
+//   * K chunks are ordered [ky][64-channel chunk][kx].  For the stride-1 modes (all but four layers of the network) the
+//     three kx taps of a group are the SAME pixels shifted by one operand row, so a gather thread loads its pixel once per
+//     group and stores it into the three operand tiles at rows r+1, r, r-1 (zero rows at the image's left / right edge;
+//     the two pixels beyond the tile's ends come from a two-lane halo warp): a third of the global loads of a
+//     tap-by-tap gather, which is what bounded the kernel (scripts/gpu_spade_conv_bound.py).
 //   * warp roles: warp 0 weight producer, warp 1 MMA issuer, warps 2-5 gather (128 threads = 128 operand rows; the
-//     loads of the next chunk are issued before the current one is stored, so two chunks of global loads are in flight
-//     per CTA and the gather never waits for a free slot with nothing requested), warps 6-9 epilogue.  The accumulator is
-//     double buffered in TMEM (2 x 128 columns): the epilogue of tile t runs under the main loop of tile t+1, and the
-//     gather runs straight through tile boundaries.  Bounded mbarrier waits (trap + status word), as everywhere in this
-//     library.
+//     loads of the next group are issued before the current one is stored), warp 6 halo, warps 7-10 epilogue.  The
+//     accumulator is double buffered in TMEM (2 x 128 columns): the epilogue of tile t runs under the main loop of tile
+//     t+1, and the gather runs straight through tile boundaries.  Bounded mbarrier waits (trap + status word), as
+//     everywhere in this library.
 #include <cuda_fp16.h>
 #include "sahs_common.cuh"
 
 namespace {
 
-constexpr int kCThreads = 320;
+constexpr int kCThreads = 352;                       // warps: 0 weights, 1 MMA, 2-5 gather, 6 halo, 7-10 epilogue
 constexpr int kCSlots = 3;
 constexpr int kCChunk = 16384;                       // one [128 x 64] fp16 operand tile
 constexpr int kCOffB = kCSlots * kCChunk;            // B ring after the A ring
@@ -55,7 +59,7 @@ struct ConvP {
   void* out;
   int out_cs, cout;
   int* status;
-  int dbg;   // measurement switches (SAHS_CONV_DBG): 1 no gather loads, 2 no operand stores, 4 no MMAs, 8 16-byte weight copies, 16 no output stores
+  int dbg;   // measurement switches (SAHS_CONV_DBG): 1 no gather loads, 2 no operand stores, 4 no MMAs, 8 16-byte weight copies, 16 no output stores, 32 tap-by-tap gather for the stride-1 modes too, 64 no zero-tap skipping in transposed convs
 };
 
 // input pixel of output pixel (oy, ox) for tap (ky, kx); false: outside (contributes zero)
@@ -92,11 +96,12 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
   const int nt = blockIdx.y;                                   // N tile of this CTA
   const long long P = (long long)c.out_h * c.out_w;
   const int tiles = (int)((P + 127) / 128);
+  const bool fast = c.mode == MODE_S1 && !(c.dbg & 32);      // one load per (ky, chunk) feeds the three kx taps
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) { c.status[0] = 2; __trap(); }
     for (int i = 0; i < kCSlots; ++i) {
-      mbar_init(&a_full[i], 128);
+      mbar_init(&a_full[i], (fast && i != 1) ? 129 : 128);      // stride-1 path: + the halo lane of taps kx = 0 / 2
       mbar_init(&a_empty[i], 1);
       mbar_init(&b_full[i], 1);
       mbar_init(&b_empty[i], 1);
@@ -118,13 +123,26 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t b_bytes = (uint32_t)c.ntile * 128u;
+  // Transposed conv: output row oy only receives the taps with (oy + 1 - ky) even.  When a tile lies inside one output
+  // row (always, for widths that are multiples of 128) the chunks of the other ky are all zeros and every role skips them.
+  const int kcs_all = c.cin >> 6;
+  auto tile_row = [&](int tile) -> int {
+    if (c.mode != MODE_T2 || (c.dbg & 64)) return -1;
+    const long long p0 = (long long)tile * 128;
+    if (p0 + 127 >= P) return -1;
+    const int r0 = (int)(p0 / c.out_w), r1 = (int)((p0 + 127) / c.out_w);
+    return r0 == r1 ? r0 : -1;
+  };
+  auto skipped = [&](int oyrow, int q) -> bool { return oyrow >= 0 && (((oyrow + 1 - (q / 3) / kcs_all) & 1) != 0); };
 
   if (warp == 0) {
     // ================= weights of this N tile: one [ntile x 64] block per K chunk, re-streamed per pixel tile (L2) ========
     uint32_t slot = 0, phase = 0;
     const uint8_t* wsrc = c.packed_w + (size_t)nt * c.nchunks * b_bytes;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int trow = tile_row(tile);
       for (int q = 0; q < c.nchunks; ++q) {
+        if (skipped(trow, q)) continue;
         mbar_wait(&b_empty[slot], phase ^ 1, c.status, 100);
         if (lane == 0) {
           const uint32_t nbytes = (c.dbg & 8) ? 16u : b_bytes;
@@ -146,18 +164,22 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
       mbar_wait_uniform<false>(&acc_empty[buf], (uint32_t)(((tcount >> 1) & 1) ^ 1), c.status, 300);
       tc_fence_after();
       const uint32_t d = tmem_base + (uint32_t)buf * 128u;
+      const int trow = tile_row(tile);
+      uint32_t accumulate = 0u;
       for (int q = 0; q < c.nchunks; ++q) {
+        if (skipped(trow, q)) continue;
         mbar_wait_uniform<false>(&a_full[slot], phase, c.status, 400);
         mbar_wait_uniform<false>(&b_full[slot], phase, c.status, 401);
         tc_fence_after();
         const uint64_t a0 = umma_smem_desc_sw128(smem_u32(smem + slot * kCChunk));
         const uint64_t b0 = umma_smem_desc_sw128(smem_u32(smem + kCOffB + slot * kCChunk));
         if (!(c.dbg & 4)) {
-          tc_mma_f16_w(d, a0, b0, idesc, q > 0 ? 1u : 0u);
+          tc_mma_f16_w(d, a0, b0, idesc, accumulate);
           tc_mma_f16_w(d, a0 + 2, b0 + 2, idesc, 1u);
           tc_mma_f16_w(d, a0 + 4, b0 + 4, idesc, 1u);
           tc_mma_f16_w(d, a0 + 6, b0 + 6, idesc, 1u);
         }
+        accumulate = 1u;
         tc_commit_w(&a_empty[slot]);
         tc_commit_w(&b_empty[slot]);
         if (++slot == kCSlots) { slot = 0; phase ^= 1; }
@@ -165,11 +187,10 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
       tc_commit_w(&acc_full[buf]);
     }
   } else if (warp < 6) {
-    // ================= gather: the A operand, one thread per row, next chunk's loads in flight =================
+    // ================= gather: the A operand, one thread per row, next loads in flight =================
     // (a coalesced mapping -- eight lanes per pixel -- was measured too: the same time on the large layers, slower on
     // the small ones through its eight coordinate computations per chunk)
     const int row = (warp - 2) * 32 + lane;
-    uint8_t* a_row = smem + (row >> 3) * 1024 + (row & 7) * 128;
     const int kcs = c.cin >> 6;                            // 64-channel chunks per tap (MODE_FIRST: unused)
     bool live = false;
     int oy = 0, ox = 0;
@@ -179,7 +200,13 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
       oy = live ? (int)(p / c.out_w) : 0;
       ox = live ? (int)(p - (long long)oy * c.out_w) : 0;
     };
-    auto load = [&](int q, uint4 (&v)[8]) {
+    auto row_ptr = [&](int slot, int r) -> uint8_t* { return smem + slot * kCChunk + (r >> 3) * 1024 + (r & 7) * 128; };
+    auto store_row = [&](uint8_t* dst, int r, const uint4 (&v)[8]) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) *reinterpret_cast<uint4*>(dst + (((u ^ r) & 7) << 4)) = v[u];
+    };
+    // chunk q = (ky * kcs + kc) * 3 + kx; group g = q / 3.  load(): the pixel of tap (ky, kx) for my row.
+    auto load = [&](int g, int kx, uint4 (&v)[8]) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) v[u] = make_uint4(0u, 0u, 0u, 0u);
       if (c.dbg & 1) return;
@@ -197,44 +224,155 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
 #pragma unroll
         for (int u = 0; u < 5; ++u) v[u] = make_uint4(t[2 * u].x, t[2 * u].y, t[2 * u + 1].x, t[2 * u + 1].y);
       } else {
-        const int tap = q / kcs, kc = q - tap * kcs;
+        const int ky = g / kcs, kc = g - ky * kcs;
         int iy, ix;
-        if (live && src_pixel(c, oy, ox, tap / 3, tap % 3, iy, ix)) {
+        if (live && src_pixel(c, oy, ox, ky, kx, iy, ix)) {
           const uint4* src = reinterpret_cast<const uint4*>(c.in + ((size_t)iy * c.in_w + ix) * c.in_cs + kc * 64);
 #pragma unroll
           for (int u = 0; u < 8; ++u) v[u] = __ldg(src + u);
         }
       }
     };
-    uint32_t slot = 0, phase = 0;
-    int tile = blockIdx.x, q = 0;
+    int tile = blockIdx.x;
     uint4 vn[8];
-    if (tile < tiles) {
-      set_tile(tile);
-      load(0, vn);
+    if (fast) {
+      // ---- stride-1 modes: one load per group, three operand tiles (slot = kx) ----
+      const int ngroups = 3 * kcs;
+      uint32_t phase = 0;
+      int g = 0;
+      if (tile < tiles) {
+        set_tile(tile);
+        load(0, 1, vn);
+      }
+      while (tile < tiles) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = vn[u];
+        const bool my_live = live;
+        const int my_ox = ox;
+        int ng = g + 1, ntile = tile;
+        if (ng == ngroups) {
+          ng = 0;
+          ntile = tile + (int)gridDim.x;
+          if (ntile < tiles) set_tile(ntile);
+        }
+        if (ntile < tiles) load(ng, 1, vn);                // requested before this group's slots are even free
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          mbar_wait(&a_empty[kx], phase ^ 1, c.status, 200 + kx);
+          if (!(c.dbg & 2)) {
+            // my pixel is tap kx of the output pixel one row up / the same / one row down (same image row only)
+            const int dr = row - kx + 1, dx = my_ox - kx + 1;
+            if (kx == 1 || (my_live && dr >= 0 && dr < 128 && dx >= 0 && dx < c.out_w)) store_row(row_ptr(kx, dr), dr, v);
+            // my own row's tap kx lies outside the image (or I am beyond the last pixel): zeros, nobody else writes it
+            if (kx != 1 && (!my_live || my_ox + kx - 1 < 0 || my_ox + kx - 1 >= c.out_w)) {
+              const uint4 z[8] = {};
+              store_row(row_ptr(kx, row), row, z);
+            }
+            fence_proxy_async_smem();
+          }
+          mbar_arrive(&a_full[kx]);
+        }
+        phase ^= 1;
+        g = ng;
+        tile = ntile;
+      }
+    } else {
+      // ---- stride-2 / transposed / first-layer modes: tap by tap ----
+      uint32_t slot = 0, phase = 0;
+      int q = -1, trow = -1;
+      auto advance = [&](int& t, int& qq, int& tr) {      // next chunk that is not skipped (set_tile on a tile change)
+        do {
+          if (qq < 0) { tr = tile_row(t); set_tile(t); }
+          if (++qq == c.nchunks) {
+            qq = 0;
+            t += (int)gridDim.x;
+            if (t >= tiles) return;
+            tr = tile_row(t);
+            set_tile(t);
+          }
+        } while (skipped(tr, qq));
+      };
+      if (tile < tiles) {
+        advance(tile, q, trow);
+        if (tile < tiles) load(q / 3, q % 3, vn);
+      }
+      while (tile < tiles) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = vn[u];
+        int nq = q, ntile = tile, ntrow = trow;
+        advance(ntile, nq, ntrow);
+        if (ntile < tiles) load(nq / 3, nq % 3, vn);
+        mbar_wait(&a_empty[slot], phase ^ 1, c.status, 210);
+        if (!(c.dbg & 2)) {
+          store_row(row_ptr((int)slot, row), row, v);
+          fence_proxy_async_smem();
+        }
+        mbar_arrive(&a_full[slot]);
+        if (++slot == kCSlots) { slot = 0; phase ^= 1; }
+        q = nq;
+        tile = ntile;
+        trow = ntrow;
+      }
     }
-    while (tile < tiles) {
-      uint4 v[8];
+  } else if (warp == 6) {
+    // ================= halo (stride-1 modes): the pixel left of the tile's first row (tap kx = 0) and right of its last
+    // row (kx = 2), when they lie in the same image row =================
+    if (fast && lane < 2) {
+      const int kx = lane == 0 ? 0 : 2, drow = lane == 0 ? 0 : 127;
+      const int kcs = c.cin >> 6, ngroups = 3 * kcs;
+      bool need = false;
+      int oy = 0, ox = 0;
+      auto set_tile = [&](int tile) {
+        const long long p = (long long)tile * 128 + drow;
+        const bool live = p < P;
+        oy = live ? (int)(p / c.out_w) : 0;
+        ox = live ? (int)(p - (long long)oy * c.out_w) : 0;
+        need = live && (kx == 0 ? ox >= 1 : ox + 1 < c.out_w);
+      };
+      auto load = [&](int g, uint4 (&v)[8]) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = vn[u];
-      int nq = q + 1, ntile = tile;
-      if (nq == c.nchunks) {
-        nq = 0;
-        ntile = tile + (int)gridDim.x;
-        if (ntile < tiles) set_tile(ntile);
-      }
-      if (ntile < tiles) load(nq, vn);                     // requested before this chunk's slot is even free
-      mbar_wait(&a_empty[slot], phase ^ 1, c.status, 200);
-      if (!(c.dbg & 2)) {
-        uint8_t* dst = a_row + slot * kCChunk;
+        for (int u = 0; u < 8; ++u) v[u] = make_uint4(0u, 0u, 0u, 0u);
+        const int ky = g / kcs, kc = g - ky * kcs;
+        int iy, ix;
+        if (need && !(c.dbg & 1) && src_pixel(c, oy, ox, ky, kx, iy, ix)) {
+          const uint4* src = reinterpret_cast<const uint4*>(c.in + ((size_t)iy * c.in_w + ix) * c.in_cs + kc * 64);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) *reinterpret_cast<uint4*>(dst + (((u ^ row) & 7) << 4)) = v[u];
-        fence_proxy_async_smem();
+          for (int u = 0; u < 8; ++u) v[u] = __ldg(src + u);
+        }
+      };
+      uint32_t phase = 0;
+      int tile = blockIdx.x, g = 0;
+      uint4 vn[8];
+      if (tile < tiles) {
+        set_tile(tile);
+        load(0, vn);
       }
-      mbar_arrive(&a_full[slot]);
-      if (++slot == kCSlots) { slot = 0; phase ^= 1; }
-      q = nq;
-      tile = ntile;
+      while (tile < tiles) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = vn[u];
+        const bool my_need = need;
+        int ng = g + 1, ntile = tile;
+        if (ng == ngroups) {
+          ng = 0;
+          ntile = tile + (int)gridDim.x;
+          if (ntile < tiles) set_tile(ntile);
+        }
+        if (ntile < tiles) load(ng, vn);
+        mbar_wait(&a_empty[kx], phase ^ 1, c.status, 220 + kx);
+        if (my_need && !(c.dbg & 2)) {
+          uint8_t* dst = smem + kx * kCChunk + (drow >> 3) * 1024 + (drow & 7) * 128;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) *reinterpret_cast<uint4*>(dst + (((u ^ drow) & 7) << 4)) = v[u];
+          fence_proxy_async_smem();
+        }
+        mbar_arrive(&a_full[kx]);
+        phase ^= 1;
+        g = ng;
+        tile = ntile;
+      }
     }
   } else {
     // ================= epilogue: TMEM -> registers -> NHWC, under the next tile's main loop =================

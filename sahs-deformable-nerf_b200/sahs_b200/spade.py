@@ -176,8 +176,8 @@ class _Packed:
         if first:
             blocks = rows.reshape(self.ntiles, ntile, 1, 64).permute(0, 2, 1, 3)
         else:
-            kcs = rows.shape[2] // 64
-            blocks = rows.reshape(self.ntiles, ntile, 9, kcs, 64).permute(0, 2, 3, 1, 4).reshape(self.ntiles, 9 * kcs, ntile, 64)
+            kcs = rows.shape[2] // 64                   # K chunk order: [ky][64-channel chunk][kx] (csrc/spade_conv.cu)
+            blocks = rows.reshape(self.ntiles, ntile, 3, 3, kcs, 64).permute(0, 2, 4, 3, 1, 5).reshape(self.ntiles, 9 * kcs, ntile, 64)
         self.packed = _swizzle_rows(blocks.to(torch.float16).contiguous())
         self.bias = bias.float().contiguous()
 

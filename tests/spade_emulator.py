@@ -51,7 +51,9 @@ def conv(p, x, out_h, out_w, mode, up=0, down=0, relu=False, add=None, spade=Non
                 A[:, 4 * k:4 * k + 4] = torch.where(ok[:, None], vals, torch.zeros_like(vals))
         else:
             kcs = p.cin // 64
-            tap, kc = q // kcs, q % kcs
+            kx, g = q % 3, q // 3                       # chunk order [ky][64-channel chunk][kx]
+            ky, kc = g // kcs, g % kcs
+            tap = 3 * ky + kx
             ok, iy, ix = src_pixel(mode, oy, ox, tap // 3, tap % 3, in_h, in_w, out_h, out_w, up, down)
             vals = xf[iy.clamp(0, in_h - 1), ix.clamp(0, in_w - 1), kc * 64:(kc + 1) * 64]
             A = torch.where(ok[:, None], vals, torch.zeros_like(vals))
