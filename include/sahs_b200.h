@@ -305,7 +305,7 @@ int sahs_spade_conv(const sahs_conv_desc* desc, void* stream);
 /* bounded-wait diagnostic of the conv kernel (0 = healthy), as sahs_field_status */
 int sahs_spade_conv_status(int* out4_host);
 /* Per-channel mean and 1 / sqrt(biased variance + eps) over num_pixels of an NHWC fp16 tensor (nn.InstanceNorm2d,
- * affine=False; ref: nerf/_init_spade.py:118).  sums_workspace: 2 * channels doubles. */
+ * affine=False; ref: nerf/_init_spade.py:118).  Deterministic (no atomics).  sums_workspace: 512 * channels doubles. */
 int sahs_instnorm_stats(const void* x, int64_t num_pixels, int channels, int channel_stride, float eps,
                         double* sums_workspace, float* mean, float* rstd, void* stream);
 /* nn.AvgPool2d(2, stride=2) on NHWC fp16 (ref: :240-249, :292) */

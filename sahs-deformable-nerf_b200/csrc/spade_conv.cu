@@ -472,45 +472,54 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
   }
 }
 
-// ---- instance-norm statistics of an NHWC fp16 tensor: per-channel sum and sum of squares (fp32 per thread, fp64 across) ----
+// ---- instance-norm statistics of an NHWC fp16 tensor: per-channel sum and sum of squares ----
+// Deterministic (run-to-run bit-identical, so a CUDA-graph replay equals the eager forward): fp32 per thread over a
+// fixed pixel sequence, fixed-order fp64 reduction over the block's pixel lanes, one fp64 partial per block, and a
+// fixed-order sum over blocks in the finalize kernel.  No atomics.
+constexpr int kStatBlocks = 256;      // upper bound of the grid; the workspace holds kStatBlocks x 2C doubles
 __global__ void __launch_bounds__(256) instnorm_sums_kernel(const __half* __restrict__ x, long long P, int C, int cs,
-                                                           double* __restrict__ sums) {
-  __shared__ float sh[2 * 256];
+                                                           double* __restrict__ partial) {
+  __shared__ float sh[256 * 16];                     // [pixel lane][2C]
   const int groups = C >> 3;                         // 8-channel groups (uint4)
   const int cgp = threadIdx.x % groups, pl = threadIdx.x / groups, lanes = 256 / groups;
-  for (int i = threadIdx.x; i < 2 * C; i += 256) sh[i] = 0.f;
-  __syncthreads();
   float s[8], ss[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s[e] = ss[e] = 0.f;
-  if (pl < lanes) {
-    for (long long p = (long long)blockIdx.x * lanes + pl; p < P; p += (long long)gridDim.x * lanes) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (size_t)p * cs + cgp * 8));
-      const __half* h = reinterpret_cast<const __half*>(&v);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float f = __half2float(h[e]);
-        s[e] += f;
-        ss[e] += f * f;
-      }
-    }
+  for (long long p = (long long)blockIdx.x * lanes + pl; p < P; p += (long long)gridDim.x * lanes) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + (size_t)p * cs + cgp * 8));
+    const __half* h = reinterpret_cast<const __half*>(&v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      atomicAdd(&sh[cgp * 8 + e], s[e]);
-      atomicAdd(&sh[C + cgp * 8 + e], ss[e]);
+      const float f = __half2float(h[e]);
+      s[e] += f;
+      ss[e] += f * f;
     }
   }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    sh[pl * 2 * C + cgp * 8 + e] = s[e];
+    sh[pl * 2 * C + C + cgp * 8 + e] = ss[e];
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(&sums[i], (double)sh[i]);
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    double acc = 0.0;
+    for (int l = 0; l < lanes; ++l) acc += (double)sh[l * 2 * C + i];
+    partial[(size_t)blockIdx.x * 2 * C + i] = acc;
+  }
 }
 
 // mean and 1/sqrt(biased variance + eps), ref: nn.InstanceNorm2d(affine=False), nerf/_init_spade.py:118
-__global__ void instnorm_finalize_kernel(const double* __restrict__ sums, int C, double inv_count, float eps,
+__global__ void instnorm_finalize_kernel(const double* __restrict__ partial, int nblocks, int C, double inv_count, float eps,
                                          float* __restrict__ mean, float* __restrict__ rstd) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= C) return;
-  const double m = sums[ch] * inv_count;
-  double var = sums[C + ch] * inv_count - m * m;
+  double su = 0.0, sq = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    su += partial[(size_t)b * 2 * C + ch];
+    sq += partial[(size_t)b * 2 * C + C + ch];
+  }
+  const double m = su * inv_count;
+  double var = sq * inv_count - m * m;
   if (var < 0.0) var = 0.0;
   mean[ch] = (float)m;
   rstd[ch] = (float)(1.0 / sqrt(var + (double)eps));
@@ -621,16 +630,14 @@ extern "C" int sahs_instnorm_stats(const void* x, int64_t num_pixels, int channe
                      channel_stride % 8 == 0 && channel_stride >= channels && ((uintptr_t)x & 15) == 0,
                  "channels must be 8..256 (a power-of-two number of 8-channel groups), 16-byte aligned rows");
   cudaStream_t s = (cudaStream_t)stream;
-  SAHS_CUDA(cudaMemsetAsync(sums_workspace, 0, 2 * (size_t)channels * sizeof(double), s));
   const int lanes = 256 / (channels / 8);
   long long blocks = (num_pixels + lanes * 16 - 1) / (lanes * 16);
-  const long long cap = 4LL * sahs_num_sms();
-  if (blocks > cap) blocks = cap;
+  if (blocks > kStatBlocks) blocks = kStatBlocks;
   if (blocks < 1) blocks = 1;
   instnorm_sums_kernel<<<(unsigned)blocks, 256, 0, s>>>((const __half*)x, num_pixels, channels, channel_stride, sums_workspace);
   SAHS_LAUNCH_CHECK();
-  instnorm_finalize_kernel<<<(channels + 127) / 128, 128, 0, s>>>(sums_workspace, channels, 1.0 / (double)num_pixels, eps, mean,
-                                                                  rstd);
+  instnorm_finalize_kernel<<<(channels + 127) / 128, 128, 0, s>>>(sums_workspace, (int)blocks, channels,
+                                                                  1.0 / (double)num_pixels, eps, mean, rstd);
   SAHS_LAUNCH_CHECK();
   return SAHS_OK;
 }

@@ -11,7 +11,7 @@ NotImplementedError from the dispatcher -- the product path has no fallback.
   stage (2)  sahs_b200::field_fwd, ::field_fwd_train, ::field_bwd
   stage (3)  sahs_b200::composite_fwd, ::composite_bwd
   stage (4)  sahs_b200::sample_pdf, ::sample_pdf_merge
-  next rows  sahs_b200::frame_postprocess, ::normal_map, ::weighted_sample
+  next rows  sahs_b200::frame_postprocess, ::normal_map, ::weighted_sample; Stage II: ::spade_conv, ::instnorm_stats, ::avgpool2
 
 The reference-named Python functions (train_utils / nerf_helpers / volume_rendering_utils / models) call these ops;
 autograd is wired by torch.autograd.Function classes on top (volume_rendering_utils._CompositeFn, train.FieldTrainFn).
@@ -179,7 +179,23 @@ _define("normal_map(Tensor depthmap, float fx, float fy, float cx, float cy, Ten
         lambda d, fx, fy, cx, cy, w, central: ops.normal_map(d, (fx, fy, cx, cy), w, central),
         lambda d, fx, fy, cx, cy, w, central: _e((d.shape[0] - (2 if central else 1), d.shape[1] - (2 if central else 1), 3), d))
 
+# ---- Stage II (SPADE generator) -----------------------------------------------------------------------------------------
+_define("spade_conv(Tensor x, Tensor packed, Tensor bias, int cin, int cout, int out_h, int out_w, int mode, int up, int down, "
+        "int epilogue, Tensor? aux, int aux_shift, Tensor? mean, Tensor? rstd) -> Tensor",
+        lambda x, packed, bias, cin, cout, oh, ow, mode, up, down, epi, aux, ash, mean, rstd:
+            ops.spade_conv(x, packed, bias, cin, cout, oh, ow, mode, up, down, epi, aux, ash, mean, rstd),
+        lambda x, packed, bias, cin, cout, oh, ow, mode, up, down, epi, aux, ash, mean, rstd:
+            _e((oh, ow, cout), x, torch.float32 if (epi & 8) else torch.float16))
+
+_define("instnorm_stats(Tensor x, float eps) -> (Tensor, Tensor)",
+        lambda x, eps: ops.instnorm_stats(x, eps),
+        lambda x, eps: (_e((x.shape[2],), x), _e((x.shape[2],), x)))
+
+_define("avgpool2(Tensor x) -> Tensor",
+        lambda x: ops.avgpool2(x),
+        lambda x: _e((x.shape[0] // 2, x.shape[1] // 2, x.shape[2]), x, torch.float16))
+
 OP_NAMES = ("get_ray_bundle", "coarse_z", "coarse_z_rng", "positional_encoding", "field_fwd", "field_fwd_train", "field_bwd",
             "composite_fwd", "composite_bwd", "composite_fwd_rng", "composite_bwd_rng", "sample_pdf_merge",
             "sample_pdf_merge_rng", "sample_pdf", "frame_postprocess", "weighted_sample",
-            "normal_map")
+            "normal_map", "spade_conv", "instnorm_stats", "avgpool2")

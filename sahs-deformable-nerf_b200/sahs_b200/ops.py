@@ -338,3 +338,51 @@ def normal_map(depthmap: torch.Tensor, focal, weights: Optional[torch.Tensor] = 
     L.check(lib.sahs_normal_map(L.ptr(d), n, fx, fy, cx, cy, L.ptr(w), int(bool(central_difference)), L.ptr(out),
                                 L.stream_ptr(d.device)), "normal_map")
     return out
+
+
+# ---- Stage II (SPADE generator): csrc/spade_conv.cu -----------------------------------------------------------------
+def spade_conv(x, packed, bias, cin: int, cout: int, out_h: int, out_w: int, mode: int, up: int = 0, down: int = 0,
+               epilogue: int = 0, aux=None, aux_shift: int = 0, mean=None, rstd=None):
+    """One 3x3 convolution of the Stage-II network on NHWC fp16 (include/sahs_b200.h `sahs_conv_desc`).
+    x [in_h, in_w, cs]; packed [ntiles, chunks, ntile, 64] fp16 swizzled blocks; returns [out_h, out_w, cout]
+    (fp16, or fp32 with epilogue flag 8).  ref: nerf/_init_spade.py:114-139, :235-282."""
+    lib = L.load()
+    dev = x.device
+    f32 = bool(epilogue & 8)
+    out = torch.empty(out_h, out_w, cout, dtype=torch.float32 if f32 else torch.float16, device=dev)
+    d = L.ConvDescC()
+    d.in_, d.in_h, d.in_w, d.in_cs, d.cin = L.ptr(x), x.shape[0], x.shape[1], x.stride(1), int(cin)
+    d.out_h, d.out_w, d.mode, d.up_shift, d.down_shift = int(out_h), int(out_w), int(mode), int(up), int(down)
+    d.packed_w, d.bias, d.ntile, d.ntiles, d.epilogue = L.ptr(packed), L.ptr(bias), packed.shape[2], packed.shape[0], int(epilogue)
+    d.aux, d.aux_cs, d.aux_shift = (L.ptr(aux), aux.stride(1), int(aux_shift)) if aux is not None else (None, 0, 0)
+    d.mean, d.rstd = L.ptr(mean), L.ptr(rstd)
+    d.out, d.out_cs, d.cout = L.ptr(out), int(cout), int(cout)
+    L.check(lib.sahs_spade_conv(C.byref(d), L.stream_ptr(dev)), "spade_conv")
+    return out
+
+
+def instnorm_stats(x, eps: float = 1e-5):
+    """Per-channel (mean, 1 / sqrt(biased var + eps)) of an NHWC fp16 tensor [H, W, C] (nn.InstanceNorm2d, affine=False)."""
+    lib = L.load()
+    c = x.shape[2]
+    ws = torch.empty(512 * c, dtype=torch.float64, device=x.device)          # one fp64 partial per block (<= 256 blocks)
+    mean = torch.empty(c, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(c, dtype=torch.float32, device=x.device)
+    L.check(lib.sahs_instnorm_stats(L.ptr(x), x.shape[0] * x.shape[1], c, x.stride(1), float(eps), L.ptr(ws), L.ptr(mean),
+                                    L.ptr(rstd), L.stream_ptr(x.device)), "instnorm_stats")
+    return mean, rstd
+
+
+def avgpool2(x):
+    """nn.AvgPool2d(2, stride=2) on NHWC fp16 [H, W, C]."""
+    lib = L.load()
+    y = torch.empty(x.shape[0] // 2, x.shape[1] // 2, x.shape[2], dtype=torch.float16, device=x.device)
+    L.check(lib.sahs_avgpool2(L.ptr(x), x.shape[0], x.shape[1], x.shape[2], L.ptr(y), L.stream_ptr(x.device)), "avgpool2")
+    return y
+
+
+def spade_conv_status():
+    lib = L.load()
+    out = (C.c_int * 4)()
+    L.check(lib.sahs_spade_conv_status(out), "spade_conv_status")
+    return list(out)

@@ -13,14 +13,13 @@ Conv1d over a 16-step window, like Stage I's AudioNet) and the image layout conv
 Training of Stage II (discriminator, VGG loss; train_get_texture_photo*.py) is out of scope."""
 from __future__ import annotations
 
-import ctypes as C
 from typing import Dict, Optional, Tuple
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import lib as L
+from . import custom_ops  # noqa: F401  (registers torch.ops.sahs_b200.spade_conv / instnorm_stats / avgpool2)
 
 MODE_S1, MODE_S2, MODE_T2, MODE_FIRST = 0, 1, 2, 3
 EPI_RELU, EPI_ADD, EPI_SPADE, EPI_F32 = 1, 2, 4, 8
@@ -226,7 +225,6 @@ class Generator(nn.Module):
         self.idencoder = IdEncoder()
         self.refine_network = RefineNetwork(64, 128, 256)
         self._packed: Optional[Dict[str, _Packed]] = None
-        self._ws: Dict[int, torch.Tensor] = {}
         self.tally: Optional[Dict[str, float]] = None     # set to {} to count launches and algorithmic FLOPs of a forward
 
     # -- packing (redone after load_state_dict / device moves; call invalidate_packed() after editing parameters in place)
@@ -293,25 +291,17 @@ class Generator(nn.Module):
         self._packed = P
         return P
 
-    # -- kernels
+    # -- kernels (torch.ops.sahs_b200.* custom operators over the C ABI, sahs_b200/custom_ops.py)
     def _conv(self, p: _Packed, x: torch.Tensor, out_h: int, out_w: int, mode: int, up=0, down=0, relu=False, add=None,
               spade=None, aux_shift=0, f32=False) -> torch.Tensor:
-        lib = L.load()
-        dev = x.device
         if p.first:
             mode = MODE_FIRST
         epi = (EPI_RELU if relu else 0) | (EPI_ADD if add is not None else 0) | (EPI_SPADE if spade is not None else 0) | \
               (EPI_F32 if f32 else 0)
-        out = torch.empty(out_h, out_w, p.cout, dtype=torch.float32 if f32 else torch.float16, device=dev)
-        d = L.ConvDescC()
-        d.in_, d.in_h, d.in_w, d.in_cs, d.cin = L.ptr(x), x.shape[0], x.shape[1], x.stride(1), p.cin
-        d.out_h, d.out_w, d.mode, d.up_shift, d.down_shift = out_h, out_w, mode, up, down
-        d.packed_w, d.bias, d.ntile, d.ntiles, d.epilogue = L.ptr(p.packed), L.ptr(p.bias), p.ntile, p.ntiles, epi
         aux = spade[0] if spade is not None else add
-        d.aux, d.aux_cs, d.aux_shift = (L.ptr(aux), aux.stride(1), aux_shift) if aux is not None else (None, 0, 0)
-        d.mean, d.rstd = (L.ptr(spade[1]), L.ptr(spade[2])) if spade is not None else (None, None)
-        d.out, d.out_cs, d.cout = L.ptr(out), p.cout, p.cout
-        L.check(lib.sahs_spade_conv(C.byref(d), L.stream_ptr(dev)), "spade_conv")
+        mean, rstd = (spade[1], spade[2]) if spade is not None else (None, None)
+        out = torch.ops.sahs_b200.spade_conv(x, p.packed, p.bias, p.cin, p.cout, out_h, out_w, mode, up, down, epi, aux,
+                                             aux_shift, mean, rstd)
         if self.tally is not None:
             n_out = 2 * p.cout if spade is not None else p.cout
             taps = 9.0 / 4.0 if mode == MODE_T2 else 9.0          # a stride-2 transposed conv touches 9/4 taps per output
@@ -320,26 +310,14 @@ class Generator(nn.Module):
         return out
 
     def _stats(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        lib = L.load()
-        c = x.shape[2]
-        ws = self._ws.get(c)
-        if ws is None or ws.device != x.device:
-            ws = self._ws[c] = torch.empty(2 * c, dtype=torch.float64, device=x.device)
-        mean = torch.empty(c, dtype=torch.float32, device=x.device)
-        rstd = torch.empty(c, dtype=torch.float32, device=x.device)
-        L.check(lib.sahs_instnorm_stats(L.ptr(x), x.shape[0] * x.shape[1], c, x.stride(1), 1e-5, L.ptr(ws), L.ptr(mean),
-                                        L.ptr(rstd), L.stream_ptr(x.device)), "instnorm_stats")
         if self.tally is not None:
             self.tally["other_launches"] = self.tally.get("other_launches", 0) + 2
-        return mean, rstd
+        return torch.ops.sahs_b200.instnorm_stats(x, 1e-5)
 
     def _avgpool(self, x: torch.Tensor) -> torch.Tensor:
-        lib = L.load()
-        y = torch.empty(x.shape[0] // 2, x.shape[1] // 2, x.shape[2], dtype=torch.float16, device=x.device)
-        L.check(lib.sahs_avgpool2(L.ptr(x), x.shape[0], x.shape[1], x.shape[2], L.ptr(y), L.stream_ptr(x.device)), "avgpool2")
         if self.tally is not None:
             self.tally["other_launches"] = self.tally.get("other_launches", 0) + 1
-        return y
+        return torch.ops.sahs_b200.avgpool2(x)
 
     # -- network
     @staticmethod

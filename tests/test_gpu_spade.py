@@ -32,11 +32,8 @@ def gen():
 
 
 def _status():
-    import ctypes as C
-    from sahs_b200 import lib as L
-    out = (C.c_int * 4)()
-    L.check(L.load().sahs_spade_conv_status(out), "status")
-    return list(out)
+    from sahs_b200 import ops
+    return ops.spade_conv_status()
 
 
 CASES = [
@@ -191,3 +188,31 @@ def test_generator_full_frame_vs_oracle_and_timing():
     _report(f"[spade e2e] Generator 512x512: {ms:.2f} ms per frame; max-abs {err:.2e} of range {rng:.2f}, "
             f"PSNR {10 * np.log10(rng * rng / max(mse, 1e-30)):.1f} dB")
     assert err <= 3e-2 * rng
+
+
+@pytest.mark.parametrize("kind", ["generator", "generator_audio"])
+def test_graphed_generator_equals_eager(kind):
+    """one CUDA graph per frame (GraphedGenerator) = the eager forward, bit for bit, also after the inputs change"""
+    from sahs_b200 import spade as SP
+    m = SP.Generator() if kind == "generator" else SP.Generator_audio()
+    m.load_state_dict(SF.make_state_dict(kind, seed=2), strict=True)
+    m = m.to(DEV)
+    i0, i1 = SF.make_inputs(64, 96, seed=1), SF.make_inputs(64, 96, seed=2)
+    args = lambda i: tuple(i[k].to(DEV) for k in (("i_src", "i_raw") if kind == "generator" else ("i_src", "i_raw", "audio")))
+    g = SP.GraphedGenerator(m, *args(i0))
+    for i in (i0, i1, i0):
+        want = m(*args(i)).clone()
+        got = g(*args(i))
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)
+    assert _status()[0] == 0
+    g.graph.reset()
+
+
+def test_custom_ops_cover_stage2():
+    from sahs_b200 import custom_ops
+    for name in ("spade_conv", "instnorm_stats", "avgpool2"):
+        assert name in custom_ops.OP_NAMES and hasattr(torch.ops.sahs_b200, name)
+    x = torch.randn(8, 8, 64, device=DEV).half()
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.sahs_b200.avgpool2(x.cpu())                      # no CPU kernel: the dispatcher raises
