@@ -45,6 +45,16 @@ for name in ("predict_and_render_radiance", "run_network", "volume_render_radian
     assert hasattr(nerf, name), name
 assert callable(utils.shrink) and callable(utils.label2color) and callable(utils.color2label_np)
 model = getattr(models, "AudioFaceModel")
+# Stage II inference scripts (ref: eval_get_texture_photo_audio.py:22,36,154-159, eval_get_texture_photo_3dmm.py:36,125)
+from nerf._init_spade import *
+from nerf._init_spade import Generator as Generator
+G = Generator_audio()
+assert hasattr(G, "load_state_dict") and hasattr(G, "refine_network") and hasattr(G, "idencoder") and hasattr(G, "AudioNet")
+try:
+    Discriminator()
+    raise SystemExit("Discriminator must raise")
+except NotImplementedError:
+    pass
 print("OK")
 '''
 
