@@ -194,7 +194,7 @@ def cpu_train_step_rays_per_s(cfg_name, n_rays, frame_seed=100):
     return n_rays / dt, dt, torch.get_num_threads()
 
 
-def bench_stage2(dev, peak_tf, steps, cpu_leg=True):
+def bench_stage2(dev, peak_tf, steps, cpu_leg=True, world=1, rank=0, dist=None):
     """Stage II: the SPADE Generator refining one 512x512 Stage-I frame.  Device-resident time as
     one CUDA graph per frame, e2e with host buffers (H2D of the identity photo and the Stage-I frame, D2H of the refined
     frame), algorithmic FLOPs against the tensor peak, parity against the oracle on the host, and two baselines: the
@@ -215,14 +215,30 @@ def bench_stage2(dev, peak_tf, steps, cpu_leg=True):
     g = SP.GraphedGenerator(m, a, b)
     for _ in range(3):
         g(a, b)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    sync_all()
     e0.record()
     for _ in range(steps):
         g(a, b)
     e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    sync_all()
+    ms_t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:                                   # every rank refines its own frames (weak scaling): max over ranks
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms = float(ms_t)
+    if world > 1:
+        g.graph.reset()
+        tf = tally["flop"] / 1e12
+        return {"workload": f"Stage-II SPADE Generator, one {H}x{W} frame per step on each of {world} GPUs (frames over ranks, "
+                            "no collective; same frame sharding as the clip)", "ms_per_frame": ms,
+                "frames_per_s": world * 1e3 / ms, "scaling": "weak", "achieved_tflops": world * tf / ms * 1e3}
     out_host = torch.empty(1, 3, H, W, dtype=torch.float32).pin_memory()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -793,9 +809,10 @@ def main():
             del ref_t
             torch.cuda.empty_cache()
     stage2 = None
-    if rank == 0 and world == 1 and not args.no_stage2:
+    if not args.no_stage2:
         torch.cuda.empty_cache()
-        stage2 = bench_stage2(dev, peak_tf, max(5, min(args.steps, 20)), cpu_leg=not args.no_cpu_baseline)
+        stage2 = bench_stage2(dev, peak_tf, max(5, min(args.steps, 20)), cpu_leg=not args.no_cpu_baseline, world=world,
+                              rank=rank, dist=dist if world > 1 else None)
     if rank == 0:
         line = {
             "metric": "render_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
