@@ -276,7 +276,11 @@ int sahs_counter_add(unsigned long long* counter_dev, unsigned long long inc, vo
  *           (F.interpolate(fid, size=x.size()) of :132 and nn.Upsample(scale_factor=2) of :254 are never materialised);
  *   mode 1: the same with stride 2 (residual_downsample :250, ResBlock2d downsample :17-18);
  *   mode 2: nn.ConvTranspose2d(3x3, stride 2, padding 1, output_padding 1) (residual_upsample :255);
- *   mode 3: 3-channel input stored as [H, W, 4] fp16: all nine taps in one K chunk (layer1 of both networks).
+ *   mode 3: 3-channel input stored as [H, W, 4] fp16: all nine taps in one K chunk (layer1 of both networks);
+ *   mode 4: one output-parity class (t2_class = 2 py + px) of the mode-2 transposed conv as a plain conv over the input grid
+ *           with the class's 1, 2, 2 or 4 taps, written to output pixels (2i + py, 2j + px): four launches per layer, no
+ *           multiplications by zero (mode 2 in one launch spends 9 taps per output where 2.25 contribute).  packed_w then
+ *           holds only the class's taps, [ky ascending][chunk][kx ascending].
  * packed_w: [ntiles][9 * cin / 64 chunks (mode 3: 1)][ntile rows x 64 columns fp16, 128B-swizzled K-major], chunk order
  * [ky][64-channel chunk][kx]; bias: [ntiles * ntile] fp32.  Built by sahs_b200/spade.py from the state_dict (spectral
  * norm and eval-mode BatchNorm folded in).
@@ -300,6 +304,7 @@ typedef struct sahs_conv_desc {
   const float* rstd;
   void* out;               /* fp16 NHWC [out_h, out_w, out_cs] (fp32 with flag 8) */
   int out_cs, cout;
+  int t2_class;            /* mode 4 only */
 } sahs_conv_desc;
 int sahs_spade_conv(const sahs_conv_desc* desc, void* stream);
 /* bounded-wait diagnostic of the conv kernel (0 = healthy), as sahs_field_status */

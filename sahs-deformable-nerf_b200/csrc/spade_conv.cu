@@ -40,7 +40,7 @@ constexpr int kCOffStage = kCOffBar + 256;           // floats: bias[128] | mean
 constexpr int kCSmem = kCOffStage + 256 * 4;
 constexpr int kCTmemCols = 256;                      // two accumulators of 128 columns
 
-enum { MODE_S1 = 0, MODE_S2 = 1, MODE_T2 = 2, MODE_FIRST = 3 };
+enum { MODE_S1 = 0, MODE_S2 = 1, MODE_T2 = 2, MODE_FIRST = 3, MODE_T2C = 4 };
 enum { EPI_RELU = 1, EPI_ADD = 2, EPI_SPADE = 4, EPI_F32 = 8 };
 
 struct ConvP {
@@ -58,6 +58,9 @@ struct ConvP {
   const float* rstd;
   void* out;
   int out_cs, cout;
+  int nkx, nky;          // taps per row / column of the kernel window (3 x 3; a parity class of a transposed conv: 1 or 2)
+  int dy[2], dx[2];      // MODE_T2C: source offset of tap index ky / kx
+  int rm, rm_w, rm_py, rm_px;   // MODE_T2C: tile pixel (i, j) is output pixel (2 i + py, 2 j + px) of a rm_w wide image
   int* status;
   int dbg;   // measurement switches (SAHS_CONV_DBG): 1 no gather loads, 2 no operand stores, 4 no MMAs, 8 16-byte weight copies, 16 no output stores, 32 tap-by-tap gather for the stride-1 modes too, 64 no zero-tap skipping in transposed convs
 };
@@ -68,6 +71,11 @@ __device__ __forceinline__ bool src_pixel(const ConvP& c, int oy, int ox, int ky
     iy = 2 * oy + ky - 1;
     ix = 2 * ox + kx - 1;
     return iy >= 0 && iy < c.in_h && ix >= 0 && ix < c.in_w;
+  }
+  if (c.mode == MODE_T2C) {        // ky / kx: tap INDEX within the parity class; every tap is a plain shifted read
+    iy = oy + c.dy[ky];
+    ix = ox + c.dx[kx];
+    return iy < c.in_h && ix < c.in_w;
   }
   if (c.mode == MODE_T2) {
     const int ty = oy + 1 - ky, tx = ox + 1 - kx;
@@ -295,7 +303,7 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
       };
       if (tile < tiles) {
         advance(tile, q, trow);
-        if (tile < tiles) load(q / 3, q % 3, vn);
+        if (tile < tiles) load(q / c.nkx, q % c.nkx, vn);
       }
       while (tile < tiles) {
         uint4 v[8];
@@ -303,7 +311,7 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
         for (int u = 0; u < 8; ++u) v[u] = vn[u];
         int nq = q, ntile = tile, ntrow = trow;
         advance(ntile, nq, ntrow);
-        if (ntile < tiles) load(nq / 3, nq % 3, vn);
+        if (ntile < tiles) load(nq / c.nkx, nq % c.nkx, vn);
         mbar_wait(&a_empty[slot], phase ^ 1, c.status, 210);
         if (!(c.dbg & 2)) {
           store_row(row_ptr((int)slot, row), row, v);
@@ -387,6 +395,7 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
       mbar_wait(&acc_full[buf], (uint32_t)((tcount >> 1) & 1), c.status, 500);
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * 128u;
+      const long long po = c.rm ? ((long long)(2 * oy + c.rm_py) * c.rm_w + 2 * ox + c.rm_px) : p;   // output pixel
       if (c.epi & EPI_SPADE) {
         // columns [0,64) gamma, [64,128) beta of channels nt*64 .. nt*64+63
         const long long ap = c.aux_shift ? ((long long)(oy >> c.aux_shift) * (c.out_w >> c.aux_shift) + (ox >> c.aux_shift)) : p;
@@ -445,7 +454,7 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
               for (int e = 0; e < 16; ++e) r[e] += __half2float(ah[e]);
             }
             if (c.epi & EPI_F32) {
-              float* orow = reinterpret_cast<float*>(c.out) + (size_t)p * c.out_cs;
+              float* orow = reinterpret_cast<float*>(c.out) + (size_t)po * c.out_cs;
 #pragma unroll
               for (int e = 0; e < 16; ++e)
                 if (ch0 + e < c.cout) orow[ch0 + e] = r[e];
@@ -454,7 +463,7 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
               __half2* oh = reinterpret_cast<__half2*>(ov);
 #pragma unroll
               for (int e = 0; e < 16; e += 2) oh[e >> 1] = __floats2half2_rn(r[e], r[e + 1]);
-              uint4* orow = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(c.out) + (size_t)p * c.out_cs + ch0);
+              uint4* orow = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(c.out) + (size_t)po * c.out_cs + ch0);
               orow[0] = ov[0];
               orow[1] = ov[1];
             }
@@ -560,7 +569,7 @@ extern "C" int sahs_spade_conv(const sahs_conv_desc* d, void* stream) {
                  "bad geometry");
   SAHS_CHECK_ARG(d->ntile == 16 || d->ntile == 64 || d->ntile == 128, "ntile must be 16, 64 or 128");
   SAHS_CHECK_ARG(d->ntiles >= 1 && d->ntiles <= 64, "bad N tile count");
-  SAHS_CHECK_ARG(d->mode >= MODE_S1 && d->mode <= MODE_FIRST, "bad mode");
+  SAHS_CHECK_ARG(d->mode >= MODE_S1 && d->mode <= MODE_T2C, "bad mode");
   const bool spade = (d->epilogue & EPI_SPADE) != 0;
   if (d->mode == MODE_FIRST) {
     SAHS_CHECK_ARG(d->in_cs == 4 && d->in_h == d->out_h && d->in_w == d->out_w, "first-layer mode: [H,W,4] fp16 input");
@@ -578,6 +587,7 @@ extern "C" int sahs_spade_conv(const sahs_conv_desc* d, void* stream) {
     SAHS_CHECK_ARG(d->out_h == (d->in_h + 1) / 2 && d->out_w == (d->in_w + 1) / 2, "stride-2 geometry");
   } else {
     SAHS_CHECK_ARG(d->out_h == 2 * d->in_h && d->out_w == 2 * d->in_w, "transposed-conv geometry");
+    SAHS_CHECK_ARG(d->mode != MODE_T2C || (d->t2_class >= 0 && d->t2_class < 4 && !d->aux && !spade), "parity class 0..3, no aux");
   }
   if (spade) {
     SAHS_CHECK_ARG(d->ntile == 128 && d->aux && d->mean && d->rstd && !(d->epilogue & (EPI_RELU | EPI_ADD | EPI_F32)),
@@ -605,7 +615,20 @@ extern "C" int sahs_spade_conv(const sahs_conv_desc* d, void* stream) {
   c.packed_w = (const uint8_t*)d->packed_w;
   c.bias = d->bias;
   c.ntile = d->ntile; c.ntiles_n = d->ntiles;
-  c.nchunks = d->mode == MODE_FIRST ? 1 : 9 * (d->cin / 64);
+  c.nkx = c.nky = 3;
+  c.dy[0] = c.dy[1] = c.dx[0] = c.dx[1] = 0;
+  c.rm = 0; c.rm_w = 0; c.rm_py = c.rm_px = 0;
+  if (d->mode == MODE_T2C) {
+    // output (2i + py, 2j + px) = sum over the taps with (o + 1 - k) even of input ((o + 1 - k) / 2):
+    // parity 0: k = 1 -> input i;  parity 1: k = 0 -> input i + 1, k = 2 -> input i   (tap order as packed: ascending k)
+    const int py = d->t2_class >> 1, px = d->t2_class & 1;
+    c.nky = py ? 2 : 1; c.nkx = px ? 2 : 1;
+    c.dy[0] = py ? 1 : 0; c.dy[1] = 0;
+    c.dx[0] = px ? 1 : 0; c.dx[1] = 0;
+    c.rm = 1; c.rm_w = d->out_w; c.rm_py = py; c.rm_px = px;
+    c.out_h = d->in_h; c.out_w = d->in_w;              // tiles run over the input grid
+  }
+  c.nchunks = d->mode == MODE_FIRST ? 1 : c.nky * c.nkx * (d->cin / 64);
   c.epi = d->epilogue;
   c.aux = (const __half*)d->aux; c.aux_cs = d->aux_cs; c.aux_shift = d->aux_shift;
   c.mean = d->mean; c.rstd = d->rstd;
@@ -613,7 +636,7 @@ extern "C" int sahs_spade_conv(const sahs_conv_desc* d, void* stream) {
   c.status = sahs_status_words(3);
   { const char* e = getenv("SAHS_CONV_DBG"); c.dbg = e ? atoi(e) : 0; }
   SAHS_CHECK_ARG(c.status, "status word allocation failed");
-  const long long P = (long long)d->out_h * d->out_w;
+  const long long P = (long long)c.out_h * c.out_w;
   const int tiles = (int)((P + 127) / 128);
   int gx = (2 * sahs_num_sms() + d->ntiles - 1) / d->ntiles;
   if (gx > tiles) gx = tiles;

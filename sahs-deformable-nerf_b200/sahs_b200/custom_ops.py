@@ -11,7 +11,7 @@ NotImplementedError from the dispatcher -- the product path has no fallback.
   stage (2)  sahs_b200::field_fwd, ::field_fwd_train, ::field_bwd
   stage (3)  sahs_b200::composite_fwd, ::composite_bwd
   stage (4)  sahs_b200::sample_pdf, ::sample_pdf_merge
-  next rows  sahs_b200::frame_postprocess, ::normal_map, ::weighted_sample; Stage II: ::spade_conv, ::instnorm_stats, ::avgpool2
+  next rows  sahs_b200::frame_postprocess, ::normal_map, ::weighted_sample; Stage II: ::spade_conv, ::spade_conv_t2, ::instnorm_stats, ::avgpool2
 
 The reference-named Python functions (train_utils / nerf_helpers / volume_rendering_utils / models) call these ops;
 autograd is wired by torch.autograd.Function classes on top (volume_rendering_utils._CompositeFn, train.FieldTrainFn).
@@ -187,6 +187,10 @@ _define("spade_conv(Tensor x, Tensor packed, Tensor bias, int cin, int cout, int
         lambda x, packed, bias, cin, cout, oh, ow, mode, up, down, epi, aux, ash, mean, rstd:
             _e((oh, ow, cout), x, torch.float32 if (epi & 8) else torch.float16))
 
+_define("spade_conv_t2(Tensor x, Tensor[] packed, Tensor[] bias, int cin, int cout) -> Tensor",
+        lambda x, packed, bias, cin, cout: ops.spade_conv_t2(x, packed, bias, cin, cout),
+        lambda x, packed, bias, cin, cout: _e((2 * x.shape[0], 2 * x.shape[1], cout), x, torch.float16))
+
 _define("instnorm_stats(Tensor x, float eps) -> (Tensor, Tensor)",
         lambda x, eps: ops.instnorm_stats(x, eps),
         lambda x, eps: (_e((x.shape[2],), x), _e((x.shape[2],), x)))
@@ -198,4 +202,4 @@ _define("avgpool2(Tensor x) -> Tensor",
 OP_NAMES = ("get_ray_bundle", "coarse_z", "coarse_z_rng", "positional_encoding", "field_fwd", "field_fwd_train", "field_bwd",
             "composite_fwd", "composite_bwd", "composite_fwd_rng", "composite_bwd_rng", "sample_pdf_merge",
             "sample_pdf_merge_rng", "sample_pdf", "frame_postprocess", "weighted_sample",
-            "normal_map", "spade_conv", "instnorm_stats", "avgpool2")
+            "normal_map", "spade_conv", "spade_conv_t2", "instnorm_stats", "avgpool2")

@@ -37,7 +37,8 @@ class ConvDescC(C.Structure):
                 ("out_h", C.c_int), ("out_w", C.c_int), ("mode", C.c_int), ("up_shift", C.c_int), ("down_shift", C.c_int),
                 ("packed_w", C.c_void_p), ("bias", C.c_void_p), ("ntile", C.c_int), ("ntiles", C.c_int),
                 ("epilogue", C.c_int), ("aux", C.c_void_p), ("aux_cs", C.c_int), ("aux_shift", C.c_int),
-                ("mean", C.c_void_p), ("rstd", C.c_void_p), ("out", C.c_void_p), ("out_cs", C.c_int), ("cout", C.c_int)]
+                ("mean", C.c_void_p), ("rstd", C.c_void_p), ("out", C.c_void_p), ("out_cs", C.c_int), ("cout", C.c_int),
+                ("t2_class", C.c_int)]
 
 
 EXPORTS = (

@@ -361,6 +361,24 @@ def spade_conv(x, packed, bias, cin: int, cout: int, out_h: int, out_w: int, mod
     return out
 
 
+def spade_conv_t2(x, packed4, bias4, cin: int, cout: int):
+    """nn.ConvTranspose2d(3x3, stride 2, padding 1, output_padding 1) on NHWC fp16: four parity-class launches (mode 4)
+    that together write every pixel of the [2 in_h, 2 in_w, cout] output.  ref: nerf/_init_spade.py:255."""
+    lib = L.load()
+    dev = x.device
+    out = torch.empty(2 * x.shape[0], 2 * x.shape[1], cout, dtype=torch.float16, device=dev)
+    for cls in range(4):
+        packed, bias = packed4[cls], bias4[cls]
+        d = L.ConvDescC()
+        d.in_, d.in_h, d.in_w, d.in_cs, d.cin = L.ptr(x), x.shape[0], x.shape[1], x.stride(1), int(cin)
+        d.out_h, d.out_w, d.mode, d.up_shift, d.down_shift = out.shape[0], out.shape[1], 4, 0, 0
+        d.packed_w, d.bias, d.ntile, d.ntiles, d.epilogue = L.ptr(packed), L.ptr(bias), packed.shape[2], packed.shape[0], 0
+        d.aux, d.aux_cs, d.aux_shift, d.mean, d.rstd = None, 0, 0, None, None
+        d.out, d.out_cs, d.cout, d.t2_class = L.ptr(out), int(cout), int(cout), cls
+        L.check(lib.sahs_spade_conv(C.byref(d), L.stream_ptr(dev)), "spade_conv (transposed, class %d)" % cls)
+    return out
+
+
 def instnorm_stats(x, eps: float = 1e-5):
     """Per-channel (mean, 1 / sqrt(biased var + eps)) of an NHWC fp16 tensor [H, W, C] (nn.InstanceNorm2d, affine=False)."""
     lib = L.load()

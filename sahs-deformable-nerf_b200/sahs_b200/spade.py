@@ -21,8 +21,9 @@ import torch.nn.functional as F
 
 from . import custom_ops  # noqa: F401  (registers torch.ops.sahs_b200.spade_conv / instnorm_stats / avgpool2)
 
-MODE_S1, MODE_S2, MODE_T2, MODE_FIRST = 0, 1, 2, 3
+MODE_S1, MODE_S2, MODE_T2, MODE_FIRST, MODE_T2C = 0, 1, 2, 3, 4
 EPI_RELU, EPI_ADD, EPI_SPADE, EPI_F32 = 1, 2, 4, 8
+T2_CLASS_MIN_PIXELS = 128 * 128      # transposed convs on smaller inputs run as one nine-tap launch (measured: 64^2 input 0.043 vs 0.067 ms)
 
 
 # ---- parameter holders with the reference's attribute names -------------------------------------------------------------
@@ -168,15 +169,18 @@ def _swizzle_rows(t: torch.Tensor) -> torch.Tensor:
 class _Packed:
     """One convolution ready for sahs_spade_conv."""
 
-    def __init__(self, rows: torch.Tensor, bias: torch.Tensor, ntile: int, cin: int, cout: int, first: bool):
-        # rows: [ntiles * ntile, 9, cin_padded] fp32 (first: [.., 64] with the nine taps folded into one chunk)
+    def __init__(self, rows: torch.Tensor, bias: torch.Tensor, ntile: int, cin: int, cout: int, first: bool, taps=(3, 3)):
+        # rows: [ntiles * ntile, nky * nkx, cin_padded] fp32 (first: [.., 64] with the nine taps folded into one chunk)
         n = rows.shape[0]
         self.ntile, self.ntiles, self.cin, self.cout, self.first = ntile, n // ntile, cin, cout, first
+        self.taps = taps
         if first:
             blocks = rows.reshape(self.ntiles, ntile, 1, 64).permute(0, 2, 1, 3)
         else:
+            nky, nkx = taps
             kcs = rows.shape[2] // 64                   # K chunk order: [ky][64-channel chunk][kx] (csrc/spade_conv.cu)
-            blocks = rows.reshape(self.ntiles, ntile, 3, 3, kcs, 64).permute(0, 2, 4, 3, 1, 5).reshape(self.ntiles, 9 * kcs, ntile, 64)
+            blocks = rows.reshape(self.ntiles, ntile, nky, nkx, kcs, 64).permute(0, 2, 4, 3, 1, 5).reshape(
+                self.ntiles, nky * nkx * kcs, ntile, 64)
         self.packed = _swizzle_rows(blocks.to(torch.float16).contiguous())
         self.bias = bias.float().contiguous()
 
@@ -189,10 +193,31 @@ def _pad_rows(t: torch.Tensor, n: int) -> torch.Tensor:
     return out
 
 
-def _pack_conv(w: torch.Tensor, b: torch.Tensor, transposed=False) -> _Packed:
+class _PackedT2:
+    """nn.ConvTranspose2d(3x3, stride 2, padding 1, output_padding 1) as four output-parity classes (py, px): output
+    (2i + py, 2j + px) only receives the taps with (o + 1 - k) even -- k = 1 for parity 0, k = 0 and 2 for parity 1 -- so
+    each class is a plain conv over the input grid with 1, 2, 2 or 4 taps (csrc/spade_conv.cu mode 4)."""
+
+    def __init__(self, rows: torch.Tensor, b: torch.Tensor, cin: int, cout: int):
+        ntile = 128 if cout >= 128 else (64 if cout >= 64 else 16)
+        n = (cout + ntile - 1) // ntile * ntile
+        self.cin, self.cout, self.first = cin, cout, False
+        # small inputs (few tiles) run better as ONE launch over all nine taps (mode 2, zero taps skipped per tile)
+        self.full = _Packed(_pad_rows(rows.reshape(cout, 9, cin), n), _pad_rows(b, n), ntile, cin, cout, False)
+        self.classes = []
+        for py in (0, 1):
+            for px in (0, 1):
+                kys, kxs = ([0, 2] if py else [1]), ([0, 2] if px else [1])
+                sel = rows[:, kys][:, :, kxs].reshape(cout, len(kys) * len(kxs), cin)
+                self.classes.append(_Packed(_pad_rows(sel, n), _pad_rows(b, n), ntile, cin, cout, False, (len(kys), len(kxs))))
+
+
+def _pack_conv(w: torch.Tensor, b: torch.Tensor, transposed=False):
     """w: effective fp32 weight, [cout, cin, 3, 3] (transposed: [cin, cout, 3, 3])"""
     rows = (w.permute(1, 2, 3, 0) if transposed else w.permute(0, 2, 3, 1))          # [cout, ky, kx, cin]
     cout, cin = rows.shape[0], rows.shape[3]
+    if transposed:
+        return _PackedT2(rows, b, cin, cout)
     if cin == 3:
         r = torch.zeros(cout, 9, 4, dtype=w.dtype, device=w.device)
         r[:, :, :3] = rows.reshape(cout, 9, 3)
@@ -294,6 +319,14 @@ class Generator(nn.Module):
     # -- kernels (torch.ops.sahs_b200.* custom operators over the C ABI, sahs_b200/custom_ops.py)
     def _conv(self, p: _Packed, x: torch.Tensor, out_h: int, out_w: int, mode: int, up=0, down=0, relu=False, add=None,
               spade=None, aux_shift=0, f32=False) -> torch.Tensor:
+        if isinstance(p, _PackedT2) and x.shape[0] * x.shape[1] < T2_CLASS_MIN_PIXELS:
+            p = p.full                                   # one launch, mode 2
+        if isinstance(p, _PackedT2):                 # transposed conv: four parity-class launches into one output
+            out = torch.ops.sahs_b200.spade_conv_t2(x, [c.packed for c in p.classes], [c.bias for c in p.classes], p.cin, p.cout)
+            if self.tally is not None:
+                self.tally["flop"] = self.tally.get("flop", 0.0) + 2.0 * out_h * out_w * p.cout * 2.25 * p.cin
+                self.tally["conv_launches"] = self.tally.get("conv_launches", 0) + 4
+            return out
         if p.first:
             mode = MODE_FIRST
         epi = (EPI_RELU if relu else 0) | (EPI_ADD if add is not None else 0) | (EPI_SPADE if spade is not None else 0) | \

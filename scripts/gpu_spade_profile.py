@@ -61,6 +61,12 @@ def main():
         e0.record()
         out = orig(p, x, oh, ow, mode, **kw)
         e1.record()
+        if isinstance(p, SP._PackedT2):             # four parity-class launches
+            for cls, c in enumerate(p.classes):
+                nt = c.taps[0] * c.taps[1]
+                rows.append((e0, e1, f"{p.cin:>3}->{p.cout:<3} {oh:>3}x{ow:<3} transposed, parity classes (1/2/2/4 taps) "
+                                     f"ntile {c.ntile}x{c.ntiles}", 2.0 * x.shape[0] * x.shape[1] * p.cout * nt * p.cin))
+            return out
         n_out = 2 * p.cout if kw.get("spade") is not None else p.cout
         taps = 2.25 if mode == SP.MODE_T2 else 9.0
         rows.append((e0, e1, f"{p.cin:>3}->{n_out:<3} {oh:>3}x{ow:<3} mode {SP.MODE_FIRST if p.first else mode} "

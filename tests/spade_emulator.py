@@ -29,9 +29,44 @@ def src_pixel(mode, oy, ox, ky, kx, in_h, in_w, out_h, out_w, up, down):
     return (ly >= 0) & (ly < out_h) & (lx >= 0) & (lx < out_w), (ly << down) >> up, (lx << down) >> up
 
 
+def conv_t2(p, x):
+    """_PackedT2: four parity classes (py, px), each a plain conv over the input grid with the class's taps (mode 4 of the
+    kernel: tap index ky -> source row i + dy[ky], dy = [1, 0] for parity 1 and [0] for parity 0), scattered to
+    (2i + py, 2j + px)."""
+    in_h, in_w = x.shape[0], x.shape[1]
+    out = torch.zeros(2 * in_h, 2 * in_w, p.cout)
+    xf = x.float()
+    pix = torch.arange(in_h * in_w)
+    oy, ox = pix // in_w, pix % in_w
+    kcs = p.cin // 64
+    for cls, c in enumerate(p.classes):
+        py, px = cls >> 1, cls & 1
+        dys, dxs = ([1, 0] if py else [0]), ([1, 0] if px else [0])
+        nky, nkx = c.taps
+        assert (nky, nkx) == (len(dys), len(dxs))
+        W = unswizzle(c.packed.cpu())
+        acc = torch.zeros(in_h * in_w, c.ntiles * c.ntile)
+        for q in range(W.shape[1]):
+            kx, g = q % nkx, q // nkx
+            ky, kc = g // kcs, g % kcs
+            iy, ix = oy + dys[ky], ox + dxs[kx]
+            ok = (iy < in_h) & (ix < in_w)
+            vals = xf[iy.clamp(0, in_h - 1), ix.clamp(0, in_w - 1), kc * 64:(kc + 1) * 64]
+            A = torch.where(ok[:, None], vals, torch.zeros_like(vals))
+            for t in range(c.ntiles):
+                acc[:, t * c.ntile:(t + 1) * c.ntile] += A @ W[t, q].T
+        acc = (acc + c.bias.cpu()[None, :])[:, :p.cout]
+        out[2 * oy + py, 2 * ox + px] = acc
+    return out
+
+
 def conv(p, x, out_h, out_w, mode, up=0, down=0, relu=False, add=None, spade=None, aux_shift=0, f32=False):
     """same signature as Generator._conv; tensors are fp32 [H, W, C] on the CPU (fp16 rounding of activations is the
     GPU tests' subject)."""
+    if isinstance(p, SP._PackedT2):                  # same choice as Generator._conv
+        if x.shape[0] * x.shape[1] >= SP.T2_CLASS_MIN_PIXELS:
+            return conv_t2(p, x)
+        p = p.full
     if p.first:
         mode = SP.MODE_FIRST
     W = unswizzle(p.packed.cpu())

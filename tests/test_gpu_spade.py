@@ -45,6 +45,7 @@ CASES = [
     ("s1_down", 64, 128, (16, 24), (8, 12), 0, 0, 1, "relu"),
     ("s2", 128, 128, (16, 24), (8, 12), 1, 0, 0, "add"),
     ("t2", 256, 256, (6, 10), (12, 20), 2, 0, 0, ""),
+    ("t2_wide", 128, 128, (8, 128), (16, 256), 2, 0, 0, ""),
     ("first", 3, 64, (20, 28), (20, 28), 3, 0, 0, ""),
     ("last_f32", 64, 3, (20, 28), (20, 28), 0, 0, 0, "f32"),
     ("many_tiles", 64, 64, (96, 128), (96, 128), 0, 0, 0, "relu"),
@@ -70,6 +71,10 @@ def test_conv_kernel_vs_cpu_interpretation(gen, case):
     want = EM.conv(p, x.float(), oh, ow, mode, **{**kw, "add": None if add is None else add.float()})
     kw["add"] = None if add is None else add.to(DEV)
     got = gen._conv(pd, x.to(DEV), oh, ow, mode, **kw)
+    if mode == 2:      # the transposed conv has two implementations (one nine-tap launch / four parity-class launches)
+        cls = torch.ops.sahs_b200.spade_conv_t2(x.to(DEV), [c.packed for c in pd.classes], [c.bias for c in pd.classes], cin, cout)
+        one = gen._conv(pd.full, x.to(DEV), oh, ow, 2)
+        assert float((cls.float() - one.float()).abs().max()) <= 2e-3 * max(1.0, float(one.float().abs().max()))
     torch.cuda.synchronize()
     assert _status()[0] == 0, _status()
     assert got.dtype == (torch.float32 if epi == "f32" else torch.float16) and tuple(got.shape) == (oh, ow, cout)

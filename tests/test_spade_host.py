@@ -80,8 +80,9 @@ def test_packed_conv_and_gather_rules_vs_torch(case):
         x = xin[0].permute(1, 2, 0).contiguous()
         if case == "t2":
             p, w, b = _packed_conv(cin, cout, transposed=True)
-            got = EM.conv(p, x, 12, 20, SP.MODE_T2)
+            got = EM.conv(p, x, 12, 20, SP.MODE_T2)                     # small input: one nine-tap launch (mode 2)
             want = F.conv_transpose2d(xin, w, b, stride=2, padding=1, output_padding=1)
+            assert float((EM.conv_t2(p, x) - got).abs().max()) <= 1e-5     # = the four parity-class convs (mode 4)
         else:
             p, w, b = _packed_conv(cin, cout)
             assert (p.ntile, p.ntiles) == (128, 2)
