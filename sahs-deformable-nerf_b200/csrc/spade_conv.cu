@@ -65,6 +65,14 @@ struct ConvP {
   int dbg;   // measurement switches (SAHS_CONV_DBG): 1 no gather loads, 2 no operand stores, 4 no MMAs, 8 16-byte weight copies, 16 no output stores, 32 tap-by-tap gather for the stride-1 modes too, 64 no zero-tap skipping in transposed convs
 };
 
+// fp32 pair -> fp16 pair, saturating at +-65504 like every other fp16 conversion of this library: an activation that
+// outgrows fp16 is clamped instead of becoming inf (which InstanceNorm would turn into a frame of NaNs)
+__device__ __forceinline__ __half2 sat_half2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return *reinterpret_cast<__half2*>(&r);
+}
+
 // input pixel of output pixel (oy, ox) for tap (ky, kx); false: outside (contributes zero)
 __device__ __forceinline__ bool src_pixel(const ConvP& c, int oy, int ox, int ky, int kx, int& iy, int& ix) {
   if (c.mode == MODE_S2) {
@@ -426,7 +434,7 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
                 const float y = xn * (1.f + g) + b;
                 r[k] = y > 0.f ? y : 0.2f * y;
               }
-              oh[e >> 1] = __floats2half2_rn(r[0], r[1]);
+              oh[e >> 1] = sat_half2(r[0], r[1]);
             }
             reinterpret_cast<uint4*>(orow + i)[0] = ov[0];
             reinterpret_cast<uint4*>(orow + i)[1] = ov[1];
@@ -462,7 +470,7 @@ __global__ void __launch_bounds__(kCThreads, 2) spade_conv_kernel(const ConvP c)
               uint4 ov[2];
               __half2* oh = reinterpret_cast<__half2*>(ov);
 #pragma unroll
-              for (int e = 0; e < 16; e += 2) oh[e >> 1] = __floats2half2_rn(r[e], r[e + 1]);
+              for (int e = 0; e < 16; e += 2) oh[e >> 1] = sat_half2(r[e], r[e + 1]);
               uint4* orow = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(c.out) + (size_t)po * c.out_cs + ch0);
               orow[0] = ov[0];
               orow[1] = ov[1];

@@ -322,6 +322,8 @@ class Generator(nn.Module):
         if isinstance(p, _PackedT2) and x.shape[0] * x.shape[1] < T2_CLASS_MIN_PIXELS:
             p = p.full                                   # one launch, mode 2
         if isinstance(p, _PackedT2):                 # transposed conv: four parity-class launches into one output
+            if relu or add is not None or spade is not None or f32:
+                raise RuntimeError("the parity-class transposed conv has the plain bias epilogue only")
             out = torch.ops.sahs_b200.spade_conv_t2(x, [c.packed for c in p.classes], [c.bias for c in p.classes], p.cin, p.cout)
             if self.tally is not None:
                 self.tally["flop"] = self.tally.get("flop", 0.0) + 2.0 * out_h * out_w * p.cout * 2.25 * p.cin
