@@ -241,6 +241,18 @@ def _pack_gamma_beta(wg, bg, wb, bb) -> _Packed:
     return p
 
 
+class Identity:
+    """Everything a generator derives from the identity photo alone: the IdEncoder feature maps and -- filled on the first
+    frame that uses them -- the `mlp_shared` activations of every SPADE layer conditioned on one of those maps.  A clip is
+    refined with ONE identity photo (ref: eval_get_texture_photo_audio.py:163-173, `frame = indenty_photo` inside the frame
+    loop), so all of this is frame independent: `G.refine(identity, frame)` skips the IdEncoder and 18 (Generator) / 12
+    (Generator_audio) of the 70 convolutions of `G(I_src, frame)` and returns the same bits."""
+
+    def __init__(self, fids, shape):
+        self.fids, self.shape = fids, shape
+        self.actv: Dict[Tuple[str, int, int], torch.Tensor] = {}
+
+
 # ---- the generators ------------------------------------------------------------------------------------------------------
 class Generator(nn.Module):
     """ref: nerf/_init_spade.py:318-328.  forward(I_src, I_raw) -> refined frame, all [1, 3, H, W] fp32 (H, W multiples of 8)."""
@@ -394,16 +406,21 @@ class Generator(nn.Module):
             return fid, 0, 1
         raise RuntimeError(f"conditioning map {fh}x{fw} cannot be resized to {h}x{w} by a factor of two")
 
-    def _spade_act(self, P, pfx, x, x_shift, fid, h, w):
+    def _spade_act(self, P, pfx, x, x_shift, fid, h, w, ident=None):
         """leaky_relu(SPADELayer(x, fid), 0.2) at (h, w); x is stored at (h >> x_shift, w >> x_shift)"""
         mean, rstd = self._stats(x)          # statistics of a nearest-upsampled tensor are those of the stored one
-        f, up, down = self._fid_at(fid, h, w)
-        actv = self._conv(P[pfx + ".mlp_shared.0"], f, h, w, MODE_S1, up=up, down=down, relu=True)
+        key = (pfx, h, w)
+        actv = ident.actv.get(key) if (ident is not None and not callable(fid)) else None
+        if actv is None:
+            f, up, down = self._fid_at(fid, h, w)
+            actv = self._conv(P[pfx + ".mlp_shared.0"], f, h, w, MODE_S1, up=up, down=down, relu=True)
+            if ident is not None and not callable(fid):      # a map of the identity photo: the same for every frame
+                ident.actv[key] = actv
         return self._conv(P[pfx + ".gb"], actv, h, w, MODE_S1, spade=(x, mean, rstd), aux_shift=x_shift)
 
-    def _block(self, P, pfx, x, fid, down=False, up=False):
+    def _block(self, P, pfx, x, fid, down=False, up=False, ident=None):
         h, w = x.shape[0], x.shape[1]
-        x1 = self._conv(P[pfx + ".conv1"], self._spade_act(P, pfx + ".spade1", x, 0, fid, h, w), h, w, MODE_S1)
+        x1 = self._conv(P[pfx + ".conv1"], self._spade_act(P, pfx + ".spade1", x, 0, fid, h, w, ident), h, w, MODE_S1)
         idn, oh, ow, s1 = x, h, w, 0
         if down:
             x1 = self._avgpool(x1)
@@ -412,16 +429,16 @@ class Generator(nn.Module):
         if up:
             oh, ow, s1 = 2 * h, 2 * w, 1                    # x1 stays at (h, w): nn.Upsample is folded into its consumers
             idn = self._conv(P[pfx + ".residual_upsample"], x, oh, ow, MODE_T2)
-        x2 = self._conv(P[pfx + ".conv2"], self._spade_act(P, pfx + ".spade2", x1, s1, fid, oh, ow), oh, ow, MODE_S1)
-        hs = self._spade_act(P, pfx + ".spade_s", idn, 0, fid, oh, ow)
+        x2 = self._conv(P[pfx + ".conv2"], self._spade_act(P, pfx + ".spade2", x1, s1, fid, oh, ow, ident), oh, ow, MODE_S1)
+        hs = self._spade_act(P, pfx + ".spade_s", idn, 0, fid, oh, ow, ident)
         return self._conv(P[pfx + ".conv_s"], hs, oh, ow, MODE_S1, add=x2)
 
-    def _refine(self, P, raw, fid1, fid2, fid3, taps=None):
+    def _refine(self, P, raw, fid1, fid2, fid3, taps=None, ident=None):
         H, W = raw.shape[0], raw.shape[1]
         x = self._avgpool(self._conv(P["refine_network.layer1.0"], raw, H, W, MODE_FIRST))
         for name, fid, kw in (("layer2", fid1, dict(down=True)), ("layer3", fid2, dict(down=True)), ("layer4", fid3, {}),
                               ("layer5", fid3, dict(up=True)), ("layer6", fid2, dict(up=True)), ("layer7", fid1, dict(up=True))):
-            x = self._block(P, "refine_network." + name, x, fid, **kw)
+            x = self._block(P, "refine_network." + name, x, fid, ident=ident, **kw)
             if taps is not None:
                 taps[name] = x
         return self._conv(P["refine_network.layer8"], x, H, W, MODE_S1, f32=True)
@@ -433,6 +450,25 @@ class Generator(nn.Module):
         for im in imgs:
             if tuple(im.shape) != (1, 3, h, w):
                 raise RuntimeError("I_src and I_raw must both be [1, 3, H, W]")
+
+    @torch.no_grad()
+    def encode_identity(self, I_src) -> Identity:
+        """The frame-independent part of a clip: IdEncoder(I_src) (+ the conditioning activations, filled by the first
+        `refine`).  Invalid after the weights change."""
+        self._check(I_src, I_src)
+        P = self._prepare()
+        return Identity(tuple(self._id_encoder(P, self._image(I_src))), tuple(I_src.shape))
+
+    @torch.no_grad()
+    def refine(self, identity: Identity, I_raw, taps=None):
+        """G(I_src, I_raw) with everything that depends on I_src alone taken from `identity`: same result, bit for bit."""
+        self._check(I_raw, I_raw)
+        if tuple(I_raw.shape) != identity.shape:
+            raise RuntimeError("the frame and the identity photo must have the same size")
+        P = self._prepare()
+        fid1, fid2, fid3 = identity.fids
+        out = self._refine(P, self._image(I_raw), fid1, fid2, fid3, taps, identity)
+        return out.permute(2, 0, 1).unsqueeze(0)
 
     @torch.no_grad()
     def forward(self, I_src, I_raw, taps=None):
@@ -452,11 +488,7 @@ class Generator_audio(Generator):
         super().__init__()
         self.AudioNet = AudioNet(76, 16)
 
-    @torch.no_grad()
-    def forward(self, I_src, I_raw, driving_data, taps=None):
-        self._check(I_src, I_raw)
-        P = self._prepare()
-        fid1, fid2, _ = self._id_encoder(P, self._image(I_src))
+    def _audio_fid(self, driving_data):
         a = self.AudioNet(driving_data.unsqueeze(0).float())[0]                    # [64]
         maps: Dict[Tuple[int, int], torch.Tensor] = {}
 
@@ -467,6 +499,26 @@ class Generator_audio(Generator):
                 maps[(h, w)] = a[idx].to(torch.float16).view(1, w, 1).expand(h, w, 256).contiguous()
             return maps[(h, w)]
 
+        return fid3
+
+    @torch.no_grad()
+    def refine(self, identity: Identity, I_raw, driving_data, taps=None):
+        """G(I_src, I_raw, driving_data) with the identity photo's part taken from `identity` (the audio-conditioned SPADE
+        layers are per frame and are not cached)."""
+        self._check(I_raw, I_raw)
+        if tuple(I_raw.shape) != identity.shape:
+            raise RuntimeError("the frame and the identity photo must have the same size")
+        P = self._prepare()
+        fid1, fid2, _ = identity.fids
+        out = self._refine(P, self._image(I_raw), fid1, fid2, self._audio_fid(driving_data), taps, identity)
+        return out.permute(2, 0, 1).unsqueeze(0)
+
+    @torch.no_grad()
+    def forward(self, I_src, I_raw, driving_data, taps=None):
+        self._check(I_src, I_raw)
+        P = self._prepare()
+        fid1, fid2, _ = self._id_encoder(P, self._image(I_src))
+        fid3 = self._audio_fid(driving_data)
         out = self._refine(P, self._image(I_raw), fid1, fid2, fid3, taps)
         return out.permute(2, 0, 1).unsqueeze(0)
 
@@ -476,18 +528,21 @@ class GraphedGenerator:
     recorded once for fixed input shapes and replayed; inputs are copied into the graph's static buffers.  Use for clip
     refinement (one identity photo, many Stage-I frames)."""
 
-    def __init__(self, gen: Generator, *example_inputs: torch.Tensor, warmup: int = 2):
+    def __init__(self, gen: Generator, *example_inputs: torch.Tensor, warmup: int = 2, identity: Optional[Identity] = None):
+        """example_inputs: (I_src, I_raw[, audio]) -- or, with `identity=gen.encode_identity(I_src)`, (I_raw[, audio]): the
+        graph then holds only the per-frame work (`gen.refine`), the identity photo's part having been computed once."""
         self.gen = gen
         self.inputs = [t.detach().clone() for t in example_inputs]
+        run = (lambda: gen.refine(identity, *self.inputs)) if identity is not None else (lambda: gen(*self.inputs))
         side = torch.cuda.Stream(device=self.inputs[0].device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(warmup):
-                gen(*self.inputs)
+            for _ in range(max(1, warmup)):              # (fills the identity's conditioning activations)
+                run()
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.output = gen(*self.inputs)
+            self.output = run()
 
     def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
         for dst, src in zip(self.inputs, inputs):

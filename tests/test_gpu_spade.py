@@ -221,3 +221,31 @@ def test_custom_ops_cover_stage2():
     x = torch.randn(8, 8, 64, device=DEV).half()
     with pytest.raises((NotImplementedError, RuntimeError)):
         torch.ops.sahs_b200.avgpool2(x.cpu())                      # no CPU kernel: the dispatcher raises
+
+
+@pytest.mark.parametrize("kind", ["generator", "generator_audio"])
+def test_identity_cache_equals_full_forward_on_gpu(kind):
+    """clip refinement: the identity photo's part (IdEncoder + the conditioning activations of its maps) once per clip;
+    every frame then equals the full forward bit for bit, eagerly and as a CUDA graph of the per-frame work only"""
+    from sahs_b200 import spade as SP
+    m = SP.Generator() if kind == "generator" else SP.Generator_audio()
+    m.load_state_dict(SF.make_state_dict(kind, seed=2), strict=True)
+    m = m.to(DEV)
+    i0, i1 = SF.make_inputs(64, 96, seed=1), SF.make_inputs(64, 96, seed=2)
+    frame = (lambda i: (i["i_raw"].to(DEV), i["audio"].to(DEV))) if kind == "generator_audio" else (lambda i: (i["i_raw"].to(DEV),))
+    src = i0["i_src"].to(DEV)
+    ident = m.encode_identity(src)
+    m.tally = {}
+    m(src, *frame(i0))
+    full, m.tally = m.tally["conv_launches"], {}
+    first = m.refine(ident, *frame(i0)).clone()
+    m.tally = {}
+    second = m.refine(ident, *frame(i1)).clone()
+    cached, m.tally = m.tally["conv_launches"], None
+    assert full == 70 and cached == 70 - 9 - (18 if kind == "generator" else 12)
+    assert torch.equal(first, m(src, *frame(i0))) and torch.equal(second, m(src, *frame(i1)))
+    g = SP.GraphedGenerator(m, *frame(i0), identity=ident)
+    for i in (i1, i0):
+        assert torch.equal(g(*frame(i)), m(src, *frame(i)))
+    assert _status()[0] == 0
+    g.graph.reset()

@@ -130,3 +130,22 @@ def test_generator_audio_host_logic_vs_oracle():
     got = m(inp["i_src"], inp["i_raw"], inp["audio"])
     want = SO.generator_audio(sd, inp["i_src"], inp["i_raw"], inp["audio"])
     assert float((got - want).abs().max()) <= 5e-3 * float(want.abs().max())
+
+
+@pytest.mark.parametrize("kind", ["generator", "generator_audio"])
+def test_identity_cache_equals_full_forward(kind):
+    """G.refine(G.encode_identity(I_src), frame) = G(I_src, frame) exactly, with the IdEncoder and the identity-conditioned
+    mlp_shared convs computed once per clip (18 of them for Generator, 12 for Generator_audio)"""
+    import spade_emulator as EM
+    m = EM.EmulatedGenerator() if kind == "generator" else EM.EmulatedGeneratorAudio()
+    m.load_state_dict(SF.make_state_dict(kind, seed=0), strict=True)
+    i0, i1 = SF.make_inputs(16, 24, seed=1), SF.make_inputs(16, 24, seed=2)
+    extra = (lambda i: (i["audio"],)) if kind == "generator_audio" else (lambda i: ())
+    ident = m.encode_identity(i0["i_src"])
+    first = m.refine(ident, i0["i_raw"], *extra(i0))
+    assert len(ident.actv) == (18 if kind == "generator" else 12)
+    second = m.refine(ident, i1["i_raw"], *extra(i1))
+    assert torch.equal(first, m(i0["i_src"], i0["i_raw"], *extra(i0)))
+    assert torch.equal(second, m(i0["i_src"], i1["i_raw"], *extra(i1)))
+    with pytest.raises(RuntimeError):
+        m.refine(ident, torch.zeros(1, 3, 32, 24), *extra(i0))
