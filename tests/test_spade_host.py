@@ -149,3 +149,50 @@ def test_identity_cache_equals_full_forward(kind):
     assert torch.equal(second, m(i0["i_src"], i1["i_raw"], *extra(i1)))
     with pytest.raises(RuntimeError):
         m.refine(ident, torch.zeros(1, 3, 32, 24), *extra(i0))
+
+
+@pytest.mark.parametrize("out_w,out_h,up,down", [(128, 3, 0, 0), (24, 16, 0, 0), (7, 9, 0, 0), (20, 12, 1, 0), (12, 8, 0, 1), (256, 2, 0, 0)])
+def test_one_load_three_taps_rule_equals_tap_by_tap_gather(out_w, out_h, up, down):
+    """Model of the stride-1 gather of csrc/spade_conv.cu: per (ky, chunk) a thread loads ITS pixel once and stores it into
+    the three kx operand tiles at rows r+1, r, r-1 (same image row only); its own row gets zeros where tap kx falls outside
+    the image; the two pixels beyond the tile's ends come from the halo lanes.  The three tiles must equal the tap-by-tap
+    gather (src_pixel) for every tile, width (tiles spanning several image rows, ragged last tile) and resize mode."""
+    import spade_emulator as EM
+    from sahs_b200 import spade as SP
+    in_h, in_w = (out_h << down) >> up, (out_w << down) >> up
+    img = torch.arange(1, in_h * in_w + 1, dtype=torch.float32).reshape(in_h, in_w)      # pixel id; 0 = padding
+    P = out_h * out_w
+
+    def px(oy, ox, ky, kx):          # tap-by-tap reference value
+        ok, iy, ix = EM.src_pixel(SP.MODE_S1, torch.tensor(oy), torch.tensor(ox), ky, kx, in_h, in_w, out_h, out_w, up, down)
+        return float(img[int(iy), int(ix)]) if bool(ok) else 0.0
+
+    for tile in range((P + 127) // 128):
+        for ky in range(3):
+            tiles3 = torch.full((3, 128), float("nan"))
+            for r in range(128):                                  # the 128 gather threads
+                p = tile * 128 + r
+                live = p < P
+                oy, ox = (p // out_w, p % out_w) if live else (0, 0)
+                v = px(oy, ox, ky, 1) if live else 0.0
+                for kx in range(3):
+                    dr, dx = r - kx + 1, ox - kx + 1
+                    if kx == 1 or (live and 0 <= dr < 128 and 0 <= dx < out_w):
+                        assert torch.isnan(tiles3[kx, dr]), "two writers for one operand row"
+                        tiles3[kx, dr] = v
+                    if kx != 1 and (not live or ox + kx - 1 < 0 or ox + kx - 1 >= out_w):
+                        assert torch.isnan(tiles3[kx, r]), "two writers for one operand row"
+                        tiles3[kx, r] = 0.0
+            for kx, drow in ((0, 0), (2, 127)):                   # the two halo lanes
+                p = tile * 128 + drow
+                if p < P:
+                    oy, ox = p // out_w, p % out_w
+                    if (ox >= 1) if kx == 0 else (ox + 1 < out_w):
+                        assert torch.isnan(tiles3[kx, drow]), "two writers for one operand row"
+                        tiles3[kx, drow] = px(oy, ox, ky, kx)
+            for kx in range(3):
+                for r in range(128):
+                    p = tile * 128 + r
+                    if p < P:                                     # rows beyond the last pixel are never stored
+                        assert not torch.isnan(tiles3[kx, r]), (tile, ky, kx, r, "operand row never written")
+                        assert float(tiles3[kx, r]) == px(p // out_w, p % out_w, ky, kx), (tile, ky, kx, r)
