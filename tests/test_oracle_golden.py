@@ -230,3 +230,48 @@ def test_stage1_loss_oracle_matches_reference_golden():
     assert float(loss.detach()) == float(g["ref_loss"]) and np.array_equal(prob.numpy(), g["ref_prob"])
     assert np.array_equal(mc.grad.numpy(), g["ref_d_coarse"]) and np.array_equal(mf.grad.numpy(), g["ref_d_fine"])
     assert abs(float(prob.sum()) - 1.0) < 1e-6
+
+
+@pytest.mark.parametrize("mode", ["det", "ties", "flat"])
+def test_search_free_merge_rule_of_the_64x64_sample_pdf_kernel(mode):
+    """Model of the merge in csrc/sample_pdf.cu `sample_pdf_merge64_kernel`: sample j came out of bin ind_j, so the number
+    of coarse depths <= s_j is ind_j or ind_j + 1 -- the hint is corrected against z itself; with ascending samples sample
+    j lands at slot j + #{z <= s_j}, the slots are tagged, an untagged slot p holds coarse depth number (#untagged before
+    p).  Must equal sort(cat(z, samples)) whenever the samples are ascending (the kernel checks that per ray)."""
+    gen = torch.Generator().manual_seed(3)
+    R = 400
+    z, _ = torch.sort(0.48 + 0.6 * torch.rand(R, 64, generator=gen), -1)
+    w = torch.rand(R, 62, generator=gen) ** 8
+    if mode == "ties":
+        z = (z * 16).round() / 16
+        w = (w > 0.5).float()
+    elif mode == "flat":
+        w = torch.zeros(R, 62)
+    mids = 0.5 * (z[:, 1:] + z[:, :-1])
+    s, inds = O.sample_pdf(mids, w, 64, det=True, return_inds=True)
+    want, _ = torch.sort(torch.cat((z, s), -1), -1)
+    checked = 0
+    for r in range(R):
+        zr, sr = z[r], s[r]
+        if bool((sr[1:] < sr[:-1]).any()):
+            continue                                           # the kernel sorts these first (register bitonic network)
+        checked += 1
+        tag = [0] * 128
+        for j in range(64):
+            c = int(inds[r, j])                                # hint
+            while c < 64 and float(zr[c]) <= float(sr[j]):
+                c += 1
+            while c > 0 and float(zr[c - 1]) > float(sr[j]):
+                c -= 1
+            assert c == int((zr <= sr[j]).sum()) and abs(c - int(inds[r, j])) <= 1 or mode == "ties"
+            assert tag[j + c] == 0
+            tag[j + c] = j + 1
+        out, coarse_before = [], 0
+        for p in range(128):
+            if tag[p]:
+                out.append(float(sr[tag[p] - 1]))
+            else:
+                out.append(float(zr[coarse_before]))
+                coarse_before += 1
+        assert out == want[r].tolist()
+    assert checked > R // 2
