@@ -536,7 +536,7 @@ def main():
         hbm_entry("composite_fwd_kernel (coarse, S=64)", "composite_coarse", 72 * nc + 144,
                   "reads raw[S,16] + z[S] + rd + bg, writes weights[S] + 18 outputs: 72 S + 144 B per ray (SURVEY 8d)"),
         hbm_entry("composite_fwd_kernel (fine, S=128)", "composite_fine", 72 * (nc + nf) + 144, "as above, S = 128"),
-        hbm_entry("sample_pdf_merge_kernel", "sample_pdf_merge", 4 * (nc + nc + nf + nc + nf),
+        hbm_entry("sample_pdf_merge64_kernel (64 coarse + 64 new samples; other shapes: sample_pdf_merge_kernel)", "sample_pdf_merge", 4 * (nc + nc + nf + nc + nf),
                   "reads z[64] + w[64], writes z_samples[64] + merged z[128]: 1,280 B per ray"),
     ]
     composite_frame = {"ms": stage_ms["composite_coarse"] + stage_ms["composite_fine"],
