@@ -91,3 +91,38 @@ def test_shard_ranges_cover_exactly():
             sizes = [e - b for b, e in spans]
             assert max(sizes) - min(sizes) <= PL.TILE
     assert [PL.frame_owner(f, 8) for f in range(10)] == [0, 1, 2, 3, 4, 5, 6, 7, 0, 1]
+
+
+def _stage2_clip_worker(rank, world, port, num_frames):
+    """Stage II over ranks: frame f is refined entirely by rank f mod world (same sharding as the Stage-I clip), with the
+    identity photo's part computed once per rank; the product's host logic runs on the CPU through tests/spade_emulator."""
+    import spade_emulator as EM
+    import spade_fixtures as SF
+    from sahs_b200 import parallel as PL
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        m = EM.EmulatedGenerator()
+        m.load_state_dict(SF.make_state_dict("generator", seed=0), strict=True)
+        src = SF.make_inputs(16, 16, seed=0)["i_src"]
+        ident = m.encode_identity(src)
+
+        def refine_frame(f):                  # uint8 frame like eval_get_texture_photo_audio.py:187-193 (clip, * 255)
+            out = m.refine(ident, SF.make_inputs(16, 16, seed=10 + f)["i_raw"])
+            return (out[0].permute(1, 2, 0).clamp(0, 1) * 255).to(torch.uint8)
+
+        clip = PL.render_clip(refine_frame, num_frames)
+        if rank == 0:
+            assert clip.shape == (num_frames, 16, 16, 3)
+            for f in range(num_frames):       # = the full forward of that frame, whichever rank refined it
+                want = m(src, SF.make_inputs(16, 16, seed=10 + f)["i_raw"])
+                assert torch.equal(clip[f], (want[0].permute(1, 2, 0).clamp(0, 1) * 255).to(torch.uint8))
+        else:
+            assert clip is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_stage2_clip_refinement_over_ranks_world2():
+    mp.spawn(_stage2_clip_worker, args=(2, _free_port(), 3), nprocs=2, join=True)
